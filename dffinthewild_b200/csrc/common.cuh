@@ -1,0 +1,95 @@
+// Shared device/host helpers for the dff_b200 library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace dff {
+
+// ---- element access: activations are stored either as fp32 (parity mode) or bf16 (throughput mode) ---------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static __device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+  static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+    uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    float4 v;
+    v.x = __uint_as_float(r.x << 16);
+    v.y = __uint_as_float(r.x & 0xffff0000u);
+    v.z = __uint_as_float(r.y << 16);
+    v.w = __uint_as_float(r.y & 0xffff0000u);
+    return v;
+  }
+  static __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+  static __device__ __forceinline__ float load(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// ---- host-side error plumbing ------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int check_cuda(cudaError_t e, const char* what);
+#define DFF_CUDA(x)                                 \
+  do {                                              \
+    int _rc = ::dff::check_cuda((x), #x);           \
+    if (_rc) return _rc;                            \
+  } while (0)
+#define DFF_LAUNCH_CHECK(what) DFF_CUDA((cudaGetLastError()))
+#define DFF_TRY(x)          \
+  do {                      \
+    int _rc = (x);          \
+    if (_rc) return _rc;    \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- generic convolution description (shared by the FFMA and tcgen05 paths) --------------------------------
+constexpr int kMaxTaps = 81;
+struct TapTable {
+  int n;
+  int8_t dz[kMaxTaps], dy[kMaxTaps], dx[kMaxTaps];  // input offset of the tap (input coordinates)
+  uint8_t widx[kMaxTaps];                           // index of the tap inside the packed weight
+};
+
+// A (phase of a) convolution as "strided gather over a tap table":
+//   out[b,s, oy*osy+ooy, ox*osx+oox, co] = epi( sum_t sum_ci in[b, s+dz_t, oy*isy+dy_t, ox*isx+dx_t, ci] * w[widx_t][ci][co] )
+struct ConvArgs {
+  const void* in0;
+  const void* in1;
+  int C0, C1;              // stored channels of the two sources (C1 = 0: single source); multiples of 4
+  int B, S, IH, IW;        // input extent
+  int OHt, OWt;            // output positions computed by this launch (phase grid)
+  int OH, OW;              // output tensor extent
+  int isy, isx, osy, osx, ooy, oox;
+  int dzmin, dymin, dxmin; // min tap offsets
+  int RZ, RY, RX, RXP;     // staged input region per tile (RXP: padded row pitch)
+  int TY;                  // tile rows (tile cols = 32)
+  const float* w;          // [ntaps_total][CinP][CoutP] fp32
+  int CinP, CoutP;
+  const float* scale;      // [CoutP] or null
+  const float* shift;      // [CoutP] or null
+  const void* res_pre;     // added before ReLU (same layout as out) or null
+  const void* res_post;    // added after ReLU or null
+  int relu;
+  void* out;
+  void* out_aux;           // optional second output: out_aux = out_value + aux_add
+  const void* aux_add;
+  int Cout;                // stored channels of out
+  int out_f32;             // store `out` as fp32 even when activations are bf16 (cost volumes feeding the depth head)
+  TapTable taps;
+};
+
+}  // namespace dff

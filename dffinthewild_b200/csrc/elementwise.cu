@@ -1,0 +1,266 @@
+// Bandwidth kernels of the depth-from-focus path: layout conversion, pooling, the depth head, the FOV warp and the
+// weight/BatchNorm packing.  All are coalesced, vectorised where alignment allows, and read every byte once.
+#include "common.cuh"
+
+namespace dff {
+
+// ------------------------------------------------------------------------------------------------------------
+// reference layout (B,C,S,H,W) fp32  ->  channels-last (B,S,H,W,Cp), zero padded channels
+// (first thing DFF_net.forward needs: FS arrives as (B,3,S,H,W), reference :79-81)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void to_cl_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int S, int H, int W, int Cp) {
+  const size_t npix = (size_t)B * S * H * W;
+  const size_t plane = (size_t)S * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / plane, r = i % plane;
+    const float* s = src + b * C * plane + r;
+    T* d = dst + i * Cp;
+    for (int c = 0; c < Cp; c += 4) {
+      float4 v;
+      v.x = c < C ? __ldg(s + (size_t)c * plane) : 0.f;
+      v.y = c + 1 < C ? __ldg(s + (size_t)(c + 1) * plane) : 0.f;
+      v.z = c + 2 < C ? __ldg(s + (size_t)(c + 2) * plane) : 0.f;
+      v.w = c + 3 < C ? __ldg(s + (size_t)(c + 3) * plane) : 0.f;
+      Elem<T>::store4(d + c, v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void from_cl_kernel(const T* __restrict__ src, float* __restrict__ dst, int B, int C, int S, int H, int W, int Cp) {
+  const size_t npix = (size_t)B * S * H * W;
+  const size_t plane = (size_t)S * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / plane, r = i % plane;
+    for (int c = 0; c < C; ++c) dst[(b * C + c) * plane + r] = Elem<T>::load(src + i * Cp + c);
+  }
+}
+
+static inline int grid_for(size_t n, int threads, int cap = 148 * 16) {
+  size_t g = (n + threads - 1) / threads;
+  return (int)(g < (size_t)cap ? (g ? g : 1) : cap);
+}
+
+int launch_to_cl(const float* src, int B, int C, int S, int H, int W, void* dst, int Cp, bool bf16, cudaStream_t st) {
+  if (Cp % 4 || Cp < C) return fail(-1, "to_channels_last: Cp must be a multiple of 4 and >= C");
+  const size_t n = (size_t)B * S * H * W;
+  if (bf16) to_cl_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, B, C, S, H, W, Cp);
+  else to_cl_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (float*)dst, B, C, S, H, W, Cp);
+  DFF_LAUNCH_CHECK("to_cl");
+  return 0;
+}
+int launch_from_cl(const void* src, int B, int C, int S, int H, int W, int Cp, bool bf16, float* dst, cudaStream_t st) {
+  const size_t n = (size_t)B * S * H * W;
+  if (bf16) from_cl_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)src, dst, B, C, S, H, W, Cp);
+  else from_cl_kernel<<<grid_for(n, 256), 256, 0, st>>>((const float*)src, dst, B, C, S, H, W, Cp);
+  DFF_LAUNCH_CHECK("from_cl");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// (1,k,k) pooling on channels-last volumes: MaxPool3d((1,2,2)) of EFD (reference :387) and the AvgPool3d
+// pyramid of hourglassup (reference :183-187, 248-250).  One thread = one output pixel x 4 channels.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, bool kMax>
+__global__ void pool_kernel(const T* __restrict__ src, T* __restrict__ dst, int BS, int H, int W, int C, int k) {
+  const int OH = H / k, OW = W / k, C4 = C / 4;
+  const size_t n = (size_t)BS * OH * OW * C4;
+  const float inv = 1.f / (float)(k * k);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    size_t r = i / C4;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const size_t bs = r / OH;
+    const T* p = src + ((bs * H + (size_t)oy * k) * W + (size_t)ox * k) * C + 4 * c4;
+    float4 acc = kMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) {
+        const float4 v = Elem<T>::load4(p + ((size_t)dy * W + dx) * C);
+        if (kMax) {
+          acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+        } else {
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+    if (!kMax) { acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
+    Elem<T>::store4(dst + i * 4, acc);
+  }
+}
+
+int launch_pool(const void* src, void* dst, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st) {
+  if (C % 4 || H % k || W % k) return fail(-1, "pool: C % 4, H % k, W % k must be 0");
+  const size_t n = (size_t)BS * (H / k) * (W / k) * (C / 4);
+  const int g = grid_for(n, 256);
+  if (bf16) {
+    if (is_max) pool_kernel<__nv_bfloat16, true><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, BS, H, W, C, k);
+    else pool_kernel<__nv_bfloat16, false><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, BS, H, W, C, k);
+  } else {
+    if (is_max) pool_kernel<float, true><<<g, 256, 0, st>>>((const float*)src, (float*)dst, BS, H, W, C, k);
+    else pool_kernel<float, false><<<g, 256, 0, st>>>((const float*)src, (float*)dst, BS, H, W, C, k);
+  }
+  DFF_LAUNCH_CHECK("pool");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Depth head (reference :92-98, 118-136): bilinear upsample (align_corners=False) of the per-slice cost,
+// softplus(beta=1, threshold=20) + 1e-6, normalise over the S slices, expectation of the focus distance.
+// One thread per output pixel, slices walked in order; cost rows are re-used through L1/L2, focus_dists and the
+// output are touched exactly once.  num/den form: depth = (sum fd*p) / (sum p).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_ref(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+__global__ void depth_head_kernel(const float* __restrict__ cost, int h, int w, const float* __restrict__ fd, long long sb,
+                                  long long ss, long long sy, long long sx, int B, int S, int H, int W,
+                                  float* __restrict__ depth) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= W) return;
+  // source coordinates exactly as ATen's upsample_bilinear2d: src = scale*(dst+0.5)-0.5, clamped at 0
+  const float ry = (float)h / (float)H, rx = (float)w / (float)W;
+  float fy = ry * ((float)y + 0.5f) - 0.5f, fx = rx * ((float)x + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  fx = fx < 0.f ? 0.f : fx;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const bool same = (h == H) && (w == W);
+  float num = 0.f, den = 0.f;
+  const float* fp = fd + b * sb + y * sy + x * sx;
+  for (int s = 0; s < S; ++s) {
+    const float* c = cost + ((size_t)b * S + s) * h * w;
+    float v;
+    if (same) v = __ldg(c + (size_t)y * w + x);
+    else
+      v = ly0 * (lx0 * __ldg(c + (size_t)y0 * w + x0) + lx1 * __ldg(c + (size_t)y0 * w + x1)) +
+          ly1 * (lx0 * __ldg(c + (size_t)y1 * w + x0) + lx1 * __ldg(c + (size_t)y1 * w + x1));
+    const float p = softplus_ref(v) + 1e-6f;
+    den += p;
+    num = fmaf(__ldg(fp + s * ss), p, num);
+  }
+  depth[((size_t)b * H + y) * W + x] = num / den;
+}
+
+int launch_depth_head(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
+                      float* depth, cudaStream_t st) {
+  if (h <= 0 || w <= 0 || H % h || W % w) return fail(-1, "depth_head: H,W must be multiples of the cost resolution");
+  dim3 grid(cdiv(W, 128), H, B);
+  depth_head_kernel<<<grid, 128, 0, st>>>(cost, h, w, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W, depth);
+  DFF_LAUNCH_CHECK("depth_head");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FOV warp (reference End_to_End/End_to_End.py:106-134) with analytic sampling coordinates — no grid tensor.
+//   f = fov[b,s] + a0 ; flow_x = (W//2)(f-1)*lin(-1,1,W)[x] + a1 ; flow_y likewise ; sample at (x-flow_x, y-flow_y)
+//   through grid_sample's normalise/un-normalise round trip (align_corners=True), bilinear, zero padding.
+// The scale correction a0 is taken from sample 0 (the reference's batch>1 broadcast quirk).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void fov_warp_kernel(const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ fov,
+                                int B, int C, int S, int H, int W, float* __restrict__ out, float* __restrict__ flow) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int py = blockIdx.y;
+  const int bs = blockIdx.z, b = bs / S, s = bs % S;
+  if (px >= W) return;
+  const float a0 = alpha ? __ldg(alpha + (0 * 3 + 0) * S + s) : 0.f;  // sample 0 on purpose
+  const float a1 = alpha ? __ldg(alpha + ((size_t)b * 3 + 1) * S + s) : 0.f;
+  const float a2 = alpha ? __ldg(alpha + ((size_t)b * 3 + 2) * S + s) : 0.f;
+  const float f = a0 + __ldg(fov + (size_t)b * S + s);
+  // torch.linspace(-1, 1, n): start + i*step for i < n/2, end - (n-1-i)*step otherwise
+  auto lin = [](int i, int n) -> float {
+    if (n == 1) return -1.f;
+    const float step = 2.f / (float)(n - 1);
+    return i < n / 2 ? -1.f + step * (float)i : 1.f - step * (float)(n - 1 - i);
+  };
+  const float flx = (float)(W / 2) * (f - 1.f) * lin(px, W) + a1;
+  const float fly = (float)(H / 2) * (f - 1.f) * lin(py, H) + a2;
+  if (flow) {
+    const size_t plane = (size_t)S * H * W, o = ((size_t)s * H + py) * W + px;
+    flow[((size_t)b * 2 + 0) * plane + o] = flx;
+    flow[((size_t)b * 2 + 1) * plane + o] = fly;
+  }
+  // normalise (as the reference does) then un-normalise (as grid_sample does, align_corners=True)
+  const float gx = 2.0f * ((float)px - flx) / (float)max(W - 1, 1) - 1.0f;
+  const float gy = 2.0f * ((float)py - fly) / (float)max(H - 1, 1) - 1.0f;
+  const float ix = (gx + 1.f) * 0.5f * (float)(W - 1);
+  const float iy = (gy + 1.f) * 0.5f * (float)(H - 1);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+  const float tx = ix - fx0, ty = iy - fy0;
+  // trilinear weights degenerate to bilinear: the z coordinate is the slice itself
+  const float w00 = (1.f - tx) * (1.f - ty), w01 = tx * (1.f - ty), w10 = (1.f - tx) * ty, w11 = tx * ty;
+  const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+  for (int c = 0; c < C; ++c) {
+    const float* p = x + (((size_t)b * C + c) * S + s) * H * W;
+    float v = 0.f;
+    if (vy0 && vx0) v += __ldg(p + (size_t)y0 * W + x0) * w00;
+    if (vy0 && vx1) v += __ldg(p + (size_t)y0 * W + x1) * w01;
+    if (vy1 && vx0) v += __ldg(p + (size_t)y1 * W + x0) * w10;
+    if (vy1 && vx1) v += __ldg(p + (size_t)y1 * W + x1) * w11;
+    out[((((size_t)b * C + c) * S + s) * H + py) * W + px] = v;
+  }
+}
+
+int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
+                    float* flow, cudaStream_t st) {
+  dim3 grid(cdiv(W, 128), H, B * S);
+  fov_warp_kernel<<<grid, 128, 0, st>>>(x, alpha, fov, B, C, S, H, W, out, flow);
+  DFF_LAUNCH_CHECK("fov_warp");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight packing: reference layouts -> [tap][CinP][CoutP] fp32 (zero padded), BatchNorm(eval) -> scale/shift
+// ------------------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin, int ntaps,
+                                   int CinP, int CoutP, int transposed) {
+  const int n = ntaps * CinP * CoutP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int co = i % CoutP, ci = (i / CoutP) % CinP, t = i / (CoutP * CinP);
+    float v = 0.f;
+    if (co < Cout && ci < Cin)
+      v = transposed ? w[((size_t)ci * Cout + co) * ntaps + t] : w[((size_t)co * Cin + ci) * ntaps + t];
+    dst[i] = v;
+  }
+}
+
+// scale = gamma / sqrt(var + eps), shift = beta - mean * scale   (nn.BatchNorm3d eval, eps 1e-5, reference :355)
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, const float* __restrict__ bias, float* __restrict__ scale,
+                               float* __restrict__ shift, int C, int CP) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= CP) return;
+  float sc = 1.f, sh = 0.f;
+  if (c < C) {
+    if (gamma) {
+      const double inv = 1.0 / sqrt((double)var[c] + 1e-5);
+      const double s = (double)gamma[c] * inv;
+      sc = (float)s;
+      sh = (float)((double)beta[c] - (double)mean[c] * s);
+    } else if (bias) {
+      sh = bias[c];
+    }
+  }
+  scale[c] = sc;
+  shift[c] = sh;
+}
+
+int launch_pack_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int CinP, int CoutP, int transposed,
+                       cudaStream_t st) {
+  const int n = ntaps * CinP * CoutP;
+  pack_weight_kernel<<<grid_for(n, 256, 256), 256, 0, st>>>(w, dst, Cout, Cin, ntaps, CinP, CoutP, transposed);
+  DFF_LAUNCH_CHECK("pack_weight");
+  return 0;
+}
+int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
+                   float* scale, float* shift, int C, int CP, cudaStream_t st) {
+  bn_fold_kernel<<<cdiv(CP, 128), 128, 0, st>>>(gamma, beta, mean, var, bias, scale, shift, C, CP);
+  DFF_LAUNCH_CHECK("bn_fold");
+  return 0;
+}
+
+}  // namespace dff

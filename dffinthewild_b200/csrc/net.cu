@@ -1,0 +1,627 @@
+// Host side of the dff_b200 library: the layer table of DFF_net, the raw-parameter handshake, weight packing,
+// the forward schedule (reference train_codes/Depth_Estimation_Network.py:77-137) and the C-ABI of
+// include/dff_b200.h.  No device memory is allocated here; activations live in the caller's workspace.
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/dff_b200.h"
+#include "common.cuh"
+
+namespace dff {
+
+// ---- launchers implemented in the other translation units --------------------------------------------------
+int launch_conv_ffma(ConvArgs a, bool bf16, cudaStream_t st);
+int launch_to_cl(const float* src, int B, int C, int S, int H, int W, void* dst, int Cp, bool bf16, cudaStream_t st);
+int launch_from_cl(const void* src, int B, int C, int S, int H, int W, int Cp, bool bf16, float* dst, cudaStream_t st);
+int launch_pool(const void* src, void* dst, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st);
+int launch_depth_head(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
+                      float* depth, cudaStream_t st);
+int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
+                    float* flow, cudaStream_t st);
+int launch_pack_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int CinP, int CoutP, int transposed,
+                       cudaStream_t st);
+int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
+                   float* scale, float* shift, int C, int CP, cudaStream_t st);
+
+// ---- errors ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+  return DFF_E_CUDA;
+}
+
+// ---- layer table -------------------------------------------------------------------------------------------
+struct Layer {
+  std::string name;  // state_dict prefix of the conv (key = name + ".weight")
+  std::string bn;    // state_dict prefix of its BatchNorm3d ("" = none)
+  int cin, cout, kd, kh, kw, stride, dil;
+  bool transposed, bias;
+  // derived
+  int CinP, CoutP, ntaps;
+  int64_t raw_w, raw_gamma, raw_beta, raw_mean, raw_var, raw_bias;  // element offsets in the raw buffer (-1: none)
+  size_t pk_w, pk_scale, pk_shift;                                   // byte offsets in the packed buffer
+};
+struct Param {
+  std::string name;
+  int64_t numel, offset;
+};
+struct Net {
+  std::vector<Layer> layers;
+  std::map<std::string, int> index;
+  std::vector<Param> params;
+  int64_t raw_numel = 0;
+  size_t packed_bytes = 0;
+
+  void add(const std::string& name, const std::string& bn, int cin, int cout, int kd, int kh, int kw, int stride, int dil,
+           bool transposed = false, bool bias = false) {
+    Layer l{name, bn, cin, cout, kd, kh, kw, stride, dil, transposed, bias};
+    l.CinP = (int)align_up(cin, 4);
+    l.CoutP = (int)align_up(cout, 8);
+    l.ntaps = kd * kh * kw;
+    auto reg = [&](const std::string& n, int64_t numel) {
+      params.push_back({n, numel, raw_numel});
+      raw_numel += numel;
+      return params.back().offset;
+    };
+    l.raw_w = reg(name + ".weight", (int64_t)cin * cout * l.ntaps);
+    l.raw_bias = bias ? reg(name + ".bias", cout) : -1;
+    l.raw_gamma = l.raw_beta = l.raw_mean = l.raw_var = -1;
+    if (!bn.empty()) {
+      l.raw_gamma = reg(bn + ".weight", cout);
+      l.raw_beta = reg(bn + ".bias", cout);
+      l.raw_mean = reg(bn + ".running_mean", cout);
+      l.raw_var = reg(bn + ".running_var", cout);
+    }
+    l.pk_w = packed_bytes;
+    packed_bytes += align_up((size_t)l.ntaps * l.CinP * l.CoutP * sizeof(float), 256);
+    l.pk_scale = packed_bytes;
+    packed_bytes += align_up(l.CoutP * sizeof(float), 256);
+    l.pk_shift = packed_bytes;
+    packed_bytes += align_up(l.CoutP * sizeof(float), 256);
+    index[name] = (int)layers.size();
+    layers.push_back(l);
+  }
+  // convbn_3d: `p.0` conv + `p.1` BN
+  void cbn(const std::string& p, int cin, int cout, int kd, int kh, int kw, int stride = 1, int dil = 1) {
+    add(p + ".0", p + ".1", cin, cout, kd, kh, kw, stride, dil);
+  }
+  void up(const std::string& p, int cin, int cout) { add(p + ".0", p + ".1", cin, cout, 3, 3, 3, 2, 1, true); }
+  void srd(const std::string& p, int c) {
+    cbn(p + ".Focus_Measure.conv.0", c, c, 1, 3, 3);
+    cbn(p + ".Focus_Measure.conv.2", c, c, 1, 3, 3);
+    add(p + ".N_ch_attention.0", "", c, c, 3, 1, 1, 1, 1);
+    add(p + ".N_ch_attention.2", "", c, c, 1, 1, 1, 1, 1);
+  }
+  void efd(const std::string& p, int cin, int cout) {
+    cbn(p + ".stride_conv", cin, cout, 3, 3, 3, 2);
+    cbn(p + ".max_pooling.1", cin, cout, 3, 3, 3, 1);
+  }
+  void hourglass(const std::string& p, int c) {
+    cbn(p + ".conv0.0", 2 * c, c, 3, 3, 3);
+    cbn(p + ".conv1.0", c, 2 * c, 3, 3, 3, 2);
+    cbn(p + ".conv2", 2 * c, 2 * c, 3, 3, 3);
+    cbn(p + ".conv3.0", 2 * c, 2 * c, 3, 3, 3, 2);
+    cbn(p + ".conv4.0", 2 * c, 2 * c, 3, 3, 3);
+    up(p + ".conv5", 2 * c, 2 * c);
+    up(p + ".conv6", 2 * c, c);
+  }
+};
+
+// DFF_net (reference train_codes/Depth_Estimation_Network.py:17-57); only executed layers are listed: `redir3` and
+// `pre_conv` exist in the state_dict but never run (reference :244, :285-286).
+static Net build_dff() {
+  Net n;
+  n.cbn("FM_measure.Focus_extraction.0", 3, 8, 1, 9, 9, 1, 2);
+  n.srd("FM_measure.Focus_extraction.2", 8);
+  n.efd("FM_conv1.0", 8, 16);
+  n.srd("FM_conv1.1", 16);
+  n.efd("FM_conv2.0", 16, 32);
+  n.srd("FM_conv2.1", 32);
+  const std::string sp = "SPP_module.";
+  const int c = 32;
+  auto tower = [&](const std::string& a, const std::string& b, int ci, int co) {
+    n.cbn(sp + a + ".0", ci, co, 3, 3, 3);
+    n.cbn(sp + a + ".2", co, co, 3, 3, 3);
+    n.cbn(sp + b + ".0", co, co, 3, 3, 3);
+    n.cbn(sp + b + ".2", co, co, 3, 3, 3);
+  };
+  tower("dres8_0", "dres8_1", c, c);
+  tower("dres16_0", "dres16_1", c, 2 * c);
+  tower("dres32_0", "dres32_1", c, 2 * c);
+  n.add(sp + "conv1", "", c, 2 * c, 3, 3, 3, 2, 1);
+  n.cbn(sp + "conv2.0", 2 * c, 2 * c, 3, 3, 3);
+  n.add(sp + "conv3", "", 2 * c, 4 * c, 3, 3, 3, 2, 1);
+  n.cbn(sp + "conv4.0", 4 * c, 4 * c, 3, 3, 3);
+  n.up(sp + "conv8", 4 * c, 2 * c);
+  n.up(sp + "conv9", 2 * c, c);
+  n.cbn(sp + "combine1.0", 4 * c, 2 * c, 3, 3, 3);
+  n.cbn(sp + "combine2.0", 6 * c, 4 * c, 3, 3, 3);
+  n.cbn(sp + "redir1", c, c, 1, 1, 1);
+  n.cbn(sp + "redir2", 2 * c, 2 * c, 1, 1, 1);
+  n.cbn("confidence.0", 32, 32, 3, 3, 3);
+  n.add("confidence.2", "", 32, 1, 3, 3, 3, 1, 1);
+  n.cbn("dres0.0", 32, 64, 3, 3, 3);
+  n.cbn("dres0.2", 64, 64, 3, 3, 3);
+  n.up("deconv_1", 64, 32);
+  n.hourglass("dres2", 32);
+  n.up("deconv_2", 32, 16);
+  n.hourglass("dres3", 16);
+  n.up("deconv_3", 16, 8);
+  n.hourglass("dres4", 8);
+  n.add("classif1.0", "", 32, 1, 1, 1, 1, 1, 1);
+  n.add("classif2.0", "", 16, 1, 1, 1, 1, 1, 1);
+  n.add("classif3.0", "", 8, 1, 1, 1, 1, 1, 1);
+  return n;
+}
+
+static const Net& net_of(int which) {
+  static const Net dffnet = build_dff();
+  (void)which;
+  return dffnet;
+}
+
+// ---- tap tables --------------------------------------------------------------------------------------------
+// Ordinary convolution: tap (kd,kh,kw) reads in[s + kd - pd, oy*stride + kh*dil - ph, ...] with "same"-style padding
+// p = dil*(k-1)/2 (every conv of the network uses it: reference :144, 352-355, 361-367, 383-403).
+static void conv_taps(const Layer& l, TapTable& t) {
+  t.n = 0;
+  const int pd = (l.kd - 1) / 2, ph = l.dil * (l.kh - 1) / 2, pw = l.dil * (l.kw - 1) / 2;
+  for (int a = 0; a < l.kd; ++a)
+    for (int b = 0; b < l.kh; ++b)
+      for (int c = 0; c < l.kw; ++c) {
+        t.dz[t.n] = (int8_t)(a - pd);
+        t.dy[t.n] = (int8_t)(b * l.dil - ph);
+        t.dx[t.n] = (int8_t)(c * l.dil - pw);
+        t.widx[t.n] = (uint8_t)((a * l.kh + b) * l.kw + c);
+        ++t.n;
+      }
+}
+// Transposed convolution k=3, stride (1,2,2), pad 1, output_padding (0,1,1) (reference :43-50), output parity phase
+// (py,px):  out[d, 2i+py, 2j+px] = sum_{kd} sum_{kh in K(py)} sum_{kw in K(px)} in[d+1-kd, i+dy(kh), j+dx(kw)] * w[kd,kh,kw]
+// with K(0) = {1} (offset 0) and K(1) = {0 (offset +1), 2 (offset 0)}: 3 / 6 / 6 / 12 taps.
+static void deconv_taps(int py, int px, TapTable& t) {
+  t.n = 0;
+  const int ky[2][2] = {{1, -1}, {0, 2}}, off[2][2] = {{0, 0}, {1, 0}};
+  for (int kd = 0; kd < 3; ++kd)
+    for (int iy = 0; iy < (py ? 2 : 1); ++iy)
+      for (int ix = 0; ix < (px ? 2 : 1); ++ix) {
+        const int kh = ky[py][iy], kw = ky[px][ix];
+        t.dz[t.n] = (int8_t)(1 - kd);
+        t.dy[t.n] = (int8_t)off[py][iy];
+        t.dx[t.n] = (int8_t)off[px][ix];
+        t.widx[t.n] = (uint8_t)((kd * 3 + kh) * 3 + kw);
+        ++t.n;
+      }
+}
+
+// ---- activation tensors in the workspace -------------------------------------------------------------------
+struct Ten {
+  void* p = nullptr;
+  int B = 0, S = 0, H = 0, W = 0, C = 0;
+  bool f32 = false;  // stored as fp32 regardless of the mode
+};
+
+struct EpiOpt {
+  const Ten* in1 = nullptr;       // second source (virtual concat)
+  const Ten* res_pre = nullptr;   // added before ReLU
+  const Ten* res_post = nullptr;  // added after ReLU
+  bool relu = false;
+  const Ten* aux_add = nullptr;   // second output = out + aux_add
+  Ten* aux_out = nullptr;
+  bool out_f32 = false;
+};
+
+// Runs one conv layer (all phases) given packed weights.
+static int run_conv(const Layer& l, const float* w, const float* scale, const float* shift, const Ten& in, const EpiOpt& e,
+                    Ten& out, bool bf16, cudaStream_t st) {
+  ConvArgs a{};
+  a.in0 = in.p;
+  a.C0 = in.C;
+  a.in1 = e.in1 ? e.in1->p : nullptr;
+  a.C1 = e.in1 ? e.in1->C : 0;
+  if (a.C0 + a.C1 != l.CinP) return fail(DFF_E_ARG, "conv " + l.name + ": input channels do not match the layer");
+  a.B = in.B; a.S = in.S; a.IH = in.H; a.IW = in.W;
+  a.OH = out.H; a.OW = out.W;
+  a.w = w; a.CinP = l.CinP; a.CoutP = l.CoutP;
+  a.scale = scale; a.shift = shift;
+  a.res_pre = e.res_pre ? e.res_pre->p : nullptr;
+  a.res_post = e.res_post ? e.res_post->p : nullptr;
+  a.relu = e.relu ? 1 : 0;
+  a.out = out.p;
+  a.out_aux = e.aux_out ? e.aux_out->p : nullptr;
+  a.aux_add = e.aux_add ? e.aux_add->p : nullptr;
+  a.Cout = out.C;
+  a.out_f32 = e.out_f32 ? 1 : 0;
+  if (!l.transposed) {
+    conv_taps(l, a.taps);
+    a.isy = a.isx = l.stride; a.osy = a.osx = 1; a.ooy = a.oox = 0;
+    a.OHt = out.H; a.OWt = out.W;
+    return launch_conv_ffma(a, bf16, st);
+  }
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      deconv_taps(py, px, a.taps);
+      a.isy = a.isx = 1; a.osy = a.osx = 2; a.ooy = py; a.oox = px;
+      a.OHt = in.H; a.OWt = in.W;
+      DFF_TRY(launch_conv_ffma(a, bf16, st));
+    }
+  return 0;
+}
+
+// ---- the forward schedule -----------------------------------------------------------------------------------
+struct Runner {
+  const Net& net;
+  const char* packed;
+  char* ws;
+  size_t ws_bytes, off = 0;
+  bool dry, bf16;
+  cudaStream_t st;
+  int rc = 0;
+
+  size_t esize(bool f32) const { return (bf16 && !f32) ? 2 : 4; }
+  Ten alloc(int B, int S, int H, int W, int C, bool f32 = false) {
+    Ten t;
+    t.B = B; t.S = S; t.H = H; t.W = W; t.C = C; t.f32 = f32;
+    const size_t bytes = align_up((size_t)B * S * H * W * C * esize(f32), 256);
+    if (!dry) {
+      if (off + bytes > ws_bytes) {
+        if (!rc) rc = fail(DFF_E_WORKSPACE, "workspace too small");
+      } else {
+        t.p = ws + off;
+      }
+    }
+    off += bytes;
+    return t;
+  }
+  Ten conv(const std::string& name, const Ten& in, EpiOpt e = EpiOpt()) {
+    const Layer& l = net.layers[net.index.at(name)];
+    Ten out;
+    if (l.transposed) out = alloc(in.B, in.S, in.H * 2, in.W * 2, e.out_f32 ? l.cout : l.CoutP, e.out_f32);
+    else out = alloc(in.B, in.S, in.H / l.stride, in.W / l.stride, e.out_f32 ? l.cout : l.CoutP, e.out_f32);
+    Ten aux;
+    if (e.aux_add) {
+      aux = alloc(out.B, out.S, out.H, out.W, out.C);
+      aux_last = aux;
+      e.aux_out = &aux;
+    }
+    if (dry || rc) return out;
+    rc = run_conv(l, (const float*)(packed + l.pk_w), (const float*)(packed + l.pk_scale),
+                  (const float*)(packed + l.pk_shift), in, e, out, bf16, st);
+    return out;
+  }
+  Ten aux_last;
+  Ten pool(const Ten& in, int k, bool is_max) {
+    Ten out = alloc(in.B, in.S, in.H / k, in.W / k, in.C);
+    if (dry || rc) return out;
+    rc = launch_pool(in.p, out.p, in.B * in.S, in.H, in.W, in.C, k, is_max, bf16, st);
+    return out;
+  }
+  static EpiOpt relu() {
+    EpiOpt e;
+    e.relu = true;
+    return e;
+  }
+  // SRD / Feature_Extraction (reference :394-407)
+  Ten srd(const std::string& p, const Ten& x) {
+    Ten t = conv(p + ".Focus_Measure.conv.0.0", x, relu());
+    EpiOpt e = relu();
+    e.res_pre = &x;
+    Ten f = conv(p + ".Focus_Measure.conv.2.0", t, e);
+    Ten a = conv(p + ".N_ch_attention.0", f, relu());
+    EpiOpt e2 = relu();
+    e2.res_post = &f;
+    return conv(p + ".N_ch_attention.2", a, e2);
+  }
+  // EFD / res_stride_conv_3d (reference :383-392)
+  Ten efd(const std::string& p, const Ten& x) {
+    Ten a = conv(p + ".stride_conv.0", x);
+    Ten mp = pool(x, 2, true);
+    EpiOpt e = relu();
+    e.res_pre = &a;
+    return conv(p + ".max_pooling.1.0", mp, e);
+  }
+  Ten tower(const std::string& a, const std::string& b, const Ten& x) {
+    Ten r = conv(a + ".2.0", conv(a + ".0.0", x, relu()), relu());
+    EpiOpt e;
+    e.res_pre = &r;  // conv -> BN -> + residual, no ReLU (reference :252,255,258)
+    return conv(b + ".2.0", conv(b + ".0.0", r, relu()), e);
+  }
+  // hourglassup (reference :247-273)
+  Ten pyramid(const Ten& v3) {
+    const std::string sp = "SPP_module.";
+    Ten x8 = pool(v3, 2, false), x16 = pool(v3, 4, false), x32 = pool(v3, 8, false);
+    x8 = tower(sp + "dres8_0", sp + "dres8_1", x8);
+    x16 = tower(sp + "dres16_0", sp + "dres16_1", x16);
+    x32 = tower(sp + "dres32_0", sp + "dres32_1", x32);
+    Ten c1 = conv(sp + "conv1", x8);
+    EpiOpt e = relu();
+    e.in1 = &x16;
+    c1 = conv(sp + "combine1.0.0", c1, e);
+    Ten c2 = conv(sp + "conv2.0.0", c1, relu());
+    Ten c3 = conv(sp + "conv3", c2);
+    EpiOpt e3 = relu();
+    e3.in1 = &x32;
+    c3 = conv(sp + "combine2.0.0", c3, e3);
+    Ten c4 = conv(sp + "conv4.0.0", c3, relu());
+    Ten r2 = conv(sp + "redir2.0", c2);
+    EpiOpt e8 = relu();
+    e8.res_pre = &r2;
+    Ten c8 = conv(sp + "conv8.0", c4, e8);
+    Ten r1 = conv(sp + "redir1.0", x8);
+    EpiOpt e9 = relu();
+    e9.res_pre = &r1;
+    return conv(sp + "conv9.0", c8, e9);
+  }
+  // hourglass (reference :302-321).  Returns `out`; pre_1 through *pre1; out_in = skip + out through *out_in.
+  Ten hourglass(const std::string& p, const Ten& x, const Ten& skip_feat, const Ten* presqu, const Ten* postsqu, Ten* pre1,
+                Ten* out_in, bool need_out) {
+    EpiOpt e0 = relu();
+    e0.in1 = &skip_feat;
+    *pre1 = conv(p + ".conv0.0.0", x, e0);
+    Ten o = conv(p + ".conv1.0.0", *pre1, relu());
+    EpiOpt e2 = relu();
+    e2.res_pre = postsqu;
+    Ten pre = conv(p + ".conv2.0", o, e2);
+    o = conv(p + ".conv3.0.0", pre, relu());
+    o = conv(p + ".conv4.0.0", o, relu());
+    EpiOpt e5 = relu();
+    e5.res_pre = presqu ? presqu : &pre;
+    o = conv(p + ".conv5.0", o, e5);
+    EpiOpt e6;
+    if (need_out) {
+      e6.aux_add = &x;
+      Ten out = conv(p + ".conv6.0", o, e6);
+      *out_in = aux_last;
+      return out;
+    }
+    e6.res_post = &x;  // last stage: only out2 + out is needed (reference :115)
+    *out_in = conv(p + ".conv6.0", o, e6);
+    return *out_in;
+  }
+};
+
+static int forward_impl(const void* packed, const float* FS, const float* fd, const int64_t* fds, int B, int S, int H, int W,
+                        float* const* out4, float* const* cost4, void* ws, size_t ws_bytes, int mode, cudaStream_t st,
+                        bool dry, size_t* need) {
+  if (B < 1 || S < 1 || H < 32 || W < 32 || H % 32 || W % 32)
+    return fail(DFF_E_ARG, "dff_forward: need B,S >= 1 and H,W positive multiples of 32 (pad with -1 like the reference dataloaders)");
+  if (mode & DFF_TRAIN) return fail(DFF_E_UNSUPPORTED, "dff_forward: DFF_TRAIN is not available in this build");
+  Runner r{net_of(DFF_NET_DFF), (const char*)packed, (char*)ws, ws_bytes, 0, dry, (mode & DFF_BF16) != 0, st};
+  Ten x0 = r.alloc(B, S, H, W, 4);
+  if (!dry && !r.rc) r.rc = launch_to_cl(FS, B, 3, S, H, W, x0.p, 4, r.bf16, st);
+  Ten t = r.conv("FM_measure.Focus_extraction.0.0", x0, Runner::relu());
+  Ten v1 = r.srd("FM_measure.Focus_extraction.2", t);
+  Ten v2 = r.srd("FM_conv1.1", r.efd("FM_conv1.0", v1));
+  Ten v3 = r.srd("FM_conv2.1", r.efd("FM_conv2.0", v2));
+  Ten vol = r.pyramid(v3);
+
+  EpiOpt ec;
+  ec.out_f32 = true;
+  Ten cm = r.conv("confidence.2", r.conv("confidence.0.0", vol, Runner::relu()), ec);
+
+  Ten x = r.conv("dres0.2.0", r.conv("dres0.0.0", vol, Runner::relu()), Runner::relu());
+  x = r.conv("deconv_1.0", x);
+  Ten pre, out_in, pre2, pre3;
+  Ten out = r.hourglass("dres2", x, v3, nullptr, nullptr, &pre, &out_in, true);
+  Ten cost1 = r.conv("classif1.0", out_in, ec);
+  Ten o2 = r.conv("deconv_2.0", out_in);
+  Ten out_in2;
+  Ten outb = r.hourglass("dres3", o2, v2, &pre, &out, &pre2, &out_in2, true);
+  Ten cost2 = r.conv("classif2.0", out_in2, ec);
+  Ten o3 = r.conv("deconv_3.0", out_in2);
+  Ten out_in3;
+  r.hourglass("dres4", o3, v1, &pre2, &outb, &pre3, &out_in3, false);
+  Ten cost3 = r.conv("classif3.0", out_in3, ec);
+  if (need) *need = r.off;
+  if (dry) return 0;
+  if (r.rc) return r.rc;
+  const Ten* costs[4] = {&cm, &cost1, &cost2, &cost3};
+  for (int i = 0; i < 4; ++i) {
+    DFF_TRY(launch_depth_head((const float*)costs[i]->p, costs[i]->H, costs[i]->W, fd, fds, B, S, H, W, out4[i], st));
+    if (cost4 && cost4[i])
+      DFF_CUDA(cudaMemcpyAsync(cost4[i], costs[i]->p, (size_t)B * S * costs[i]->H * costs[i]->W * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  int rc = 0;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (dev != prev) rc = check_cuda(cudaSetDevice(dev), "cudaSetDevice");
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace dff
+
+using namespace dff;
+
+// =============================================================================================================
+// C-ABI
+// =============================================================================================================
+extern "C" {
+
+int dff_abi_version(void) { return DFF_ABI_VERSION; }
+const char* dff_last_error(void) { return g_err.c_str(); }
+
+int dff_check_device(int device) {
+  cudaDeviceProp p;
+  DFF_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) return fail(DFF_E_DEVICE, std::string("dff_b200 needs an sm_100 (B200) device, found sm_") +
+                                                   std::to_string(p.major) + std::to_string(p.minor));
+  return 0;
+}
+
+int dff_param_count(int net) { return (int)net_of(net).params.size(); }
+const char* dff_param_name(int net, int i) {
+  const Net& n = net_of(net);
+  return (i < 0 || i >= (int)n.params.size()) ? nullptr : n.params[i].name.c_str();
+}
+int64_t dff_param_numel(int net, int i) {
+  const Net& n = net_of(net);
+  return (i < 0 || i >= (int)n.params.size()) ? -1 : n.params[i].numel;
+}
+int64_t dff_param_offset(int net, int i) {
+  const Net& n = net_of(net);
+  return (i < 0 || i >= (int)n.params.size()) ? -1 : n.params[i].offset;
+}
+int64_t dff_raw_numel(int net) { return net_of(net).raw_numel; }
+size_t dff_packed_bytes(int net) { return net_of(net).packed_bytes; }
+
+int dff_pack_weights(int net, const float* raw, void* packed, int device, void* stream) {
+  if (!raw || !packed) return fail(DFF_E_ARG, "dff_pack_weights: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Net& n = net_of(net);
+  char* pk = (char*)packed;
+  for (const Layer& l : n.layers) {
+    DFF_TRY(launch_pack_weight(raw + l.raw_w, (float*)(pk + l.pk_w), l.cout, l.cin, l.ntaps, l.CinP, l.CoutP,
+                               l.transposed ? 1 : 0, st));
+    const bool bn = l.raw_gamma >= 0;
+    DFF_TRY(launch_bn_fold(bn ? raw + l.raw_gamma : nullptr, bn ? raw + l.raw_beta : nullptr, bn ? raw + l.raw_mean : nullptr,
+                           bn ? raw + l.raw_var : nullptr, l.raw_bias >= 0 ? raw + l.raw_bias : nullptr,
+                           (float*)(pk + l.pk_scale), (float*)(pk + l.pk_shift), l.cout, l.CoutP, st));
+  }
+  return 0;
+}
+
+size_t dff_workspace_bytes(int B, int S, int H, int W, int mode) {
+  size_t need = 0;
+  if (forward_impl(nullptr, nullptr, nullptr, nullptr, B, S, H, W, nullptr, nullptr, nullptr, 0, mode, nullptr, true, &need))
+    return 0;
+  return need;
+}
+
+int dff_forward(const void* packed, const float* FS, const float* fd, const int64_t fd_strides[4], int B, int S, int H,
+                int W, float* const out4[4], float* const cost4[4], void* workspace, size_t workspace_bytes, int mode,
+                int device, void* stream) {
+  if (!packed || !FS || !fd || !fd_strides || !out4 || !workspace) return fail(DFF_E_ARG, "dff_forward: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return forward_impl(packed, FS, fd, fd_strides, B, S, H, W, out4, cost4, workspace, workspace_bytes, mode,
+                      (cudaStream_t)stream, false, nullptr);
+}
+
+size_t dff_host_io_bytes(int B, int S, int H, int W) {
+  return align_up((size_t)B * 3 * S * H * W * 4, 256) + align_up((size_t)B * S * H * W * 4, 256) +
+         4 * align_up((size_t)B * H * W * 4, 256);
+}
+
+int dff_forward_host(const void* packed, const float* FS_host, const float* fd_host, const int64_t fd_strides[4], int B,
+                     int S, int H, int W, float* const out4_host[4], void* dev_io, void* workspace, size_t workspace_bytes,
+                     int mode, int device, void* stream) {
+  if (!packed || !FS_host || !fd_host || !fd_strides || !out4_host || !dev_io || !workspace)
+    return fail(DFF_E_ARG, "dff_forward_host: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* io = (char*)dev_io;
+  const size_t fs_bytes = (size_t)B * 3 * S * H * W * 4;
+  // number of focus-distance elements the strides address
+  const int dims[4] = {B, S, H, W};
+  size_t fd_elems = 1;
+  for (int i = 0; i < 4; ++i) fd_elems += (size_t)(dims[i] - 1) * (size_t)fd_strides[i];
+  if (fd_elems > (size_t)B * S * H * W) return fail(DFF_E_ARG, "dff_forward_host: focus_dists strides exceed (B,S,H,W)");
+  float* dFS = (float*)io;
+  float* dfd = (float*)(io + align_up(fs_bytes, 256));
+  char* o = io + align_up(fs_bytes, 256) + align_up((size_t)B * S * H * W * 4, 256);
+  float* dout[4];
+  const size_t map_bytes = (size_t)B * H * W * 4;
+  for (int i = 0; i < 4; ++i) dout[i] = (float*)(o + i * align_up(map_bytes, 256));
+  DFF_CUDA(cudaMemcpyAsync(dFS, FS_host, fs_bytes, cudaMemcpyHostToDevice, st));
+  DFF_CUDA(cudaMemcpyAsync(dfd, fd_host, fd_elems * 4, cudaMemcpyHostToDevice, st));
+  DFF_TRY(forward_impl(packed, dFS, dfd, fd_strides, B, S, H, W, dout, nullptr, workspace, workspace_bytes, mode, st, false,
+                       nullptr));
+  for (int i = 0; i < 4; ++i)
+    if (out4_host[i]) DFF_CUDA(cudaMemcpyAsync(out4_host[i], dout[i], map_bytes, cudaMemcpyDeviceToHost, st));
+  DFF_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+size_t dff_conv3d_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw) {
+  const size_t CinP = align_up(Cin, 4), CoutP = align_up(Cout, 8);
+  return align_up((size_t)kd * kh * kw * CinP * CoutP * 4, 256);
+}
+
+int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const float* weight, int Cout,
+               int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, const float* scale, const float* shift,
+               const void* res_pre, const void* res_post, int relu, void* out, int elem, int use_tensor_cores, void* scratch,
+               int device, void* stream) {
+  if (!in0 || !weight || !out || !scratch) return fail(DFF_E_ARG, "dff_conv3d: null pointer");
+  if (use_tensor_cores) return fail(DFF_E_UNSUPPORTED, "dff_conv3d: tensor-core path not available for this layer");
+  if (kd * kh * kw > kMaxTaps) return fail(DFF_E_ARG, "dff_conv3d: too many taps");
+  if (transposed && !(kd == 3 && kh == 3 && kw == 3 && stride_hw == 2 && dil_hw == 1))
+    return fail(DFF_E_ARG, "dff_conv3d: transposed conv must be k=3, stride (1,2,2)");
+  if (C0 % 4 || C1 % 4) return fail(DFF_E_ARG, "dff_conv3d: stored channels must be multiples of 4");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cin = C0 + C1;
+  Layer l{"adhoc", "", Cin, Cout, kd, kh, kw, stride_hw, dil_hw, transposed != 0, false};
+  l.CinP = Cin;
+  l.CoutP = (int)align_up(Cout, 8);
+  l.ntaps = kd * kh * kw;
+  DFF_TRY(launch_pack_weight(weight, (float*)scratch, Cout, Cin, l.ntaps, l.CinP, l.CoutP, transposed ? 1 : 0, st));
+  Ten in;
+  in.p = const_cast<void*>(in0); in.B = B; in.S = S; in.H = IH; in.W = IW; in.C = C0;
+  Ten t1;
+  t1.p = const_cast<void*>(in1); t1.C = C1;
+  Ten o;
+  o.p = out; o.B = B; o.S = S; o.C = Cout;
+  o.H = transposed ? IH * 2 : IH / stride_hw;
+  o.W = transposed ? IW * 2 : IW / stride_hw;
+  Ten rp, rq;
+  rp.p = const_cast<void*>(res_pre);
+  rq.p = const_cast<void*>(res_post);
+  EpiOpt e;
+  e.in1 = (in1 && C1) ? &t1 : nullptr;
+  e.res_pre = res_pre ? &rp : nullptr;
+  e.res_post = res_post ? &rq : nullptr;
+  e.relu = relu != 0;
+  return run_conv(l, (const float*)scratch, scale, shift, in, e, o, elem == DFF_BF16, st);
+}
+
+int dff_depth_head(const float* cost, int h, int w, const float* fd, const int64_t fd_strides[4], int B, int S, int H, int W,
+                   float* depth, int device, void* stream) {
+  if (!cost || !fd || !fd_strides || !depth) return fail(DFF_E_ARG, "dff_depth_head: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_depth_head(cost, h, w, fd, fd_strides, B, S, H, W, depth, (cudaStream_t)stream);
+}
+
+int dff_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
+                 float* flow, int device, void* stream) {
+  if (!x || !fov || !out) return fail(DFF_E_ARG, "dff_fov_warp: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_fov_warp(x, alpha, fov, B, C, S, H, W, out, flow, (cudaStream_t)stream);
+}
+
+int dff_to_channels_last(const float* src, int B, int C, int S, int H, int W, void* dst, int Cp, int elem, int device,
+                         void* stream) {
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_to_cl(src, B, C, S, H, W, dst, Cp, elem == DFF_BF16, (cudaStream_t)stream);
+}
+int dff_from_channels_last(const void* src, int B, int C, int S, int H, int W, int Cp, int elem, float* dst, int device,
+                           void* stream) {
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_from_cl(src, B, C, S, H, W, Cp, elem == DFF_BF16, dst, (cudaStream_t)stream);
+}
+
+}  // extern "C"

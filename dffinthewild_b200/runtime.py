@@ -1,0 +1,313 @@
+"""ctypes binding of the C-ABI library (`include/dff_b200.h`) and the glue the drop-in modules use.
+
+Torch is plumbing here: it owns device memory (inputs, outputs, packed weights, workspace) and the current
+stream; every computation happens inside `libdff_b200.so`.  There is deliberately no fallback: if the library is
+missing, the device is not sm_100, or a tensor lives on the CPU, the call raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdff_b200.so")
+
+FP32, BF16, TRAIN = 0, 1, 2
+NET_DFF, NET_FLOW = 0, 1
+
+_lib = None
+_lock = threading.Lock()
+
+
+class DffError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i, i64, sz, fp = c.c_void_p, c.c_int, c.c_int64, c.c_size_t, c.c_void_p
+    sig = {
+        "dff_abi_version": (i, []),
+        "dff_last_error": (c.c_char_p, []),
+        "dff_check_device": (i, [i]),
+        "dff_param_count": (i, [i]),
+        "dff_param_name": (c.c_char_p, [i, i]),
+        "dff_param_numel": (i64, [i, i]),
+        "dff_param_offset": (i64, [i, i]),
+        "dff_raw_numel": (i64, [i]),
+        "dff_packed_bytes": (sz, [i]),
+        "dff_pack_weights": (i, [i, fp, vp, i, vp]),
+        "dff_workspace_bytes": (sz, [i, i, i, i, i]),
+        "dff_forward": (i, [vp, fp, fp, c.POINTER(i64), i, i, i, i, c.POINTER(vp), c.POINTER(vp), vp, sz, i, i, vp]),
+        "dff_host_io_bytes": (sz, [i, i, i, i]),
+        "dff_forward_host": (i, [vp, fp, fp, c.POINTER(i64), i, i, i, i, c.POINTER(vp), vp, vp, sz, i, i, vp]),
+        "dff_conv3d_scratch_bytes": (sz, [i, i, i, i, i]),
+        "dff_conv3d": (i, [vp, i, vp, i, i, i, i, i, fp, i, i, i, i, i, i, i, fp, fp, vp, vp, i, vp, i, i, vp, i, vp]),
+        "dff_depth_head": (i, [fp, i, i, fp, c.POINTER(i64), i, i, i, i, fp, i, vp]),
+        "dff_fov_warp": (i, [fp, fp, fp, i, i, i, i, i, fp, fp, i, vp]),
+        "dff_to_channels_last": (i, [fp, i, i, i, i, i, vp, i, i, i, vp]),
+        "dff_from_channels_last": (i, [vp, i, i, i, i, i, i, i, fp, i, vp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, args
+    return sig
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built (`python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise DffError("dff_b200: %s is missing — build it with __graft_entry__.build(); there is no "
+                                   "CPU or eager fallback" % LIB_PATH)
+                l = ctypes.CDLL(LIB_PATH)
+                _declare(l)
+                _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DffError("dff_b200 error %d: %s" % (rc, lib().dff_last_error().decode()))
+
+
+def default_precision():
+    return os.environ.get("DFF_B200_PRECISION", "fp32")
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def param_names(net=NET_DFF):
+    l = lib()
+    return [l.dff_param_name(net, i).decode() for i in range(l.dff_param_count(net))]
+
+
+def _require_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise DffError("dff_b200: %s must be a CUDA tensor (the hot path has no CPU implementation)" % what)
+
+
+_checked_devices = set()
+
+
+def _check_device(index):
+    if index not in _checked_devices:
+        check(lib().dff_check_device(index))
+        _checked_devices.add(index)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# weights
+# ---------------------------------------------------------------------------------------------------------------
+class PackedWeights:
+    """Raw flat fp32 parameter buffer + kernel-layout pack for one module replica, refreshed when any tensor changes."""
+
+    def __init__(self, module, prefix_net=NET_DFF):
+        self.net = prefix_net
+        self.names = param_names(prefix_net)
+        self.key = None
+        self.raw = None
+        self.packed = None
+
+    def _tensors(self, module):
+        own = dict(module.named_parameters())
+        own.update(dict(module.named_buffers()))
+        try:
+            return [own[n] for n in self.names]
+        except KeyError as e:
+            raise DffError("dff_b200: module has no tensor named %s (state_dict layout mismatch)" % e)
+
+    def get(self, module, device):
+        ts = self._tensors(module)
+        key = (device.index,) + tuple((t.data_ptr(), t._version) for t in ts)
+        if key != self.key:
+            l = lib()
+            with torch.no_grad():
+                raw = torch.cat([t.detach().reshape(-1).to(device=device, dtype=torch.float32) for t in ts])
+            if raw.numel() != l.dff_raw_numel(self.net):
+                raise DffError("dff_b200: raw parameter count %d != %d" % (raw.numel(), l.dff_raw_numel(self.net)))
+            packed = torch.empty(l.dff_packed_bytes(self.net), dtype=torch.uint8, device=device)
+            check(l.dff_pack_weights(self.net, _ptr(raw), _ptr(packed), device.index, _stream(device)))
+            self.raw, self.packed, self.key = raw, packed, key
+        return self.packed
+
+
+_ws_cache = {}
+
+
+def _workspace(device, B, S, H, W, mode):
+    key = (device.index, B, S, H, W, mode)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        n = lib().dff_workspace_bytes(B, S, H, W, mode)
+        if n == 0:
+            check(-1)
+        for k in [k for k in _ws_cache if k[0] == device.index]:
+            del _ws_cache[k]
+        ws = torch.empty(n, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _mode(net):
+    prec = getattr(net, "precision", "fp32")
+    if prec not in ("fp32", "bf16"):
+        raise DffError("dff_b200: precision must be 'fp32' or 'bf16'")
+    return BF16 if prec == "bf16" else FP32
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DFF_net forward (reference train_codes/Depth_Estimation_Network.py:77-137)
+# ---------------------------------------------------------------------------------------------------------------
+def dff_net_forward(net, FS, focus_dists, return_costs=False):
+    _require_cuda(FS, "FS")
+    _require_cuda(focus_dists, "focus_dists")
+    if FS.dim() != 5 or FS.shape[1] != 3:
+        raise DffError("dff_b200: FS must be (B,3,S,H,W), got %s" % (tuple(FS.shape),))
+    if FS.dtype != torch.float32 or focus_dists.dtype != torch.float32:
+        raise DffError("dff_b200: FS and focus_dists must be float32 (as the reference dataloaders produce)")
+    if net.training:
+        raise DffError("dff_b200: train-mode forward (batch-statistics BatchNorm + backward) is not available in this build")
+    dev = FS.device
+    _check_device(dev.index)
+    B, _, S, H, W = FS.shape
+    FS = FS.contiguous()
+    fd = focus_dists.to(dev)
+    while fd.dim() < 4:
+        fd = fd.unsqueeze(0)
+    fd = fd.expand(B, S, H, W)
+    strides = (ctypes.c_int64 * 4)(*fd.stride())
+    mode = _mode(net)
+    cache = net.__dict__.get("_dff_packed")
+    if cache is None:
+        cache = PackedWeights(net)
+        net.__dict__["_dff_packed"] = cache
+    packed = cache.get(net, dev)
+    ws = _workspace(dev, B, S, H, W, mode)
+    outs = [torch.empty((B, H, W), dtype=torch.float32, device=dev) for _ in range(4)]
+    out_ptrs = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in outs])
+    costs, cost_ptrs = None, None
+    if return_costs:
+        costs = [torch.empty((B, S, H // r, W // r), dtype=torch.float32, device=dev) for r in (8, 4, 2, 1)]
+        cost_ptrs = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in costs])
+    with torch.cuda.device(dev):
+        check(lib().dff_forward(_ptr(packed), _ptr(FS), _ptr(fd), strides, B, S, H, W, out_ptrs, cost_ptrs, _ptr(ws),
+                                ws.numel(), mode, dev.index, _stream(dev)))
+    if return_costs:
+        return tuple(outs), tuple(costs)
+    return tuple(outs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# single operators (unit-parity surface of the C-ABI; tensors in the reference's (B,C,S,H,W) layout)
+# ---------------------------------------------------------------------------------------------------------------
+def _elem(bf16):
+    return BF16 if bf16 else FP32
+
+
+def to_channels_last(x, Cp=None, bf16=False):
+    """(B,C,S,H,W) fp32 -> channels-last (B,S,H,W,Cp) fp32|bf16 via the library's layout kernel."""
+    _require_cuda(x, "x")
+    B, C, S, H, W = x.shape
+    Cp = Cp or (C + 3) // 4 * 4
+    out = torch.empty((B, S, H, W, Cp), dtype=torch.bfloat16 if bf16 else torch.float32, device=x.device)
+    check(lib().dff_to_channels_last(_ptr(x.contiguous()), B, C, S, H, W, _ptr(out), Cp, _elem(bf16), x.device.index,
+                                     _stream(x.device)))
+    return out
+
+
+def from_channels_last(x, C=None):
+    _require_cuda(x, "x")
+    B, S, H, W, Cp = x.shape
+    C = C or Cp
+    out = torch.empty((B, C, S, H, W), dtype=torch.float32, device=x.device)
+    check(lib().dff_from_channels_last(_ptr(x.contiguous()), B, C, S, H, W, Cp, _elem(x.dtype == torch.bfloat16), _ptr(out),
+                                       x.device.index, _stream(x.device)))
+    return out
+
+
+def conv3d(x, weight, stride_hw=1, dil_hw=1, transposed=False, scale=None, shift=None, res_pre=None, res_post=None,
+           relu=False, x2=None, bf16=False, tensor_cores=False):
+    """One fused conv call on reference-layout tensors.  x (B,C0,S,H,W) [x2 (B,C1,S,H,W) = virtual concat];
+    weight in the reference layout; res_* (B,Cout,S,OH,OW).  Returns (B,Cout,S,OH,OW) fp32."""
+    l = lib()
+    dev = x.device
+    B, C0, S, IH, IW = x.shape
+    Cout = weight.shape[1] if transposed else weight.shape[0]
+    kd, kh, kw = weight.shape[2:]
+    C0p = (C0 + 3) // 4 * 4
+    a = to_channels_last(x, C0p, bf16)
+    b, C1p = None, 0
+    w = weight.detach().to(dev, torch.float32)
+    if x2 is not None:
+        C1 = x2.shape[1]
+        C1p = (C1 + 3) // 4 * 4
+        b = to_channels_last(x2, C1p, bf16)
+    if C0p != C0 or (x2 is not None and C1p != x2.shape[1]):
+        # zero weights for the padded input channels
+        cin_axis = 0 if transposed else 1
+        parts = [w.narrow(cin_axis, 0, C0), w.new_zeros(_with(w.shape, cin_axis, C0p - C0))]
+        if x2 is not None:
+            parts += [w.narrow(cin_axis, C0, x2.shape[1]), w.new_zeros(_with(w.shape, cin_axis, C1p - x2.shape[1]))]
+        w = torch.cat(parts, cin_axis)
+    w = w.contiguous()
+    OH, OW = (IH * 2, IW * 2) if transposed else (IH // stride_hw, IW // stride_hw)
+    Cop = Cout if Cout % 8 == 0 else Cout  # stored output channels = Cout (scalar store path when not a multiple of 8)
+    out = torch.empty((B, S, OH, OW, Cop), dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
+    rp = to_channels_last(res_pre, Cop, bf16) if res_pre is not None else None
+    rq = to_channels_last(res_post, Cop, bf16) if res_post is not None else None
+    sc = scale.detach().to(dev, torch.float32).contiguous() if scale is not None else None
+    sh = shift.detach().to(dev, torch.float32).contiguous() if shift is not None else None
+    if sc is not None and sc.numel() % 8:
+        sc = torch.cat([sc, sc.new_ones(8 - sc.numel() % 8)])
+    if sh is not None and sh.numel() % 8:
+        sh = torch.cat([sh, sh.new_zeros(8 - sh.numel() % 8)])
+    scratch = torch.empty(l.dff_conv3d_scratch_bytes(C0p + C1p, Cout, kd, kh, kw), dtype=torch.uint8, device=dev)
+    check(l.dff_conv3d(_ptr(a), C0p, _ptr(b), C1p, B, S, IH, IW, _ptr(w), Cout, kd, kh, kw, stride_hw, dil_hw,
+                       1 if transposed else 0, _ptr(sc), _ptr(sh), _ptr(rp), _ptr(rq), 1 if relu else 0, _ptr(out),
+                       _elem(bf16), 1 if tensor_cores else 0, _ptr(scratch), dev.index, _stream(dev)))
+    return from_channels_last(out, Cout)
+
+
+def _with(shape, axis, n):
+    s = list(shape)
+    s[axis] = n
+    return s
+
+
+def depth_head(cost, focus_dists, H, W):
+    """cost (B,S,h,w) fp32, focus_dists broadcastable to (B,S,H,W) -> (B,H,W)."""
+    _require_cuda(cost, "cost")
+    B, S, h, w = cost.shape
+    fd = focus_dists.to(cost.device)
+    while fd.dim() < 4:
+        fd = fd.unsqueeze(0)
+    fd = fd.expand(B, S, H, W)
+    strides = (ctypes.c_int64 * 4)(*fd.stride())
+    out = torch.empty((B, H, W), dtype=torch.float32, device=cost.device)
+    check(lib().dff_depth_head(_ptr(cost.contiguous()), h, w, _ptr(fd), strides, B, S, H, W, _ptr(out), cost.device.index,
+                               _stream(cost.device)))
+    return out
+
+
+def fov_warp(x, alpha, fovs, want_flow=True):
+    """FlowNetwork.FOV_warp on (B,C,S,H,W) fp32; alpha (B,3,S,1,1) or None; fovs (B,1,S,1,1)."""
+    _require_cuda(x, "x")
+    B, C, S, H, W = x.shape
+    out = torch.empty_like(x)
+    flow = torch.empty((B, 2, S, H, W), dtype=torch.float32, device=x.device) if want_flow else None
+    al = alpha.reshape(B, 3, S).contiguous().float() if alpha is not None else None
+    fv = fovs.reshape(B, S).contiguous().float()
+    check(lib().dff_fov_warp(_ptr(x.contiguous()), _ptr(al), _ptr(fv), B, C, S, H, W, _ptr(out), _ptr(flow), x.device.index,
+                             _stream(x.device)))
+    return out, flow

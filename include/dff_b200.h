@@ -1,0 +1,130 @@
+/*
+ * dff_b200.h — C-ABI of the B200-native (sm_100a) depth-from-focus hot path.
+ *
+ * This is the drop-in boundary: plain C types only (pointers, sizes, ints), no torch / ATen types.  Every entry
+ * point replaces a piece of the reference's Python hot path (paths relative to the reference repository,
+ * wcy199705/DfFintheWild):
+ *
+ *   dff_forward            <- DFF_net.forward        train_codes/Depth_Estimation_Network.py:77-137
+ *                                                    Depth_Estimation_Test/Depth_Estimation_Network.py:74-127
+ *   dff_backward           <- autograd of the above  (invoked at train_codes/train_code_Defocus.py:167)
+ *   dff_pack_weights       <- nn.Module parameter/buffer storage read by every conv/BN call
+ *                             (convbn_3d, train_codes/Depth_Estimation_Network.py:352-355)
+ *   dff_conv3d             <- one nn.Conv3d / nn.ConvTranspose3d (+BatchNorm3d eval +ReLU +residual) call site,
+ *                             e.g. train_codes/Depth_Estimation_Network.py:144-148, 278-301
+ *   dff_depth_head         <- upsample + softplus-normalise + expected focus distance,
+ *                             train_codes/Depth_Estimation_Network.py:92-98, 118-136
+ *   dff_fov_warp           <- FlowNetwork.FOV_warp    End_to_End/End_to_End.py:106-134
+ *   dff_flow_forward       <- FlowNetwork.forward     End_to_End/End_to_End.py:63-104
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in `_host`.  The library never allocates or frees
+ *     device memory and keeps no pointer past the call: inputs, outputs, packed weights and workspace belong to
+ *     the caller (PyTorch tensors in the Python binding).
+ *   - Every launch goes to `stream` (a cudaStream_t passed as void*) on CUDA device `device`.
+ *   - Return value: 0 on success, a negative DFF_E_* code on failure; `dff_last_error` returns the thread-local
+ *     message.  There is no CPU fallback: an unsupported shape, precision or device is an error.
+ *   - Thread-safe / re-entrant: no mutable global state (nn.DataParallel may call from one thread per GPU).
+ *   - Tensors at the boundary use the reference's layouts: FS (B,3,S,H,W) fp32 contiguous; focus_dists addressed
+ *     through four element strides (0 = broadcast) so (B,S,H,W), (B,S,1,1) ... are accepted; outputs (B,H,W) fp32.
+ *     Internally activations are channels-last (B,S,H,W,C).
+ */
+#ifndef DFF_B200_H_
+#define DFF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFF_ABI_VERSION 1
+
+/* error codes */
+#define DFF_OK 0
+#define DFF_E_ARG (-1)       /* bad argument / unsupported shape (H or W not a multiple of 32, S < 1 ...) */
+#define DFF_E_WORKSPACE (-2) /* workspace too small */
+#define DFF_E_CUDA (-3)      /* CUDA runtime / launch error */
+#define DFF_E_DEVICE (-4)    /* not an sm_100 device */
+#define DFF_E_UNSUPPORTED (-5)
+
+/* precision / mode flags (bit-or) */
+#define DFF_FP32 0  /* fp32 activations, FFMA kernels: parity mode (<= 1e-4 relative per pixel) */
+#define DFF_BF16 1  /* bf16 activations, tcgen05/TMEM implicit-GEMM kernels, fp32 accumulate */
+#define DFF_TRAIN 2 /* BatchNorm in batch-statistics mode; activations are kept for dff_backward */
+
+/* which parameter set a call refers to */
+#define DFF_NET_DFF 0  /* DFF_net (384-key state_dict)                                */
+#define DFF_NET_FLOW 1 /* End_to_End FlowNetwork (`optical_flow_aggregation.*` keys) */
+
+/* ---- introspection / handshake ---------------------------------------------------------------------------- */
+int dff_abi_version(void);
+/* message of the last failure on this thread */
+const char *dff_last_error(void);
+/* 0 if `device` is a usable sm_100 GPU */
+int dff_check_device(int device);
+
+/* The library declares the parameters it expects, by reference state_dict key (without the `DFF_net.` /
+ * `optical_flow_aggregation.` prefix).  The caller concatenates them as fp32 in this order into one flat device
+ * buffer ("raw parameters"); `num_batches_tracked` is not part of it. */
+int dff_param_count(int net);
+const char *dff_param_name(int net, int index);
+int64_t dff_param_numel(int net, int index);
+int64_t dff_param_offset(int net, int index); /* element offset inside the raw buffer */
+int64_t dff_raw_numel(int net);               /* total fp32 elements of the raw buffer */
+
+/* ---- weights ---------------------------------------------------------------------------------------------- */
+/* bytes of the packed-weight buffer for `net` */
+size_t dff_packed_bytes(int net);
+/* raw fp32 parameters -> packed kernels layouts ([tap][cin][cout] fp32, [tap][cout][cin] bf16) and, for eval,
+ * per-channel BatchNorm scale/shift (gamma/sqrt(var+eps), beta-mean*scale).  Runs on `stream`. */
+int dff_pack_weights(int net, const float *raw, void *packed, int device, void *stream);
+
+/* ---- whole-network forward -------------------------------------------------------------------------------- */
+size_t dff_workspace_bytes(int B, int S, int H, int W, int mode);
+/* FS (B,3,S,H,W) fp32; fd + 4 element strides; out4[0..3] = mid_out, pred1, pred2, pred3, each (B,H,W) fp32.
+ * cost4 (optional, may be NULL): pre-softplus costs (B,S,H/8,W/8), (B,S,H/4,W/4), (B,S,H/2,W/2), (B,S,H,W). */
+int dff_forward(const void *packed, const float *FS, const float *fd, const int64_t fd_strides[4], int B, int S,
+                int H, int W, float *const out4[4], float *const cost4[4], void *workspace, size_t workspace_bytes,
+                int mode, int device, void *stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies FS / fd in, runs, copies the four maps out and
+ * synchronises the stream.  `dev_io` is caller-owned device scratch of dff_host_io_bytes() bytes. */
+size_t dff_host_io_bytes(int B, int S, int H, int W);
+int dff_forward_host(const void *packed, const float *FS_host, const float *fd_host, const int64_t fd_strides[4],
+                     int B, int S, int H, int W, float *const out4_host[4], void *dev_io, void *workspace,
+                     size_t workspace_bytes, int mode, int device, void *stream);
+
+/* ---- single operators (unit-parity surface; also what dff_forward is made of) ----------------------------- */
+/* Generic 3-D convolution on channels-last activations.
+ *   in0 (B,S,IH,IW,C0) [+ in1 (B,S,IH,IW,C1): virtual channel concat]  ->  out (B,S,OH,OW,Cout)
+ *   weight: reference layout, fp32: conv (Cout,Cin,kd,kh,kw); transposed (Cin,Cout,3,3,3) with stride (1,2,2).
+ *   y = acc*scale[c] + shift[c] (+ res_pre) ; ReLU if relu ; (+ res_post).  scale/shift may be NULL (1 / 0).
+ *   elem: DFF_FP32 or DFF_BF16 storage of in/out/res tensors.  `scratch` >= dff_conv3d_scratch_bytes(). */
+size_t dff_conv3d_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw);
+int dff_conv3d(const void *in0, int C0, const void *in1, int C1, int B, int S, int IH, int IW, const float *weight,
+               int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, const float *scale,
+               const float *shift, const void *res_pre, const void *res_post, int relu, void *out, int elem,
+               int use_tensor_cores, void *scratch, int device, void *stream);
+
+/* cost (B,S,h,w) fp32 with H % h == 0 -> depth (B,H,W) fp32 */
+int dff_depth_head(const float *cost, int h, int w, const float *fd, const int64_t fd_strides[4], int B, int S, int H,
+                   int W, float *depth, int device, void *stream);
+
+/* x (B,C,S,H,W) fp32 reference layout; alpha (B,3,S) [a0,a1,a2 per slice] or NULL (zeros); fov (B,S);
+ * out (B,C,S,H,W); flow (B,2,S,H,W) or NULL.  Bug-compatible with the reference only for B == 1 (B > 1 uses
+ * sample 0's scale correction exactly as End_to_End.py:112-118 does). */
+int dff_fov_warp(const float *x, const float *alpha, const float *fov, int B, int C, int S, int H, int W, float *out,
+                 float *flow, int device, void *stream);
+
+/* layout helpers: reference (B,C,S,H,W) fp32 <-> channels-last (B,S,H,W,Cp) of `elem` type (Cp >= C, zero pad) */
+int dff_to_channels_last(const float *src, int B, int C, int S, int H, int W, void *dst, int Cp, int elem, int device,
+                         void *stream);
+int dff_from_channels_last(const void *src, int B, int C, int S, int H, int W, int Cp, int elem, float *dst,
+                           int device, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFF_B200_H_ */

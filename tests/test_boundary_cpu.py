@@ -1,0 +1,98 @@
+"""Host-side logic that needs no GPU: the drop-in module's state_dict contract, seed-identical construction,
+the C-ABI library's exports and its parameter handshake, and the refusal to run on the CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+
+
+def _net():
+    from dffinthewild_b200.Depth_Estimation_Network import Network
+    torch.manual_seed(0)
+    return Network()
+
+
+def test_state_dict_layout_matches_reference():
+    lay = golden("state_layout.npz")
+    sd = _net().state_dict()
+    assert list(sd.keys()) == [str(k) for k in lay["keys"]]
+    assert len(sd) == 384
+    for (k, v), shp, dt in zip(sd.items(), lay["shapes"], lay["dtypes"]):
+        assert str(tuple(v.shape)) == str(shp), k
+        assert str(v.dtype) == str(dt), k
+
+
+def test_seeded_construction_is_reference_identical():
+    lay = golden("state_layout.npz")
+    sd = _net().state_dict()
+    for v, s, a in zip(sd.values(), lay["seed0_sum"], lay["seed0_abs"]):
+        assert abs(float(v.double().sum()) - s) <= 1e-9 * max(1.0, abs(a))
+        assert abs(float(v.double().abs().sum()) - a) <= 1e-9 * max(1.0, abs(a))
+
+
+def test_call_site_surface():
+    """The model-handling lines of test.py:30-32,77-85 and train_code_DDFF.py:48,62-67 work unchanged."""
+    net = _net().cpu()
+    dp = torch.nn.DataParallel(net)
+    sd = dp.module.state_dict()
+    dp.module.load_state_dict(sd, strict=True)
+    dp.load_state_dict(dp.state_dict(), strict=True)
+    assert all(k.startswith("module.DFF_net.") for k in dp.state_dict())
+    opt = torch.optim.Adam(dp.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    assert sum(p.numel() for g in opt.param_groups for p in g["params"]) == 4038832
+    dp.eval(); dp.train()
+    assert hasattr(net, "DFF_net")
+
+
+def test_cpu_forward_is_refused(built_lib):
+    from dffinthewild_b200.runtime import DffError
+    net = _net().eval()
+    with pytest.raises(DffError):
+        net(torch.zeros(1, 3, 2, 32, 32), torch.zeros(1, 2, 32, 32))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "dff_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(dff_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 18
+    lib = ctypes.CDLL(built_lib)
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.dff_abi_version.restype = ctypes.c_int
+    assert lib.dff_abi_version() == 1
+
+
+def test_parameter_handshake(built_lib):
+    from dffinthewild_b200 import runtime as rt
+    sd = _net().DFF_net.state_dict()
+    names = rt.param_names(rt.NET_DFF)
+    l = rt.lib()
+    assert len(names) == len(set(names))
+    off = 0
+    for i, n in enumerate(names):
+        assert n in sd, n
+        assert sd[n].numel() == l.dff_param_numel(rt.NET_DFF, i), n
+        assert l.dff_param_offset(rt.NET_DFF, i) == off
+        off += sd[n].numel()
+    assert off == l.dff_raw_numel(rt.NET_DFF)
+    # everything the forward never touches: the 12 dead parameters, their BN buffers, and num_batches_tracked
+    unused = [k for k in sd if k not in names and not k.endswith("num_batches_tracked")]
+    assert all(("redir3" in k) or ("pre_conv" in k) for k in unused), unused
+    assert len([k for k in unused if "running" not in k]) == 12
+
+
+def test_workspace_size_and_shape_errors(built_lib):
+    from dffinthewild_b200 import runtime as rt
+    l = rt.lib()
+    a = l.dff_workspace_bytes(1, 10, 224, 224, rt.FP32)
+    b = l.dff_workspace_bytes(2, 10, 224, 224, rt.FP32)
+    h = l.dff_workspace_bytes(1, 10, 224, 224, rt.BF16)
+    assert a > 0 and abs(b - 2 * a) <= 1 << 16 and h < a
+    assert l.dff_workspace_bytes(1, 10, 100, 224, rt.FP32) == 0  # H not a multiple of 32
+    assert b"multiples of 32" in l.dff_last_error()

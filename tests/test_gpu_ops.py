@@ -1,0 +1,133 @@
+"""Kernel-level parity on the GPU, called through the C-ABI: every conv flavour of the network against
+torch's fp64 CPU convolution (the primitive the reference calls), the depth head against the oracle, the FOV warp
+against the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt(built_lib):
+    from dffinthewild_b200 import runtime
+    assert torch.cuda.is_available()
+    return runtime
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g) * 2 - 1) * scale
+
+
+CASES = [
+    # name, Cin, Cout, k, stride, dil, transposed, S, H, W
+    ("fm_9x9_dil2", 3, 8, (1, 9, 9), 1, 2, False, 2, 40, 72),
+    ("srd_1x3x3_c8", 8, 8, (1, 3, 3), 1, 1, False, 3, 32, 40),
+    ("att_3x1x1_c16", 16, 16, (3, 1, 1), 1, 1, False, 5, 16, 48),
+    ("att_1x1x1_c32", 32, 32, (1, 1, 1), 1, 1, False, 2, 16, 16),
+    ("c3_32_32", 32, 32, (3, 3, 3), 1, 1, False, 4, 24, 40),
+    ("c3_64_64", 64, 64, (3, 3, 3), 1, 1, False, 3, 12, 20),
+    ("c3_128_128", 128, 128, (3, 3, 3), 1, 1, False, 2, 6, 10),
+    ("c3_16_8", 16, 8, (3, 3, 3), 1, 1, False, 3, 64, 64),
+    ("s2_8_16", 8, 16, (3, 3, 3), 2, 1, False, 3, 64, 96),
+    ("s2_32_64", 32, 64, (3, 3, 3), 2, 1, False, 2, 24, 40),
+    ("s2_64_128", 64, 128, (3, 3, 3), 2, 1, False, 1, 12, 20),
+    ("up_64_32", 64, 32, (3, 3, 3), 2, 1, True, 3, 12, 20),
+    ("up_16_8", 16, 8, (3, 3, 3), 2, 1, True, 2, 32, 48),
+    ("up_128_64", 128, 64, (3, 3, 3), 2, 1, True, 2, 3, 5),
+    ("conf_32_1", 32, 1, (3, 3, 3), 1, 1, False, 3, 12, 20),
+    ("cls_8_1", 8, 1, (1, 1, 1), 1, 1, False, 2, 32, 64),
+]
+
+
+def _ref_conv(x, w, stride, dil, transposed):
+    x, w = x.double(), w.double()
+    if transposed:
+        return F.conv_transpose3d(x, w, None, stride=(1, 2, 2), padding=1, output_padding=(0, 1, 1))
+    k = w.shape[2:]
+    pad = ((k[0] - 1) // 2, dil * (k[1] - 1) // 2, dil * (k[2] - 1) // 2)
+    return F.conv3d(x, w, None, (1, stride, stride), pad, (1, dil, dil))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_fp32_matches_torch_fp64(rt, case):
+    name, cin, cout, k, stride, dil, tr, S, H, W = case
+    B = 2
+    x = _rand(B, cin, S, H, W, seed=1)
+    wshape = (cin, cout) + k if tr else (cout, cin) + k
+    w = _rand(*wshape, seed=2, scale=(2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5 * 1.7)
+    ref = _ref_conv(x, w, stride, dil, tr)
+    scale = _rand(cout, seed=3) * 0.4 + 1.0
+    shift = _rand(cout, seed=4) * 0.3
+    res1 = _rand(*ref.shape, seed=5)
+    res2 = _rand(*ref.shape, seed=6)
+    full = F.relu(ref * scale.double().view(1, -1, 1, 1, 1) + shift.double().view(1, -1, 1, 1, 1) + res1.double()) + res2.double()
+    out_plain = rt.conv3d(x.cuda(), w.cuda(), stride, dil, tr).cpu().double()
+    out_full = rt.conv3d(x.cuda(), w.cuda(), stride, dil, tr, scale=scale.cuda(), shift=shift.cuda(), res_pre=res1.cuda(),
+                         res_post=res2.cuda(), relu=True).cpu().double()
+    tol = 2e-6 * max(1.0, ref.abs().max().item())
+    assert (out_plain - ref).abs().max().item() <= tol
+    assert (out_full - full).abs().max().item() <= 2 * tol
+
+
+def test_conv_two_sources_is_channel_concat(rt):
+    """hourglass conv0 reads torch.cat([decoder, encoder_skip], 1) without materialising it (reference :103,109,114)."""
+    for c0, c1, cout in ((16, 16, 16), (8, 8, 8), (64, 64, 64), (128, 64, 128)):
+        x0, x1 = _rand(1, c0, 3, 12, 36, seed=7), _rand(1, c1, 3, 12, 36, seed=8)
+        w = _rand(cout, c0 + c1, 3, 3, 3, seed=9, scale=0.05)
+        ref = _ref_conv(torch.cat([x0, x1], 1), w, 1, 1, False)
+        out = rt.conv3d(x0.cuda(), w.cuda(), x2=x1.cuda()).cpu().double()
+        assert (out - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+
+
+def test_conv_bf16_storage(rt):
+    """bf16 activations in HBM, fp32 accumulate: error bounded by the bf16 rounding of inputs/outputs."""
+    x, w = _rand(1, 32, 3, 16, 40, seed=10), _rand(32, 32, 3, 3, 3, seed=11, scale=0.05)
+    ref = _ref_conv(x.bfloat16().float(), w, 1, 1, False)
+    out = rt.conv3d(x.cuda(), w.cuda(), bf16=True).cpu().double()
+    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("r", [1, 2, 4, 8])
+def test_depth_head(rt, r):
+    from oracle import dff_oracle as O
+    B, S, H, W = 2, 5, 32, 64
+    cost = _rand(B, S, H // r, W // r, seed=20, scale=12.0)
+    cost[0, 0, 0, 0] = 30.0  # softplus threshold branch
+    for fd in (_rand(B, S, H, W, seed=21).abs() + 0.1, torch.linspace(0.1, 1.5, S).view(1, S, 1, 1)):
+        ref = O.depth_head(cost.double(), fd.double(), (H, W))
+        out = rt.depth_head(cost.cuda(), fd.cuda(), H, W).cpu().double()
+        assert ((out - ref).abs() / ref.abs()).max().item() <= 2e-6
+
+
+def test_depth_head_many_slices(rt):
+    from oracle import dff_oracle as O
+    cost, fd = _rand(1, 49, 8, 8, seed=22, scale=5.0), _rand(1, 49, 32, 32, seed=23).abs() + 0.05
+    ref = O.depth_head(cost.double(), fd.double(), (32, 32))
+    out = rt.depth_head(cost.cuda(), fd.cuda(), 32, 32).cpu().double()
+    assert ((out - ref).abs() / ref.abs()).max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("tag", ["b1", "b2"])
+def test_fov_warp_matches_reference_golden(rt, tag):
+    g = golden("g5_fov_warp_%s.npz" % tag)
+    x, alpha, fov = (torch.from_numpy(g[k]).cuda() for k in ("x", "alpha", "fov"))
+    out, flow = rt.fov_warp(x, alpha, fov)
+    assert np.abs(flow.cpu().numpy() - g["flow"]).max() <= 2e-5
+    assert np.abs(out.cpu().numpy() - g["out"]).max() <= 2e-4   # bilinear weights amplify 1-ulp coordinate noise
+    out0, _ = rt.fov_warp(x, None, fov)
+    from oracle import dff_oracle as O
+    ref0, _ = O.fov_warp(torch.from_numpy(g["x"]), torch.zeros(1, 3, 1, 1), torch.from_numpy(g["fov"]))
+    assert (out0.cpu() - ref0).abs().max().item() <= 2e-4
+
+
+def test_layout_round_trip(rt):
+    x = _rand(2, 3, 4, 8, 12, seed=30).cuda()
+    cl = rt.to_channels_last(x, 4)
+    assert cl.shape == (2, 4, 8, 12, 4) and float(cl[..., 3].abs().max()) == 0.0
+    assert torch.equal(rt.from_channels_last(cl, 3), x)
+    assert torch.equal(cl[..., :3].permute(0, 4, 1, 2, 3), x)
