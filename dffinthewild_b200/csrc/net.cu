@@ -1,6 +1,7 @@
 // Host side of the dff_b200 library: the layer table of DFF_net, the raw-parameter handshake, weight packing,
 // the forward schedule (reference train_codes/Depth_Estimation_Network.py:77-137) and the C-ABI of
 // include/dff_b200.h.  No device memory is allocated here; activations live in the caller's workspace.
+#include <cstdio>
 #include <map>
 #include <mutex>
 #include <string>
@@ -256,6 +257,18 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
   return 0;
 }
 
+// ---- optional per-operator profiling (CUDA events on the launching stream) --------------------------------------
+struct OpRecord {
+  std::string name;
+  double flops = 0, bytes = 0;  // algorithmic: 2*MACs without padding/zero taps; compulsory activation+weight bytes
+  int launches = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+struct Profile {
+  std::vector<OpRecord> ops;
+  bool events = false;  // record CUDA events (false: only count launches / flops / bytes)
+};
+
 // ---- the forward schedule -----------------------------------------------------------------------------------
 struct Runner {
   const Net& net;
@@ -265,6 +278,22 @@ struct Runner {
   bool dry, bf16;
   cudaStream_t st;
   int rc = 0;
+  Profile* prof = nullptr;
+
+  void op_begin(const std::string& name, double flops, double bytes, int launches) {
+    if (!prof) return;
+    OpRecord r;
+    r.name = name; r.flops = flops; r.bytes = bytes; r.launches = launches;
+    if (prof->events && !dry && !rc) {
+      cudaEventCreate(&r.e0);
+      cudaEventCreate(&r.e1);
+      cudaEventRecord(r.e0, st);
+    }
+    prof->ops.push_back(r);
+  }
+  void op_end() {
+    if (prof && prof->events && !dry && !rc && prof->ops.back().e1) cudaEventRecord(prof->ops.back().e1, st);
+  }
 
   size_t esize(bool f32) const { return (bf16 && !f32) ? 2 : 4; }
   Ten alloc(int B, int S, int H, int W, int C, bool f32 = false) {
@@ -292,16 +321,30 @@ struct Runner {
       aux_last = aux;
       e.aux_out = &aux;
     }
-    if (dry || rc) return out;
-    rc = run_conv(l, (const float*)(packed + l.pk_w), (const float*)(packed + l.pk_scale),
-                  (const float*)(packed + l.pk_shift), in, e, out, bf16, st);
+    {
+      // algorithmic work: every output voxel sees cin*cout*taps MACs for a conv; a transposed conv spends
+      // cin*cout*27 MACs per INPUT voxel (= 27/4 per output voxel).  Bytes: in + out + residuals + weights, once.
+      const double ovox = (double)out.B * out.S * out.H * out.W, ivox = (double)in.B * in.S * in.H * in.W;
+      const double macs = (l.transposed ? ivox : ovox) * l.cin * l.cout * l.ntaps;
+      double bytes = ivox * l.CinP * esize(false) + ovox * out.C * esize(out.f32) + (double)l.ntaps * l.cin * l.cout * 4;
+      if (e.res_pre) bytes += ovox * out.C * esize(false);
+      if (e.res_post) bytes += ovox * out.C * esize(false);
+      if (e.aux_add) bytes += 2 * ovox * out.C * esize(false);
+      op_begin(name, 2.0 * macs, bytes, l.transposed ? 4 : 1);
+    }
+    if (!dry && !rc)
+      rc = run_conv(l, (const float*)(packed + l.pk_w), (const float*)(packed + l.pk_scale),
+                    (const float*)(packed + l.pk_shift), in, e, out, bf16, st);
+    op_end();
     return out;
   }
   Ten aux_last;
   Ten pool(const Ten& in, int k, bool is_max) {
     Ten out = alloc(in.B, in.S, in.H / k, in.W / k, in.C);
-    if (dry || rc) return out;
-    rc = launch_pool(in.p, out.p, in.B * in.S, in.H, in.W, in.C, k, is_max, bf16, st);
+    const double ivox = (double)in.B * in.S * in.H * in.W;
+    op_begin(is_max ? "maxpool" : "avgpool", 0, ivox * in.C * esize(false) * (1.0 + 1.0 / (k * k)), 1);
+    if (!dry && !rc) rc = launch_pool(in.p, out.p, in.B * in.S, in.H, in.W, in.C, k, is_max, bf16, st);
+    op_end();
     return out;
   }
   static EpiOpt relu() {
@@ -390,13 +433,17 @@ struct Runner {
 
 static int forward_impl(const void* packed, const float* FS, const float* fd, const int64_t* fds, int B, int S, int H, int W,
                         float* const* out4, float* const* cost4, void* ws, size_t ws_bytes, int mode, cudaStream_t st,
-                        bool dry, size_t* need) {
+                        bool dry, size_t* need, Profile* prof = nullptr) {
   if (B < 1 || S < 1 || H < 32 || W < 32 || H % 32 || W % 32)
     return fail(DFF_E_ARG, "dff_forward: need B,S >= 1 and H,W positive multiples of 32 (pad with -1 like the reference dataloaders)");
   if (mode & DFF_TRAIN) return fail(DFF_E_UNSUPPORTED, "dff_forward: DFF_TRAIN is not available in this build");
   Runner r{net_of(DFF_NET_DFF), (const char*)packed, (char*)ws, ws_bytes, 0, dry, (mode & DFF_BF16) != 0, st};
+  r.prof = prof;
+  const double vox = (double)B * S * H * W;
   Ten x0 = r.alloc(B, S, H, W, 4);
+  r.op_begin("to_channels_last", 0, vox * (12 + 4 * r.esize(false)), 1);
   if (!dry && !r.rc) r.rc = launch_to_cl(FS, B, 3, S, H, W, x0.p, 4, r.bf16, st);
+  r.op_end();
   Ten t = r.conv("FM_measure.Focus_extraction.0.0", x0, Runner::relu());
   Ten v1 = r.srd("FM_measure.Focus_extraction.2", t);
   Ten v2 = r.srd("FM_conv1.1", r.efd("FM_conv1.0", v1));
@@ -421,11 +468,17 @@ static int forward_impl(const void* packed, const float* FS, const float* fd, co
   r.hourglass("dres4", o3, v1, &pre2, &outb, &pre3, &out_in3, false);
   Ten cost3 = r.conv("classif3.0", out_in3, ec);
   if (need) *need = r.off;
-  if (dry) return 0;
-  if (r.rc) return r.rc;
   const Ten* costs[4] = {&cm, &cost1, &cost2, &cost3};
+  if (dry) {
+    for (int i = 0; i < 4; ++i)
+      r.op_begin("depth_head", 0, 4.0 * B * S * costs[i]->H * costs[i]->W + 4.0 * vox + 4.0 * B * H * W, 1);
+    return 0;
+  }
+  if (r.rc) return r.rc;
   for (int i = 0; i < 4; ++i) {
+    r.op_begin("depth_head", 0, 4.0 * B * S * costs[i]->H * costs[i]->W + 4.0 * vox + 4.0 * B * H * W, 1);
     DFF_TRY(launch_depth_head((const float*)costs[i]->p, costs[i]->H, costs[i]->W, fd, fds, B, S, H, W, out4[i], st));
+    r.op_end();
     if (cost4 && cost4[i])
       DFF_CUDA(cudaMemcpyAsync(cost4[i], costs[i]->p, (size_t)B * S * costs[i]->H * costs[i]->W * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
@@ -514,6 +567,47 @@ int dff_forward(const void* packed, const float* FS, const float* fd, const int6
   if (g.rc) return g.rc;
   return forward_impl(packed, FS, fd, fd_strides, B, S, H, W, out4, cost4, workspace, workspace_bytes, mode,
                       (cudaStream_t)stream, false, nullptr);
+}
+
+int dff_forward_profiled(const void* packed, const float* FS, const float* fd, const int64_t fd_strides[4], int B, int S,
+                         int H, int W, float* const out4[4], void* workspace, size_t workspace_bytes, int mode, int device,
+                         void* stream, int max_ops, float* op_ms_host, double* op_flops_host, double* op_bytes_host,
+                         int* op_launches_host, char* op_names_host, int* n_ops) {
+  if (!n_ops) return fail(DFF_E_ARG, "dff_forward_profiled: null pointer");
+  Profile prof;
+  const bool dry = packed == nullptr;  // plan only: operator list, flops, bytes, launches (no GPU work)
+  prof.events = !dry;
+  int rc = 0;
+  if (dry) {
+    rc = forward_impl(nullptr, nullptr, nullptr, nullptr, B, S, H, W, nullptr, nullptr, nullptr, 0, mode, nullptr, true,
+                      nullptr, &prof);
+  } else {
+    if (!FS || !fd || !fd_strides || !out4 || !workspace) return fail(DFF_E_ARG, "dff_forward_profiled: null pointer");
+    DeviceGuard g(device);
+    if (g.rc) return g.rc;
+    rc = forward_impl(packed, FS, fd, fd_strides, B, S, H, W, out4, nullptr, workspace, workspace_bytes, mode,
+                      (cudaStream_t)stream, false, nullptr, &prof);
+    if (!rc) rc = check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+  }
+  const int n = (int)prof.ops.size();
+  for (int i = 0; i < n; ++i) {
+    OpRecord& o = prof.ops[i];
+    float ms = 0.f;
+    if (!rc && o.e0 && o.e1) cudaEventElapsedTime(&ms, o.e0, o.e1);
+    if (o.e0) cudaEventDestroy(o.e0);
+    if (o.e1) cudaEventDestroy(o.e1);
+    if (i < max_ops) {
+      if (op_ms_host) op_ms_host[i] = ms;
+      if (op_flops_host) op_flops_host[i] = o.flops;
+      if (op_bytes_host) op_bytes_host[i] = o.bytes;
+      if (op_launches_host) op_launches_host[i] = o.launches;
+      if (op_names_host) {
+        snprintf(op_names_host + (size_t)i * 64, 64, "%s", o.name.c_str());
+      }
+    }
+  }
+  *n_ops = n;
+  return rc;
 }
 
 size_t dff_host_io_bytes(int B, int S, int H, int W) {

@@ -40,6 +40,8 @@ def _declare(lib):
         "dff_pack_weights": (i, [i, fp, vp, i, vp]),
         "dff_workspace_bytes": (sz, [i, i, i, i, i]),
         "dff_forward": (i, [vp, fp, fp, c.POINTER(i64), i, i, i, i, c.POINTER(vp), c.POINTER(vp), vp, sz, i, i, vp]),
+        "dff_forward_profiled": (i, [vp, fp, fp, c.POINTER(i64), i, i, i, i, c.POINTER(vp), vp, sz, i, i, vp, i, vp, vp, vp, vp,
+                                     vp, c.POINTER(i)]),
         "dff_host_io_bytes": (sz, [i, i, i, i]),
         "dff_forward_host": (i, [vp, fp, fp, c.POINTER(i64), i, i, i, i, c.POINTER(vp), vp, vp, sz, i, i, vp]),
         "dff_conv3d_scratch_bytes": (sz, [i, i, i, i, i]),

@@ -89,6 +89,15 @@ int dff_forward(const void *packed, const float *FS, const float *fd, const int6
                 int H, int W, float *const out4[4], float *const cost4[4], void *workspace, size_t workspace_bytes,
                 int mode, int device, void *stream);
 
+/* Profiled variant (bench / roofline): CUDA events around every operator on `stream`, then a stream synchronise.
+ * Reports, per operator in schedule order: device ms, algorithmic FLOPs (2*MACs, no padding or zero-tap MACs),
+ * compulsory bytes, kernel launches and a 64-byte name slot.  With packed == NULL nothing runs and only the plan
+ * (names / flops / bytes / launches) is reported. */
+int dff_forward_profiled(const void *packed, const float *FS, const float *fd, const int64_t fd_strides[4], int B, int S,
+                         int H, int W, float *const out4[4], void *workspace, size_t workspace_bytes, int mode, int device,
+                         void *stream, int max_ops, float *op_ms_host, double *op_flops_host, double *op_bytes_host,
+                         int *op_launches_host, char *op_names_host, int *n_ops);
+
 /* Same call with HOST buffers (pinned or pageable): copies FS / fd in, runs, copies the four maps out and
  * synchronises the stream.  `dev_io` is caller-owned device scratch of dff_host_io_bytes() bytes. */
 size_t dff_host_io_bytes(int B, int S, int H, int W);

@@ -252,7 +252,8 @@ LOSS_WEIGHTS = (0.3, 0.5, 0.7, 1.0)   # (mid, pred1, pred2, pred3)
 
 def defocus_loss(outs, gt, mask):
     """0.5*L1 + 0.7*L2 + 1.0*L3 + 0.3*Lmid, L = mean squared error over masked pixels."""
-    return sum(w * F.mse_loss(o[mask], gt[mask]) for w, o in zip(LOSS_WEIGHTS, outs))
+    mid, p1, p2, p3 = (F.mse_loss(o[mask], gt[mask]) for o in outs)
+    return 0.5 * p1 + 0.7 * p2 + 1.0 * p3 + 0.3 * mid      # the reference's summation order
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -13,6 +13,9 @@ import torch
 
 DDFF_FD = (0.28248, 0.020177)
 DEFOCUS_FD = (0.1, 0.15, 0.3, 0.7, 1.5)
+# conv std = CONV_GAIN/sqrt(fan_in): 1.2 keeps activations O(1-30) and the pre-softplus costs at |c| ~ 10-40 through all 70
+# layers (sqrt(2) blows them up to ~1e3, 1.0 collapses the depth maps to the mean focus distance) — "trained-like".
+CONV_GAIN = 1.2
 
 
 def _rng(seed, name):
@@ -38,7 +41,7 @@ def synthetic_state(template, seed=1):
             t = torch.from_numpy(r.normal(0, 0.1, shp).astype(np.float32))
         else:                                              # conv (Cout,Cin,kd,kh,kw) / deconv (Cin,Cout,kd,kh,kw)
             fan_in = int(np.prod(shp[1:]))
-            t = torch.from_numpy(r.normal(0, np.sqrt(2.0 / max(fan_in, 1)), shp).astype(np.float32))
+            t = torch.from_numpy(r.normal(0, CONV_GAIN / np.sqrt(max(fan_in, 1)), shp).astype(np.float32))
         out[k] = t
     return out
 
