@@ -23,6 +23,10 @@ int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B,
                     float* flow, cudaStream_t st);
 int launch_pack_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int CinP, int CoutP, int transposed,
                        cudaStream_t st);
+bool conv_tc_supported(const ConvArgs& a, int Ntc);
+int launch_conv_tc(const ConvArgs& a, const void* wtc, int ntaps_total, int Ntc, int num_sms, cudaStream_t st);
+int launch_pack_weight_tc(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
+                          cudaStream_t st);
 int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
                    float* scale, float* shift, int C, int CP, cudaStream_t st);
 
@@ -36,6 +40,7 @@ int fail(int code, const std::string& msg) {
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return 0;
   g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+  cudaGetLastError();  // clear the (non-sticky) error so the next call starts clean
   return DFF_E_CUDA;
 }
 
@@ -47,8 +52,9 @@ struct Layer {
   bool transposed, bias;
   // derived
   int CinP, CoutP, ntaps;
+  int CinT, Ntc;  // tensor-core path: stored input channels (multiple of 8) and MMA N (multiple of 16, >= 16)
   int64_t raw_w, raw_gamma, raw_beta, raw_mean, raw_var, raw_bias;  // element offsets in the raw buffer (-1: none)
-  size_t pk_w, pk_scale, pk_shift;                                   // byte offsets in the packed buffer
+  size_t pk_w, pk_scale, pk_shift, pk_wtc;                           // byte offsets in the packed buffer
 };
 struct Param {
   std::string name;
@@ -67,6 +73,8 @@ struct Net {
     l.CinP = (int)align_up(cin, 4);
     l.CoutP = (int)align_up(cout, 8);
     l.ntaps = kd * kh * kw;
+    l.CinT = (int)align_up(cin, 8);
+    l.Ntc = (int)align_up(cout, 16);
     auto reg = [&](const std::string& n, int64_t numel) {
       params.push_back({n, numel, raw_numel});
       raw_numel += numel;
@@ -87,6 +95,8 @@ struct Net {
     packed_bytes += align_up(l.CoutP * sizeof(float), 256);
     l.pk_shift = packed_bytes;
     packed_bytes += align_up(l.CoutP * sizeof(float), 256);
+    l.pk_wtc = packed_bytes;
+    packed_bytes += align_up((size_t)(l.ntaps + 1) * l.Ntc * l.CinT * 2, 256);
     index[name] = (int)layers.size();
     layers.push_back(l);
   }
@@ -221,14 +231,27 @@ struct EpiOpt {
 };
 
 // Runs one conv layer (all phases) given packed weights.
+static int num_sms_of_current_device() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  static int cache[64] = {0};
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
+
+// `wtc` != null selects the tcgen05 path (bf16 only); otherwise the FFMA kernel runs.
 static int run_conv(const Layer& l, const float* w, const float* scale, const float* shift, const Ten& in, const EpiOpt& e,
-                    Ten& out, bool bf16, cudaStream_t st) {
+                    Ten& out, bool bf16, cudaStream_t st, const void* wtc = nullptr) {
   ConvArgs a{};
   a.in0 = in.p;
   a.C0 = in.C;
   a.in1 = e.in1 ? e.in1->p : nullptr;
   a.C1 = e.in1 ? e.in1->C : 0;
-  if (a.C0 + a.C1 != l.CinP) return fail(DFF_E_ARG, "conv " + l.name + ": input channels do not match the layer");
+  if (a.C0 + a.C1 != (wtc ? l.CinT : l.CinP))
+    return fail(DFF_E_ARG, "conv " + l.name + ": input channels do not match the layer");
+  const int nsm = wtc ? num_sms_of_current_device() : 0;
   a.B = in.B; a.S = in.S; a.IH = in.H; a.IW = in.W;
   a.OH = out.H; a.OW = out.W;
   a.w = w; a.CinP = l.CinP; a.CoutP = l.CoutP;
@@ -245,6 +268,7 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     conv_taps(l, a.taps);
     a.isy = a.isx = l.stride; a.osy = a.osx = 1; a.ooy = a.oox = 0;
     a.OHt = out.H; a.OWt = out.W;
+    if (wtc) return launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st);
     return launch_conv_ffma(a, bf16, st);
   }
   for (int py = 0; py < 2; ++py)
@@ -252,7 +276,8 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
       deconv_taps(py, px, a.taps);
       a.isy = a.isx = 1; a.osy = a.osx = 2; a.ooy = py; a.oox = px;
       a.OHt = in.H; a.OWt = in.W;
-      DFF_TRY(launch_conv_ffma(a, bf16, st));
+      if (wtc) DFF_TRY(launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st));
+      else DFF_TRY(launch_conv_ffma(a, bf16, st));
     }
   return 0;
 }
@@ -279,6 +304,7 @@ struct Runner {
   cudaStream_t st;
   int rc = 0;
   Profile* prof = nullptr;
+  bool use_tc = false;
 
   void op_begin(const std::string& name, double flops, double bytes, int launches) {
     if (!prof) return;
@@ -334,7 +360,7 @@ struct Runner {
     }
     if (!dry && !rc)
       rc = run_conv(l, (const float*)(packed + l.pk_w), (const float*)(packed + l.pk_scale),
-                    (const float*)(packed + l.pk_shift), in, e, out, bf16, st);
+                    (const float*)(packed + l.pk_shift), in, e, out, bf16, st, use_tc ? packed + l.pk_wtc : nullptr);
     op_end();
     return out;
   }
@@ -439,10 +465,12 @@ static int forward_impl(const void* packed, const float* FS, const float* fd, co
   if (mode & DFF_TRAIN) return fail(DFF_E_UNSUPPORTED, "dff_forward: DFF_TRAIN is not available in this build");
   Runner r{net_of(DFF_NET_DFF), (const char*)packed, (char*)ws, ws_bytes, 0, dry, (mode & DFF_BF16) != 0, st};
   r.prof = prof;
+  r.use_tc = r.bf16 && !(mode & DFF_NO_TC);
   const double vox = (double)B * S * H * W;
-  Ten x0 = r.alloc(B, S, H, W, 4);
-  r.op_begin("to_channels_last", 0, vox * (12 + 4 * r.esize(false)), 1);
-  if (!dry && !r.rc) r.rc = launch_to_cl(FS, B, 3, S, H, W, x0.p, 4, r.bf16, st);
+  const int c_in = r.use_tc ? 8 : 4;  // stored channels of the converted focal stack (TMA needs 16-byte pixels)
+  Ten x0 = r.alloc(B, S, H, W, c_in);
+  r.op_begin("to_channels_last", 0, vox * (12 + c_in * r.esize(false)), 1);
+  if (!dry && !r.rc) r.rc = launch_to_cl(FS, B, 3, S, H, W, x0.p, c_in, r.bf16, st);
   r.op_end();
   Ten t = r.conv("FM_measure.Focus_extraction.0.0", x0, Runner::relu());
   Ten v1 = r.srd("FM_measure.Focus_extraction.2", t);
@@ -544,6 +572,7 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
   for (const Layer& l : n.layers) {
     DFF_TRY(launch_pack_weight(raw + l.raw_w, (float*)(pk + l.pk_w), l.cout, l.cin, l.ntaps, l.CinP, l.CoutP,
                                l.transposed ? 1 : 0, st));
+    DFF_TRY(launch_pack_weight_tc(raw + l.raw_w, pk + l.pk_wtc, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
     const bool bn = l.raw_gamma >= 0;
     DFF_TRY(launch_bn_fold(bn ? raw + l.raw_gamma : nullptr, bn ? raw + l.raw_beta : nullptr, bn ? raw + l.raw_mean : nullptr,
                            bn ? raw + l.raw_var : nullptr, l.raw_bias >= 0 ? raw + l.raw_bias : nullptr,
@@ -648,7 +677,9 @@ int dff_forward_host(const void* packed, const float* FS_host, const float* fd_h
 
 size_t dff_conv3d_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw) {
   const size_t CinP = align_up(Cin, 4), CoutP = align_up(Cout, 8);
-  return align_up((size_t)kd * kh * kw * CinP * CoutP * 4, 256);
+  const size_t ffma = align_up((size_t)kd * kh * kw * CinP * CoutP * 4, 256);
+  const size_t tcb = align_up(((size_t)kd * kh * kw + 1) * align_up(Cout, 16) * align_up(Cin, 8) * 2, 256);
+  return ffma > tcb ? ffma : tcb;
 }
 
 int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const float* weight, int Cout,
@@ -656,7 +687,8 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
                const void* res_pre, const void* res_post, int relu, void* out, int elem, int use_tensor_cores, void* scratch,
                int device, void* stream) {
   if (!in0 || !weight || !out || !scratch) return fail(DFF_E_ARG, "dff_conv3d: null pointer");
-  if (use_tensor_cores) return fail(DFF_E_UNSUPPORTED, "dff_conv3d: tensor-core path not available for this layer");
+  if (use_tensor_cores && (elem != DFF_BF16 || (C0 % 8) || (C1 % 8)))
+    return fail(DFF_E_UNSUPPORTED, "dff_conv3d: the tensor-core path needs bf16 tensors with channel counts that are multiples of 8");
   if (kd * kh * kw > kMaxTaps) return fail(DFF_E_ARG, "dff_conv3d: too many taps");
   if (transposed && !(kd == 3 && kh == 3 && kw == 3 && stride_hw == 2 && dil_hw == 1))
     return fail(DFF_E_ARG, "dff_conv3d: transposed conv must be k=3, stride (1,2,2)");
@@ -669,7 +701,12 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
   l.CinP = Cin;
   l.CoutP = (int)align_up(Cout, 8);
   l.ntaps = kd * kh * kw;
-  DFF_TRY(launch_pack_weight(weight, (float*)scratch, Cout, Cin, l.ntaps, l.CinP, l.CoutP, transposed ? 1 : 0, st));
+  l.CinT = Cin;
+  l.Ntc = (int)align_up(Cout, 16);
+  if (use_tensor_cores)
+    DFF_TRY(launch_pack_weight_tc(weight, scratch, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
+  else
+    DFF_TRY(launch_pack_weight(weight, (float*)scratch, Cout, Cin, l.ntaps, l.CinP, l.CoutP, transposed ? 1 : 0, st));
   Ten in;
   in.p = const_cast<void*>(in0); in.B = B; in.S = S; in.H = IH; in.W = IW; in.C = C0;
   Ten t1;
@@ -686,7 +723,7 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
   e.res_pre = res_pre ? &rp : nullptr;
   e.res_post = res_post ? &rq : nullptr;
   e.relu = relu != 0;
-  return run_conv(l, (const float*)scratch, scale, shift, in, e, o, elem == DFF_BF16, st);
+  return run_conv(l, (const float*)scratch, scale, shift, in, e, o, elem == DFF_BF16, st, use_tensor_cores ? scratch : nullptr);
 }
 
 int dff_depth_head(const float* cost, int h, int w, const float* fd, const int64_t fd_strides[4], int B, int S, int H, int W,

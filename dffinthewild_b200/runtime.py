@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdff_b200.so")
 
-FP32, BF16, TRAIN = 0, 1, 2
+FP32, BF16, TRAIN, NO_TC = 0, 1, 2, 4
 NET_DFF, NET_FLOW = 0, 1
 
 _lib = None
@@ -165,6 +165,8 @@ def _mode(net):
     prec = getattr(net, "precision", "fp32")
     if prec not in ("fp32", "bf16"):
         raise DffError("dff_b200: precision must be 'fp32' or 'bf16'")
+    if prec == "bf16" and os.environ.get("DFF_B200_NO_TC") == "1":
+        return BF16 | NO_TC   # debugging aid: bf16 storage, FFMA kernels
     return BF16 if prec == "bf16" else FP32
 
 
@@ -247,13 +249,14 @@ def conv3d(x, weight, stride_hw=1, dil_hw=1, transposed=False, scale=None, shift
     B, C0, S, IH, IW = x.shape
     Cout = weight.shape[1] if transposed else weight.shape[0]
     kd, kh, kw = weight.shape[2:]
-    C0p = (C0 + 3) // 4 * 4
+    cal = 8 if tensor_cores else 4
+    C0p = (C0 + cal - 1) // cal * cal
     a = to_channels_last(x, C0p, bf16)
     b, C1p = None, 0
     w = weight.detach().to(dev, torch.float32)
     if x2 is not None:
         C1 = x2.shape[1]
-        C1p = (C1 + 3) // 4 * 4
+        C1p = (C1 + cal - 1) // cal * cal
         b = to_channels_last(x2, C1p, bf16)
     if C0p != C0 or (x2 is not None and C1p != x2.shape[1]):
         # zero weights for the padded input channels
@@ -270,10 +273,10 @@ def conv3d(x, weight, stride_hw=1, dil_hw=1, transposed=False, scale=None, shift
     rq = to_channels_last(res_post, Cop, bf16) if res_post is not None else None
     sc = scale.detach().to(dev, torch.float32).contiguous() if scale is not None else None
     sh = shift.detach().to(dev, torch.float32).contiguous() if shift is not None else None
-    if sc is not None and sc.numel() % 8:
-        sc = torch.cat([sc, sc.new_ones(8 - sc.numel() % 8)])
-    if sh is not None and sh.numel() % 8:
-        sh = torch.cat([sh, sh.new_zeros(8 - sh.numel() % 8)])
+    if sc is not None and sc.numel() % 16:
+        sc = torch.cat([sc, sc.new_ones(16 - sc.numel() % 16)])
+    if sh is not None and sh.numel() % 16:
+        sh = torch.cat([sh, sh.new_zeros(16 - sh.numel() % 16)])
     scratch = torch.empty(l.dff_conv3d_scratch_bytes(C0p + C1p, Cout, kd, kh, kw), dtype=torch.uint8, device=dev)
     check(l.dff_conv3d(_ptr(a), C0p, _ptr(b), C1p, B, S, IH, IW, _ptr(w), Cout, kd, kh, kw, stride_hw, dil_hw,
                        1 if transposed else 0, _ptr(sc), _ptr(sh), _ptr(rp), _ptr(rq), 1 if relu else 0, _ptr(out),
