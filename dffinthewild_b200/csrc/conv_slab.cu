@@ -1,0 +1,389 @@
+// "Slab" implicit-GEMM convolution on tcgen05/TMEM — the main bf16 kernel of the network.
+//
+// Replaces the cuDNN conv3d / conv_transpose3d calls of the reference (train_codes/Depth_Estimation_Network.py:352-355,
+// 43-50, 278-301) for every layer whose weights fit in shared memory (all full-, half- and quarter-resolution layers).
+//
+// What bounds a focal-volume convolution on B200 is not the tensor pipe but how often the activation tile is re-read: a
+// per-tap TMA implicit GEMM (conv_tc.cu) pulls the same 128 pixels 27 times from L2.  Here one CTA owns an 8 x 16 pixel
+// column of the focal volume and walks the S slices:
+//   * 4 producer warps stage each slice's halo'd tile ONCE in shared memory with 16-byte cp.async (zero-fill = padding,
+//     second source pointer = torch.cat, parity views = stride 2) in the UMMA no-swizzle K-major layout: per 8-channel chunk
+//     a plane of [row][pixel] x 16 B, so 8 horizontally adjacent pixels form one 128-byte core matrix.  A ring of NP
+//     planes holds slices s-1, s, s+1 (the 3-tap focal dimension) plus look-ahead;
+//   * a convolution tap is then nothing but a byte offset added to the matrix-descriptor start address (dy rows, dx pixels,
+//     dz = which ring slot) — no data movement per tap; the K=16 of one tcgen05.mma is two 8-channel chunk planes (LBO = plane
+//     stride) or, for 8-channel tensors, two neighbouring taps (LBO = their distance);
+//   * the layer's weights are loaded once per CTA into shared memory, already ordered by MMA;
+//   * one thread issues the MMAs of a slice (taps x Cin/16) into a double-buffered TMEM accumulator; 4 epilogue warps apply
+//     BatchNorm/bias, residuals, ReLU and store while the next slice is being multiplied.
+// HBM/L2 traffic per output pixel drops from taps x Cin to ~1.4 x Cin, and there is no per-tap barrier round trip.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "tc_common.cuh"
+
+namespace dff {
+
+constexpr int kSlabThreads = 288;  // warps 0-3 producers, warp 4 MMA issuer (+TMEM alloc), warps 5-8 epilogue
+constexpr int kSlabMaxOps = 112;
+constexpr int kSlabMaxPlanes = 8;
+constexpr int kSlabTW = 8, kSlabTH = 16;
+constexpr int kSlabSmemBudget = 220 * 1024;
+
+struct alignas(16) SlabParams {
+  const void* in0;
+  const void* in1;
+  const void* wslab;  // bf16 [tap][chunk][N][8]
+  int C0, C1, nchunk, nch0;
+  int B, S, IH, IW;
+  int st, nviews, vpy[4], vpx[4];
+  int oy, ox, RX, RY, CPS, plane_bytes, NP, LA, hz;
+  int N, nops, g[4];
+  int tilesX, tilesY, nsplit, slen, nitems;
+  int OHt, OWt, OH, OW, osy, osx, ooy, oox;
+  int w_bytes, tmem_cols;
+  EpiArgs epi;
+  uint32_t tab[kSlabMaxOps];      // per MMA: (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
+  int16_t wsrc[2 * kSlabMaxOps];  // per MMA and K half: 8-channel weight block (tap * nchunk + chunk) in `wslab`, -1 = zeros
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait(int n) {  // wait until at most n groups are pending
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid_constant__ SlabParams p) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kSlabMaxPlanes + 4];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t tab_s = smem0;                                  // nops x u32 (512 B reserved)
+  const uint32_t w_s = smem0 + 512;                              // weights, MMA order: [op][half][N][8] bf16
+  const uint32_t planes_s = w_s + ((p.w_bytes + 127) & ~127);    // ring of NP slice planes
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kSlabMaxPlanes]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * kSlabMaxPlanes]), tempty0 = smem_u32(&bars[2 * kSlabMaxPlanes + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.NP; ++i) {
+      mbar_init(full0 + 8 * i, 128);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // ---- one-time: MMA table and the layer's weights into shared memory (MMA order) ----------------------------------
+  for (int i = threadIdx.x; i < p.nops; i += kSlabThreads)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_s + 4 * i), "r"(p.tab[i]) : "memory");
+  {
+    const int total = 2 * p.nops * p.N;  // 16-byte rows
+    const uint4* wg = reinterpret_cast<const uint4*>(p.wslab);
+    for (int i = threadIdx.x; i < total; i += kSlabThreads) {
+      const int blk = i / p.N, r = i - blk * p.N;
+      const int src = p.wsrc[blk];
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (src >= 0) v = __ldg(wg + (size_t)src * p.N + r);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_s + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+  }
+  fence_proxy_async();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int hz = p.hz;
+
+  if (warp < 4) {
+    // =============================== producers: stage slice planes with cp.async ===============================
+    const int ptid = threadIdx.x;
+    const int npix = p.nviews * p.RY * p.RX;
+    const int nelem = npix * p.nchunk;
+    int n = 0, sig = 0;  // planes issued / planes published
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      int r = item;
+      const int isp = r % p.nsplit; r /= p.nsplit;
+      const int tx0 = (r % p.tilesX) * kSlabTW; r /= p.tilesX;
+      const int ty0 = (r % p.tilesY) * kSlabTH;
+      const int b = r / p.tilesY;
+      const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
+      const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
+      for (int z = zlo; z < zhi; ++z, ++n) {
+        const int slot = n % p.NP;
+        mbar_wait(empty0 + 8 * slot, ((n / p.NP) & 1) ^ 1);
+        const uint32_t dst0 = planes_s + slot * p.plane_bytes;
+        const size_t slice_pix = ((size_t)b * p.S + z) * p.IH;
+        for (int e = ptid; e < nelem; e += 128) {
+          const int c = e % p.nchunk, pix = e / p.nchunk;
+          const int rx = pix % p.RX, t = pix / p.RX;
+          const int ry = t % p.RY, v = t / p.RY;
+          const int gy = p.st * (ty0 + p.oy + ry) + p.vpy[v], gx = p.st * (tx0 + p.ox + rx) + p.vpx[v];
+          const bool ok = gy >= 0 && gy < p.IH && gx >= 0 && gx < p.IW;
+          const bool second = c >= p.nch0;
+          const char* base = reinterpret_cast<const char*>(second ? p.in1 : p.in0);
+          const int C = second ? p.C1 : p.C0, cc = second ? c - p.nch0 : c;
+          const char* src = ok ? base + (((slice_pix + gy) * p.IW + gx) * C + cc * 8) * 2 : base;
+          cp_async16(dst0 + c * p.CPS + pix * 16, src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        // publish every plane whose copies have certainly landed (all but the newest LA-1 groups)
+        cp_async_wait(p.LA - 1);
+        while (sig <= n - (p.LA - 1)) {
+          fence_proxy_async();
+          mbar_arrive(full0 + 8 * (sig % p.NP));
+          ++sig;
+        }
+      }
+    }
+    cp_async_wait(0);
+    while (sig < n) {
+      fence_proxy_async();
+      mbar_arrive(full0 + 8 * (sig % p.NP));
+      ++sig;
+    }
+  } else if (warp == 4) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+      // descriptor high words: SBO (8-row group stride) | version 1 | no swizzle
+      const uint32_t a_hi = ((uint32_t)(p.RX * 16) >> 4) | (1u << 14);
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);
+      const uint32_t b_lbo = ((uint32_t)(p.N * 16) >> 4) << 16;
+      int n_base = 0, waited = 0, sc = 0;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        const int isp = item % p.nsplit;
+        const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
+        const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
+        for (int s = s_begin; s < s_end; ++s, ++sc) {
+          const int need_n = n_base + (min(s + hz, zhi - 1) - zlo);
+          while (waited <= need_n) {
+            mbar_wait(full0 + 8 * (waited % p.NP), (waited / p.NP) & 1);
+            ++waited;
+          }
+          const int buf = sc & 1;
+          mbar_wait(tempty0 + 8 * buf, ((sc >> 1) & 1) ^ 1);
+          fence_after();
+          const uint32_t dacc = tmem_base + buf * p.N;
+          uint32_t acc = 0;
+          for (int k = (hz ? 0 : 1); k < (hz ? 3 : 2); ++k) {
+            const int z = s + k - 1;
+            if (z < 0 || z >= p.S) continue;  // focal-dimension zero padding: nothing to multiply
+            const uint32_t plane_lo = (planes_s + ((n_base + z - zlo) % p.NP) * p.plane_bytes) >> 4;
+            for (int i = p.g[k]; i < p.g[k + 1]; ++i) {
+              uint32_t a_lo;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a_lo) : "r"(tab_s + 4 * i));
+              a_lo += plane_lo;
+              const uint32_t b_lo = ((w_s + (uint32_t)i * p.N * 32) >> 4) | b_lbo;
+              umma(dacc, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(tfull0 + 8 * buf);
+          // ring slots whose last reader was this slice
+          if (s - hz >= zlo) umma_commit(empty0 + 8 * ((n_base + s - hz - zlo) % p.NP));
+          if (s == s_end - 1)
+            for (int z = max(zlo, s - hz + 1); z < zhi; ++z) umma_commit(empty0 + 8 * ((n_base + z - zlo) % p.NP));
+        }
+        n_base += zhi - zlo;
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ty = row >> 3, tx = row & 7;
+    int sc = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      int r = item;
+      const int isp = r % p.nsplit; r /= p.nsplit;
+      const int ox = (r % p.tilesX) * kSlabTW + tx; r /= p.tilesX;
+      const int oy = (r % p.tilesY) * kSlabTH + ty;
+      const int b = r / p.tilesY;
+      const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
+      const bool valid = oy < p.OHt && ox < p.OWt;
+      for (int s = s_begin; s < s_end; ++s, ++sc) {
+        const int buf = sc & 1;
+        const size_t pix = (((size_t)b * p.S + s) * p.OH + (oy * p.osy + p.ooy)) * p.OW + (ox * p.osx + p.oox);
+        mbar_wait(tfull0 + 8 * buf, (sc >> 1) & 1);
+        fence_after();
+        tc_epilogue_tile(p.epi, tmem_base + ((uint32_t)(q * 32) << 16) + buf * p.N, valid, pix);
+        fence_before();
+        mbar_arrive(tempty0 + 8 * buf);
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side: plan (geometry, MMA table, ring depth) + launch
+// ------------------------------------------------------------------------------------------------------------------
+static bool slab_plan(const ConvArgs& a, int Ntc, int num_sms, SlabParams& p, size_t* smem_out) {
+  memset(&p, 0, sizeof(p));
+  if (a.C0 % 8 || a.C1 % 8 || a.C0 < 8) return false;
+  if (Ntc < 16 || Ntc > 128 || Ntc % 16) return false;
+  if (a.isy != a.isx || (a.isy != 1 && a.isy != 2)) return false;
+  const int nchunk = (a.C0 + a.C1) / 8;
+  if (nchunk != 1 && (nchunk & 1)) return false;
+  p.in0 = a.in0; p.in1 = a.in1; p.C0 = a.C0; p.C1 = a.C1; p.nchunk = nchunk; p.nch0 = a.C0 / 8;
+  p.B = a.B; p.S = a.S; p.IH = a.IH; p.IW = a.IW; p.st = a.isy;
+  p.nviews = p.st == 2 ? 4 : 1;
+  for (int v = 0; v < 4; ++v) { p.vpy[v] = v >> 1; p.vpx[v] = v & 1; }
+  // ---- taps in view coordinates -------------------------------------------------------------------------------------
+  struct VT { int dz, view, vy, vx, widx; };
+  std::vector<VT> vt;
+  int vymin = 1000, vymax = -1000, vxmin = 1000, vxmax = -1000, dzmin = 1000, dzmax = -1000;
+  for (int t = 0; t < a.taps.n; ++t) {
+    VT x;
+    x.dz = a.taps.dz[t]; x.widx = a.taps.widx[t];
+    int dy = a.taps.dy[t], dx = a.taps.dx[t];
+    if (p.st == 2) {
+      const int py = dy & 1, px = dx & 1;
+      x.view = py * 2 + px; x.vy = (dy - py) / 2; x.vx = (dx - px) / 2;
+    } else {
+      x.view = 0; x.vy = dy; x.vx = dx;
+    }
+    vymin = std::min(vymin, x.vy); vymax = std::max(vymax, x.vy);
+    vxmin = std::min(vxmin, x.vx); vxmax = std::max(vxmax, x.vx);
+    dzmin = std::min(dzmin, x.dz); dzmax = std::max(dzmax, x.dz);
+    vt.push_back(x);
+  }
+  if (dzmin < -1 || dzmax > 1) return false;
+  p.hz = (dzmin < 0 || dzmax > 0) ? 1 : 0;
+  p.oy = vymin; p.ox = vxmin;
+  p.RY = kSlabTH + (vymax - vymin);
+  p.RX = kSlabTW + (vxmax - vxmin);
+  p.CPS = p.nviews * p.RY * p.RX * 16;
+  p.plane_bytes = (nchunk * p.CPS + 127) & ~127;
+  if ((p.CPS >> 4) >= (1 << 14) || p.RX * 16 >= (1 << 18)) return false;
+  auto aoff = [&](const VT& x, int chunk) { return chunk * p.CPS + ((x.view * p.RY + (x.vy - p.oy)) * p.RX + (x.vx - p.ox)) * 16; };
+  // ---- MMA table, grouped by focal offset dz = -1, 0, +1 ---------------------------------------------------------------
+  int nops = 0;
+  for (int k = 0; k < 3; ++k) {
+    p.g[k] = nops;
+    std::vector<VT> grp;
+    for (auto& x : vt)
+      if (x.dz == k - 1) grp.push_back(x);
+    if (nchunk > 1) {
+      for (auto& x : grp)
+        for (int j = 0; j < nchunk; j += 2) {
+          if (nops >= kSlabMaxOps) return false;
+          p.tab[nops] = (uint32_t)(aoff(x, j) >> 4) | ((uint32_t)(p.CPS >> 4) << 16);
+          p.wsrc[2 * nops] = (int16_t)(x.widx * nchunk + j);
+          p.wsrc[2 * nops + 1] = (int16_t)(x.widx * nchunk + j + 1);
+          ++nops;
+        }
+    } else {  // 8-channel tensor: K = 16 is two taps; an odd tap is paired with zero weights
+      std::sort(grp.begin(), grp.end(), [&](const VT& l, const VT& r) { return aoff(l, 0) < aoff(r, 0); });
+      for (size_t i = 0; i < grp.size(); i += 2) {
+        if (nops >= kSlabMaxOps) return false;
+        const bool pair = i + 1 < grp.size();
+        const int o1 = aoff(grp[i], 0), o2 = pair ? aoff(grp[i + 1], 0) : o1;
+        if (((o2 - o1) >> 4) >= (1 << 14)) return false;
+        p.tab[nops] = (uint32_t)(o1 >> 4) | ((uint32_t)((o2 - o1) >> 4) << 16);
+        p.wsrc[2 * nops] = (int16_t)grp[i].widx;
+        p.wsrc[2 * nops + 1] = pair ? (int16_t)grp[i + 1].widx : (int16_t)-1;
+        ++nops;
+      }
+    }
+  }
+  p.g[3] = nops;
+  p.nops = nops;
+  if (nops == 0) return false;
+  p.N = Ntc;
+  p.w_bytes = nops * Ntc * 32;
+  // ---- shared memory: table + weights + ring ---------------------------------------------------------------------------
+  const int fixed = 512 + ((p.w_bytes + 127) & ~127) + 256;
+  const int np_min = 2 * p.hz + 2;
+  int NP = (kSlabSmemBudget - fixed) / p.plane_bytes;
+  if (NP < np_min) return false;
+  if (NP > kSlabMaxPlanes) NP = kSlabMaxPlanes;
+  p.NP = NP;
+  p.LA = std::min(5, NP - 2 * p.hz - 1);
+  *smem_out = (size_t)fixed + (size_t)NP * p.plane_bytes;
+  const int cols = 2 * Ntc;
+  p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
+  // ---- work items ----------------------------------------------------------------------------------------------------------
+  p.OHt = a.OHt; p.OWt = a.OWt; p.OH = a.OH; p.OW = a.OW;
+  p.osy = a.osy; p.osx = a.osx; p.ooy = a.ooy; p.oox = a.oox;
+  p.tilesX = cdiv(a.OWt, kSlabTW);
+  p.tilesY = cdiv(a.OHt, kSlabTH);
+  const int cols_items = a.B * p.tilesX * p.tilesY;
+  int nsplit = 1;
+  if (cols_items < 2 * num_sms) nsplit = std::min(a.S, cdiv(2 * num_sms, cols_items));
+  p.slen = cdiv(a.S, nsplit);
+  p.nsplit = cdiv(a.S, p.slen);
+  p.nitems = cols_items * p.nsplit;
+  p.epi.scale = a.scale; p.epi.shift = a.shift; p.epi.res_pre = a.res_pre; p.epi.res_post = a.res_post;
+  p.epi.out = a.out; p.epi.out_aux = a.out_aux; p.epi.aux_add = a.aux_add;
+  p.epi.cstore = a.Cout; p.epi.relu = a.relu; p.epi.out_f32 = a.out_f32; p.epi.N = Ntc;
+  return true;
+}
+
+bool conv_slab_supported(const ConvArgs& a, int Ntc) {
+  SlabParams p;
+  size_t smem;
+  return slab_plan(a, Ntc, 148, p, &smem);
+}
+
+// `wslab`: bf16 weights [ntaps][Cin/8][Ntc][8]
+int launch_conv_slab(const ConvArgs& a, const void* wslab, int Ntc, int num_sms, cudaStream_t st) {
+  SlabParams p;
+  size_t smem = 0;
+  if (!slab_plan(a, Ntc, num_sms, p, &smem)) return fail(-5, "conv_slab: unsupported layer shape");
+  p.wslab = wslab;
+  DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.nitems < num_sms ? p.nitems : num_sms;
+  conv_slab_kernel<<<grid, kSlabThreads, smem, st>>>(p);
+  DFF_LAUNCH_CHECK("conv_slab");
+  return 0;
+}
+
+__global__ void pack_weight_slab_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin, int CinP,
+                                        int ntaps, int Ntc, int transposed) {
+  const int nchunk = CinP / 8;
+  const int n = ntaps * nchunk * Ntc * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int j = i & 7, co = (i >> 3) % Ntc, c = (i / (8 * Ntc)) % nchunk, t = i / (8 * Ntc * nchunk);
+    const int ci = c * 8 + j;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = transposed ? w[((size_t)ci * Cout + co) * ntaps + t] : w[((size_t)co * Cin + ci) * ntaps + t];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
+                            cudaStream_t st) {
+  const int n = ntaps * CinP * Ntc;
+  int g = cdiv(n, 256);
+  if (g > 512) g = 512;
+  pack_weight_slab_kernel<<<g, 256, 0, st>>>(w, (__nv_bfloat16*)dst, Cout, Cin, CinP, ntaps, Ntc, transposed);
+  DFF_LAUNCH_CHECK("pack_weight_slab");
+  return 0;
+}
+
+}  // namespace dff

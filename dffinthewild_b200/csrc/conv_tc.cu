@@ -15,11 +15,9 @@
 //   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), apply BatchNorm scale/shift (or bias), residual adds, ReLU,
 //     and store bf16 channels-last (or fp32 cost volumes) while the next tile's MMAs run.
 // Persistent CTAs (one per SM) walk the tile list; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
-#include <cuda.h>
-
 #include <cstring>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dff {
 
@@ -56,91 +54,7 @@ struct alignas(64) TcParams {
   TcLoad loads[kTcMaxLoads];
 };
 
-namespace tc {
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must not hang the GPU (a hung box is a lost lease) — trap after ~2 s.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
-}
-// UMMA shared-memory matrix descriptor (K-major).  layout: 0 none, 2 128B, 4 64B, 6 32B swizzle.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
-  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) { return Elem<__nv_bfloat16>::load4(p); }
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-}  // namespace tc
 
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   using namespace tc;
@@ -233,11 +147,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
     const int ty = row >> p.twshift, tx = row & (p.TW - 1);
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-    const __nv_bfloat16* rpre = reinterpret_cast<const __nv_bfloat16*>(p.res_pre);
-    const __nv_bfloat16* rpost = reinterpret_cast<const __nv_bfloat16*>(p.res_post);
-    __nv_bfloat16* oaux = reinterpret_cast<__nv_bfloat16*>(p.out_aux);
-    const __nv_bfloat16* aadd = reinterpret_cast<const __nv_bfloat16*>(p.aux_add);
+    EpiArgs ep;
+    ep.scale = p.scale; ep.shift = p.shift; ep.res_pre = p.res_pre; ep.res_post = p.res_post; ep.out = p.out;
+    ep.out_aux = p.out_aux; ep.aux_add = p.aux_add; ep.cstore = p.cstore; ep.relu = p.relu; ep.out_f32 = p.out_f32; ep.N = p.N;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -247,66 +159,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const size_t pix = ((size_t)bs * p.OH + (oy * p.osy + p.ooy)) * p.OW + (ox * p.osx + p.oox);
       mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
       fence_after();
-      for (int c0 = 0; c0 < p.N; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * p.N + c0, v);
-        if (!valid || c0 >= p.cstore) continue;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float sc = p.scale ? __ldg(p.scale + c0 + j) : 1.f, sh = p.shift ? __ldg(p.shift + c0 + j) : 0.f;
-          f[j] = fmaf(__uint_as_float(v[j]), sc, sh);
-        }
-        const size_t o = pix * p.cstore + c0;
-        if (p.out_f32) {  // cost volumes (Cout = 1..): fp32, scalar stores
-          for (int j = 0; j < 16 && c0 + j < p.cstore; ++j) {
-            float x = f[j];
-            if (p.relu) x = fmaxf(x, 0.f);
-            reinterpret_cast<float*>(p.out)[o + j] = x;
-          }
-          continue;
-        }
-        const int nv = min(16, p.cstore - c0);  // 8 or 16 channels (stored channel counts are multiples of 8)
-        if (rpre) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            if (j < nv) {
-              const float4 t = ld_bf16x4(rpre + o + j);
-              f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
-            }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (rpost) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            if (j < nv) {
-              const float4 t = ld_bf16x4(rpost + o + j);
-              f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 8)
-          if (j < nv) {
-            uint4 w;
-            w.x = pack2(f[j], f[j + 1]); w.y = pack2(f[j + 2], f[j + 3]);
-            w.z = pack2(f[j + 4], f[j + 5]); w.w = pack2(f[j + 6], f[j + 7]);
-            *reinterpret_cast<uint4*>(out + o + j) = w;
-          }
-        if (oaux) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 8)
-            if (j < nv) {
-              const float4 t0 = ld_bf16x4(aadd + o + j), t1 = ld_bf16x4(aadd + o + j + 4);
-              uint4 w;
-              w.x = pack2(f[j] + t0.x, f[j + 1] + t0.y); w.y = pack2(f[j + 2] + t0.z, f[j + 3] + t0.w);
-              w.z = pack2(f[j + 4] + t1.x, f[j + 5] + t1.y); w.w = pack2(f[j + 6] + t1.z, f[j + 7] + t1.w);
-              *reinterpret_cast<uint4*>(oaux + o + j) = w;
-            }
-        }
-      }
+      tc_epilogue_tile(ep, tmem_base + ((uint32_t)(q * 32) << 16) + buf * p.N, valid, pix);
       fence_before();
       mbar_arrive(tempty0 + 8 * buf);
     }

@@ -27,6 +27,10 @@ bool conv_tc_supported(const ConvArgs& a, int Ntc);
 int launch_conv_tc(const ConvArgs& a, const void* wtc, int ntaps_total, int Ntc, int num_sms, cudaStream_t st);
 int launch_pack_weight_tc(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
                           cudaStream_t st);
+bool conv_slab_supported(const ConvArgs& a, int Ntc);
+int launch_conv_slab(const ConvArgs& a, const void* wslab, int Ntc, int num_sms, cudaStream_t st);
+int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
+                            cudaStream_t st);
 int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
                    float* scale, float* shift, int C, int CP, cudaStream_t st);
 
@@ -54,7 +58,7 @@ struct Layer {
   int CinP, CoutP, ntaps;
   int CinT, Ntc;  // tensor-core path: stored input channels (multiple of 8) and MMA N (multiple of 16, >= 16)
   int64_t raw_w, raw_gamma, raw_beta, raw_mean, raw_var, raw_bias;  // element offsets in the raw buffer (-1: none)
-  size_t pk_w, pk_scale, pk_shift, pk_wtc;                           // byte offsets in the packed buffer
+  size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab;                           // byte offsets in the packed buffer
 };
 struct Param {
   std::string name;
@@ -97,6 +101,8 @@ struct Net {
     packed_bytes += align_up(l.CoutP * sizeof(float), 256);
     l.pk_wtc = packed_bytes;
     packed_bytes += align_up((size_t)(l.ntaps + 1) * l.Ntc * l.CinT * 2, 256);
+    l.pk_wslab = packed_bytes;
+    packed_bytes += align_up((size_t)l.ntaps * l.Ntc * l.CinT * 2, 256);
     index[name] = (int)layers.size();
     layers.push_back(l);
   }
@@ -243,7 +249,7 @@ static int num_sms_of_current_device() {
 
 // `wtc` != null selects the tcgen05 path (bf16 only); otherwise the FFMA kernel runs.
 static int run_conv(const Layer& l, const float* w, const float* scale, const float* shift, const Ten& in, const EpiOpt& e,
-                    Ten& out, bool bf16, cudaStream_t st, const void* wtc = nullptr) {
+                    Ten& out, bool bf16, cudaStream_t st, const void* wtc = nullptr, const void* wslab = nullptr) {
   ConvArgs a{};
   a.in0 = in.p;
   a.C0 = in.C;
@@ -268,7 +274,10 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     conv_taps(l, a.taps);
     a.isy = a.isx = l.stride; a.osy = a.osx = 1; a.ooy = a.oox = 0;
     a.OHt = out.H; a.OWt = out.W;
-    if (wtc) return launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st);
+    if (wtc) {
+      if (wslab && conv_slab_supported(a, l.Ntc)) return launch_conv_slab(a, wslab, l.Ntc, nsm, st);
+      return launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st);
+    }
     return launch_conv_ffma(a, bf16, st);
   }
   for (int py = 0; py < 2; ++py)
@@ -276,8 +285,12 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
       deconv_taps(py, px, a.taps);
       a.isy = a.isx = 1; a.osy = a.osx = 2; a.ooy = py; a.oox = px;
       a.OHt = in.H; a.OWt = in.W;
-      if (wtc) DFF_TRY(launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st));
-      else DFF_TRY(launch_conv_ffma(a, bf16, st));
+      if (wtc) {
+        if (wslab && conv_slab_supported(a, l.Ntc)) DFF_TRY(launch_conv_slab(a, wslab, l.Ntc, nsm, st));
+        else DFF_TRY(launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st));
+      } else {
+        DFF_TRY(launch_conv_ffma(a, bf16, st));
+      }
     }
   return 0;
 }
@@ -304,7 +317,7 @@ struct Runner {
   cudaStream_t st;
   int rc = 0;
   Profile* prof = nullptr;
-  bool use_tc = false;
+  bool use_tc = false, use_slab = true;
 
   void op_begin(const std::string& name, double flops, double bytes, int launches) {
     if (!prof) return;
@@ -360,7 +373,8 @@ struct Runner {
     }
     if (!dry && !rc)
       rc = run_conv(l, (const float*)(packed + l.pk_w), (const float*)(packed + l.pk_scale),
-                    (const float*)(packed + l.pk_shift), in, e, out, bf16, st, use_tc ? packed + l.pk_wtc : nullptr);
+                    (const float*)(packed + l.pk_shift), in, e, out, bf16, st, use_tc ? packed + l.pk_wtc : nullptr,
+                    (use_tc && use_slab) ? packed + l.pk_wslab : nullptr);
     op_end();
     return out;
   }
@@ -466,6 +480,7 @@ static int forward_impl(const void* packed, const float* FS, const float* fd, co
   Runner r{net_of(DFF_NET_DFF), (const char*)packed, (char*)ws, ws_bytes, 0, dry, (mode & DFF_BF16) != 0, st};
   r.prof = prof;
   r.use_tc = r.bf16 && !(mode & DFF_NO_TC);
+  r.use_slab = !(mode & DFF_NO_SLAB);
   const double vox = (double)B * S * H * W;
   const int c_in = r.use_tc ? 8 : 4;  // stored channels of the converted focal stack (TMA needs 16-byte pixels)
   Ten x0 = r.alloc(B, S, H, W, c_in);
@@ -573,6 +588,7 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
     DFF_TRY(launch_pack_weight(raw + l.raw_w, (float*)(pk + l.pk_w), l.cout, l.cin, l.ntaps, l.CinP, l.CoutP,
                                l.transposed ? 1 : 0, st));
     DFF_TRY(launch_pack_weight_tc(raw + l.raw_w, pk + l.pk_wtc, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
+    DFF_TRY(launch_pack_weight_slab(raw + l.raw_w, pk + l.pk_wslab, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
     const bool bn = l.raw_gamma >= 0;
     DFF_TRY(launch_bn_fold(bn ? raw + l.raw_gamma : nullptr, bn ? raw + l.raw_beta : nullptr, bn ? raw + l.raw_mean : nullptr,
                            bn ? raw + l.raw_var : nullptr, l.raw_bias >= 0 ? raw + l.raw_bias : nullptr,
@@ -679,7 +695,7 @@ size_t dff_conv3d_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw) {
   const size_t CinP = align_up(Cin, 4), CoutP = align_up(Cout, 8);
   const size_t ffma = align_up((size_t)kd * kh * kw * CinP * CoutP * 4, 256);
   const size_t tcb = align_up(((size_t)kd * kh * kw + 1) * align_up(Cout, 16) * align_up(Cin, 8) * 2, 256);
-  return ffma > tcb ? ffma : tcb;
+  return (ffma > 2 * tcb ? ffma : 2 * tcb);  // tensor-core path keeps two layouts (per-tap TMA + slab)
 }
 
 int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const float* weight, int Cout,
@@ -703,9 +719,11 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
   l.ntaps = kd * kh * kw;
   l.CinT = Cin;
   l.Ntc = (int)align_up(Cout, 16);
-  if (use_tensor_cores)
+  const size_t tcb = align_up(((size_t)l.ntaps + 1) * l.Ntc * Cin * 2, 256);
+  if (use_tensor_cores) {
     DFF_TRY(launch_pack_weight_tc(weight, scratch, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
-  else
+    DFF_TRY(launch_pack_weight_slab(weight, (char*)scratch + tcb, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
+  } else
     DFF_TRY(launch_pack_weight(weight, (float*)scratch, Cout, Cin, l.ntaps, l.CinP, l.CoutP, transposed ? 1 : 0, st));
   Ten in;
   in.p = const_cast<void*>(in0); in.B = B; in.S = S; in.H = IH; in.W = IW; in.C = C0;
@@ -723,7 +741,9 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
   e.res_pre = res_pre ? &rp : nullptr;
   e.res_post = res_post ? &rq : nullptr;
   e.relu = relu != 0;
-  return run_conv(l, (const float*)scratch, scale, shift, in, e, o, elem == DFF_BF16, st, use_tensor_cores ? scratch : nullptr);
+  // use_tensor_cores: 1 = slab kernel when the layer fits (else per-tap TMA kernel), 2 = force the per-tap TMA kernel
+  return run_conv(l, (const float*)scratch, scale, shift, in, e, o, elem == DFF_BF16, st, use_tensor_cores ? scratch : nullptr,
+                  use_tensor_cores == 1 ? (char*)scratch + tcb : nullptr);
 }
 
 int dff_depth_head(const float* cost, int h, int w, const float* fd, const int64_t fd_strides[4], int B, int S, int H, int W,

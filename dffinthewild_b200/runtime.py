@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdff_b200.so")
 
-FP32, BF16, TRAIN, NO_TC = 0, 1, 2, 4
+FP32, BF16, TRAIN, NO_TC, NO_SLAB = 0, 1, 2, 4, 8
 NET_DFF, NET_FLOW = 0, 1
 
 _lib = None
@@ -167,6 +167,8 @@ def _mode(net):
         raise DffError("dff_b200: precision must be 'fp32' or 'bf16'")
     if prec == "bf16" and os.environ.get("DFF_B200_NO_TC") == "1":
         return BF16 | NO_TC   # debugging aid: bf16 storage, FFMA kernels
+    if prec == "bf16" and os.environ.get("DFF_B200_NO_SLAB") == "1":
+        return BF16 | NO_SLAB
     return BF16 if prec == "bf16" else FP32
 
 
@@ -280,7 +282,7 @@ def conv3d(x, weight, stride_hw=1, dil_hw=1, transposed=False, scale=None, shift
     scratch = torch.empty(l.dff_conv3d_scratch_bytes(C0p + C1p, Cout, kd, kh, kw), dtype=torch.uint8, device=dev)
     check(l.dff_conv3d(_ptr(a), C0p, _ptr(b), C1p, B, S, IH, IW, _ptr(w), Cout, kd, kh, kw, stride_hw, dil_hw,
                        1 if transposed else 0, _ptr(sc), _ptr(sh), _ptr(rp), _ptr(rq), 1 if relu else 0, _ptr(out),
-                       _elem(bf16), 1 if tensor_cores else 0, _ptr(scratch), dev.index, _stream(dev)))
+                       _elem(bf16), int(tensor_cores), _ptr(scratch), dev.index, _stream(dev)))
     return from_channels_last(out, Cout)
 
 

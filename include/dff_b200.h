@@ -54,6 +54,7 @@ extern "C" {
 #define DFF_BF16 1  /* bf16 activations, tcgen05/TMEM implicit-GEMM kernels, fp32 accumulate */
 #define DFF_TRAIN 2 /* BatchNorm in batch-statistics mode; activations are kept for dff_backward */
 #define DFF_NO_TC 4 /* debugging aid with DFF_BF16: bf16 storage but FFMA kernels instead of tcgen05 */
+#define DFF_NO_SLAB 8 /* debugging aid with DFF_BF16: only the per-tap TMA tcgen05 kernel, never the slab kernel */
 
 /* which parameter set a call refers to */
 #define DFF_NET_DFF 0  /* DFF_net (384-key state_dict)                                */

@@ -67,8 +67,12 @@ def test_conv_fp32_matches_torch_fp64(rt, case):
     res2 = _rand(*ref.shape, seed=6)
     full = F.relu(ref * scale.double().view(1, -1, 1, 1, 1) + shift.double().view(1, -1, 1, 1, 1) + res1.double()) + res2.double()
     out_plain = rt.conv3d(x.cuda(), w.cuda(), stride, dil, tr).cpu().double()
-    out_full = rt.conv3d(x.cuda(), w.cuda(), stride, dil, tr, scale=scale.cuda(), shift=shift.cuda(), res_pre=res1.cuda(),
-                         res_post=res2.cuda(), relu=True).cpu().double()
+    if cout % 4:   # C -> 1 projections (confidence.2, classif*): no residual operands in the network either
+        res1, res2 = None, None
+        full = F.relu(ref * scale.double().view(1, -1, 1, 1, 1) + shift.double().view(1, -1, 1, 1, 1))
+    out_full = rt.conv3d(x.cuda(), w.cuda(), stride, dil, tr, scale=scale.cuda(), shift=shift.cuda(),
+                         res_pre=res1.cuda() if res1 is not None else None,
+                         res_post=res2.cuda() if res2 is not None else None, relu=True).cpu().double()
     K = cin * k[0] * k[1] * k[2]
     tol = 2e-7 * K ** 0.5 * max(1.0, ref.abs().max().item())   # sequential fp32 accumulation over K terms
     assert (out_plain - ref).abs().max().item() <= tol
@@ -78,8 +82,9 @@ def test_conv_fp32_matches_torch_fp64(rt, case):
 TC_CASES = [c for c in CASES if c[2] % 8 == 0]
 
 
+@pytest.mark.parametrize("kernel", [1, 2], ids=["slab", "per_tap_tma"])
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
-def test_conv_tcgen05_bf16(rt, case):
+def test_conv_tcgen05_bf16(rt, case, kernel):
     """tcgen05/TMA implicit-GEMM path: exact products of the bf16-rounded operands, fp32 accumulate, bf16 store."""
     name, cin, cout, k, stride, dil, tr, S, H, W = case
     B = 2
@@ -87,7 +92,7 @@ def test_conv_tcgen05_bf16(rt, case):
     wshape = (cin, cout) + k if tr else (cout, cin) + k
     w = (_rand(*wshape, seed=2, scale=(2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5 * 1.7)).bfloat16().float()
     ref = _ref_conv(x, w, stride, dil, tr)
-    out = rt.conv3d(x.cuda(), w.cuda(), stride, dil, tr, bf16=True, tensor_cores=True).cpu().double()
+    out = rt.conv3d(x.cuda(), w.cuda(), stride, dil, tr, bf16=True, tensor_cores=kernel).cpu().double()
     scale_ = ref.abs().max().item()
     assert (out - ref).abs().max().item() <= 6e-3 * scale_, name
     scale = _rand(cout, seed=3) * 0.4 + 1.0
@@ -96,25 +101,27 @@ def test_conv_tcgen05_bf16(rt, case):
     res2 = _rand(*ref.shape, seed=6).bfloat16().float()
     full = F.relu(ref * scale.double().view(1, -1, 1, 1, 1) + shift.double().view(1, -1, 1, 1, 1) + res1.double()) + res2.double()
     out_full = rt.conv3d(x.cuda(), w.cuda(), stride, dil, tr, scale=scale.cuda(), shift=shift.cuda(), res_pre=res1.cuda(),
-                         res_post=res2.cuda(), relu=True, bf16=True, tensor_cores=True).cpu().double()
+                         res_post=res2.cuda(), relu=True, bf16=True, tensor_cores=kernel).cpu().double()
     assert (out_full - full).abs().max().item() <= 6e-3 * full.abs().max().item(), name
 
 
-def test_conv_tcgen05_two_sources(rt):
+@pytest.mark.parametrize("kernel", [1, 2], ids=["slab", "per_tap_tma"])
+def test_conv_tcgen05_two_sources(rt, kernel):
     for c0, c1, cout in ((16, 16, 16), (8, 8, 8), (32, 32, 32), (64, 64, 64), (128, 64, 128)):
         x0, x1 = _rand(1, c0, 3, 12, 36, seed=7).bfloat16().float(), _rand(1, c1, 3, 12, 36, seed=8).bfloat16().float()
         w = _rand(cout, c0 + c1, 3, 3, 3, seed=9, scale=0.05).bfloat16().float()
         ref = _ref_conv(torch.cat([x0, x1], 1), w, 1, 1, False)
-        out = rt.conv3d(x0.cuda(), w.cuda(), x2=x1.cuda(), bf16=True, tensor_cores=True).cpu().double()
+        out = rt.conv3d(x0.cuda(), w.cuda(), x2=x1.cuda(), bf16=True, tensor_cores=kernel).cpu().double()
         assert (out - ref).abs().max().item() <= 6e-3 * ref.abs().max().item(), (c0, c1, cout)
 
 
-def test_conv_tcgen05_many_tiles_persistent(rt):
+@pytest.mark.parametrize("kernel", [1, 2], ids=["slab", "per_tap_tma"])
+def test_conv_tcgen05_many_tiles_persistent(rt, kernel):
     """More tiles than SMs: every CTA walks several tiles through both TMEM accumulator buffers."""
     x = _rand(2, 16, 6, 96, 160, seed=12).bfloat16().float()
     w = _rand(16, 16, 3, 3, 3, seed=13, scale=0.08).bfloat16().float()
     ref = _ref_conv(x, w, 1, 1, False)
-    out = rt.conv3d(x.cuda(), w.cuda(), bf16=True, tensor_cores=True).cpu().double()
+    out = rt.conv3d(x.cuda(), w.cuda(), bf16=True, tensor_cores=kernel).cpu().double()
     assert (out - ref).abs().max().item() <= 6e-3 * ref.abs().max().item()
 
 
@@ -125,7 +132,7 @@ def test_conv_two_sources_is_channel_concat(rt):
         w = _rand(cout, c0 + c1, 3, 3, 3, seed=9, scale=0.05)
         ref = _ref_conv(torch.cat([x0, x1], 1), w, 1, 1, False)
         out = rt.conv3d(x0.cuda(), w.cuda(), x2=x1.cuda()).cpu().double()
-        assert (out - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+        assert (out - ref).abs().max().item() <= 2e-7 * (27 * (c0 + c1)) ** 0.5 * max(1.0, ref.abs().max().item())
 
 
 def test_conv_bf16_storage(rt):
