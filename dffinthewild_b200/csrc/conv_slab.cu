@@ -18,6 +18,7 @@
 //     BatchNorm/bias, residuals, ReLU and store while the next slice is being multiplied.
 // HBM/L2 traffic per output pixel drops from taps x Cin to ~1.4 x Cin, and there is no per-tap barrier round trip.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -25,11 +26,13 @@
 
 namespace dff {
 
-constexpr int kSlabThreads = 288;  // warps 0-3 producers, warp 4 MMA issuer (+TMEM alloc), warps 5-8 epilogue
-constexpr int kSlabMaxOps = 112;
+constexpr int kSlabProducers = 64;                     // warps 0-1: cp.async producers
+constexpr int kSlabMmaWarp = kSlabProducers / 32;      // warp 2: MMA issuer (+TMEM alloc)
+constexpr int kSlabThreads = kSlabProducers + 32 + 128;  // + warps 3-6: epilogue (one per TMEM lane quadrant)
+constexpr int kSlabMaxOps = 128;
 constexpr int kSlabMaxPlanes = 8;
 constexpr int kSlabTW = 8, kSlabTH = 16;
-constexpr int kSlabSmemBudget = 220 * 1024;
+constexpr int kSlabSmemBudget = 220 * 1024;   // per SM, shared by the co-resident CTAs
 
 struct alignas(16) SlabParams {
   const void* in0;
@@ -39,10 +42,11 @@ struct alignas(16) SlabParams {
   int B, S, IH, IW;
   int st, nviews, vpy[4], vpx[4];
   int oy, ox, RX, RY, CPS, plane_bytes, NP, LA, hz;
-  int N, nops, g[4];
+  int N, nops, nph;          // MMA N; table entries; output phases (1 = convolution, 4 = fused transposed convolution)
+  int g[12], ge[12];         // MMA groups by (phase, focal offset): table range [g[ph*3+k], ge[ph*3+k])
   int tilesX, tilesY, nsplit, slen, nitems;
   int OHt, OWt, OH, OW, osy, osx, ooy, oox;
-  int w_bytes, tmem_cols;
+  int w_bytes, tmem_cols, nelem, elem_off, ss_off, planes_off;
   EpiArgs epi;
   uint32_t tab[kSlabMaxOps];      // per MMA: (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
   int16_t wsrc[2 * kSlabMaxOps];  // per MMA and K half: 8-channel weight block (tap * nchunk + chunk) in `wslab`, -1 = zeros
@@ -61,24 +65,35 @@ __device__ __forceinline__ void cp_async_wait(int n) {  // wait until at most n 
     default: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
   }
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid_constant__ SlabParams p) {
+// staged-element table entry (built once per CTA): where one 16-byte piece of a slice plane comes from / goes to
+struct SlabElem {
+  int32_t rel;       // element offset from the tile-origin pixel of the slice, in the source's own channel stride
+  uint16_t dst16;    // (byte offset inside the ring slot) >> 4, bit 15 = second source
+  int8_t gy, gx;     // input row / column relative to the tile origin (bounds check)
+};
+
+__global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid_constant__ SlabParams p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kSlabMaxPlanes + 4];
   __shared__ uint32_t tmem_base_s;
   const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
-  const uint32_t tab_s = smem0;                                  // nops x u32 (512 B reserved)
-  const uint32_t w_s = smem0 + 512;                              // weights, MMA order: [op][half][N][8] bf16
-  const uint32_t planes_s = w_s + ((p.w_bytes + 127) & ~127);    // ring of NP slice planes
+  uint8_t* const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const uint32_t tab_s = smem0;                    // nops x u32 (1 KB reserved)
+  const uint32_t w_s = smem0 + 1024;               // weights, MMA order: [op][half][N][8] bf16
+  const uint32_t planes_s = smem0 + p.planes_off;  // ring of NP slice planes
+  const SlabElem* const elems = reinterpret_cast<const SlabElem*>(smem_gen + p.elem_off);
+  float* const ss = reinterpret_cast<float*>(smem_gen + p.ss_off);  // scale[N], shift[N]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kSlabMaxPlanes]);
   const uint32_t tfull0 = smem_u32(&bars[2 * kSlabMaxPlanes]), tempty0 = smem_u32(&bars[2 * kSlabMaxPlanes + 2]);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.NP; ++i) {
-      mbar_init(full0 + 8 * i, 128);
+      mbar_init(full0 + 8 * i, kSlabProducers);
       mbar_init(empty0 + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -87,12 +102,12 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kSlabMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // ---- one-time: MMA table and the layer's weights into shared memory (MMA order) ----------------------------------
+  // ---- one-time: MMA table, weights (MMA order), BatchNorm scale/shift and the staging table into shared memory --------
   for (int i = threadIdx.x; i < p.nops; i += kSlabThreads)
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_s + 4 * i), "r"(p.tab[i]) : "memory");
   {
@@ -106,6 +121,24 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
       asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_s + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
   }
+  for (int i = threadIdx.x; i < p.N; i += kSlabThreads) {
+    ss[i] = p.epi.scale ? __ldg(p.epi.scale + i) : 1.f;
+    ss[p.N + i] = p.epi.shift ? __ldg(p.epi.shift + i) : 0.f;
+  }
+  for (int e = threadIdx.x; e < p.nelem; e += kSlabThreads) {
+    const int c = e % p.nchunk, pix = e / p.nchunk;
+    const int rx = pix % p.RX, t = pix / p.RX;
+    const int ry = t % p.RY, v = t / p.RY;
+    const int gy = p.st * (p.oy + ry) + p.vpy[v], gx = p.st * (p.ox + rx) + p.vpx[v];
+    const bool second = c >= p.nch0;
+    const int C = second ? p.C1 : p.C0, cc = second ? c - p.nch0 : c;
+    SlabElem el;
+    el.rel = (gy * p.IW + gx) * C + cc * 8;
+    el.dst16 = (uint16_t)(((c * p.CPS + pix * 16) >> 4) | (second ? 0x8000 : 0));
+    el.gy = (int8_t)gy;
+    el.gx = (int8_t)gx;
+    const_cast<SlabElem*>(elems)[e] = el;
+  }
   fence_proxy_async();
   fence_before();
   __syncthreads();
@@ -113,17 +146,17 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
   const uint32_t tmem_base = tmem_base_s;
   const int hz = p.hz;
 
-  if (warp < 4) {
+  if (warp < kSlabMmaWarp) {
     // =============================== producers: stage slice planes with cp.async ===============================
     const int ptid = threadIdx.x;
-    const int npix = p.nviews * p.RY * p.RX;
-    const int nelem = npix * p.nchunk;
+    const char* const base0 = reinterpret_cast<const char*>(p.in0);
+    const char* const base1 = reinterpret_cast<const char*>(p.in1);
     int n = 0, sig = 0;  // planes issued / planes published
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int r = item;
       const int isp = r % p.nsplit; r /= p.nsplit;
-      const int tx0 = (r % p.tilesX) * kSlabTW; r /= p.tilesX;
-      const int ty0 = (r % p.tilesY) * kSlabTH;
+      const int tx0 = (r % p.tilesX) * kSlabTW * p.st; r /= p.tilesX;   // tile origin in input coordinates
+      const int ty0 = (r % p.tilesY) * kSlabTH * p.st;
       const int b = r / p.tilesY;
       const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
       const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
@@ -131,18 +164,15 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
         const int slot = n % p.NP;
         mbar_wait(empty0 + 8 * slot, ((n / p.NP) & 1) ^ 1);
         const uint32_t dst0 = planes_s + slot * p.plane_bytes;
-        const size_t slice_pix = ((size_t)b * p.S + z) * p.IH;
-        for (int e = ptid; e < nelem; e += 128) {
-          const int c = e % p.nchunk, pix = e / p.nchunk;
-          const int rx = pix % p.RX, t = pix / p.RX;
-          const int ry = t % p.RY, v = t / p.RY;
-          const int gy = p.st * (ty0 + p.oy + ry) + p.vpy[v], gx = p.st * (tx0 + p.ox + rx) + p.vpx[v];
+        const size_t pix0 = (((size_t)b * p.S + z) * p.IH + ty0) * p.IW + tx0;
+        const char* const o0 = base0 + pix0 * p.C0 * 2;
+        const char* const o1 = base1 + pix0 * p.C1 * 2;
+        for (int e = ptid; e < p.nelem; e += kSlabProducers) {
+          const SlabElem el = elems[e];
+          const int gy = ty0 + el.gy, gx = tx0 + el.gx;
           const bool ok = gy >= 0 && gy < p.IH && gx >= 0 && gx < p.IW;
-          const bool second = c >= p.nch0;
-          const char* base = reinterpret_cast<const char*>(second ? p.in1 : p.in0);
-          const int C = second ? p.C1 : p.C0, cc = second ? c - p.nch0 : c;
-          const char* src = ok ? base + (((slice_pix + gy) * p.IW + gx) * C + cc * 8) * 2 : base;
-          cp_async16(dst0 + c * p.CPS + pix * 16, src, ok ? 16u : 0u);
+          const char* src = ((el.dst16 & 0x8000) ? o1 : o0) + (ptrdiff_t)el.rel * 2;
+          cp_async16(dst0 + ((uint32_t)(el.dst16 & 0x7fff) << 4), ok ? src : base0, ok ? 16u : 0u);
         }
         cp_async_commit();
         // publish every plane whose copies have certainly landed (all but the newest LA-1 groups)
@@ -160,7 +190,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
       mbar_arrive(full0 + 8 * (sig % p.NP));
       ++sig;
     }
-  } else if (warp == 4) {
+  } else if (warp == kSlabMmaWarp) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
@@ -182,19 +212,28 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
           const int buf = sc & 1;
           mbar_wait(tempty0 + 8 * buf, ((sc >> 1) & 1) ^ 1);
           fence_after();
-          const uint32_t dacc = tmem_base + buf * p.N;
-          uint32_t acc = 0;
-          for (int k = (hz ? 0 : 1); k < (hz ? 3 : 2); ++k) {
-            const int z = s + k - 1;
-            if (z < 0 || z >= p.S) continue;  // focal-dimension zero padding: nothing to multiply
-            const uint32_t plane_lo = (planes_s + ((n_base + z - zlo) % p.NP) * p.plane_bytes) >> 4;
-            for (int i = p.g[k]; i < p.g[k + 1]; ++i) {
-              uint32_t a_lo;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a_lo) : "r"(tab_s + 4 * i));
-              a_lo += plane_lo;
-              const uint32_t b_lo = ((w_s + (uint32_t)i * p.N * 32) >> 4) | b_lbo;
-              umma(dacc, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, acc);
-              acc = 1;
+          for (int ph = 0; ph < p.nph; ++ph) {
+            const uint32_t dacc = tmem_base + (buf * p.nph + ph) * p.N;
+            uint32_t acc = 0;
+            for (int k = (hz ? 0 : 1); k < (hz ? 3 : 2); ++k) {
+              const int z = s + k - 1;
+              if (z < 0 || z >= p.S) continue;  // focal-dimension zero padding: nothing to multiply
+              const uint32_t plane_lo = (planes_s + ((n_base + z - zlo) % p.NP) * p.plane_bytes) >> 4;
+              // table entries are read four at a time (groups start 16-byte aligned); B blocks are consecutive in MMA order
+              const int i0 = p.g[ph * 3 + k], i1 = p.ge[ph * 3 + k];
+              uint32_t b_lo = ((w_s + (uint32_t)i0 * p.N * 32) >> 4) | b_lbo;
+              const uint32_t b_step = (uint32_t)(p.N * 32) >> 4;
+              for (int i = i0; i < i1; i += 4) {
+                uint32_t t0, t1, t2, t3;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(tab_s + 4 * i));
+                const int m = i1 - i;
+                umma(dacc, ((uint64_t)a_hi << 32) | (t0 + plane_lo), ((uint64_t)b_hi << 32) | b_lo, idesc, acc);
+                acc = 1;
+                if (m > 1) umma(dacc, ((uint64_t)a_hi << 32) | (t1 + plane_lo), ((uint64_t)b_hi << 32) | (b_lo + b_step), idesc, 1);
+                if (m > 2) umma(dacc, ((uint64_t)a_hi << 32) | (t2 + plane_lo), ((uint64_t)b_hi << 32) | (b_lo + 2 * b_step), idesc, 1);
+                if (m > 3) umma(dacc, ((uint64_t)a_hi << 32) | (t3 + plane_lo), ((uint64_t)b_hi << 32) | (b_lo + 3 * b_step), idesc, 1);
+                b_lo += 4 * b_step;
+              }
             }
           }
           umma_commit(tfull0 + 8 * buf);
@@ -211,6 +250,10 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ty = row >> 3, tx = row & 7;
+    EpiArgs ep = p.epi;
+    ep.scale = ss;
+    ep.shift = ss + p.N;
+    const int esz = ep.out_f32 ? 4 : 2;
     int sc = 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int r = item;
@@ -222,10 +265,25 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
       const bool valid = oy < p.OHt && ox < p.OWt;
       for (int s = s_begin; s < s_end; ++s, ++sc) {
         const int buf = sc & 1;
-        const size_t pix = (((size_t)b * p.S + s) * p.OH + (oy * p.osy + p.ooy)) * p.OW + (ox * p.osx + p.oox);
+        const size_t row0 = ((size_t)b * p.S + s) * p.OH;
+        if (valid && (ep.res_pre || ep.res_post || ep.aux_add)) {
+          // the residual operands do not depend on the accumulator: pull them towards L1 while the MMAs run
+          for (int ph = 0; ph < p.nph; ++ph) {
+            const size_t pix = (row0 + (oy * p.osy + (p.nph > 1 ? (ph >> 1) : p.ooy))) * p.OW + (ox * p.osx + (p.nph > 1 ? (ph & 1) : p.oox));
+            const size_t ob = pix * ep.cstore * esz;
+            for (int k = 0; k < ep.cstore * esz; k += 128) {
+              if (ep.res_pre) prefetch_l1(reinterpret_cast<const char*>(ep.res_pre) + ob + k);
+              if (ep.res_post) prefetch_l1(reinterpret_cast<const char*>(ep.res_post) + ob + k);
+              if (ep.aux_add) prefetch_l1(reinterpret_cast<const char*>(ep.aux_add) + ob + k);
+            }
+          }
+        }
         mbar_wait(tfull0 + 8 * buf, (sc >> 1) & 1);
         fence_after();
-        tc_epilogue_tile(p.epi, tmem_base + ((uint32_t)(q * 32) << 16) + buf * p.N, valid, pix);
+        for (int ph = 0; ph < p.nph; ++ph) {
+          const size_t pix = (row0 + (oy * p.osy + (p.nph > 1 ? (ph >> 1) : p.ooy))) * p.OW + (ox * p.osx + (p.nph > 1 ? (ph & 1) : p.oox));
+          tc_epilogue_tile(ep, tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N, valid, pix);
+        }
         fence_before();
         mbar_arrive(tempty0 + 8 * buf);
       }
@@ -233,7 +291,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
   }
   fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kSlabMmaWarp) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -242,7 +300,9 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
 // ------------------------------------------------------------------------------------------------------------------
 // host side: plan (geometry, MMA table, ring depth) + launch
 // ------------------------------------------------------------------------------------------------------------------
-static bool slab_plan(const ConvArgs& a, int Ntc, int num_sms, SlabParams& p, size_t* smem_out) {
+// `ptaps`/`nph`: tap table per output phase (nph = 1: a.taps; nph = 4: the parity phases of a transposed convolution).
+static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc, int num_sms, SlabParams& p, size_t* smem_out,
+                      int* occ_out) {
   memset(&p, 0, sizeof(p));
   if (a.C0 % 8 || a.C1 % 8 || a.C0 < 8) return false;
   if (Ntc < 16 || Ntc > 128 || Ntc % 16) return false;
@@ -254,13 +314,18 @@ static bool slab_plan(const ConvArgs& a, int Ntc, int num_sms, SlabParams& p, si
   p.nviews = p.st == 2 ? 4 : 1;
   for (int v = 0; v < 4; ++v) { p.vpy[v] = v >> 1; p.vpx[v] = v & 1; }
   // ---- taps in view coordinates -------------------------------------------------------------------------------------
-  struct VT { int dz, view, vy, vx, widx; };
+  struct VT { int dz, view, vy, vx, widx, ph; };
   std::vector<VT> vt;
   int vymin = 1000, vymax = -1000, vxmin = 1000, vxmax = -1000, dzmin = 1000, dzmax = -1000;
-  for (int t = 0; t < a.taps.n; ++t) {
+  if (nph != 1 && nph != 4) return false;
+  p.nph = nph;
+  for (int ph = 0; ph < nph; ++ph)
+  for (int t = 0; t < ptaps[ph].n; ++t) {
+    const TapTable& tt = ptaps[ph];
     VT x;
-    x.dz = a.taps.dz[t]; x.widx = a.taps.widx[t];
-    int dy = a.taps.dy[t], dx = a.taps.dx[t];
+    x.ph = ph;
+    x.dz = tt.dz[t]; x.widx = tt.widx[t];
+    int dy = tt.dy[t], dx = tt.dx[t];
     if (p.st == 2) {
       const int py = dy & 1, px = dx & 1;
       x.view = py * 2 + px; x.vy = (dy - py) / 2; x.vx = (dx - px) / 2;
@@ -277,17 +342,30 @@ static bool slab_plan(const ConvArgs& a, int Ntc, int num_sms, SlabParams& p, si
   p.oy = vymin; p.ox = vxmin;
   p.RY = kSlabTH + (vymax - vymin);
   p.RX = kSlabTW + (vxmax - vxmin);
+  // DFF_SLAB_EXPERIMENT=aligned: timing experiment only (wrong results) — force 128-byte aligned core matrices
+  static const bool exp_aligned = getenv("DFF_SLAB_EXPERIMENT") && !strcmp(getenv("DFF_SLAB_EXPERIMENT"), "aligned");
+  if (exp_aligned) p.RX = (p.RX + 7) & ~7;
   p.CPS = p.nviews * p.RY * p.RX * 16;
   p.plane_bytes = (nchunk * p.CPS + 127) & ~127;
   if ((p.CPS >> 4) >= (1 << 14) || p.RX * 16 >= (1 << 18)) return false;
-  auto aoff = [&](const VT& x, int chunk) { return chunk * p.CPS + ((x.view * p.RY + (x.vy - p.oy)) * p.RX + (x.vx - p.ox)) * 16; };
+  auto aoff = [&](const VT& x, int chunk) {
+    int o = chunk * p.CPS + ((x.view * p.RY + (x.vy - p.oy)) * p.RX + (x.vx - p.ox)) * 16;
+    if (exp_aligned) o &= ~127;
+    return o;
+  };
   // ---- MMA table, grouped by focal offset dz = -1, 0, +1 ---------------------------------------------------------------
   int nops = 0;
+  for (int ph = 0; ph < nph; ++ph)
   for (int k = 0; k < 3; ++k) {
-    p.g[k] = nops;
+    while (nops & 3) {  // groups start on a 16-byte table boundary (the issuer reads four entries per load); pads never run
+      if (nops >= kSlabMaxOps) return false;
+      p.tab[nops] = 0; p.wsrc[2 * nops] = -1; p.wsrc[2 * nops + 1] = -1;
+      ++nops;
+    }
+    p.g[ph * 3 + k] = nops;
     std::vector<VT> grp;
     for (auto& x : vt)
-      if (x.dz == k - 1) grp.push_back(x);
+      if (x.dz == k - 1 && x.ph == ph) grp.push_back(x);
     if (nchunk > 1) {
       for (auto& x : grp)
         for (int j = 0; j < nchunk; j += 2) {
@@ -310,23 +388,38 @@ static bool slab_plan(const ConvArgs& a, int Ntc, int num_sms, SlabParams& p, si
         ++nops;
       }
     }
+    p.ge[ph * 3 + k] = nops;
   }
-  p.g[3] = nops;
   p.nops = nops;
   if (nops == 0) return false;
   p.N = Ntc;
   p.w_bytes = nops * Ntc * 32;
-  // ---- shared memory: table + weights + ring ---------------------------------------------------------------------------
-  const int fixed = 512 + ((p.w_bytes + 127) & ~127) + 256;
+  // ---- shared memory: table + weights + scale/shift + staging table + ring; as many co-resident CTAs as fit -----------------
+  p.nelem = p.nviews * p.RY * p.RX * nchunk;
+  int off = 1024 + ((p.w_bytes + 127) & ~127);
+  p.ss_off = off;
+  off += (2 * Ntc * 4 + 127) & ~127;
+  p.elem_off = off;
+  off += (p.nelem * 8 + 127) & ~127;
+  p.planes_off = off;
+  const int fixed = off + 128;  // + slack for the 128-byte alignment of the dynamic window
   const int np_min = 2 * p.hz + 2;
-  int NP = (kSlabSmemBudget - fixed) / p.plane_bytes;
-  if (NP < np_min) return false;
+  const int cols = 2 * nph * Ntc;
+  if (cols > 512) return false;
+  p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  int occ = 4, NP = 0;
+  for (; occ >= 1; --occ) {
+    if (occ * p.tmem_cols > 512) continue;
+    const int budget = kSlabSmemBudget / occ - 1024;  // static shared memory + allocation granularity
+    NP = (budget - fixed) / p.plane_bytes;
+    if (NP >= np_min) break;
+  }
+  if (occ < 1) return false;
   if (NP > kSlabMaxPlanes) NP = kSlabMaxPlanes;
   p.NP = NP;
   p.LA = std::min(5, NP - 2 * p.hz - 1);
   *smem_out = (size_t)fixed + (size_t)NP * p.plane_bytes;
-  const int cols = 2 * Ntc;
-  p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
+  *occ_out = occ;
   // ---- work items ----------------------------------------------------------------------------------------------------------
   p.OHt = a.OHt; p.OWt = a.OWt; p.OH = a.OH; p.OW = a.OW;
   p.osy = a.osy; p.osx = a.osx; p.ooy = a.ooy; p.oox = a.oox;
@@ -334,7 +427,7 @@ static bool slab_plan(const ConvArgs& a, int Ntc, int num_sms, SlabParams& p, si
   p.tilesY = cdiv(a.OHt, kSlabTH);
   const int cols_items = a.B * p.tilesX * p.tilesY;
   int nsplit = 1;
-  if (cols_items < 2 * num_sms) nsplit = std::min(a.S, cdiv(2 * num_sms, cols_items));
+  if (cols_items < 2 * num_sms * occ) nsplit = std::min(a.S, cdiv(2 * num_sms * occ, cols_items));
   p.slen = cdiv(a.S, nsplit);
   p.nsplit = cdiv(a.S, p.slen);
   p.nitems = cols_items * p.nsplit;
@@ -344,20 +437,25 @@ static bool slab_plan(const ConvArgs& a, int Ntc, int num_sms, SlabParams& p, si
   return true;
 }
 
-bool conv_slab_supported(const ConvArgs& a, int Ntc) {
+bool conv_slab_supported(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc) {
   SlabParams p;
   size_t smem;
-  return slab_plan(a, Ntc, 148, p, &smem);
+  int occ;
+  return slab_plan(a, ptaps ? ptaps : &a.taps, ptaps ? nph : 1, Ntc, 148, p, &smem, &occ);
 }
 
 // `wslab`: bf16 weights [ntaps][Cin/8][Ntc][8]
-int launch_conv_slab(const ConvArgs& a, const void* wslab, int Ntc, int num_sms, cudaStream_t st) {
+// `ptaps` == null: one convolution phase described by a.taps; otherwise `nph` phases (fused transposed convolution: a.osy =
+// a.osx = 2 and phase ph writes output parity (ph >> 1, ph & 1)).
+int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const void* wslab, int Ntc, int num_sms, cudaStream_t st) {
   SlabParams p;
   size_t smem = 0;
-  if (!slab_plan(a, Ntc, num_sms, p, &smem)) return fail(-5, "conv_slab: unsupported layer shape");
+  int occ = 1;
+  if (!slab_plan(a, ptaps ? ptaps : &a.taps, ptaps ? nph : 1, Ntc, num_sms, p, &smem, &occ))
+    return fail(-5, "conv_slab: unsupported layer shape");
   p.wslab = wslab;
   DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = p.nitems < num_sms ? p.nitems : num_sms;
+  const int grid = p.nitems < num_sms * occ ? p.nitems : num_sms * occ;
   conv_slab_kernel<<<grid, kSlabThreads, smem, st>>>(p);
   DFF_LAUNCH_CHECK("conv_slab");
   return 0;

@@ -27,8 +27,8 @@ bool conv_tc_supported(const ConvArgs& a, int Ntc);
 int launch_conv_tc(const ConvArgs& a, const void* wtc, int ntaps_total, int Ntc, int num_sms, cudaStream_t st);
 int launch_pack_weight_tc(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
                           cudaStream_t st);
-bool conv_slab_supported(const ConvArgs& a, int Ntc);
-int launch_conv_slab(const ConvArgs& a, const void* wslab, int Ntc, int num_sms, cudaStream_t st);
+bool conv_slab_supported(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc);
+int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const void* wslab, int Ntc, int num_sms, cudaStream_t st);
 int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
                             cudaStream_t st);
 int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
@@ -249,7 +249,11 @@ static int num_sms_of_current_device() {
 
 // `wtc` != null selects the tcgen05 path (bf16 only); otherwise the FFMA kernel runs.
 static int run_conv(const Layer& l, const float* w, const float* scale, const float* shift, const Ten& in, const EpiOpt& e,
-                    Ten& out, bool bf16, cudaStream_t st, const void* wtc = nullptr, const void* wslab = nullptr) {
+                    Ten& out, bool bf16, cudaStream_t st, const void* wtc = nullptr, const void* wslab = nullptr,
+                    int* nlaunch = nullptr, bool count_only = false) {
+  int dummy = 0;
+  if (!nlaunch) nlaunch = &dummy;
+  *nlaunch = 0;
   ConvArgs a{};
   a.in0 = in.p;
   a.C0 = in.C;
@@ -274,19 +278,34 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     conv_taps(l, a.taps);
     a.isy = a.isx = l.stride; a.osy = a.osx = 1; a.ooy = a.oox = 0;
     a.OHt = out.H; a.OWt = out.W;
+    *nlaunch = 1;
+    if (count_only) return 0;
     if (wtc) {
-      if (wslab && conv_slab_supported(a, l.Ntc)) return launch_conv_slab(a, wslab, l.Ntc, nsm, st);
+      if (wslab && conv_slab_supported(a, nullptr, 1, l.Ntc)) return launch_conv_slab(a, nullptr, 1, wslab, l.Ntc, nsm, st);
       return launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st);
     }
     return launch_conv_ffma(a, bf16, st);
   }
+  if (wtc && wslab) {  // all four output-parity phases in one launch: the input planes are staged once
+    TapTable pt[4];
+    for (int ph = 0; ph < 4; ++ph) deconv_taps(ph >> 1, ph & 1, pt[ph]);
+    a.taps = pt[3];
+    a.isy = a.isx = 1; a.osy = a.osx = 2; a.ooy = a.oox = 0;
+    a.OHt = in.H; a.OWt = in.W;
+    if (conv_slab_supported(a, pt, 4, l.Ntc)) {
+      *nlaunch = 1;
+      return count_only ? 0 : launch_conv_slab(a, pt, 4, wslab, l.Ntc, nsm, st);
+    }
+  }
+  *nlaunch = 4;
+  if (count_only) return 0;
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       deconv_taps(py, px, a.taps);
       a.isy = a.isx = 1; a.osy = a.osx = 2; a.ooy = py; a.oox = px;
       a.OHt = in.H; a.OWt = in.W;
       if (wtc) {
-        if (wslab && conv_slab_supported(a, l.Ntc)) DFF_TRY(launch_conv_slab(a, wslab, l.Ntc, nsm, st));
+        if (wslab && conv_slab_supported(a, nullptr, 1, l.Ntc)) DFF_TRY(launch_conv_slab(a, nullptr, 1, wslab, l.Ntc, nsm, st));
         else DFF_TRY(launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st));
       } else {
         DFF_TRY(launch_conv_ffma(a, bf16, st));
@@ -371,10 +390,14 @@ struct Runner {
       if (e.aux_add) bytes += 2 * ovox * out.C * esize(false);
       op_begin(name, 2.0 * macs, bytes, l.transposed ? 4 : 1);
     }
-    if (!dry && !rc)
-      rc = run_conv(l, (const float*)(packed + l.pk_w), (const float*)(packed + l.pk_scale),
-                    (const float*)(packed + l.pk_shift), in, e, out, bf16, st, use_tc ? packed + l.pk_wtc : nullptr,
-                    (use_tc && use_slab) ? packed + l.pk_wslab : nullptr);
+    if (!rc) {
+      // in a dry run only the launch count is planned (pointers are placeholders that are never dereferenced)
+      const char* pk = dry ? reinterpret_cast<const char*>(0x1000) : packed;
+      int nl = 0;
+      rc = run_conv(l, (const float*)(pk + l.pk_w), (const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), in, e, out,
+                    bf16, st, use_tc ? pk + l.pk_wtc : nullptr, (use_tc && use_slab) ? pk + l.pk_wslab : nullptr, &nl, dry);
+      if (prof && !prof->ops.empty()) prof->ops.back().launches = nl;
+    }
     op_end();
     return out;
   }
@@ -706,6 +729,8 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
   if (use_tensor_cores && (elem != DFF_BF16 || (C0 % 8) || (C1 % 8)))
     return fail(DFF_E_UNSUPPORTED, "dff_conv3d: the tensor-core path needs bf16 tensors with channel counts that are multiples of 8");
   if (kd * kh * kw > kMaxTaps) return fail(DFF_E_ARG, "dff_conv3d: too many taps");
+  if (use_tensor_cores && ((scale == nullptr) != (shift == nullptr)))
+    return fail(DFF_E_ARG, "dff_conv3d: the tensor-core path takes scale and shift together (or neither)");
   if (transposed && !(kd == 3 && kh == 3 && kw == 3 && stride_hw == 2 && dil_hw == 1))
     return fail(DFF_E_ARG, "dff_conv3d: transposed conv must be k=3, stride (1,2,2)");
   if (C0 % 4 || C1 % 4) return fail(DFF_E_ARG, "dff_conv3d: stored channels must be multiples of 4");

@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }  // namespace tc
 
 // ---- fused epilogue of one 128-pixel x N accumulator tile --------------------------------------------------------------
-// y = acc*scale[c] + shift[c] (BatchNorm eval / bias) ; += res_pre ; ReLU ; += res_post ; store bf16 channels-last (or fp32
+// y = acc*scale[c] + shift[c] (BatchNorm eval / bias; scale and shift are both given or both null, 16-byte aligned) ; += res_pre ; ReLU ; += res_post ; store bf16 channels-last (or fp32
 // for cost volumes) ; optional second output out_aux = y + aux_add.  (epilogue classes E1-E9.)
 struct EpiArgs {
   const float* scale;
@@ -119,10 +119,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiArgs& p, uint32_t tacc
     tmem_ld16(tacc + c0, v);
     if (!valid || c0 >= p.cstore) continue;
     float f[16];
+    if (p.scale) {  // 16-byte loads (generic: the slab kernel points scale/shift at shared memory)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float sc = p.scale ? __ldg(p.scale + c0 + j) : 1.f, sh = p.shift ? __ldg(p.shift + c0 + j) : 0.f;
-      f[j] = fmaf(__uint_as_float(v[j]), sc, sh);
+      for (int j = 0; j < 16; j += 4) {
+        const float4 sc = *reinterpret_cast<const float4*>(p.scale + c0 + j);
+        const float4 sh = *reinterpret_cast<const float4*>(p.shift + c0 + j);
+        f[j] = fmaf(__uint_as_float(v[j]), sc.x, sh.x);
+        f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+        f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
+        f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
     }
     const size_t o = pix * p.cstore + c0;
     if (p.out_f32) {  // cost volumes (Cout = 1): fp32, scalar stores
