@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
   __shared__ uint32_t tmem_base_s;
   const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
-  const uint32_t tab_s = smem0;                    // nops x u32 (1 KB reserved)
   const uint32_t w_s = smem0 + 1024;               // weights, MMA order: [op][half][N][8] bf16
   const uint32_t planes_s = smem0 + p.planes_off;  // ring of NP slice planes
   const SlabElem* const elems = reinterpret_cast<const SlabElem*>(smem_gen + p.elem_off);
@@ -108,8 +107,6 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // ---- one-time: MMA table, weights (MMA order), BatchNorm scale/shift and the staging table into shared memory --------
-  for (int i = threadIdx.x; i < p.nops; i += kSlabThreads)
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_s + 4 * i), "r"(p.tab[i]) : "memory");
   {
     const int total = 2 * p.nops * p.N;  // 16-byte rows
     const uint4* wg = reinterpret_cast<const uint4*>(p.wslab);
@@ -192,58 +189,77 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
     }
   } else if (warp == kSlabMmaWarp) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-      // descriptor high words: SBO (8-row group stride) | version 1 | no swizzle
-      const uint32_t a_hi = ((uint32_t)(p.RX * 16) >> 4) | (1u << 14);
-      const uint32_t b_hi = (128u >> 4) | (1u << 14);
-      const uint32_t b_lbo = ((uint32_t)(p.N * 16) >> 4) << 16;
-      int n_base = 0, waited = 0, sc = 0;
-      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-        const int isp = item % p.nsplit;
-        const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
-        const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
-        for (int s = s_begin; s < s_end; ++s, ++sc) {
-          const int need_n = n_base + (min(s + hz, zhi - 1) - zlo);
-          while (waited <= need_n) {
-            mbar_wait(full0 + 8 * (waited % p.NP), (waited / p.NP) & 1);
-            ++waited;
-          }
-          const int buf = sc & 1;
-          mbar_wait(tempty0 + 8 * buf, ((sc >> 1) & 1) ^ 1);
-          fence_after();
+    // The whole warp walks the schedule with warp-uniform values (everything derives from blockIdx and kernel parameters, the
+    // MMA table is read from the parameter bank with a uniform index), so descriptors live in uniform registers and the
+    // tcgen05.mma stream is issued back to back by one elected lane — no per-instruction lane serialisation.
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+    // descriptor high words: SBO (8-row group stride) | version 1 | no swizzle
+    const uint64_t a_hi = (uint64_t)(((uint32_t)(p.RX * 16) >> 4) | (1u << 14)) << 32;
+    const uint64_t b_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+    const uint32_t b_lbo = ((uint32_t)(p.N * 16) >> 4) << 16;
+    const uint32_t b_step = (uint32_t)(p.N * 32) >> 4;
+    const uint32_t w_lo = (w_s >> 4) | b_lbo;
+    const int NP = p.NP;
+    int waited = 0, wslot = 0, sc = 0;
+    uint32_t wphase = 0;
+    int base_slot = 0;  // ring slot of plane zlo of the current item
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      const int isp = item % p.nsplit;
+      const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
+      const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
+      int need = min(s_begin + hz, zhi - 1) - zlo + 1;  // planes of this item that must have landed before slice s_begin
+      int have = 0;
+      int slot_s = base_slot + (s_begin - zlo);          // ring slot of plane s
+      if (slot_s >= NP) slot_s -= NP;
+      for (int s = s_begin; s < s_end; ++s, ++sc) {
+        while (have < need) {
+          mbar_wait(full0 + 8 * wslot, wphase);
+          if (++wslot == NP) { wslot = 0; wphase ^= 1; }
+          ++have; ++waited;
+        }
+        if (s + hz + 1 < zhi) ++need;
+        const int buf = sc & 1;
+        mbar_wait(tempty0 + 8 * buf, ((sc >> 1) & 1) ^ 1);
+        fence_after();
+        if (leader) {
           for (int ph = 0; ph < p.nph; ++ph) {
             const uint32_t dacc = tmem_base + (buf * p.nph + ph) * p.N;
             uint32_t acc = 0;
             for (int k = (hz ? 0 : 1); k < (hz ? 3 : 2); ++k) {
               const int z = s + k - 1;
               if (z < 0 || z >= p.S) continue;  // focal-dimension zero padding: nothing to multiply
-              const uint32_t plane_lo = (planes_s + ((n_base + z - zlo) % p.NP) * p.plane_bytes) >> 4;
-              // table entries are read four at a time (groups start 16-byte aligned); B blocks are consecutive in MMA order
+              int slot = slot_s + k - 1;
+              slot = slot < 0 ? slot + NP : (slot >= NP ? slot - NP : slot);
+              const uint32_t plane_lo = (planes_s + slot * p.plane_bytes) >> 4;
               const int i0 = p.g[ph * 3 + k], i1 = p.ge[ph * 3 + k];
-              uint32_t b_lo = ((w_s + (uint32_t)i0 * p.N * 32) >> 4) | b_lbo;
-              const uint32_t b_step = (uint32_t)(p.N * 32) >> 4;
-              for (int i = i0; i < i1; i += 4) {
-                uint32_t t0, t1, t2, t3;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(tab_s + 4 * i));
-                const int m = i1 - i;
-                umma(dacc, ((uint64_t)a_hi << 32) | (t0 + plane_lo), ((uint64_t)b_hi << 32) | b_lo, idesc, acc);
+              uint32_t b_lo = w_lo + (uint32_t)i0 * (b_step);
+#pragma unroll 4
+              for (int i = i0; i < i1; ++i) {
+                umma(dacc, a_hi | (uint64_t)(p.tab[i] + plane_lo), b_hi | (uint64_t)b_lo, idesc, acc);
                 acc = 1;
-                if (m > 1) umma(dacc, ((uint64_t)a_hi << 32) | (t1 + plane_lo), ((uint64_t)b_hi << 32) | (b_lo + b_step), idesc, 1);
-                if (m > 2) umma(dacc, ((uint64_t)a_hi << 32) | (t2 + plane_lo), ((uint64_t)b_hi << 32) | (b_lo + 2 * b_step), idesc, 1);
-                if (m > 3) umma(dacc, ((uint64_t)a_hi << 32) | (t3 + plane_lo), ((uint64_t)b_hi << 32) | (b_lo + 3 * b_step), idesc, 1);
-                b_lo += 4 * b_step;
+                b_lo += b_step;
               }
             }
           }
           umma_commit(tfull0 + 8 * buf);
           // ring slots whose last reader was this slice
-          if (s - hz >= zlo) umma_commit(empty0 + 8 * ((n_base + s - hz - zlo) % p.NP));
+          if (s - hz >= zlo) {
+            int slot = slot_s - hz;
+            if (slot < 0) slot += NP;
+            umma_commit(empty0 + 8 * slot);
+          }
           if (s == s_end - 1)
-            for (int z = max(zlo, s - hz + 1); z < zhi; ++z) umma_commit(empty0 + 8 * ((n_base + z - zlo) % p.NP));
+            for (int z = max(zlo, s - hz + 1); z < zhi; ++z) {
+              int slot = slot_s + (z - s);
+              slot = slot < 0 ? slot + NP : (slot >= NP ? slot - NP : slot);
+              umma_commit(empty0 + 8 * slot);
+            }
         }
-        n_base += zhi - zlo;
+        __syncwarp();
+        if (++slot_s == NP) slot_s = 0;
       }
+      base_slot = (base_slot + (zhi - zlo)) % NP;
     }
   } else {
     // =============================== epilogue ===============================
