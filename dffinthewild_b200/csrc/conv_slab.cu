@@ -18,6 +18,7 @@
 //     BatchNorm/bias, residuals, ReLU and store while the next slice is being multiplied.
 // HBM/L2 traffic per output pixel drops from taps x Cin to ~1.4 x Cin, and there is no per-tap barrier round trip.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -34,6 +35,13 @@ constexpr int kSlabMaxPlanes = 8;
 constexpr int kSlabTW = 8, kSlabTH = 16;
 constexpr int kSlabSmemBudget = 220 * 1024;   // per SM, shared by the co-resident CTAs
 
+// DFF_SLAB_TRACE (compile-time, debugging only): CTA 0 records clock64 timestamps of its pipeline events per slice
+#ifdef DFF_SLAB_TRACE
+#define DFF_TR(slot, idx) do { if (p.trace && blockIdx.x == 0 && (idx) < 64 && (threadIdx.x & 31) == 0) p.trace[(idx) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define DFF_TR(slot, idx) do { } while (0)
+#endif
+
 struct alignas(16) SlabParams {
   const void* in0;
   const void* in1;
@@ -47,8 +55,10 @@ struct alignas(16) SlabParams {
   int tilesX, tilesY, nsplit, slen, nitems;
   int OHt, OWt, OH, OW, osy, osx, ooy, oox;
   int w_bytes, tmem_cols, nelem, elem_off, ss_off, planes_off;
+  long long* trace;
+  int exp;                   // timing experiments only (DFF_SLAB_EXPERIMENT bit mask; results are wrong): 1 no loads, 2 no stores, 4 no MMAs
   EpiArgs epi;
-  uint32_t tab[kSlabMaxOps];      // per MMA: (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
+  alignas(16) uint64_t tab[kSlabMaxOps + 4];  // (+1 quad: the issuer prefetches one quad ahead) per MMA, zero-extended to 64 bits (added to the descriptor): (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
   int16_t wsrc[2 * kSlabMaxOps];  // per MMA and K half: 8-channel weight block (tap * nchunk + chunk) in `wslab`, -1 = zeros
 };
 
@@ -148,7 +158,9 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
     const int ptid = threadIdx.x;
     const char* const base0 = reinterpret_cast<const char*>(p.in0);
     const char* const base1 = reinterpret_cast<const char*>(p.in1);
-    int n = 0, sig = 0;  // planes issued / planes published
+    int slot = 0;             // ring slot of the next plane
+    int np = 0;
+    uint32_t ephase = 1;      // parity to wait for on its `empty` barrier (a fresh barrier passes parity 1)
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int r = item;
       const int isp = r % p.nsplit; r /= p.nsplit;
@@ -157,13 +169,14 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
       const int b = r / p.tilesY;
       const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
       const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
-      for (int z = zlo; z < zhi; ++z, ++n) {
-        const int slot = n % p.NP;
-        mbar_wait(empty0 + 8 * slot, ((n / p.NP) & 1) ^ 1);
+      for (int z = zlo; z < zhi; ++z) {
+        mbar_wait(empty0 + 8 * slot, ephase);
+        if (warp == 0) DFF_TR(5, np);
         const uint32_t dst0 = planes_s + slot * p.plane_bytes;
         const size_t pix0 = (((size_t)b * p.S + z) * p.IH + ty0) * p.IW + tx0;
         const char* const o0 = base0 + pix0 * p.C0 * 2;
         const char* const o1 = base1 + pix0 * p.C1 * 2;
+        if (!(p.exp & 1))
         for (int e = ptid; e < p.nelem; e += kSlabProducers) {
           const SlabElem el = elems[e];
           const int gy = ty0 + el.gy, gx = tx0 + el.gx;
@@ -171,95 +184,106 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
           const char* src = ((el.dst16 & 0x8000) ? o1 : o0) + (ptrdiff_t)el.rel * 2;
           cp_async16(dst0 + ((uint32_t)(el.dst16 & 0x7fff) << 4), ok ? src : base0, ok ? 16u : 0u);
         }
-        cp_async_commit();
-        // publish every plane whose copies have certainly landed (all but the newest LA-1 groups)
-        cp_async_wait(p.LA - 1);
-        while (sig <= n - (p.LA - 1)) {
-          fence_proxy_async();
-          mbar_arrive(full0 + 8 * (sig % p.NP));
-          ++sig;
-        }
+        // asynchronous publish: the slot's `full` barrier receives this thread's arrival when its copies have landed, so the
+        // producers never wait for data — they run ahead as far as the ring has free slots
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8 * slot) : "memory");
+        if (++slot == p.NP) { slot = 0; ephase ^= 1; }
+        if (warp == 0) DFF_TR(6, np);
+        ++np;
       }
-    }
-    cp_async_wait(0);
-    while (sig < n) {
-      fence_proxy_async();
-      mbar_arrive(full0 + 8 * (sig % p.NP));
-      ++sig;
     }
   } else if (warp == kSlabMmaWarp) {
     // =============================== MMA issuer ===============================
     // The whole warp walks the schedule with warp-uniform values (everything derives from blockIdx and kernel parameters, the
     // MMA table is read from the parameter bank with a uniform index), so descriptors live in uniform registers and the
-    // tcgen05.mma stream is issued back to back by one elected lane — no per-instruction lane serialisation.
+    // tcgen05.mma stream is issued back to back by one elected lane — no per-instruction lane serialisation.  A single warp
+    // pays the full latency of every dependent instruction, so the per-slice bookkeeping is kept to a rotating window of three
+    // plane descriptors (slices s-1, s, s+1) and the per-MMA work to two 64-bit adds.
     const bool leader = elect_one();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
     // descriptor high words: SBO (8-row group stride) | version 1 | no swizzle
     const uint64_t a_hi = (uint64_t)(((uint32_t)(p.RX * 16) >> 4) | (1u << 14)) << 32;
     const uint64_t b_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
-    const uint32_t b_lbo = ((uint32_t)(p.N * 16) >> 4) << 16;
-    const uint32_t b_step = (uint32_t)(p.N * 32) >> 4;
-    const uint32_t w_lo = (w_s >> 4) | b_lbo;
-    const int NP = p.NP;
-    int waited = 0, wslot = 0, sc = 0;
+    const uint64_t b_step = (uint32_t)(p.N * 32) >> 4;
+    const uint64_t bd_base = b_hi | (uint64_t)((w_s >> 4) | (((uint32_t)(p.N * 16) >> 4) << 16));
+    const uint32_t planes16 = planes_s >> 4, pb16 = (uint32_t)p.plane_bytes >> 4;
+    const int NP = p.NP, ngrp = 3 * p.nph;
+    int wslot = 0, sc = 0;
     uint32_t wphase = 0;
-    int base_slot = 0;  // ring slot of plane zlo of the current item
+    uint64_t a_prev = 0, a_cur = 0, a_next = 0;   // descriptor bases of the planes of slices s-1, s, s+1
+    uint32_t e_prev = 0, e_cur = 0, e_next = 0;   // their `empty` barriers
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const int isp = item % p.nsplit;
       const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
       const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
-      int need = min(s_begin + hz, zhi - 1) - zlo + 1;  // planes of this item that must have landed before slice s_begin
-      int have = 0;
-      int slot_s = base_slot + (s_begin - zlo);          // ring slot of plane s
-      if (slot_s >= NP) slot_s -= NP;
+      int zn = zlo;  // next plane of this item to take from the ring (planes arrive in order)
       for (int s = s_begin; s < s_end; ++s, ++sc) {
-        while (have < need) {
+        const int zlast = min(s + hz, zhi - 1);
+        while (zn <= zlast) {
           mbar_wait(full0 + 8 * wslot, wphase);
+          a_prev = a_cur; a_cur = a_next; a_next = a_hi | (uint64_t)(planes16 + (uint32_t)wslot * pb16);
+          e_prev = e_cur; e_cur = e_next; e_next = empty0 + 8 * wslot;
           if (++wslot == NP) { wslot = 0; wphase ^= 1; }
-          ++have; ++waited;
+          ++zn;
         }
-        if (s + hz + 1 < zhi) ++need;
+        DFF_TR(0, sc);
+        fence_proxy_async();  // cp.async wrote the planes through the generic proxy; the MMAs read them through the async proxy
+        const bool have_next = zn - 1 > s;
+        if (!have_next) { a_prev = a_cur; a_cur = a_next; e_prev = e_cur; e_cur = e_next; }  // the newest plane is slice s itself
         const int buf = sc & 1;
         mbar_wait(tempty0 + 8 * buf, ((sc >> 1) & 1) ^ 1);
         fence_after();
+        DFF_TR(1, sc);
         if (leader) {
-          for (int ph = 0; ph < p.nph; ++ph) {
-            const uint32_t dacc = tmem_base + (buf * p.nph + ph) * p.N;
-            uint32_t acc = 0;
-            for (int k = (hz ? 0 : 1); k < (hz ? 3 : 2); ++k) {
-              const int z = s + k - 1;
-              if (z < 0 || z >= p.S) continue;  // focal-dimension zero padding: nothing to multiply
-              int slot = slot_s + k - 1;
-              slot = slot < 0 ? slot + NP : (slot >= NP ? slot - NP : slot);
-              const uint32_t plane_lo = (planes_s + slot * p.plane_bytes) >> 4;
-              const int i0 = p.g[ph * 3 + k], i1 = p.ge[ph * 3 + k];
-              uint32_t b_lo = w_lo + (uint32_t)i0 * (b_step);
-#pragma unroll 4
-              for (int i = i0; i < i1; ++i) {
-                umma(dacc, a_hi | (uint64_t)(p.tab[i] + plane_lo), b_hi | (uint64_t)b_lo, idesc, acc);
+          uint32_t dacc = tmem_base + buf * p.nph * p.N;
+          uint32_t acc = 0;
+          int k = 0;
+#pragma unroll 1
+          for (int gi = 0; gi < ngrp; ++gi) {
+            const int i0 = p.g[gi], n0 = p.ge[gi] - i0;
+            const int z = s + k - 1;
+            if (n0 > 0 && z >= 0 && z < p.S && !(p.exp & 4)) {  // (focal-dimension zero padding: nothing to multiply)
+              const uint64_t ad0 = k == 0 ? a_prev : (k == 1 ? a_cur : a_next);
+              uint64_t bd = bd_base + (uint32_t)i0 * b_step;
+              const ulonglong2* tq = reinterpret_cast<const ulonglong2*>(p.tab + i0);  // groups start on quad boundaries
+              ulonglong2 t01 = tq[0], t23 = tq[1];
+              int n = n0;
+#pragma unroll 1
+              for (; n >= 4; n -= 4) {
+                tq += 2;
+                const ulonglong2 n01 = tq[0], n23 = tq[1];  // next quad (the table has one spare quad at the end)
+                umma(dacc, ad0 + t01.x, bd, idesc, acc);
+                umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
+                umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
+                umma_acc(dacc, ad0 + t23.y, bd + 3 * b_step, idesc);
                 acc = 1;
-                b_lo += b_step;
+                bd += 4 * b_step;
+                t01 = n01; t23 = n23;
+              }
+              if (n > 0) {
+                umma(dacc, ad0 + t01.x, bd, idesc, acc);
+                acc = 1;
+                if (n > 1) umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
+                if (n > 2) umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
               }
             }
+            if (++k == 3) { k = 0; dacc += p.N; acc = 0; }  // next output phase: next accumulator
           }
           umma_commit(tfull0 + 8 * buf);
           // ring slots whose last reader was this slice
-          if (s - hz >= zlo) {
-            int slot = slot_s - hz;
-            if (slot < 0) slot += NP;
-            umma_commit(empty0 + 8 * slot);
-          }
-          if (s == s_end - 1)
-            for (int z = max(zlo, s - hz + 1); z < zhi; ++z) {
-              int slot = slot_s + (z - s);
-              slot = slot < 0 ? slot + NP : (slot >= NP ? slot - NP : slot);
-              umma_commit(empty0 + 8 * slot);
+          if (hz) {
+            if (s > zlo) umma_commit(e_prev);
+            if (s == s_end - 1) {
+              umma_commit(e_cur);
+              if (have_next) umma_commit(e_next);
             }
+          } else {
+            umma_commit(e_cur);
+          }
         }
         __syncwarp();
-        if (++slot_s == NP) slot_s = 0;
+        DFF_TR(2, sc);
       }
-      base_slot = (base_slot + (zhi - zlo)) % NP;
     }
   } else {
     // =============================== epilogue ===============================
@@ -296,12 +320,15 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
         }
         mbar_wait(tfull0 + 8 * buf, (sc >> 1) & 1);
         fence_after();
+        if (q == 3) DFF_TR(3, sc);
         for (int ph = 0; ph < p.nph; ++ph) {
           const size_t pix = (row0 + (oy * p.osy + (p.nph > 1 ? (ph >> 1) : p.ooy))) * p.OW + (ox * p.osx + (p.nph > 1 ? (ph & 1) : p.oox));
+          if (p.exp & 2) continue;
           tc_epilogue_tile(ep, tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N, valid, pix);
         }
         fence_before();
-        mbar_arrive(tempty0 + 8 * buf);
+        mbar_arrive_relaxed(tempty0 + 8 * buf);
+        if (q == 3) DFF_TR(4, sc);
       }
     }
   }
@@ -360,6 +387,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.RX = kSlabTW + (vxmax - vxmin);
   // DFF_SLAB_EXPERIMENT=aligned: timing experiment only (wrong results) — force 128-byte aligned core matrices
   static const bool exp_aligned = getenv("DFF_SLAB_EXPERIMENT") && !strcmp(getenv("DFF_SLAB_EXPERIMENT"), "aligned");
+  p.exp = (getenv("DFF_SLAB_EXPERIMENT") && !exp_aligned) ? atoi(getenv("DFF_SLAB_EXPERIMENT")) : 0;
   if (exp_aligned) p.RX = (p.RX + 7) & ~7;
   p.CPS = p.nviews * p.RY * p.RX * 16;
   p.plane_bytes = (nchunk * p.CPS + 127) & ~127;
@@ -470,10 +498,24 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
   if (!slab_plan(a, ptaps ? ptaps : &a.taps, ptaps ? nph : 1, Ntc, num_sms, p, &smem, &occ))
     return fail(-5, "conv_slab: unsupported layer shape");
   p.wslab = wslab;
+#ifdef DFF_SLAB_TRACE
+  if (getenv("DFF_SLAB_TRACE")) { cudaMalloc(&p.trace, 64 * 8 * 8); cudaMemset(p.trace, 0, 64 * 8 * 8); }
+#endif
   DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.nitems < num_sms * occ ? p.nitems : num_sms * occ;
   conv_slab_kernel<<<grid, kSlabThreads, smem, st>>>(p);
   DFF_LAUNCH_CHECK("conv_slab");
+#ifdef DFF_SLAB_TRACE
+  if (p.trace) {
+    long long h[64 * 8];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    printf("trace C0=%d C1=%d N=%d nops=%d NP=%d occ=%d grid=%d (clk since first event): full-wait tempty-wait issued | tfull-wait epi-done | empty-wait loads-issued\n", p.C0, p.C1, p.N, p.nops, p.NP, occ, grid);
+    long long t0 = h[5] ? h[5] : h[0];
+    for (int i = 0; i < 40; ++i) { for (int j = 0; j < 7; ++j) printf("%8lld", h[i * 8 + j] ? h[i * 8 + j] - t0 : -1); printf("\n"); }
+  }
+#endif
   return 0;
 }
 

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       fence_after();
       tc_epilogue_tile(ep, tmem_base + ((uint32_t)(q * 32) << 16) + buf * p.N, valid, pix);
       fence_before();
-      mbar_arrive(tempty0 + 8 * buf);
+      mbar_arrive_relaxed(tempty0 + 8 * buf);
     }
   }
   fence_before();

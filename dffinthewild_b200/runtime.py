@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdff_b200.so")
+LIB_PATH = os.environ.get("DFF_B200_LIB") or os.path.join(_HERE, "libdff_b200.so")  # (override: instrumented debug builds)
 
 FP32, BF16, TRAIN, NO_TC, NO_SLAB = 0, 1, 2, 4, 8
 NET_DFF, NET_FLOW = 0, 1
