@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
 
 One step = one pass of the hot path (DFF_net forward, reference train_codes/Depth_Estimation_Network.py:77-137)
-over the global batch of 64 synthetic DDFF full-resolution stacks (10 x 3 x 383 x 552, padded to 384 x 576 with -1
-like Depth_Estimation_Test/test_Dataloader.py:128-140), sharded 64/N per rank with no collective.
+over 64 synthetic DDFF full-resolution stacks PER GPU (10 x 3 x 383 x 552, padded to 384 x 576 with -1 like
+Depth_Estimation_Test/test_Dataloader.py:128-140).  Focal stacks are independent, so ranks share nothing: weak scaling,
+no collective on the data path (N=1 is exactly BASELINE.json configs[1]: batch 64).
 
 `value`   stacks/s, inputs resident in HBM, CUDA-event timed, max over ranks.
 `e2e`     the same metric through the C-ABI call that takes HOST buffers (`dff_forward_host`): pinned-host -> device
@@ -28,7 +29,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GLOBAL_BATCH, S, H, W, VALID_HW = 64, 10, 384, 576, (383, 552)
+PER_GPU_BATCH, S, H, W, VALID_HW = 64, 10, 384, 576, (383, 552)
 FLOP_PER_VOXEL = 93563.0   # 2*MACs over the 70 executed conv layers
 METRIC = "DDFF-shape focal stacks/sec"
 
@@ -121,7 +122,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "stacks/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1000 * total / len(times), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus, 1, "cpu"),
         "cpu_baseline": {"value": val, "unit": "stacks/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "stacks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -129,10 +130,12 @@ def run_reference(args):
 
 
 def workload_config(n_gpus, micro_batch, precision):
-    return {"workload": "DDFF-12 full-res inference, 64 x (10x3x383x552 padded to 384x576), batch sharded 64/N per GPU",
-            "global_batch": GLOBAL_BATCH, "slices": S, "padded_hw": [H, W], "micro_batch": micro_batch,
-            "precision": precision, "parallelism": "batch-sharded x%d, no collective" % n_gpus,
-            "l2": "inputs (%.1f GB per rank at N=1) exceed the 126 MB L2; no explicit flush" % (GLOBAL_BATCH * 4 * 4 * S * H * W / 1e9)}
+    return {"workload": "DDFF-12 full-res inference (BASELINE.json configs[1]): 64 stacks of 10x3x383x552 (padded to 384x576) "
+                        "per GPU, independent stacks partitioned across GPUs",
+            "stacks_per_gpu": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus, "slices": S, "padded_hw": [H, W],
+            "micro_batch": micro_batch, "precision": precision,
+            "parallelism": "stack-partitioned x%d, no collective" % n_gpus,
+            "l2": "inputs (%.1f GB per rank) exceed the 126 MB L2; no explicit flush" % (PER_GPU_BATCH * 4 * 4 * S * H * W / 1e9)}
 
 
 def run_ours(args):
@@ -148,7 +151,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    n_local = GLOBAL_BATCH // world
+    n_local = PER_GPU_BATCH
     mb = min(args.micro_batch, n_local)
     assert n_local % mb == 0
     net, sd = make_net(args.precision)
@@ -199,7 +202,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = GLOBAL_BATCH / (ms_per_step / 1000.0)
+    value = PER_GPU_BATCH * world / (ms_per_step / 1000.0)
 
     # ---- per-operator profile (CUDA events on the launching stream) -> dominant kernel + roofline ---------------
     NOPS = 256
@@ -227,8 +230,14 @@ def run_ours(args):
             "share_of_step": top["ms"] / total_prof_ms, "avg_launch_ms": top["ms"] / max(top["launches"], 1),
             "algorithmic_flops_per_launch": top["flops"] / max(top["launches"], 1),
             "hbm_view": {"achieved_gbs": ach_gbs, "peak_gbs": pk["hbm"], "frac": ach_gbs / pk["hbm"]},
-            "whole_step": {"tflops": FLOP_PER_VOXEL * S * H * W * GLOBAL_BATCH / world / (ms_per_step / 1000.0) / 1e12,
-                           "frac_of_tensor_peak": FLOP_PER_VOXEL * S * H * W * GLOBAL_BATCH / world / (ms_per_step / 1000.0) / 1e12 / pk["tf_sustained"]}}
+            "whole_step": {"tflops_per_gpu": FLOP_PER_VOXEL * S * H * W * PER_GPU_BATCH / (ms_per_step / 1000.0) / 1e12,
+                           "frac_of_tensor_peak": FLOP_PER_VOXEL * S * H * W * PER_GPU_BATCH / (ms_per_step / 1000.0) / 1e12 / pk["tf_sustained"]}}
+    tr = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")   # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    if os.path.exists(tr):
+        t = json.load(open(tr))
+        if t.get("kernel") == top_name and t.get("micro_batch") == mb and t.get("precision") == args.precision:
+            roof["traffic"] = t["dram_bytes_per_launch"]
+            roof["traffic_source"] = t.get("source")
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -238,13 +247,13 @@ def run_ours(args):
     hfd.copy_(fd)
     houts = [torch.empty((n_local, H, W), dtype=torch.float32).pin_memory() for _ in range(4)]
     dev_io = torch.empty(lib.dff_host_io_bytes(mb, S, H, W), dtype=torch.uint8, device=dev)
-    hstrides = (ctypes.c_int64 * 4)(*hfd[:mb].stride())
+    hstrides = (ctypes.c_int64 * 4)(*hfd.stride())
+    hp = (ctypes.c_void_p * 4)(*[o.data_ptr() for o in houts])
 
     def e2e_step():
-        for i in range(0, n_local, mb):
-            hp = (ctypes.c_void_p * 4)(*[o[i:i + mb].data_ptr() for o in houts])
-            rt.check(lib.dff_forward_host(packed.data_ptr(), hFS[i:i + mb].data_ptr(), hfd[i:i + mb].data_ptr(), hstrides, mb, S,
-                                          H, W, hp, dev_io.data_ptr(), ws.data_ptr(), ws.numel(), mode, local, sp))
+        # ONE C-ABI call per step: the library pipelines H2D copies / kernels / D2H reads over micro-batches internally
+        rt.check(lib.dff_forward_host(packed.data_ptr(), hFS.data_ptr(), hfd.data_ptr(), hstrides, n_local, mb, S, H, W, hp,
+                                      dev_io.data_ptr(), ws.data_ptr(), ws.numel(), mode, local, sp))
 
     e2e_step()
     barrier()
@@ -257,19 +266,20 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_val = GLOBAL_BATCH * e2e_steps / e2e_s
+    e2e_val = PER_GPU_BATCH * world * e2e_steps / e2e_s
     h2d = n_local * (3 * S * H * W + S * H * W) * 4
     d2h = n_local * 4 * H * W * 4
     same = all(torch.equal(h.to(dev), o) for h, o in zip(houts, outs))
 
     line = {
         "metric": METRIC, "value": value, "unit": "stacks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": workload_config(world, mb, args.precision),
         "clocks": clk.summary(),
         "e2e": {"value": e2e_val, "unit": "stacks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "dff_forward_host (C-ABI, pinned host buffers)", "matches_device_run": bool(same)},
+                "steps": e2e_steps, "api": "dff_forward_host (C-ABI, pinned host buffers; copies pipelined with kernels over micro-batches)",
+                "matches_device_run": bool(same)},
         "gpu_launches": launches_per_chunk * (n_local // mb) * args.steps,
         "roofline": roof,
     }
@@ -290,8 +300,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DFF_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
-    ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--precision", default=os.environ.get("DFF_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--micro-batch", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

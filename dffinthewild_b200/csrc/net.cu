@@ -678,39 +678,91 @@ int dff_forward_profiled(const void* packed, const float* FS, const float* fd, c
   return rc;
 }
 
-size_t dff_host_io_bytes(int B, int S, int H, int W) {
-  return align_up((size_t)B * 3 * S * H * W * 4, 256) + align_up((size_t)B * S * H * W * 4, 256) +
-         4 * align_up((size_t)B * H * W * 4, 256);
+// ---- host-buffer entry point: a two-stage software pipeline over micro-batches ------------------------------------------------
+// stage k holds one micro-batch: FS | focus_dists | 4 depth maps.  Chunk i+1's host->device copies and chunk i-1's device->host
+// reads run on two private copy streams while chunk i computes on the caller's stream (PCIe is full duplex).
+static size_t host_stage_bytes(int mb, int S, int H, int W) {
+  return align_up((size_t)mb * 3 * S * H * W * 4, 256) + align_up((size_t)mb * S * H * W * 4, 256) +
+         4 * align_up((size_t)mb * H * W * 4, 256);
 }
+size_t dff_host_io_bytes(int micro_batch, int S, int H, int W) { return 2 * host_stage_bytes(micro_batch, S, H, W); }
+
+namespace {
+struct HostPipe {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t in_ready[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+// one pipe per (host thread, device): nn.DataParallel drives each GPU from its own thread
+HostPipe* host_pipe(int device) {
+  thread_local std::map<int, HostPipe> pipes;
+  HostPipe& hp = pipes[device];
+  if (!hp.ok) {
+    if (cudaStreamCreateWithFlags(&hp.h2d, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&hp.d2h, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int k = 0; k < 2; ++k) {
+      if (cudaEventCreateWithFlags(&hp.in_ready[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&hp.computed[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&hp.out_done[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    hp.ok = true;
+  }
+  return &hp;
+}
+}  // namespace
 
 int dff_forward_host(const void* packed, const float* FS_host, const float* fd_host, const int64_t fd_strides[4], int B,
-                     int S, int H, int W, float* const out4_host[4], void* dev_io, void* workspace, size_t workspace_bytes,
-                     int mode, int device, void* stream) {
+                     int micro_batch, int S, int H, int W, float* const out4_host[4], void* dev_io, void* workspace,
+                     size_t workspace_bytes, int mode, int device, void* stream) {
   if (!packed || !FS_host || !fd_host || !fd_strides || !out4_host || !dev_io || !workspace)
     return fail(DFF_E_ARG, "dff_forward_host: null pointer");
+  if (B < 1 || micro_batch < 1) return fail(DFF_E_ARG, "dff_forward_host: B and micro_batch must be >= 1");
   DeviceGuard g(device);
   if (g.rc) return g.rc;
+  HostPipe* hp = host_pipe(device);
+  if (!hp) return fail(DFF_E_CUDA, "dff_forward_host: cannot create the copy streams");
   cudaStream_t st = (cudaStream_t)stream;
-  char* io = (char*)dev_io;
-  const size_t fs_bytes = (size_t)B * 3 * S * H * W * 4;
-  // number of focus-distance elements the strides address
-  const int dims[4] = {B, S, H, W};
-  size_t fd_elems = 1;
-  for (int i = 0; i < 4; ++i) fd_elems += (size_t)(dims[i] - 1) * (size_t)fd_strides[i];
-  if (fd_elems > (size_t)B * S * H * W) return fail(DFF_E_ARG, "dff_forward_host: focus_dists strides exceed (B,S,H,W)");
-  float* dFS = (float*)io;
-  float* dfd = (float*)(io + align_up(fs_bytes, 256));
-  char* o = io + align_up(fs_bytes, 256) + align_up((size_t)B * S * H * W * 4, 256);
-  float* dout[4];
-  const size_t map_bytes = (size_t)B * H * W * 4;
-  for (int i = 0; i < 4; ++i) dout[i] = (float*)(o + i * align_up(map_bytes, 256));
-  DFF_CUDA(cudaMemcpyAsync(dFS, FS_host, fs_bytes, cudaMemcpyHostToDevice, st));
-  DFF_CUDA(cudaMemcpyAsync(dfd, fd_host, fd_elems * 4, cudaMemcpyHostToDevice, st));
-  DFF_TRY(forward_impl(packed, dFS, dfd, fd_strides, B, S, H, W, dout, nullptr, workspace, workspace_bytes, mode, st, false,
-                       nullptr));
-  for (int i = 0; i < 4; ++i)
-    if (out4_host[i]) DFF_CUDA(cudaMemcpyAsync(out4_host[i], dout[i], map_bytes, cudaMemcpyDeviceToHost, st));
-  DFF_CUDA(cudaStreamSynchronize(st));
+  const int mb = micro_batch < B ? micro_batch : B;
+  const size_t stage = host_stage_bytes(mb, S, H, W);
+  const size_t fs_stack = (size_t)3 * S * H * W, map_px = (size_t)H * W;
+  // focus-distance elements one chunk of n stacks addresses through the strides
+  auto fd_span = [&](int n) {
+    const int dims[4] = {n, S, H, W};
+    size_t e = 1;
+    for (int i = 0; i < 4; ++i) e += (size_t)(dims[i] - 1) * (size_t)fd_strides[i];
+    return e;
+  };
+  if (fd_span(mb) > (size_t)mb * S * H * W) return fail(DFF_E_ARG, "dff_forward_host: focus_dists strides exceed (B,S,H,W)");
+  int rc = 0, nchunk = 0;
+  for (int i0 = 0; i0 < B && !rc; i0 += mb, ++nchunk) {
+    const int n = (B - i0) < mb ? (B - i0) : mb, k = nchunk & 1;
+    char* io = (char*)dev_io + k * stage;
+    float* dFS = (float*)io;
+    float* dfd = (float*)(io + align_up((size_t)mb * fs_stack * 4, 256));
+    char* o = (char*)dfd + align_up((size_t)mb * S * H * W * 4, 256);
+    float* dout[4];
+    for (int j = 0; j < 4; ++j) dout[j] = (float*)(o + j * align_up((size_t)mb * map_px * 4, 256));
+    // stage k is free again once chunk i-2's maps have left it
+    if (nchunk >= 2) DFF_CUDA(cudaStreamWaitEvent(hp->h2d, hp->out_done[k], 0));
+    DFF_CUDA(cudaMemcpyAsync(dFS, FS_host + (size_t)i0 * fs_stack, (size_t)n * fs_stack * 4, cudaMemcpyHostToDevice, hp->h2d));
+    DFF_CUDA(cudaMemcpyAsync(dfd, fd_host + (size_t)i0 * fd_strides[0], fd_span(n) * 4, cudaMemcpyHostToDevice, hp->h2d));
+    DFF_CUDA(cudaEventRecord(hp->in_ready[k], hp->h2d));
+    DFF_CUDA(cudaStreamWaitEvent(st, hp->in_ready[k], 0));
+    rc = forward_impl(packed, dFS, dfd, fd_strides, n, S, H, W, dout, nullptr, workspace, workspace_bytes, mode, st, false, nullptr);
+    if (rc) break;
+    DFF_CUDA(cudaEventRecord(hp->computed[k], st));
+    DFF_CUDA(cudaStreamWaitEvent(hp->d2h, hp->computed[k], 0));
+    for (int j = 0; j < 4; ++j)
+      if (out4_host[j])
+        DFF_CUDA(cudaMemcpyAsync(out4_host[j] + (size_t)i0 * map_px, dout[j], (size_t)n * map_px * 4, cudaMemcpyDeviceToHost, hp->d2h));
+    DFF_CUDA(cudaEventRecord(hp->out_done[k], hp->d2h));
+  }
+  // the call returns with every map in host memory (and nothing of it still queued on the private streams)
+  cudaError_t e1 = cudaStreamSynchronize(hp->h2d), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(hp->d2h);
+  if (rc) return rc;
+  DFF_CUDA(e1);
+  DFF_CUDA(e2);
+  DFF_CUDA(e3);
   return 0;
 }
 

@@ -43,7 +43,7 @@ def _declare(lib):
         "dff_forward_profiled": (i, [vp, fp, fp, c.POINTER(i64), i, i, i, i, c.POINTER(vp), vp, sz, i, i, vp, i, vp, vp, vp, vp,
                                      vp, c.POINTER(i)]),
         "dff_host_io_bytes": (sz, [i, i, i, i]),
-        "dff_forward_host": (i, [vp, fp, fp, c.POINTER(i64), i, i, i, i, c.POINTER(vp), vp, vp, sz, i, i, vp]),
+        "dff_forward_host": (i, [vp, fp, fp, c.POINTER(i64), i, i, i, i, i, c.POINTER(vp), vp, vp, sz, i, i, vp]),
         "dff_conv3d_scratch_bytes": (sz, [i, i, i, i, i]),
         "dff_conv3d": (i, [vp, i, vp, i, i, i, i, i, fp, i, i, i, i, i, i, i, fp, fp, vp, vp, i, vp, i, i, vp, i, vp]),
         "dff_depth_head": (i, [fp, i, i, fp, c.POINTER(i64), i, i, i, i, fp, i, vp]),

@@ -100,11 +100,15 @@ int dff_forward_profiled(const void *packed, const float *FS, const float *fd, c
                          void *stream, int max_ops, float *op_ms_host, double *op_flops_host, double *op_bytes_host,
                          int *op_launches_host, char *op_names_host, int *n_ops);
 
-/* Same call with HOST buffers (pinned or pageable): copies FS / fd in, runs, copies the four maps out and
- * synchronises the stream.  `dev_io` is caller-owned device scratch of dff_host_io_bytes() bytes. */
-size_t dff_host_io_bytes(int B, int S, int H, int W);
-int dff_forward_host(const void *packed, const float *FS_host, const float *fd_host, const int64_t fd_strides[4],
-                     int B, int S, int H, int W, float *const out4_host[4], void *dev_io, void *workspace,
+/* Same computation with HOST buffers (pinned for full speed; pageable works): B stacks are processed in micro-batches of
+ * `micro_batch` through a two-stage pipeline — the host->device copies of chunk i+1 and the device->host reads of chunk i-1
+ * overlap chunk i's kernels (two private copy streams per calling thread and device).  Returns after every map is in host
+ * memory.  FS_host (B,3,S,H,W); fd_host + strides as in dff_forward; out4_host[j] (B,H,W) or NULL.  `dev_io` is caller-owned
+ * device scratch of dff_host_io_bytes(micro_batch, ...) bytes; `workspace` >= dff_workspace_bytes(micro_batch, ...).
+ * This is the call behind `model(FS.cuda(), fd.cuda())[3].cpu()` of Depth_Estimation_Test/test.py:115-121. */
+size_t dff_host_io_bytes(int micro_batch, int S, int H, int W);
+int dff_forward_host(const void *packed, const float *FS_host, const float *fd_host, const int64_t fd_strides[4], int B,
+                     int micro_batch, int S, int H, int W, float *const out4_host[4], void *dev_io, void *workspace,
                      size_t workspace_bytes, int mode, int device, void *stream);
 
 /* ---- single operators (unit-parity surface; also what dff_forward is made of) ----------------------------- */
