@@ -31,6 +31,23 @@ bool conv_slab_supported(const ConvArgs& a, const TapTable* ptaps, int nph, int 
 int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const void* wslab, int Ntc, int num_sms, cudaStream_t st);
 int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
                             cudaStream_t st);
+int launch_conv_wgrad(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, int ci_base, float* dw, int ntaps_total,
+                      int wt_transposed, bool bf16, cudaStream_t st);
+size_t bn_partial_bytes(int C);
+int launch_bn_stats(const void* x, size_t npix, int C, bool bf16, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
+                    void* partial, cudaStream_t st);
+int launch_bn_apply(const void* x, const float* scale, const float* shift, const void* res_pre, const void* res_post, int relu,
+                    size_t npix, int C, bool bf16, void* out, cudaStream_t st);
+int launch_bn_backward(const void* dy, const void* y, const void* x, const float* mean, const float* invstd, const float* gamma,
+                       size_t npix, int C, bool bf16, void* dx, void* g_out, float* dgamma, float* dbeta, void* partial,
+                       cudaStream_t st);
+int launch_add(const void* a, const void* b, size_t n, bool bf16, void* out, cudaStream_t st);
+int launch_pool_bwd(const void* x, const void* dy, void* dx, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st);
+int launch_depth_head_bwd(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
+                          const float* ddepth, float* dcost, cudaStream_t st);
+int launch_pack_weight_dgrad(const float* w, float* dst, int Cout, int Cin, int ntaps, int ci0, int nci, int CaP, int CbP,
+                             int transposed, cudaStream_t st);
 int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
                    float* scale, float* shift, int C, int CP, cudaStream_t st);
 
@@ -850,6 +867,155 @@ int dff_from_channels_last(const void* src, int B, int C, int S, int H, int W, i
   DeviceGuard g(device);
   if (g.rc) return g.rc;
   return launch_from_cl(src, B, C, S, H, W, Cp, elem == DFF_BF16, dst, (cudaStream_t)stream);
+}
+
+
+// ---- train-mode building blocks -------------------------------------------------------------------------------------
+static void taps_of(int kd, int kh, int kw, int dil, TapTable& t, bool negate) {
+  Layer l{"", "", 0, 0, kd, kh, kw, 1, dil, false, false};
+  conv_taps(l, t);
+  if (negate)
+    for (int i = 0; i < t.n; ++i) { t.dz[i] = (int8_t)-t.dz[i]; t.dy[i] = (int8_t)-t.dy[i]; t.dx[i] = (int8_t)-t.dx[i]; }
+}
+
+size_t dff_conv3d_dgrad_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw) {
+  return align_up((size_t)kd * kh * kw * align_up(Cout, 4) * align_up(Cin, 8) * 4, 256);
+}
+
+int dff_conv3d_dgrad(const void* dy, int CoS, int B, int S, int OH, int OW, const float* weight, int Cin, int Cout, int kd, int kh,
+                     int kw, int stride_hw, int dil_hw, int transposed, int ci0, int nci, void* dx, int elem, void* scratch,
+                     int device, void* stream) {
+  if (!dy || !weight || !dx || !scratch) return fail(DFF_E_ARG, "dff_conv3d_dgrad: null pointer");
+  if (CoS % 4 || CoS < Cout || nci % 4 || ci0 < 0 || ci0 + nci > (int)align_up(Cin, 4))
+    return fail(DFF_E_ARG, "dff_conv3d_dgrad: channel counts must be padded to multiples of 4");
+  if (kd * kh * kw > kMaxTaps) return fail(DFF_E_ARG, "dff_conv3d_dgrad: too many taps");
+  if ((transposed || stride_hw == 2) && !(kd == 3 && kh == 3 && kw == 3 && dil_hw == 1))
+    return fail(DFF_E_ARG, "dff_conv3d_dgrad: strided / transposed layers must be k=3");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ntaps = kd * kh * kw, CaP = CoS, CbP = (int)align_up(nci, 8);
+  DFF_TRY(launch_pack_weight_dgrad(weight, (float*)scratch, Cout, Cin, ntaps, ci0, nci, CaP, CbP, transposed ? 1 : 0, st));
+  ConvArgs a{};
+  a.in0 = dy; a.C0 = CoS; a.in1 = nullptr; a.C1 = 0;
+  a.B = B; a.S = S; a.IH = OH; a.IW = OW;
+  a.w = (const float*)scratch; a.CinP = CaP; a.CoutP = CbP;
+  a.out = dx; a.Cout = nci;
+  const bool bf16 = elem == DFF_BF16;
+  if (transposed) {  // adjoint of the transposed convolution: an ordinary stride-2 convolution of dy with the same weights
+    taps_of(3, 3, 3, 1, a.taps, false);
+    a.isy = a.isx = 2; a.osy = a.osx = 1;
+    a.OH = a.OHt = OH / 2; a.OW = a.OWt = OW / 2;
+    return launch_conv_ffma(a, bf16, st);
+  }
+  if (stride_hw == 1) {  // adjoint of a stride-1 convolution: the same taps with negated offsets
+    taps_of(kd, kh, kw, dil_hw, a.taps, true);
+    a.isy = a.isx = 1; a.osy = a.osx = 1;
+    a.OH = a.OHt = OH; a.OW = a.OWt = OW;
+    return launch_conv_ffma(a, bf16, st);
+  }
+  // adjoint of the stride-(1,2,2) convolution: four output-parity phases of a transposed convolution
+  a.OH = OH * 2; a.OW = OW * 2; a.OHt = OH; a.OWt = OW;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      deconv_taps(py, px, a.taps);
+      a.isy = a.isx = 1; a.osy = a.osx = 2; a.ooy = py; a.oox = px;
+      DFF_TRY(launch_conv_ffma(a, bf16, st));
+    }
+  return 0;
+}
+
+int dff_conv3d_wgrad(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const void* dy, int CoS,
+                     int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, float* dw, int elem,
+                     int device, void* stream) {
+  if (!in0 || !dy || !dw) return fail(DFF_E_ARG, "dff_conv3d_wgrad: null pointer");
+  if (C0 % 4 || C1 % 4) return fail(DFF_E_ARG, "dff_conv3d_wgrad: stored channels must be multiples of 4");
+  if (kd * kh * kw > kMaxTaps) return fail(DFF_E_ARG, "dff_conv3d_wgrad: too many taps");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ntaps = kd * kh * kw;
+  DFF_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cin * Cout * ntaps * sizeof(float), st));
+  ConvArgs a{};
+  a.in0 = in0; a.C0 = C0; a.in1 = (in1 && C1) ? in1 : nullptr; a.C1 = a.in1 ? C1 : 0;
+  a.B = B; a.S = S; a.IH = IH; a.IW = IW;
+  const bool bf16 = elem == DFF_BF16;
+  if (!transposed) {
+    Layer l{"", "", Cin, Cout, kd, kh, kw, stride_hw, dil_hw, false, false};
+    conv_taps(l, a.taps);
+    a.isy = a.isx = stride_hw; a.osy = a.osx = 1;
+    a.OH = a.OHt = IH / stride_hw; a.OW = a.OWt = IW / stride_hw;
+    return launch_conv_wgrad(a, dy, CoS, Cout, Cin, 0, dw, ntaps, 0, bf16, st);
+  }
+  a.OH = IH * 2; a.OW = IW * 2; a.OHt = IH; a.OWt = IW;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      deconv_taps(py, px, a.taps);
+      a.isy = a.isx = 1; a.osy = a.osx = 2; a.ooy = py; a.oox = px;
+      DFF_TRY(launch_conv_wgrad(a, dy, CoS, Cout, Cin, 0, dw, ntaps, 1, bf16, st));
+    }
+  return 0;
+}
+
+size_t dff_bn_scratch_bytes(int C) { return bn_partial_bytes(C); }
+
+int dff_bn_train_forward(const void* x, int64_t npix, int C, int elem, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float momentum, float eps, const void* res_pre, const void* res_post, int relu,
+                         void* out, float* save_mean, float* save_invstd, float* scale_shift, void* scratch, int device,
+                         void* stream) {
+  if (!x || !out) return fail(DFF_E_ARG, "dff_bn_train_forward: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool bf16 = elem == DFF_BF16;
+  if (gamma) {
+    if (!save_mean || !save_invstd || !scale_shift || !scratch) return fail(DFF_E_ARG, "dff_bn_train_forward: null pointer");
+    DFF_TRY(launch_bn_stats(x, (size_t)npix, C, bf16, gamma, beta, running_mean, running_var, momentum, eps, scale_shift,
+                            scale_shift + C, save_mean, save_invstd, scratch, st));
+    return launch_bn_apply(x, scale_shift, scale_shift + C, res_pre, res_post, relu, (size_t)npix, C, bf16, out, st);
+  }
+  return launch_bn_apply(x, nullptr, nullptr, res_pre, res_post, relu, (size_t)npix, C, bf16, out, st);
+}
+
+int dff_bn_train_backward(const void* dy, const void* y_relu, const void* x, const float* save_mean, const float* save_invstd,
+                          const float* gamma, int64_t npix, int C, int elem, void* dx, void* dres, float* dgamma, float* dbeta,
+                          void* scratch, int device, void* stream) {
+  if (!dy) return fail(DFF_E_ARG, "dff_bn_train_backward: null pointer");
+  if (save_mean && (!x || !save_invstd || !dgamma || !dbeta || !scratch)) return fail(DFF_E_ARG, "dff_bn_train_backward: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_bn_backward(dy, y_relu, x, save_mean, save_invstd, gamma, (size_t)npix, C, elem == DFF_BF16, dx, dres, dgamma, dbeta,
+                            scratch, (cudaStream_t)stream);
+}
+
+int dff_add(const void* a, const void* b, int64_t n, int elem, void* out, int device, void* stream) {
+  if (!a || !b || !out) return fail(DFF_E_ARG, "dff_add: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_add(a, b, (size_t)n, elem == DFF_BF16, out, (cudaStream_t)stream);
+}
+
+int dff_pool3d(const void* x, int BS, int H, int W, int C, int k, int is_max, int elem, void* out, int device, void* stream) {
+  if (!x || !out) return fail(DFF_E_ARG, "dff_pool3d: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_pool(x, out, BS, H, W, C, k, is_max != 0, elem == DFF_BF16, (cudaStream_t)stream);
+}
+
+int dff_pool3d_backward(const void* x, const void* dy, int BS, int H, int W, int C, int k, int is_max, int elem, void* dx,
+                        int device, void* stream) {
+  if (!dy || !dx || (is_max && !x)) return fail(DFF_E_ARG, "dff_pool3d_backward: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_pool_bwd(x, dy, dx, BS, H, W, C, k, is_max != 0, elem == DFF_BF16, (cudaStream_t)stream);
+}
+
+int dff_depth_head_backward(const float* cost, int h, int w, const float* fd, const int64_t fd_strides[4], int B, int S, int H,
+                            int W, const float* ddepth, float* dcost, int device, void* stream) {
+  if (!cost || !fd || !fd_strides || !ddepth || !dcost) return fail(DFF_E_ARG, "dff_depth_head_backward: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_depth_head_bwd(cost, h, w, fd, fd_strides, B, S, H, W, ddepth, dcost, (cudaStream_t)stream);
 }
 
 }  // extern "C"

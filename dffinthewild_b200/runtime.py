@@ -182,8 +182,11 @@ def dff_net_forward(net, FS, focus_dists, return_costs=False):
         raise DffError("dff_b200: FS must be (B,3,S,H,W), got %s" % (tuple(FS.shape),))
     if FS.dtype != torch.float32 or focus_dists.dtype != torch.float32:
         raise DffError("dff_b200: FS and focus_dists must be float32 (as the reference dataloaders produce)")
-    if net.training:
-        raise DffError("dff_b200: train-mode forward (batch-statistics BatchNorm + backward) is not available in this build")
+    if net.training or (torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()) and FS.requires_grad):
+        if return_costs:
+            raise DffError("dff_b200: return_costs is an eval-mode debugging aid")
+        from . import train as _train
+        return _train.dff_net_train_forward(net, FS, focus_dists)
     dev = FS.device
     _check_device(dev.index)
     B, _, S, H, W = FS.shape

@@ -139,6 +139,45 @@ int dff_to_channels_last(const float *src, int B, int C, int S, int H, int W, vo
 int dff_from_channels_last(const void *src, int B, int C, int S, int H, int W, int Cp, int elem, float *dst,
                            int device, void *stream);
 
+/* ---- train-mode building blocks ----------------------------------------------------------------------
+ * The train path keeps PyTorch's autograd as the tape (dffinthewild_b200/train.py: one autograd.Function per fused operator);
+ * every forward and backward computation is one of the calls below.  Tensors are channels-last (B,S,H,W,C) of `elem` type;
+ * parameter gradients, statistics and reductions are fp32.  Replaces ATen's convolution_backward, native_batch_norm(+_backward),
+ * threshold_backward, max/avg_pool3d_backward, upsample_bilinear2d_backward and softplus_backward behind `Total.backward()`
+ * (train_codes/train_code_Defocus.py:167) and nn.BatchNorm3d in batch-statistics mode (train_codes/Depth_Estimation_Network.py:355). */
+
+/* dx[.., ci0:ci0+nci] of a conv / transposed-conv layer (weight in the reference layout) from dy (B,S,OH,OW,CoS).
+ * dx is (B,S,IH,IW,nci): the gradient of one source of a (virtually concatenated) input. */
+size_t dff_conv3d_dgrad_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw);
+int dff_conv3d_dgrad(const void *dy, int CoS, int B, int S, int OH, int OW, const float *weight, int Cin, int Cout, int kd,
+                     int kh, int kw, int stride_hw, int dil_hw, int transposed, int ci0, int nci, void *dx, int elem,
+                     void *scratch, int device, void *stream);
+/* dw (fp32, reference layout, overwritten) from the layer input in0 [+ in1] (B,S,IH,IW,C0[+C1]) and dy (.., CoS). */
+int dff_conv3d_wgrad(const void *in0, int C0, const void *in1, int C1, int B, int S, int IH, int IW, const void *dy, int CoS,
+                     int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, float *dw, int elem,
+                     int device, void *stream);
+/* out = [relu]( BN_batchstats(x) + res_pre ) + res_post ; saves mean / invstd, updates running statistics in place
+ * (momentum, unbiased variance) when given.  gamma == NULL: no BatchNorm (activation / adds only).
+ * scale_shift: 2*C floats of scratch; scratch: dff_bn_scratch_bytes(C). */
+size_t dff_bn_scratch_bytes(int C);
+int dff_bn_train_forward(const void *x, int64_t npix, int C, int elem, const float *gamma, const float *beta,
+                         float *running_mean, float *running_var, float momentum, float eps, const void *res_pre,
+                         const void *res_post, int relu, void *out, float *save_mean, float *save_invstd, float *scale_shift,
+                         void *scratch, int device, void *stream);
+/* backward of the above w.r.t. x (dx), res_pre (dres = masked dy), gamma, beta.  y_relu: the stored output BEFORE res_post
+ * (ReLU mask) or NULL when there was no ReLU; save_mean == NULL: no BatchNorm. */
+int dff_bn_train_backward(const void *dy, const void *y_relu, const void *x, const float *save_mean, const float *save_invstd,
+                          const float *gamma, int64_t npix, int C, int elem, void *dx, void *dres, float *dgamma, float *dbeta,
+                          void *scratch, int device, void *stream);
+int dff_add(const void *a, const void *b, int64_t n, int elem, void *out, int device, void *stream);
+/* (1,k,k) pooling of (BS,H,W,C) channels-last volumes, forward and backward (max: first maximum in row-major order). */
+int dff_pool3d(const void *x, int BS, int H, int W, int C, int k, int is_max, int elem, void *out, int device, void *stream);
+int dff_pool3d_backward(const void *x, const void *dy, int BS, int H, int W, int C, int k, int is_max, int elem, void *dx,
+                        int device, void *stream);
+/* d cost (B,S,h,w) from d depth (B,H,W) */
+int dff_depth_head_backward(const float *cost, int h, int w, const float *fd, const int64_t fd_strides[4], int B, int S, int H,
+                            int W, const float *ddepth, float *dcost, int device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,126 @@
+"""Train-mode parity on the GPU: batch-statistics BatchNorm forward, the Defocus loss recipe
+(train_code_Defocus.py:160-165), backward through every operator, parameter gradients — against the reference's committed
+golden gradients (tests/golden/g3_train_synth.npz, produced by the unmodified reference) and against the fp64 CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+NAMES = ("mid", "p1", "p2", "p3")
+
+
+def _net(sd):
+    from dffinthewild_b200.Depth_Estimation_Network import Network
+    torch.manual_seed(0)
+    net = Network()
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().train()
+
+
+def _loss(outs, gt, mask):
+    crit = torch.nn.MSELoss()
+    return 0.5 * crit(outs[1][mask], gt[mask]) + 0.7 * crit(outs[2][mask], gt[mask]) + 1.0 * crit(outs[3][mask], gt[mask]) \
+        + 0.3 * crit(outs[0][mask], gt[mask])
+
+
+def _state():
+    from dffinthewild_b200.Depth_Estimation_Network import Network
+    from oracle import synth
+    torch.manual_seed(0)
+    return synth.synthetic_state(Network().state_dict(), seed=1)
+
+
+def test_golden_g3_train_step(built_lib):
+    from oracle import synth
+    g = golden("g3_train_synth.npz")
+    sd = _state()
+    net = _net(sd)
+    FS, fd = synth.focal_stack(2, 4, 32, 32, seed=13), synth.focus_dists(2, 4, 32, 32, "defocus")
+    gt, mask = synth.gt_and_mask(2, 32, 32, seed=13)
+    outs = net(FS.cuda(), fd.cuda())
+    for o, n in zip(outs, NAMES):
+        ref = g[n]
+        assert np.abs(o.detach().cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max(), n
+    loss = _loss(outs, gt.cuda(), mask.cuda())
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    loss.backward()
+    params = dict(net.named_parameters())
+    # the 12 parameters the reference never reaches get no gradient here either
+    assert sorted(k for k, p in params.items() if p.grad is None) == sorted(str(k) for k in g["grad_none"])
+    for k, s, a in zip(g["grad_names"], g["grad_sum"], g["grad_abs"]):
+        gr = params[str(k)].grad.double()
+        assert abs(float(gr.abs().sum()) - a) <= 2e-3 * a + 1e-12, k
+        assert abs(float(gr.sum()) - s) <= 2e-3 * a + 1e-12, k
+    worst = 1.0
+    for key in g.files:
+        if key.startswith("grad:"):
+            ref = torch.from_numpy(g[key]).double().flatten()
+            got = params[key[5:]].grad.double().cpu().flatten()
+            cos = float(torch.dot(ref, got) / (ref.norm() * got.norm() + 1e-300))
+            worst = min(worst, cos)
+            assert cos >= 0.9999, (key, cos)
+    # running statistics after one step (momentum 0.1, unbiased variance) as nn.BatchNorm3d leaves them
+    new_sd = net.state_dict()
+    for key in g.files:
+        if key.startswith("bn:"):
+            ref = g[key]
+            got = new_sd[key[3:]].cpu().numpy()
+            assert np.abs(got - ref).max() <= 1e-4 * max(1e-6, np.abs(ref).max()), key
+    k = "DFF_net.dres4.conv0.0.1.num_batches_tracked"
+    assert int(new_sd[k]) == int(sd[k]) + 1
+
+
+def test_gradients_vs_fp64_oracle(built_lib):
+    """fp32-mode gradient gate of SURVEY.md §8d: per-tensor cosine >= 0.9999 against the fp64 CPU oracle."""
+    from oracle import dff_oracle as O
+    from oracle import synth
+    sd = _state()
+    net = _net(sd)
+    B, S, H, W = 2, 5, 64, 32
+    FS, fd = synth.focal_stack(B, S, H, W, seed=21), synth.focus_dists(B, S, H, W, "defocus")
+    gt, mask = synth.gt_and_mask(B, H, W, seed=21)
+    outs = net(FS.cuda(), fd.cuda())
+    _loss(outs, gt.cuda(), mask.cuda()).backward()
+    sdo = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+           for k, v in sd.items()}
+    o = O.dff_forward(sdo, FS.double(), fd.double(), train=True)
+    O.defocus_loss(o, gt.double(), mask).backward()
+    for a, b, n in zip(outs, o, NAMES):
+        rel = ((a.detach().cpu().double() - b.detach()).abs() / b.detach().abs()).max().item()
+        assert rel <= 1e-4, (n, rel)
+    worst, worst_k = 1.0, None
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            assert sdo[k].grad is None, k
+            continue
+        ref, got = sdo[k].grad.flatten(), p.grad.double().cpu().flatten()
+        cos = float(torch.dot(ref, got) / (ref.norm() * got.norm() + 1e-300))
+        if cos < worst:
+            worst, worst_k = cos, k
+    assert worst >= 0.9999, (worst_k, worst)
+
+
+def test_adam_step_runs_on_module_parameters(built_lib):
+    """train_code_Defocus.py:67,159-168: zero_grad / backward / Adam.step on the drop-in module's own parameters."""
+    from oracle import synth
+    net = _net(_state())
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    FS, fd = synth.focal_stack(1, 3, 32, 32, seed=31).cuda(), synth.focus_dists(1, 3, 32, 32, "defocus").cuda()
+    gt, mask = synth.gt_and_mask(1, 32, 32, seed=31)
+    before = net.DFF_net.classif3[0].weight.detach().clone()
+    losses = []
+    for _ in range(3):
+        outs = net(FS, fd)
+        opt.zero_grad()
+        loss = _loss(outs, gt.cuda(), mask.cuda())
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses))
+    assert not torch.equal(before, net.DFF_net.classif3[0].weight.detach())
+    net.eval()
+    with torch.no_grad():
+        o = net(FS, fd)          # eval path picks up the updated weights and running statistics
+    assert all(torch.isfinite(t).all() for t in o)
