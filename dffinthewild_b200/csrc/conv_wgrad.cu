@@ -7,9 +7,9 @@
 // in the same "strided gather over a tap table" form as the forward kernels (conv_ffma.cu), so ordinary, strided and
 // (per output-parity phase) transposed convolutions and the two-source concat all go through one kernel.  One CTA owns a
 // 32 x TY tile of output positions of one (batch, slice): it stages the input region (halo included) channel-planar for CK
-// input channels and the dy tile for all output channels in shared memory, then every thread owns one (ci, co) pair (pixel
-// range split across thread groups when there are fewer pairs than threads), sums over the tile's positions in registers tap
-// by tap, and adds its partial sums to the fp32 gradient in the reference's weight layout with red.global.add.f32.
+// input channels and the dy tile for all output channels in shared memory; a thread owns one (tap, ci) and a block of COB output
+// channels, sums over all positions of the tile in registers (one activation load feeds COB FMAs, the dy row is a shared-memory
+// broadcast), and adds its partial sums to the fp32 gradient in the reference's weight layout with red.global.add.f32.
 // fp32 accumulate; the order of the global adds is not fixed, which moves results by ~1e-7 relative (gate: gradient cosine).
 #include "common.cuh"
 
@@ -27,18 +27,18 @@ struct WgradArgs {
   int ci_base;       // channel offset of in0 inside the layer's Cin (two-source layers: in1 starts at ci_base + C0)
 };
 
-template <typename T, int CK>
+template <typename T, int CK, int COB>
 __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_kernel(const __grid_constant__ WgradArgs g) {
   extern __shared__ __align__(16) float smem[];
   const ConvArgs& a = g.a;
   const int REG = a.RZ * a.RY * a.RXP;
-  const int NP = 32 * kWgTY;             // positions per tile
+  const int NP = 32 * a.TY;              // positions per tile
   const int CoP = (g.Cout + 3) & ~3;
   float* in_s = smem;                     // [CK][REG]
   float* dy_s = smem + CK * REG;          // [NP][CoP]
   const int tid = threadIdx.x;
   const int bs = blockIdx.z, b = bs / a.S, s = bs % a.S;
-  const int ty0 = blockIdx.y * kWgTY, tx0 = blockIdx.x * 32;
+  const int ty0 = blockIdx.y * a.TY, tx0 = blockIdx.x * 32;
   const int gy0 = ty0 * a.isy + a.dymin, gx0 = tx0 * a.isx + a.dxmin, gz0 = s + a.dzmin;
 
   // ---- dy tile (zero outside the phase grid) -----------------------------------------------------------------------
@@ -60,12 +60,11 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_kernel(const __grid_
     *reinterpret_cast<float4*>(dy_s + pos * CoP + 4 * q) = v;
   }
 
-  // thread -> (ci, co, pixel split)
-  const int npairs = CK * g.Cout;
-  const int PS = max(1, kWgThreads / npairs);         // thread groups splitting the tile's positions
   const int Ctot = a.C0 + a.C1;
   const int npos = a.RZ * a.RY * a.RX;
   constexpr int NQ = CK / 4;
+  const int cosplit = CoP / COB;                       // output-channel blocks per (tap, ci)
+  const int nitems = a.taps.n * CK * cosplit;          // work items of one channel chunk: (tap, ci, co block)
 
   for (int c0 = 0; c0 < Ctot; c0 += CK) {
     const bool second = c0 >= a.C0;
@@ -84,25 +83,42 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_kernel(const __grid_
       d[0] = v.x; d[REG] = v.y; d[2 * REG] = v.z; d[3 * REG] = v.w;
     }
     __syncthreads();
-    // every thread walks the pairs it owns: pair index pi = (tid % (npairs or 256)) + k*256 ; position split by tid / npairs
-    for (int pi = tid % min(npairs, kWgThreads); pi < npairs; pi += kWgThreads) {
-      const int ci = pi % CK, co = pi / CK;
-      const int ps = npairs >= kWgThreads ? 0 : tid / npairs;
-      if (ps >= PS) continue;
+    // a thread owns (tap, ci) x COB output channels and sums over all positions of the tile: one activation load feeds COB FMAs,
+    // the dy row is a shared-memory broadcast for the warp
+    for (int it = tid; it < nitems; it += kWgThreads) {
+      const int cs = it % cosplit, ci = (it / cosplit) % CK, t = it / (cosplit * CK);
       const int cig = g.ci_base + c0 + ci;   // channel inside the layer's Cin (stored channels beyond Cin are padding)
       if (cig >= g.Cin) continue;
-      const float* ip0 = in_s + ci * REG;
-      for (int t = 0; t < a.taps.n; ++t) {
-        const float* ip = ip0 + ((a.taps.dz[t] - a.dzmin) * a.RY + (a.taps.dy[t] - a.dymin)) * a.RXP + (a.taps.dx[t] - a.dxmin);
-        float acc = 0.f;
-        for (int pos = ps; pos < NP; pos += PS) {
-          const int px = pos & 31, py = pos >> 5;
-          acc = fmaf(ip[py * a.isy * a.RXP + px * a.isx], dy_s[pos * CoP + co], acc);
+      const float* ip = in_s + ci * REG + ((a.taps.dz[t] - a.dzmin) * a.RY + (a.taps.dy[t] - a.dymin)) * a.RXP +
+                        (a.taps.dx[t] - a.dxmin);
+      const float* dp = dy_s + cs * COB;
+      float acc[COB];
+#pragma unroll
+      for (int j = 0; j < COB; ++j) acc[j] = 0.f;
+      for (int py = 0; py < a.TY; ++py) {
+        const float* irow = ip + py * a.isy * a.RXP;
+        const float* drow = dp + (py * 32) * CoP;
+#pragma unroll 4
+        for (int px = 0; px < 32; ++px) {
+          const float av = irow[px * a.isx];
+#pragma unroll
+          for (int j4 = 0; j4 < COB / 4; ++j4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(drow + px * CoP + 4 * j4);
+            acc[4 * j4] = fmaf(av, d4.x, acc[4 * j4]);
+            acc[4 * j4 + 1] = fmaf(av, d4.y, acc[4 * j4 + 1]);
+            acc[4 * j4 + 2] = fmaf(av, d4.z, acc[4 * j4 + 2]);
+            acc[4 * j4 + 3] = fmaf(av, d4.w, acc[4 * j4 + 3]);
+          }
         }
-        const int wi = a.taps.widx[t];
+      }
+      const int wi = a.taps.widx[t];
+#pragma unroll
+      for (int j = 0; j < COB; ++j) {
+        const int co = cs * COB + j;
+        if (co >= g.Cout) continue;
         const size_t o = g.wt_transposed ? ((size_t)cig * g.Cout + co) * g.ntaps_total + wi
                                          : ((size_t)co * g.Cin + cig) * g.ntaps_total + wi;
-        atomicAdd(g.dw + o, acc);
+        atomicAdd(g.dw + o, acc[j]);
       }
     }
   }
@@ -119,13 +135,13 @@ static size_t wg_plan(ConvArgs& a, int CK, int Cout) {
     dymax = a.taps.dy[t] > dymax ? a.taps.dy[t] : dymax;
     dxmax = a.taps.dx[t] > dxmax ? a.taps.dx[t] : dxmax;
   }
-  a.TY = kWgTY;
+  const int CoP = (Cout + 3) & ~3;
+  a.TY = CoP <= 32 ? kWgTY : (CoP <= 64 ? kWgTY / 2 : kWgTY / 4);   // keep the dy tile <= 32 KB
   a.RZ = dzmax - a.dzmin + 1;
-  a.RY = (kWgTY - 1) * a.isy + (dymax - a.dymin) + 1;
+  a.RY = (a.TY - 1) * a.isy + (dymax - a.dymin) + 1;
   a.RX = 31 * a.isx + (dxmax - a.dxmin) + 1;
   a.RXP = a.RX | 1;
-  const int CoP = (Cout + 3) & ~3;
-  return ((size_t)CK * a.RZ * a.RY * a.RXP + (size_t)32 * kWgTY * CoP) * sizeof(float);
+  return ((size_t)CK * a.RZ * a.RY * a.RXP + (size_t)32 * a.TY * CoP) * sizeof(float);
 }
 
 // `a`: geometry/taps/in0/in1 as for the forward launch of the same (phase of the) layer.
@@ -139,15 +155,29 @@ int launch_conv_wgrad(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, in
   if (smem > 227 * 1024) return fail(-5, "conv_wgrad: tile does not fit shared memory");
   g.a = a; g.dy = dy; g.CoS = CoS; g.Cout = Cout; g.Cin = Cin; g.dw = dw; g.ntaps_total = ntaps_total;
   g.wt_transposed = wt_transposed; g.ci_base = ci_base;
-  dim3 grid(cdiv(a.OWt, 32), cdiv(a.OHt, kWgTY), a.B * a.S);
-#define DFF_WG(T, CK_)                                                                                              \
+  dim3 grid(cdiv(a.OWt, 32), cdiv(a.OHt, a.TY), a.B * a.S);
+  const int CoP = (Cout + 3) & ~3;
+  const int COB = CoP >= 32 ? 32 : (CoP >= 16 ? 16 : (CoP >= 8 ? 8 : 4));
+  if (CoP % COB) return fail(-5, "conv_wgrad: unsupported output channel count");
+#define DFF_WG(T, CK_, COB_)                                                                                        \
   do {                                                                                                              \
-    auto k = conv_wgrad_kernel<T, CK_>;                                                                             \
+    auto k = conv_wgrad_kernel<T, CK_, COB_>;                                                                       \
     DFF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
     k<<<grid, kWgThreads, smem, st>>>(g);                                                                           \
   } while (0)
-  if (bf16) { if (CK == 8) DFF_WG(__nv_bfloat16, 8); else DFF_WG(__nv_bfloat16, 4); }
-  else      { if (CK == 8) DFF_WG(float, 8); else DFF_WG(float, 4); }
+#define DFF_WG_T(T)                                                               \
+  do {                                                                            \
+    if (CK == 8) {                                                                \
+      if (COB == 32) DFF_WG(T, 8, 32); else if (COB == 16) DFF_WG(T, 8, 16);      \
+      else if (COB == 8) DFF_WG(T, 8, 8); else DFF_WG(T, 8, 4);                   \
+    } else {                                                                      \
+      if (COB == 32) DFF_WG(T, 4, 32); else if (COB == 16) DFF_WG(T, 4, 16);      \
+      else if (COB == 8) DFF_WG(T, 4, 8); else DFF_WG(T, 4, 4);                   \
+    }                                                                             \
+  } while (0)
+  if (bf16) DFF_WG_T(__nv_bfloat16);
+  else DFF_WG_T(float);
+#undef DFF_WG_T
 #undef DFF_WG
   DFF_LAUNCH_CHECK("conv_wgrad");
   return 0;
