@@ -48,6 +48,8 @@ int launch_depth_head_bwd(const float* cost, int h, int w, const float* fd, cons
                           const float* ddepth, float* dcost, cudaStream_t st);
 int launch_pack_weight_dgrad(const float* w, float* dst, int Cout, int Cin, int ntaps, int ci0, int nci, int CaP, int CbP,
                              int transposed, cudaStream_t st);
+bool conv_row_supported(const ConvArgs& a, int Ntc);
+int launch_conv_row(const ConvArgs& a, const void* wslab, int Ntc, int num_sms, cudaStream_t st);
 int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
                    float* scale, float* shift, int C, int CP, cudaStream_t st);
 
@@ -267,7 +269,7 @@ static int num_sms_of_current_device() {
 // `wtc` != null selects the tcgen05 path (bf16 only); otherwise the FFMA kernel runs.
 static int run_conv(const Layer& l, const float* w, const float* scale, const float* shift, const Ten& in, const EpiOpt& e,
                     Ten& out, bool bf16, cudaStream_t st, const void* wtc = nullptr, const void* wslab = nullptr,
-                    int* nlaunch = nullptr, bool count_only = false) {
+                    int* nlaunch = nullptr, bool count_only = false, bool use_row = true) {
   int dummy = 0;
   if (!nlaunch) nlaunch = &dummy;
   *nlaunch = 0;
@@ -298,6 +300,7 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     *nlaunch = 1;
     if (count_only) return 0;
     if (wtc) {
+      if (wslab && use_row && conv_row_supported(a, l.Ntc)) return launch_conv_row(a, wslab, l.Ntc, nsm, st);
       if (wslab && conv_slab_supported(a, nullptr, 1, l.Ntc)) return launch_conv_slab(a, nullptr, 1, wslab, l.Ntc, nsm, st);
       return launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st);
     }
@@ -835,9 +838,10 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
   e.res_pre = res_pre ? &rp : nullptr;
   e.res_post = res_post ? &rq : nullptr;
   e.relu = relu != 0;
-  // use_tensor_cores: 1 = slab kernel when the layer fits (else per-tap TMA kernel), 2 = force the per-tap TMA kernel
+  // use_tensor_cores: 1 = best kernel for the shape (row kernel with A in TMEM -> slab kernel -> per-tap TMA kernel),
+  // 2 = force the per-tap TMA kernel, 3 = slab kernel (never the row kernel)
   return run_conv(l, (const float*)scratch, scale, shift, in, e, o, elem == DFF_BF16, st, use_tensor_cores ? scratch : nullptr,
-                  use_tensor_cores == 1 ? (char*)scratch + tcb : nullptr);
+                  use_tensor_cores != 2 ? (char*)scratch + tcb : nullptr, nullptr, false, use_tensor_cores == 1);
 }
 
 int dff_depth_head(const float* cost, int h, int w, const float* fd, const int64_t fd_strides[4], int B, int S, int H, int W,

@@ -35,13 +35,17 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU (a hung box is a lost lease) — trap after ~2 s.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
+// Bounded wait: a protocol bug must not hang the GPU (a hung box is a lost lease) — trap after ~2 s.  The slow path is kept
+// out of line: the waiting warps are single instruction streams and every inlined instruction costs them latency.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(

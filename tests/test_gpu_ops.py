@@ -105,6 +105,75 @@ def test_conv_tcgen05_bf16(rt, case, kernel):
     assert (out_full - full).abs().max().item() <= 6e-3 * full.abs().max().item(), name
 
 
+ROW_CASES = [
+    # name, C0, C1, Cout, k, S, H, W   (stride 1; W >= 256 selects the row kernel: A operand in tensor memory)
+    ("row_c3_16_16", 16, 0, 16, (3, 3, 3), 4, 9, 288),
+    ("row_c3_8+8_8", 8, 8, 8, (3, 3, 3), 3, 8, 320),
+    ("row_c3_16+16_16", 16, 16, 16, (3, 3, 3), 5, 7, 256),
+    ("row_c3_32_32", 32, 0, 32, (3, 3, 3), 3, 8, 288),
+    ("row_c3_32+32_32", 32, 32, 32, (3, 3, 3), 2, 6, 264),
+    ("row_1x3x3_8_8", 8, 0, 8, (1, 3, 3), 3, 12, 576),
+    ("row_1x3x3_16_16", 16, 0, 16, (1, 3, 3), 2, 9, 288),
+    ("row_1x3x3_32_32", 32, 0, 32, (1, 3, 3), 2, 5, 256),
+    ("row_c3_16_16_1slice", 16, 0, 16, (3, 3, 3), 1, 4, 256),
+]
+
+
+@pytest.fixture()
+def row_kernel_on():
+    """The row kernel is opt-in (DFF_B200_ROW=1, read once per process): these tests run it in a child interpreter."""
+    import os
+    import subprocess
+    import sys
+
+    def run(case_name):
+        env = dict(os.environ, DFF_B200_ROW="1", DFF_ROW_CHILD=case_name)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", __file__, "-k", "row_kernel_child", "-m", "gpu"], env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    return run
+
+
+@pytest.mark.parametrize("case", ROW_CASES, ids=[c[0] for c in ROW_CASES])
+def test_conv_row_kernel_tmem_operand(row_kernel_on, case):
+    row_kernel_on(case[0])
+
+
+def test_row_kernel_child(rt):
+    """Body of the row-kernel parity test; only runs inside the child process started by the fixture above."""
+    import os
+    name = os.environ.get("DFF_ROW_CHILD")
+    if not name or os.environ.get("DFF_B200_ROW") != "1":
+        pytest.skip("row-kernel child only")
+    _row_case(rt, next(c for c in ROW_CASES if c[0] == name))
+
+
+def _row_case(rt, case):
+    """Row kernel (tcgen05.mma TS form, input-stationary over 9 accumulators): must agree with the slab kernel's contract —
+    exact products of bf16 operands, fp32 accumulate, fused BN/residual/ReLU epilogue, bf16 store."""
+    name, c0, c1, cout, k, S, H, W = case
+    B = 2
+    x0 = _rand(B, c0, S, H, W, seed=1).bfloat16().float()
+    x1 = _rand(B, c1, S, H, W, seed=2).bfloat16().float() if c1 else None
+    cin = c0 + c1
+    w = _rand(cout, cin, *k, seed=3, scale=(2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5 * 1.7).bfloat16().float()
+    xin = torch.cat([x0, x1], 1) if c1 else x0
+    ref = _ref_conv(xin, w, 1, 1, False)
+    out = rt.conv3d(x0.cuda(), w.cuda(), x2=x1.cuda() if c1 else None, bf16=True, tensor_cores=1).cpu().double()
+    assert (out - ref).abs().max().item() <= 6e-3 * ref.abs().max().item(), name
+    scale = _rand(cout, seed=4) * 0.4 + 1.0
+    shift = _rand(cout, seed=5) * 0.3
+    res1 = _rand(*ref.shape, seed=6).bfloat16().float()
+    res2 = _rand(*ref.shape, seed=7).bfloat16().float()
+    full = F.relu(ref * scale.double().view(1, -1, 1, 1, 1) + shift.double().view(1, -1, 1, 1, 1) + res1.double()) + res2.double()
+    out_full = rt.conv3d(x0.cuda(), w.cuda(), x2=x1.cuda() if c1 else None, scale=scale.cuda(), shift=shift.cuda(),
+                         res_pre=res1.cuda(), res_post=res2.cuda(), relu=True, bf16=True, tensor_cores=1).cpu().double()
+    assert (out_full - full).abs().max().item() <= 6e-3 * full.abs().max().item(), name
+    # and bit-for-bit the same result class as the slab kernel (same operands, same accumulation width)
+    slab = rt.conv3d(x0.cuda(), w.cuda(), x2=x1.cuda() if c1 else None, bf16=True, tensor_cores=3).cpu().double()
+    assert (out - slab).abs().max().item() <= 1.6e-2 * ref.abs().max().item(), name
+
+
 @pytest.mark.parametrize("kernel", [1, 2], ids=["slab", "per_tap_tma"])
 def test_conv_tcgen05_two_sources(rt, kernel):
     for c0, c1, cout in ((16, 16, 16), (8, 8, 8), (32, 32, 32), (64, 64, 64), (128, 64, 128)):
