@@ -89,6 +89,9 @@ struct ConvArgs {
   const void* aux_add;
   int Cout;                // stored channels of out
   int out_f32;             // store `out` as fp32 even when activations are bf16 (cost volumes feeding the depth head)
+  const float* proj_w;     // optional fused C -> 1 projection in the tensor-core epilogues (see EpiArgs)
+  float* proj_out;
+  int proj_src, skip_out;
   TapTable taps;
 };
 

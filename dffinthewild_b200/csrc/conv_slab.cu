@@ -478,6 +478,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.epi.scale = a.scale; p.epi.shift = a.shift; p.epi.res_pre = a.res_pre; p.epi.res_post = a.res_post;
   p.epi.out = a.out; p.epi.out_aux = a.out_aux; p.epi.aux_add = a.aux_add;
   p.epi.cstore = a.Cout; p.epi.relu = a.relu; p.epi.out_f32 = a.out_f32; p.epi.N = Ntc;
+  p.epi.proj_w = a.proj_w; p.epi.proj_out = a.proj_out; p.epi.proj_src = a.proj_src; p.epi.skip_out = a.skip_out;
   return true;
 }
 

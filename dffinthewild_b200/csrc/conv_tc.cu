@@ -51,6 +51,9 @@ struct alignas(64) TcParams {
   void* out_aux;
   const void* aux_add;
   int cstore, relu, out_f32;
+  const float* proj_w;
+  float* proj_out;
+  int proj_src, skip_out;
   TcLoad loads[kTcMaxLoads];
 };
 
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     EpiArgs ep;
     ep.scale = p.scale; ep.shift = p.shift; ep.res_pre = p.res_pre; ep.res_post = p.res_post; ep.out = p.out;
     ep.out_aux = p.out_aux; ep.aux_add = p.aux_add; ep.cstore = p.cstore; ep.relu = p.relu; ep.out_f32 = p.out_f32; ep.N = p.N;
+    ep.proj_w = p.proj_w; ep.proj_out = p.proj_out; ep.proj_src = p.proj_src; ep.skip_out = p.skip_out;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -258,6 +262,7 @@ int launch_conv_tc(const ConvArgs& a, const void* wtc, int ntaps_total, int Ntc,
   p.scale = a.scale; p.shift = a.shift;
   p.res_pre = a.res_pre; p.res_post = a.res_post; p.out = a.out; p.out_aux = a.out_aux; p.aux_add = a.aux_add;
   p.cstore = a.Cout; p.relu = a.relu; p.out_f32 = a.out_f32;
+  p.proj_w = a.proj_w; p.proj_out = a.proj_out; p.proj_src = a.proj_src; p.skip_out = a.skip_out;
 
   // ---- activation tensor maps: (C, W, H, S, B) channels-last; stride 2 = four parity-subsampled views -----------------
   const int st2 = a.isy;

@@ -145,6 +145,67 @@ __global__ void depth_head_kernel(const float* __restrict__ cost, int h, int w, 
   depth[((size_t)b * H + y) * W + x] = num / den;
 }
 
+// All four heads of DFF_net in one pass: `focus_dists` (the largest operand, S*H*W fp32) is read once instead of four times.
+struct Head4 {
+  const float* cost[4];
+  int h[4], w[4];
+  float* depth[4];
+};
+__global__ void depth_head4_kernel(const __grid_constant__ Head4 a, const float* __restrict__ fd, long long sb, long long ss,
+                                   long long sy, long long sx, int B, int S, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  int y0[4], x0[4], y1[4], x1[4];
+  float ly1[4], lx1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float ry = (float)a.h[k] / (float)H, rx = (float)a.w[k] / (float)W;
+    float fy = ry * ((float)y + 0.5f) - 0.5f, fx = rx * ((float)x + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    y0[k] = (int)fy; x0[k] = (int)fx;
+    y1[k] = y0[k] + (y0[k] < a.h[k] - 1 ? 1 : 0);
+    x1[k] = x0[k] + (x0[k] < a.w[k] - 1 ? 1 : 0);
+    ly1[k] = fy - (float)y0[k]; lx1[k] = fx - (float)x0[k];
+  }
+  float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* fp = fd + b * sb + y * sy + x * sx;
+  for (int s = 0; s < S; ++s) {
+    const float f = __ldg(fp + s * ss);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int h = a.h[k], w = a.w[k];
+      const float* c = a.cost[k] + ((size_t)b * S + s) * h * w;
+      float v;
+      if (h == H && w == W) v = __ldg(c + (size_t)y * w + x);
+      else {
+        const float ly0 = 1.f - ly1[k], lx0 = 1.f - lx1[k];
+        v = ly0 * (lx0 * __ldg(c + (size_t)y0[k] * w + x0[k]) + lx1[k] * __ldg(c + (size_t)y0[k] * w + x1[k])) +
+            ly1[k] * (lx0 * __ldg(c + (size_t)y1[k] * w + x0[k]) + lx1[k] * __ldg(c + (size_t)y1[k] * w + x1[k]));
+      }
+      const float p = softplus_ref(v) + 1e-6f;
+      den[k] += p;
+      num[k] = fmaf(f, p, num[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a.depth[k][((size_t)b * H + y) * W + x] = num[k] / den[k];
+}
+
+int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4], const float* fd, const int64_t* st4, int B, int S,
+                       int H, int W, float* const depth[4], cudaStream_t st) {
+  Head4 a;
+  for (int k = 0; k < 4; ++k) {
+    if (h[k] <= 0 || w[k] <= 0 || H % h[k] || W % w[k]) return fail(-1, "depth_head: H,W must be multiples of the cost resolution");
+    a.cost[k] = cost[k]; a.h[k] = h[k]; a.w[k] = w[k]; a.depth[k] = depth[k];
+  }
+  dim3 grid(cdiv(W, 128), H, B);
+  depth_head4_kernel<<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
+  DFF_LAUNCH_CHECK("depth_head4");
+  return 0;
+}
+
 int launch_depth_head(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
                       float* depth, cudaStream_t st) {
   if (h <= 0 || w <= 0 || H % h || W % w) return fail(-1, "depth_head: H,W must be multiples of the cost resolution");

@@ -19,6 +19,8 @@ int launch_from_cl(const void* src, int B, int C, int S, int H, int W, int Cp, b
 int launch_pool(const void* src, void* dst, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st);
 int launch_depth_head(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
                       float* depth, cudaStream_t st);
+int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4], const float* fd, const int64_t* st4, int B, int S,
+                       int H, int W, float* const depth[4], cudaStream_t st);
 int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
                     float* flow, cudaStream_t st);
 int launch_pack_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int CinP, int CoutP, int transposed,
@@ -77,7 +79,7 @@ struct Layer {
   int CinP, CoutP, ntaps;
   int CinT, Ntc;  // tensor-core path: stored input channels (multiple of 8) and MMA N (multiple of 16, >= 16)
   int64_t raw_w, raw_gamma, raw_beta, raw_mean, raw_var, raw_bias;  // element offsets in the raw buffer (-1: none)
-  size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab;                           // byte offsets in the packed buffer
+  size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab, pk_proj;                  // byte offsets in the packed buffer
 };
 struct Param {
   std::string name;
@@ -122,6 +124,8 @@ struct Net {
     packed_bytes += align_up((size_t)(l.ntaps + 1) * l.Ntc * l.CinT * 2, 256);
     l.pk_wslab = packed_bytes;
     packed_bytes += align_up((size_t)l.ntaps * l.Ntc * l.CinT * 2, 256);
+    l.pk_proj = packed_bytes;   // C -> 1 projections (classifiers): contiguous fp32 weights for the fused epilogue
+    if (cout == 1 && l.ntaps == 1) packed_bytes += align_up((size_t)l.CinT * sizeof(float), 256);
     index[name] = (int)layers.size();
     layers.push_back(l);
   }
@@ -253,6 +257,9 @@ struct EpiOpt {
   const Ten* aux_add = nullptr;   // second output = out + aux_add
   Ten* aux_out = nullptr;
   bool out_f32 = false;
+  const Layer* proj = nullptr;    // fused 1x1x1 classifier (tensor-core path): cost = proj(out or aux_out), fp32
+  Ten* proj_out = nullptr;
+  bool proj_aux = false, skip_out = false;
 };
 
 // Runs one conv layer (all phases) given packed weights.
@@ -269,7 +276,7 @@ static int num_sms_of_current_device() {
 // `wtc` != null selects the tcgen05 path (bf16 only); otherwise the FFMA kernel runs.
 static int run_conv(const Layer& l, const float* w, const float* scale, const float* shift, const Ten& in, const EpiOpt& e,
                     Ten& out, bool bf16, cudaStream_t st, const void* wtc = nullptr, const void* wslab = nullptr,
-                    int* nlaunch = nullptr, bool count_only = false, bool use_row = true) {
+                    int* nlaunch = nullptr, bool count_only = false, bool use_row = true, const char* packed_base = nullptr) {
   int dummy = 0;
   if (!nlaunch) nlaunch = &dummy;
   *nlaunch = 0;
@@ -293,6 +300,12 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
   a.aux_add = e.aux_add ? e.aux_add->p : nullptr;
   a.Cout = out.C;
   a.out_f32 = e.out_f32 ? 1 : 0;
+  if (e.proj && wtc && packed_base) {
+    a.proj_w = (const float*)(packed_base + e.proj->pk_proj);
+    a.proj_out = (float*)e.proj_out->p;
+    a.proj_src = e.proj_aux ? 1 : 0;
+    a.skip_out = e.skip_out ? 1 : 0;
+  }
   if (!l.transposed) {
     conv_taps(l, a.taps);
     a.isy = a.isx = l.stride; a.osy = a.osx = 1; a.ooy = a.oox = 0;
@@ -399,6 +412,12 @@ struct Runner {
       aux_last = aux;
       e.aux_out = &aux;
     }
+    Ten pj;
+    if (e.proj) {
+      pj = alloc(out.B, out.S, out.H, out.W, 1, true);
+      proj_last = pj;
+      e.proj_out = &pj;
+    }
     {
       // algorithmic work: every output voxel sees cin*cout*taps MACs for a conv; a transposed conv spends
       // cin*cout*27 MACs per INPUT voxel (= 27/4 per output voxel).  Bytes: in + out + residuals + weights, once.
@@ -408,20 +427,23 @@ struct Runner {
       if (e.res_pre) bytes += ovox * out.C * esize(false);
       if (e.res_post) bytes += ovox * out.C * esize(false);
       if (e.aux_add) bytes += 2 * ovox * out.C * esize(false);
-      op_begin(name, 2.0 * macs, bytes, l.transposed ? 4 : 1);
+      double flops = 2.0 * macs;
+      if (e.proj) { flops += 2.0 * ovox * e.proj->cin; bytes += ovox * 4; }
+      if (e.skip_out) bytes -= ovox * out.C * esize(out.f32);
+      op_begin(name, flops, bytes, l.transposed ? 4 : 1);
     }
     if (!rc) {
       // in a dry run only the launch count is planned (pointers are placeholders that are never dereferenced)
       const char* pk = dry ? reinterpret_cast<const char*>(0x1000) : packed;
       int nl = 0;
       rc = run_conv(l, (const float*)(pk + l.pk_w), (const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), in, e, out,
-                    bf16, st, use_tc ? pk + l.pk_wtc : nullptr, (use_tc && use_slab) ? pk + l.pk_wslab : nullptr, &nl, dry);
+                    bf16, st, use_tc ? pk + l.pk_wtc : nullptr, (use_tc && use_slab) ? pk + l.pk_wslab : nullptr, &nl, dry, true, pk);
       if (prof && !prof->ops.empty()) prof->ops.back().launches = nl;
     }
     op_end();
     return out;
   }
-  Ten aux_last;
+  Ten aux_last, proj_last;
   Ten pool(const Ten& in, int k, bool is_max) {
     Ten out = alloc(in.B, in.S, in.H / k, in.W / k, in.C);
     const double ivox = (double)in.B * in.S * in.H * in.W;
@@ -487,8 +509,9 @@ struct Runner {
     return conv(sp + "conv9.0", c8, e9);
   }
   // hourglass (reference :302-321).  Returns `out`; pre_1 through *pre1; out_in = skip + out through *out_in.
+  // `classif` (tensor-core path only): the 1x1x1 classifier applied to out_in is fused into conv6's epilogue; *cost gets it.
   Ten hourglass(const std::string& p, const Ten& x, const Ten& skip_feat, const Ten* presqu, const Ten* postsqu, Ten* pre1,
-                Ten* out_in, bool need_out) {
+                Ten* out_in, bool need_out, const char* classif = nullptr, Ten* cost = nullptr) {
     EpiOpt e0 = relu();
     e0.in1 = &skip_feat;
     *pre1 = conv(p + ".conv0.0.0", x, e0);
@@ -502,14 +525,20 @@ struct Runner {
     e5.res_pre = presqu ? presqu : &pre;
     o = conv(p + ".conv5.0", o, e5);
     EpiOpt e6;
+    const bool fuse = classif && use_tc;
+    if (fuse) e6.proj = &net.layers[net.index.at(classif)];
     if (need_out) {
       e6.aux_add = &x;
+      e6.proj_aux = true;
       Ten out = conv(p + ".conv6.0", o, e6);
       *out_in = aux_last;
+      if (fuse) *cost = proj_last;
       return out;
     }
-    e6.res_post = &x;  // last stage: only out2 + out is needed (reference :115)
+    e6.res_post = &x;  // last stage: only out2 + out is needed (reference :115) — and with the classifier fused, not even that
+    e6.skip_out = fuse;
     *out_in = conv(p + ".conv6.0", o, e6);
+    if (fuse) *cost = proj_last;
     return *out_in;
   }
 };
@@ -543,32 +572,37 @@ static int forward_impl(const void* packed, const float* FS, const float* fd, co
   Ten x = r.conv("dres0.2.0", r.conv("dres0.0.0", vol, Runner::relu()), Runner::relu());
   x = r.conv("deconv_1.0", x);
   Ten pre, out_in, pre2, pre3;
-  Ten out = r.hourglass("dres2", x, v3, nullptr, nullptr, &pre, &out_in, true);
-  Ten cost1 = r.conv("classif1.0", out_in, ec);
+  Ten cost1, cost2, cost3;
+  Ten out = r.hourglass("dres2", x, v3, nullptr, nullptr, &pre, &out_in, true, "classif1.0", &cost1);
+  if (!r.use_tc) cost1 = r.conv("classif1.0", out_in, ec);
   Ten o2 = r.conv("deconv_2.0", out_in);
   Ten out_in2;
-  Ten outb = r.hourglass("dres3", o2, v2, &pre, &out, &pre2, &out_in2, true);
-  Ten cost2 = r.conv("classif2.0", out_in2, ec);
+  Ten outb = r.hourglass("dres3", o2, v2, &pre, &out, &pre2, &out_in2, true, "classif2.0", &cost2);
+  if (!r.use_tc) cost2 = r.conv("classif2.0", out_in2, ec);
   Ten o3 = r.conv("deconv_3.0", out_in2);
   Ten out_in3;
-  r.hourglass("dres4", o3, v1, &pre2, &outb, &pre3, &out_in3, false);
-  Ten cost3 = r.conv("classif3.0", out_in3, ec);
+  r.hourglass("dres4", o3, v1, &pre2, &outb, &pre3, &out_in3, false, "classif3.0", &cost3);
+  if (!r.use_tc) cost3 = r.conv("classif3.0", out_in3, ec);
   if (need) *need = r.off;
   const Ten* costs[4] = {&cm, &cost1, &cost2, &cost3};
+  // the four depth heads in one launch (focus_dists is read once): 4 cost volumes + S*H*W focus distances in, 4 maps out
+  double hbytes = 4.0 * vox + 4.0 * 4.0 * B * H * W;
+  for (int i = 0; i < 4; ++i) hbytes += 4.0 * B * S * costs[i]->H * costs[i]->W;
   if (dry) {
-    for (int i = 0; i < 4; ++i)
-      r.op_begin("depth_head", 0, 4.0 * B * S * costs[i]->H * costs[i]->W + 4.0 * vox + 4.0 * B * H * W, 1);
+    r.op_begin("depth_heads", 0, hbytes, 1);
     return 0;
   }
   if (r.rc) return r.rc;
-  for (int i = 0; i < 4; ++i) {
-    r.op_begin("depth_head", 0, 4.0 * B * S * costs[i]->H * costs[i]->W + 4.0 * vox + 4.0 * B * H * W, 1);
-    DFF_TRY(launch_depth_head((const float*)costs[i]->p, costs[i]->H, costs[i]->W, fd, fds, B, S, H, W, out4[i], st));
-    r.op_end();
+  r.op_begin("depth_heads", 0, hbytes, 1);
+  const float* cp[4];
+  int ch[4], cw[4];
+  for (int i = 0; i < 4; ++i) { cp[i] = (const float*)costs[i]->p; ch[i] = costs[i]->H; cw[i] = costs[i]->W; }
+  DFF_TRY(launch_depth_head4(cp, ch, cw, fd, fds, B, S, H, W, out4, st));
+  r.op_end();
+  for (int i = 0; i < 4; ++i)
     if (cost4 && cost4[i])
       DFF_CUDA(cudaMemcpyAsync(cost4[i], costs[i]->p, (size_t)B * S * costs[i]->H * costs[i]->W * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
-  }
   return 0;
 }
 
@@ -632,6 +666,8 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
                                l.transposed ? 1 : 0, st));
     DFF_TRY(launch_pack_weight_tc(raw + l.raw_w, pk + l.pk_wtc, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
     DFF_TRY(launch_pack_weight_slab(raw + l.raw_w, pk + l.pk_wslab, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
+    if (l.cout == 1 && l.ntaps == 1)
+      DFF_TRY(launch_pack_weight(raw + l.raw_w, (float*)(pk + l.pk_proj), 1, l.cin, 1, l.CinT, 1, 0, st));
     const bool bn = l.raw_gamma >= 0;
     DFF_TRY(launch_bn_fold(bn ? raw + l.raw_gamma : nullptr, bn ? raw + l.raw_beta : nullptr, bn ? raw + l.raw_mean : nullptr,
                            bn ? raw + l.raw_var : nullptr, l.raw_bias >= 0 ? raw + l.raw_bias : nullptr,

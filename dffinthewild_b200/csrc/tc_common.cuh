@@ -135,6 +135,11 @@ struct EpiArgs {
   void* out_aux;
   const void* aux_add;
   int cstore, relu, out_f32, N;
+  // optional fused C -> 1 projection (the 1x1x1 classifiers, reference :53-57, 105, 111, 116): proj_out[pixel] = sum_c v[c] * proj_w[c]
+  // with v = the stored value (proj_src 0) or the second output out_aux (proj_src 1); skip_out: `out` itself is not needed
+  const float* proj_w;
+  float* proj_out;
+  int proj_src, skip_out;
 };
 
 // `tacc`: TMEM address of the accumulator (lane quadrant and buffer column included).  Warp-collective (tcgen05.ld).
@@ -145,6 +150,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiArgs& p, uint32_t tacc
   const __nv_bfloat16* rpost = reinterpret_cast<const __nv_bfloat16*>(p.res_post);
   __nv_bfloat16* oaux = reinterpret_cast<__nv_bfloat16*>(p.out_aux);
   const __nv_bfloat16* aadd = reinterpret_cast<const __nv_bfloat16*>(p.aux_add);
+  float pacc = 0.f;
   for (int c0 = 0; c0 < p.N; c0 += 16) {
     uint32_t v[16];
     tmem_ld16(tacc + c0, v);
@@ -192,14 +198,16 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiArgs& p, uint32_t tacc
           f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
         }
     }
+    if (!p.skip_out) {
 #pragma unroll
-    for (int j = 0; j < 16; j += 8)
-      if (j < nv) {
-        uint4 w;
-        w.x = pack2(f[j], f[j + 1]); w.y = pack2(f[j + 2], f[j + 3]);
-        w.z = pack2(f[j + 4], f[j + 5]); w.w = pack2(f[j + 6], f[j + 7]);
-        *reinterpret_cast<uint4*>(out + o + j) = w;
-      }
+      for (int j = 0; j < 16; j += 8)
+        if (j < nv) {
+          uint4 w;
+          w.x = pack2(f[j], f[j + 1]); w.y = pack2(f[j + 2], f[j + 3]);
+          w.z = pack2(f[j + 4], f[j + 5]); w.w = pack2(f[j + 6], f[j + 7]);
+          *reinterpret_cast<uint4*>(out + o + j) = w;
+        }
+    }
     if (oaux) {
 #pragma unroll
       for (int j = 0; j < 16; j += 8)
@@ -209,9 +217,25 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiArgs& p, uint32_t tacc
           w.x = pack2(f[j] + t0.x, f[j + 1] + t0.y); w.y = pack2(f[j + 2] + t0.z, f[j + 3] + t0.w);
           w.z = pack2(f[j + 4] + t1.x, f[j + 5] + t1.y); w.w = pack2(f[j + 6] + t1.z, f[j + 7] + t1.w);
           *reinterpret_cast<uint4*>(oaux + o + j) = w;
+          if (p.proj_w && p.proj_src) {   // the projection sees what the next layer will read: the bf16-rounded sums
+            f[j] += t0.x; f[j + 1] += t0.y; f[j + 2] += t0.z; f[j + 3] += t0.w;
+            f[j + 4] += t1.x; f[j + 5] += t1.y; f[j + 6] += t1.z; f[j + 7] += t1.w;
+          }
+        }
+    }
+    if (p.proj_w) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        if (j < nv) {
+          const float4 pw = __ldg(reinterpret_cast<const float4*>(p.proj_w + c0 + j));
+          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j])), pw.x, pacc);
+          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 1])), pw.y, pacc);
+          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 2])), pw.z, pacc);
+          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 3])), pw.w, pacc);
         }
     }
   }
+  if (p.proj_out && valid) p.proj_out[pix] = pacc;
 }
 
 }  // namespace dff
