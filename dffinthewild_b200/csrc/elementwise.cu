@@ -275,6 +275,108 @@ int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B,
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// SRD channel-attention branch in ONE pass (reference Feature_Extraction / SRD, train_codes/Depth_Estimation_Network.py:399-407):
+//   out = F + relu( W1 . relu( conv3x1x1(F; W0) ) )          (no BatchNorm, no bias)
+// Two tiny convolutions (3 taps along the focal dimension, then 1x1x1) with arithmetic intensity 4-12 FLOP/B: as two
+// implicit-GEMM launches they cost two full read+write passes over a full-resolution tensor.  Here a thread owns one pixel
+// and walks its S slices with a 3-slice window in registers: F is read once, out written once, the intermediate never
+// leaves registers (fp32).  Weights ([dz][ci][co] and [c][co] fp32, the FFMA pack) are shared-memory broadcasts.
+// ------------------------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void load_px(const __nv_bfloat16* p, float* v) {
+#pragma unroll
+  for (int j = 0; j < C; j += 8) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p + j));
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[j + 2 * k] = __uint_as_float(u[k] << 16);
+      v[j + 2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(128) srd_attention_kernel(const __nv_bfloat16* __restrict__ F, const float* __restrict__ w0,
+                                                            const float* __restrict__ w1, __nv_bfloat16* __restrict__ out, int B,
+                                                            int S, size_t plane /* H*W */) {
+  __shared__ __align__(16) float sw0[3 * C * C], sw1[C * C];
+  for (int i = threadIdx.x; i < 3 * C * C; i += 128) sw0[i] = __ldg(w0 + i);
+  for (int i = threadIdx.x; i < C * C; i += 128) sw1[i] = __ldg(w1 + i);
+  __syncthreads();
+  const size_t pix = blockIdx.x * (size_t)128 + threadIdx.x;
+  if (pix >= (size_t)B * plane) return;
+  const size_t b = pix / plane, r = pix % plane;
+  const __nv_bfloat16* src = F + (b * S * plane + r) * C;
+  __nv_bfloat16* dst = out + (b * S * plane + r) * C;
+  const size_t zs = plane * C;
+  float prev[C], cur[C], nxt[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) prev[j] = 0.f;
+  load_px<C>(src, cur);
+  for (int z = 0; z < S; ++z) {
+    if (z + 1 < S) load_px<C>(src + (size_t)(z + 1) * zs, nxt);
+    else {
+#pragma unroll
+      for (int j = 0; j < C; ++j) nxt[j] = 0.f;
+    }
+    float a[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) a[j] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+      for (int c4 = 0; c4 < C; c4 += 4) {
+        const float4 wa = *reinterpret_cast<const float4*>(sw0 + (0 * C + ci) * C + c4);
+        const float4 wb = *reinterpret_cast<const float4*>(sw0 + (1 * C + ci) * C + c4);
+        const float4 wc = *reinterpret_cast<const float4*>(sw0 + (2 * C + ci) * C + c4);
+        a[c4] = fmaf(prev[ci], wa.x, fmaf(cur[ci], wb.x, fmaf(nxt[ci], wc.x, a[c4])));
+        a[c4 + 1] = fmaf(prev[ci], wa.y, fmaf(cur[ci], wb.y, fmaf(nxt[ci], wc.y, a[c4 + 1])));
+        a[c4 + 2] = fmaf(prev[ci], wa.z, fmaf(cur[ci], wb.z, fmaf(nxt[ci], wc.z, a[c4 + 2])));
+        a[c4 + 3] = fmaf(prev[ci], wa.w, fmaf(cur[ci], wb.w, fmaf(nxt[ci], wc.w, a[c4 + 3])));
+      }
+    }
+    float o[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) o[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float av = fmaxf(a[c], 0.f);
+#pragma unroll
+      for (int c4 = 0; c4 < C; c4 += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(sw1 + c * C + c4);
+        o[c4] = fmaf(av, w.x, o[c4]); o[c4 + 1] = fmaf(av, w.y, o[c4 + 1]);
+        o[c4 + 2] = fmaf(av, w.z, o[c4 + 2]); o[c4 + 3] = fmaf(av, w.w, o[c4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < C; j += 8) {
+      uint4 w;
+      uint32_t* u = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(o[j + 2 * k], 0.f) + cur[j + 2 * k], fmaxf(o[j + 2 * k + 1], 0.f) + cur[j + 2 * k + 1]);
+        u[k] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)z * zs + j) = w;
+    }
+#pragma unroll
+    for (int j = 0; j < C; ++j) { prev[j] = cur[j]; cur[j] = nxt[j]; }
+  }
+}
+
+// F, out: (B,S,H,W,C) bf16 ; w0: [3][C][C] fp32 ([dz][ci][co]) ; w1: [C][C] fp32 ([c][co]).  C = 8 or 16.
+int launch_srd_attention(const void* F, const float* w0, const float* w1, void* out, int B, int S, int H, int W, int C, cudaStream_t st) {
+  const size_t plane = (size_t)H * W, npix = (size_t)B * plane;
+  const unsigned grid = (unsigned)((npix + 127) / 128);
+  if (C == 8) srd_attention_kernel<8><<<grid, 128, 0, st>>>((const __nv_bfloat16*)F, w0, w1, (__nv_bfloat16*)out, B, S, plane);
+  else if (C == 16) srd_attention_kernel<16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)F, w0, w1, (__nv_bfloat16*)out, B, S, plane);
+  else return fail(-5, "srd_attention: C must be 8 or 16");
+  DFF_LAUNCH_CHECK("srd_attention");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // weight packing: reference layouts -> [tap][CinP][CoutP] fp32 (zero padded), BatchNorm(eval) -> scale/shift
 // ------------------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin, int ntaps,

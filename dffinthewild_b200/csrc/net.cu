@@ -21,6 +21,7 @@ int launch_depth_head(const float* cost, int h, int w, const float* fd, const in
                       float* depth, cudaStream_t st);
 int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4], const float* fd, const int64_t* st4, int B, int S,
                        int H, int W, float* const depth[4], cudaStream_t st);
+int launch_srd_attention(const void* F, const float* w0, const float* w1, void* out, int B, int S, int H, int W, int C, cudaStream_t st);
 int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
                     float* flow, cudaStream_t st);
 int launch_pack_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int CinP, int CoutP, int transposed,
@@ -463,6 +464,18 @@ struct Runner {
     EpiOpt e = relu();
     e.res_pre = &x;
     Ten f = conv(p + ".Focus_Measure.conv.2.0", t, e);
+    const Layer& l0 = net.layers[net.index.at(p + ".N_ch_attention.0")];
+    const Layer& l1 = net.layers[net.index.at(p + ".N_ch_attention.2")];
+    if (use_tc && (f.C == 8 || f.C == 16) && l0.CinP == f.C && l0.CoutP == f.C) {
+      // both attention convolutions, both ReLUs and the residual in one bandwidth pass (the intermediate stays in registers)
+      Ten o = alloc(f.B, f.S, f.H, f.W, f.C);
+      const double vox = (double)f.B * f.S * f.H * f.W;
+      op_begin(p + ".N_ch_attention(fused)", 2.0 * vox * f.C * f.C * 4, 2.0 * vox * f.C * esize(false) + 4.0 * f.C * f.C * 4, 1);
+      if (!dry && !rc)
+        rc = launch_srd_attention(f.p, (const float*)(packed + l0.pk_w), (const float*)(packed + l1.pk_w), o.p, f.B, f.S, f.H, f.W, f.C, st);
+      op_end();
+      return o;
+    }
     Ten a = conv(p + ".N_ch_attention.0", f, relu());
     EpiOpt e2 = relu();
     e2.res_post = &f;
