@@ -151,40 +151,66 @@ struct Head4 {
   int h[4], w[4];
   float* depth[4];
 };
-__global__ void depth_head4_kernel(const __grid_constant__ Head4 a, const float* __restrict__ fd, long long sb, long long ss,
-                                   long long sy, long long sx, int B, int S, int H, int W) {
+// FAST (bf16 mode): exp/log through the SFU (relative error ~2e-7 on p = softplus + 1e-6, far inside that mode's tolerance).
+template <bool FAST>
+__device__ __forceinline__ float softplus_p(float v) {
+  if (FAST) return (v > 20.f ? v : __logf(1.f + __expf(v))) + 1e-6f;
+  return softplus_ref(v) + 1e-6f;
+}
+template <bool FAST>
+__global__ void __launch_bounds__(128) depth_head4_kernel(const __grid_constant__ Head4 a, const float* __restrict__ fd, long long sb,
+                                                          long long ss, long long sy, long long sx, int B, int S, int H, int W) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= W) return;
-  int y0[4], x0[4], y1[4], x1[4];
-  float ly1[4], lx1[4];
+  // heads 0-2 are bilinearly upsampled (align_corners=False); head 3 is at full resolution.  Per head: the four tap offsets
+  // inside a slice and the two interpolation weights.
+  int o00[3], o01[3], o10[3], o11[3];
+  float ly1[3], lx1[3];
+  size_t sl[3];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float ry = (float)a.h[k] / (float)H, rx = (float)a.w[k] / (float)W;
+  for (int k = 0; k < 3; ++k) {
+    const int h = a.h[k], w = a.w[k];
+    const float ry = (float)h / (float)H, rx = (float)w / (float)W;
     float fy = ry * ((float)y + 0.5f) - 0.5f, fx = rx * ((float)x + 0.5f) - 0.5f;
     fy = fy < 0.f ? 0.f : fy;
     fx = fx < 0.f ? 0.f : fx;
-    y0[k] = (int)fy; x0[k] = (int)fx;
-    y1[k] = y0[k] + (y0[k] < a.h[k] - 1 ? 1 : 0);
-    x1[k] = x0[k] + (x0[k] < a.w[k] - 1 ? 1 : 0);
-    ly1[k] = fy - (float)y0[k]; lx1[k] = fx - (float)x0[k];
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    ly1[k] = fy - (float)y0; lx1[k] = fx - (float)x0;
+    o00[k] = y0 * w + x0; o01[k] = y0 * w + x1; o10[k] = y1 * w + x0; o11[k] = y1 * w + x1;
+    sl[k] = (size_t)h * w;
   }
+  const size_t sl3 = (size_t)H * W;
+  const float* c0 = a.cost[0] + (size_t)b * S * sl[0];
+  const float* c1 = a.cost[1] + (size_t)b * S * sl[1];
+  const float* c2 = a.cost[2] + (size_t)b * S * sl[2];
+  const float* c3 = a.cost[3] + (size_t)b * S * sl3 + (size_t)y * W + x;
   float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
   const float* fp = fd + b * sb + y * sy + x * sx;
+#pragma unroll 2
   for (int s = 0; s < S; ++s) {
     const float f = __ldg(fp + s * ss);
+    float v[4];
+    {
+      const float* c = c0 + s * sl[0];
+      v[0] = (1.f - ly1[0]) * ((1.f - lx1[0]) * __ldg(c + o00[0]) + lx1[0] * __ldg(c + o01[0])) +
+             ly1[0] * ((1.f - lx1[0]) * __ldg(c + o10[0]) + lx1[0] * __ldg(c + o11[0]));
+    }
+    {
+      const float* c = c1 + s * sl[1];
+      v[1] = (1.f - ly1[1]) * ((1.f - lx1[1]) * __ldg(c + o00[1]) + lx1[1] * __ldg(c + o01[1])) +
+             ly1[1] * ((1.f - lx1[1]) * __ldg(c + o10[1]) + lx1[1] * __ldg(c + o11[1]));
+    }
+    {
+      const float* c = c2 + s * sl[2];
+      v[2] = (1.f - ly1[2]) * ((1.f - lx1[2]) * __ldg(c + o00[2]) + lx1[2] * __ldg(c + o01[2])) +
+             ly1[2] * ((1.f - lx1[2]) * __ldg(c + o10[2]) + lx1[2] * __ldg(c + o11[2]));
+    }
+    v[3] = __ldg(c3 + s * sl3);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int h = a.h[k], w = a.w[k];
-      const float* c = a.cost[k] + ((size_t)b * S + s) * h * w;
-      float v;
-      if (h == H && w == W) v = __ldg(c + (size_t)y * w + x);
-      else {
-        const float ly0 = 1.f - ly1[k], lx0 = 1.f - lx1[k];
-        v = ly0 * (lx0 * __ldg(c + (size_t)y0[k] * w + x0[k]) + lx1[k] * __ldg(c + (size_t)y0[k] * w + x1[k])) +
-            ly1[k] * (lx0 * __ldg(c + (size_t)y1[k] * w + x0[k]) + lx1[k] * __ldg(c + (size_t)y1[k] * w + x1[k]));
-      }
-      const float p = softplus_ref(v) + 1e-6f;
+      const float p = softplus_p<FAST>(v[k]);
       den[k] += p;
       num[k] = fmaf(f, p, num[k]);
     }
@@ -193,15 +219,18 @@ __global__ void depth_head4_kernel(const __grid_constant__ Head4 a, const float*
   for (int k = 0; k < 4; ++k) a.depth[k][((size_t)b * H + y) * W + x] = num[k] / den[k];
 }
 
+// cost[0..2]: upsampled heads (any resolution dividing H, W) ; cost[3]: the full-resolution head.  fast: SFU exp/log.
 int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4], const float* fd, const int64_t* st4, int B, int S,
-                       int H, int W, float* const depth[4], cudaStream_t st) {
+                       int H, int W, float* const depth[4], bool fast, cudaStream_t st) {
   Head4 a;
   for (int k = 0; k < 4; ++k) {
     if (h[k] <= 0 || w[k] <= 0 || H % h[k] || W % w[k]) return fail(-1, "depth_head: H,W must be multiples of the cost resolution");
     a.cost[k] = cost[k]; a.h[k] = h[k]; a.w[k] = w[k]; a.depth[k] = depth[k];
   }
   dim3 grid(cdiv(W, 128), H, B);
-  depth_head4_kernel<<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
+  if (h[3] != H || w[3] != W) return fail(-1, "depth_head4: the last head must be at full resolution");
+  if (fast) depth_head4_kernel<true><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
+  else depth_head4_kernel<false><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
   DFF_LAUNCH_CHECK("depth_head4");
   return 0;
 }

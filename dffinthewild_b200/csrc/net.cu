@@ -20,7 +20,7 @@ int launch_pool(const void* src, void* dst, int BS, int H, int W, int C, int k, 
 int launch_depth_head(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
                       float* depth, cudaStream_t st);
 int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4], const float* fd, const int64_t* st4, int B, int S,
-                       int H, int W, float* const depth[4], cudaStream_t st);
+                       int H, int W, float* const depth[4], bool fast, cudaStream_t st);
 int launch_srd_attention(const void* F, const float* w0, const float* w1, void* out, int B, int S, int H, int W, int C, cudaStream_t st);
 int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
                     float* flow, cudaStream_t st);
@@ -466,7 +466,7 @@ struct Runner {
     Ten f = conv(p + ".Focus_Measure.conv.2.0", t, e);
     const Layer& l0 = net.layers[net.index.at(p + ".N_ch_attention.0")];
     const Layer& l1 = net.layers[net.index.at(p + ".N_ch_attention.2")];
-    if (use_tc && (f.C == 8 || f.C == 16) && l0.CinP == f.C && l0.CoutP == f.C) {
+    if (use_tc && f.C == 8 && l0.CinP == f.C && l0.CoutP == f.C) {   // (C = 16 needs 111 registers per pixel-thread: slower than the two MMAs)
       // both attention convolutions, both ReLUs and the residual in one bandwidth pass (the intermediate stays in registers)
       Ten o = alloc(f.B, f.S, f.H, f.W, f.C);
       const double vox = (double)f.B * f.S * f.H * f.W;
@@ -610,7 +610,7 @@ static int forward_impl(const void* packed, const float* FS, const float* fd, co
   const float* cp[4];
   int ch[4], cw[4];
   for (int i = 0; i < 4; ++i) { cp[i] = (const float*)costs[i]->p; ch[i] = costs[i]->H; cw[i] = costs[i]->W; }
-  DFF_TRY(launch_depth_head4(cp, ch, cw, fd, fds, B, S, H, W, out4, st));
+  DFF_TRY(launch_depth_head4(cp, ch, cw, fd, fds, B, S, H, W, out4, r.bf16, st));
   r.op_end();
   for (int i = 0; i < 4; ++i)
     if (cost4 && cost4[i])
