@@ -406,6 +406,138 @@ int launch_srd_attention(const void* F, const float* w0, const float* w1, void* 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// End-to-End alignment network (reference End_to_End/End_to_End.py:63-134) on channels-last feature volumes
+// ------------------------------------------------------------------------------------------------------------
+// Sampling geometry of FOV_warp for output pixel (px, py) of slice s: flow (in pixels) and the bilinear taps.
+struct WarpGeom {
+  float flx, fly, w00, w01, w10, w11;
+  int x0, y0;
+  bool vx0, vx1, vy0, vy1;
+};
+__device__ __forceinline__ WarpGeom warp_geom(const float* alpha, const float* fov, int b, int s, int S, int H, int W, int px, int py) {
+  WarpGeom g;
+  const float a0 = alpha ? __ldg(alpha + (0 * 3 + 0) * S + s) : 0.f;  // sample 0 on purpose (reference broadcast quirk)
+  const float a1 = alpha ? __ldg(alpha + ((size_t)b * 3 + 1) * S + s) : 0.f;
+  const float a2 = alpha ? __ldg(alpha + ((size_t)b * 3 + 2) * S + s) : 0.f;
+  const float f = a0 + __ldg(fov + (size_t)b * S + s);
+  auto lin = [](int i, int n) -> float {
+    if (n == 1) return -1.f;
+    const float step = 2.f / (float)(n - 1);
+    return i < n / 2 ? -1.f + step * (float)i : 1.f - step * (float)(n - 1 - i);
+  };
+  g.flx = (float)(W / 2) * (f - 1.f) * lin(px, W) + a1;
+  g.fly = (float)(H / 2) * (f - 1.f) * lin(py, H) + a2;
+  const float gx = 2.0f * ((float)px - g.flx) / (float)max(W - 1, 1) - 1.0f;
+  const float gy = 2.0f * ((float)py - g.fly) / (float)max(H - 1, 1) - 1.0f;
+  const float ix = (gx + 1.f) * 0.5f * (float)(W - 1);
+  const float iy = (gy + 1.f) * 0.5f * (float)(H - 1);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  g.x0 = (int)fx0; g.y0 = (int)fy0;
+  const float tx = ix - fx0, ty = iy - fy0;
+  g.w00 = (1.f - tx) * (1.f - ty); g.w01 = tx * (1.f - ty); g.w10 = (1.f - tx) * ty; g.w11 = tx * ty;
+  g.vx0 = g.x0 >= 0 && g.x0 < W; g.vx1 = g.x0 + 1 >= 0 && g.x0 + 1 < W;
+  g.vy0 = g.y0 >= 0 && g.y0 < H; g.vy1 = g.y0 + 1 >= 0 && g.y0 + 1 < H;
+  return g;
+}
+
+// FOV_warp of a channels-last volume x (B,S,H,W,C) -> out (same layout); C % 4 == 0
+template <typename T>
+__global__ void fov_warp_cl_kernel(const T* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ fov, int B, int C,
+                                   int S, int H, int W, T* __restrict__ out) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+  const int bs = blockIdx.z, b = bs / S, s = bs % S;
+  if (px >= W) return;
+  const WarpGeom g = warp_geom(alpha, fov, b, s, S, H, W, px, py);
+  const T* base = x + (size_t)bs * H * W * C;
+  T* o = out + (((size_t)bs * H + py) * W + px) * C;
+  for (int c = 0; c < C; c += 4) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto tap = [&](int yy, int xx, float w) {
+      const float4 t = Elem<T>::load4(base + ((size_t)yy * W + xx) * C + c);
+      v.x = fmaf(t.x, w, v.x); v.y = fmaf(t.y, w, v.y); v.z = fmaf(t.z, w, v.z); v.w = fmaf(t.w, w, v.w);
+    };
+    if (g.vy0 && g.vx0) tap(g.y0, g.x0, g.w00);
+    if (g.vy0 && g.vx1) tap(g.y0, g.x0 + 1, g.w01);
+    if (g.vy1 && g.vx0) tap(g.y0 + 1, g.x0, g.w10);
+    if (g.vy1 && g.vx1) tap(g.y0 + 1, g.x0 + 1, g.w11);
+    Elem<T>::store4(o + c, v);
+  }
+}
+
+// The alignment head's input (reference :71-76, 81-86, 92-97):  out (B,S,H,W,2C+8) = [ feat[b, S-1] | feat[b, s] | flow_x, flow_y, 0 x 6 ]
+template <typename T>
+__global__ void pair_volume_kernel(const T* __restrict__ feat, const float* __restrict__ alpha, const float* __restrict__ fov, int B,
+                                   int C, int S, int H, int W, T* __restrict__ out) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+  const int bs = blockIdx.z, b = bs / S, s = bs % S;
+  if (px >= W) return;
+  const WarpGeom g = warp_geom(alpha, fov, b, s, S, H, W, px, py);
+  const size_t pin = ((size_t)py * W + px) * C;
+  const T* cur = feat + (size_t)bs * H * W * C + pin;
+  const T* last = feat + ((size_t)b * S + (S - 1)) * H * W * C + pin;
+  T* o = out + (((size_t)bs * H + py) * W + px) * (2 * C + 8);
+  for (int c = 0; c < C; c += 4) {
+    Elem<T>::store4(o + c, Elem<T>::load4(last + c));
+    Elem<T>::store4(o + C + c, Elem<T>::load4(cur + c));
+  }
+  Elem<T>::store4(o + 2 * C, make_float4(g.flx, g.fly, 0.f, 0.f));
+  Elem<T>::store4(o + 2 * C + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+// alpha_out[b][c][s] = (alpha_in ? alpha_in[b][c][s] : 0) + scale[c] * mean over (y, x) of x[b,s,y,x,c]     (c < 3; x fp32, Cs stored)
+// = AdaptiveAvgPool3d((S,1,1)) of the head's last conv + the 0.001 factor on the scale term + the running sum (reference :78-79, 88-90)
+__global__ void spatial_mean_accum_kernel(const float* __restrict__ x, int Cs, int S, int H, int W, const float* __restrict__ alpha_in,
+                                          float s0, float s1, float s2, float* __restrict__ alpha_out) {
+  const int bs = blockIdx.x, b = bs / S, s = bs % S;
+  const size_t n = (size_t)H * W;
+  const float* p = x + (size_t)bs * n * Cs;
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    a0 += p[i * Cs]; a1 += p[i * Cs + 1]; a2 += p[i * Cs + 2];
+  }
+  __shared__ double sh[3][256];
+  sh[0][threadIdx.x] = a0; sh[1][threadIdx.x] = a1; sh[2][threadIdx.x] = a2;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if ((int)threadIdx.x < k)
+      for (int c = 0; c < 3; ++c) sh[c][threadIdx.x] += sh[c][threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) {
+    const int c = threadIdx.x;
+    const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const size_t o = ((size_t)b * 3 + c) * S + s;
+    alpha_out[o] = (alpha_in ? alpha_in[o] : 0.f) + sc * (float)(sh[c][0] / (double)n);
+  }
+}
+
+int launch_fov_warp_cl(const void* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
+                       cudaStream_t st) {
+  if (C % 4) return fail(-1, "fov_warp_cl: C must be a multiple of 4");
+  dim3 grid(cdiv(W, 128), H, B * S);
+  if (bf16) fov_warp_cl_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)x, alpha, fov, B, C, S, H, W, (__nv_bfloat16*)out);
+  else fov_warp_cl_kernel<<<grid, 128, 0, st>>>((const float*)x, alpha, fov, B, C, S, H, W, (float*)out);
+  DFF_LAUNCH_CHECK("fov_warp_cl");
+  return 0;
+}
+int launch_pair_volume(const void* feat, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
+                       cudaStream_t st) {
+  if (C % 4) return fail(-1, "pair_volume: C must be a multiple of 4");
+  dim3 grid(cdiv(W, 128), H, B * S);
+  if (bf16) pair_volume_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)feat, alpha, fov, B, C, S, H, W, (__nv_bfloat16*)out);
+  else pair_volume_kernel<<<grid, 128, 0, st>>>((const float*)feat, alpha, fov, B, C, S, H, W, (float*)out);
+  DFF_LAUNCH_CHECK("pair_volume");
+  return 0;
+}
+int launch_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, const float* alpha_in, float s0, float s1, float s2,
+                              float* alpha_out, cudaStream_t st) {
+  if (Cs < 3) return fail(-1, "spatial_mean_accum: needs at least 3 stored channels");
+  spatial_mean_accum_kernel<<<B * S, 256, 0, st>>>(x, Cs, S, H, W, alpha_in, s0, s1, s2, alpha_out);
+  DFF_LAUNCH_CHECK("spatial_mean_accum");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // weight packing: reference layouts -> [tap][CinP][CoutP] fp32 (zero padded), BatchNorm(eval) -> scale/shift
 // ------------------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin, int ntaps,

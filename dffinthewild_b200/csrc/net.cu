@@ -22,6 +22,12 @@ int launch_depth_head(const float* cost, int h, int w, const float* fd, const in
 int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4], const float* fd, const int64_t* st4, int B, int S,
                        int H, int W, float* const depth[4], bool fast, cudaStream_t st);
 int launch_srd_attention(const void* F, const float* w0, const float* w1, void* out, int B, int S, int H, int W, int C, cudaStream_t st);
+int launch_fov_warp_cl(const void* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
+                       cudaStream_t st);
+int launch_pair_volume(const void* feat, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
+                       cudaStream_t st);
+int launch_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, const float* alpha_in, float s0, float s1, float s2,
+                              float* alpha_out, cudaStream_t st);
 int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
                     float* flow, cudaStream_t st);
 int launch_pack_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int CinP, int CoutP, int transposed,
@@ -1069,6 +1075,30 @@ int dff_depth_head_backward(const float* cost, int h, int w, const float* fd, co
   DeviceGuard g(device);
   if (g.rc) return g.rc;
   return launch_depth_head_bwd(cost, h, w, fd, fd_strides, B, S, H, W, ddepth, dcost, (cudaStream_t)stream);
+}
+
+
+// ---- End-to-End alignment network building blocks (channels-last) ----------------------------------------------------------
+int dff_fov_warp_cl(const void* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, int elem,
+                    int device, void* stream) {
+  if (!x || !fov || !out) return fail(DFF_E_ARG, "dff_fov_warp_cl: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_fov_warp_cl(x, alpha, fov, B, C, S, H, W, out, elem == DFF_BF16, (cudaStream_t)stream);
+}
+int dff_pair_volume(const void* feat, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, int elem,
+                    int device, void* stream) {
+  if (!feat || !fov || !out) return fail(DFF_E_ARG, "dff_pair_volume: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_pair_volume(feat, alpha, fov, B, C, S, H, W, out, elem == DFF_BF16, (cudaStream_t)stream);
+}
+int dff_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, const float* alpha_in, float s0, float s1, float s2,
+                           float* alpha_out, int device, void* stream) {
+  if (!x || !alpha_out) return fail(DFF_E_ARG, "dff_spatial_mean_accum: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_spatial_mean_accum(x, Cs, B, S, H, W, alpha_in, s0, s1, s2, alpha_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

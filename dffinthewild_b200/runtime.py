@@ -48,6 +48,9 @@ def _declare(lib):
         "dff_conv3d": (i, [vp, i, vp, i, i, i, i, i, fp, i, i, i, i, i, i, i, fp, fp, vp, vp, i, vp, i, i, vp, i, vp]),
         "dff_depth_head": (i, [fp, i, i, fp, c.POINTER(i64), i, i, i, i, fp, i, vp]),
         "dff_fov_warp": (i, [fp, fp, fp, i, i, i, i, i, fp, fp, i, vp]),
+        "dff_fov_warp_cl": (i, [vp, fp, fp, i, i, i, i, i, vp, i, i, vp]),
+        "dff_pair_volume": (i, [vp, fp, fp, i, i, i, i, i, vp, i, i, vp]),
+        "dff_spatial_mean_accum": (i, [fp, i, i, i, i, i, fp, c.c_float, c.c_float, c.c_float, fp, i, vp]),
         "dff_to_channels_last": (i, [fp, i, i, i, i, i, vp, i, i, i, vp]),
         "dff_from_channels_last": (i, [vp, i, i, i, i, i, i, i, fp, i, vp]),
     }

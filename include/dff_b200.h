@@ -178,6 +178,21 @@ int dff_pool3d_backward(const void *x, const void *dy, int BS, int H, int W, int
 int dff_depth_head_backward(const float *cost, int h, int w, const float *fd, const int64_t fd_strides[4], int B, int S, int H,
                             int W, const float *ddepth, float *dcost, int device, void *stream);
 
+/* ---- End-to-End alignment network (FlowNetwork.forward, End_to_End/End_to_End.py:63-104) --------------------------------------
+ * dffinthewild_b200/End_to_End.py composes it from dff_conv3d (the six resnet_block_2d_OF blocks and the three alignment heads,
+ * all 1x3x3 / 1x1x1 convolutions on channels-last volumes) and the three calls below. */
+/* FOV_warp (End_to_End.py:106-134) of a channels-last volume (B,S,H,W,C), C % 4 == 0; alpha (B,3,S) or NULL, fov (B,S) */
+int dff_fov_warp_cl(const void *x, const float *alpha, const float *fov, int B, int C, int S, int H, int W, void *out, int elem,
+                    int device, void *stream);
+/* input of an alignment head (End_to_End.py:71-76): out (B,S,H,W,2C+8) = [ feat[b,S-1] | feat[b,s] | flow_x, flow_y, 0 x 6 ] with the
+ * flow field of the current (alpha, fov) computed analytically */
+int dff_pair_volume(const void *feat, const float *alpha, const float *fov, int B, int C, int S, int H, int W, void *out, int elem,
+                    int device, void *stream);
+/* AdaptiveAvgPool3d((S,1,1)) of the head output x (B,S,H,W,Cs) fp32 + scaling + running sum (End_to_End.py:78-79, 88-90):
+ * alpha_out[b][c][s] = alpha_in[b][c][s] + s_c * mean_{y,x} x[b,s,y,x,c], c < 3 (alpha_in may be NULL) */
+int dff_spatial_mean_accum(const float *x, int Cs, int B, int S, int H, int W, const float *alpha_in, float s0, float s1, float s2,
+                           float *alpha_out, int device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
