@@ -70,6 +70,27 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc)
       : "memory");
 }
+// Predicated forms: the whole issuing warp runs the (warp-uniform) schedule, only the elected lane's instruction takes effect —
+// no divergent region, so the compiler keeps every descriptor and counter in uniform registers.
+__device__ __forceinline__ void umma_ts_if(uint32_t pred, uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.u32 q, 0, 0;\n"
+      "@p tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(pred)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t pred, uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %1, 0;\n"
+      "@p tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar), "r"(pred)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -221,59 +242,64 @@ __global__ void __launch_bounds__(kRowThreads, 2) conv_row_kernel(const __grid_c
     // Single instruction stream, latency-bound: per input row one table entry (parameter bank, uniform load) says which
     // accumulator columns / weight rows / N' the merged-dy MMA uses and which accumulators start; per slice the three (dz)
     // planes rotate.
-    const bool leader = elect_one();
+    const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t blk2 = 6u * (uint32_t)p.N;      // (dz, a) weight tile = two K halves of 3N rows, in 16-byte descriptor units
     const uint64_t bd_base = ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | (uint64_t)((w_s >> 4) | ((3u * p.N) << 16));
-    const int planeN = p.TH * p.N;
+    const uint32_t planeN = (uint32_t)(p.TH * p.N), acc0 = tmem_base + p.acc_col0;
+    const uint32_t dzw = (uint32_t)p.NA * blk2;    // weight stride between dz groups
     int as = 0, nrow = 0;
     uint32_t aphase = 0, te_bits = 0u;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const int band = (item % bands_x) / p.tilesX;
       const int cls = (band == 0 ? 1 : 0) | (band == p.bandsY - 1 ? 2 : 0);
       const int nrows = p.TH + 2 - (cls & 1) - (cls >> 1);
-      int zm3 = 0;
+      int zm3 = 0;   // plane of output slice s = z
       for (int z = 0; z < p.S; ++z) {
-        // planes of the output slices s = z+1, z, z-1 (dzi = 0, 1, 2); KD == 1: only s = z
-        int pl[3];
-        bool ok[3], fst[3];
-#pragma unroll
-        for (int dzi = 0; dzi < 3; ++dzi) {
-          const int dz = hz ? dzi - 1 : 0, s = z - dz;
-          int q = zm3 - dz;
-          q = q < 0 ? q + 3 : (q > 2 ? q - 3 : q);
-          pl[dzi] = q;
-          ok[dzi] = dzi < p.KD && s >= 0 && s < p.S;
-          fst[dzi] = !hz || z == max(s - 1, 0);
-        }
+        // output slices touched by input slice z: s = z+1 (dzi 0), z (dzi 1), z-1 (dzi 2); KD == 1: s = z only (as dzi 0)
+        const int p_up = zm3 == 2 ? 0 : zm3 + 1, p_dn = zm3 == 0 ? 2 : zm3 - 1;
+        const int pl0 = hz ? p_up : zm3, pl1 = zm3, pl2 = p_dn;
+        const bool ok0 = hz ? (z + 1 < p.S) : true, ok1 = hz != 0, ok2 = hz && z > 0;
+        const bool fst0 = true, fst1 = z == 0;   // s = z+1 always starts at z; s = z starts here only for z == 0 (dzi 2 never starts)
         for (int ri = 0; ri < nrows; ++ri) {
+          const uint4 e = p.tab[cls][ri];
           mbar_wait(afull0 + 8 * as, aphase);
-          fence_after();
           DFF_RT(4, nrow);
-          if (leader) {
-            const uint4 e = p.tab[cls][ri];
-            const uint32_t a_t = tmem_base + as * (p.NA * 8);
-#pragma unroll
-            for (int dzi = 0; dzi < 3; ++dzi) {
-              if (!ok[dzi]) continue;
-              if (fst[dzi]) {   // accumulators that start with this row must have been drained (and re-zeroed)
-                for (uint32_t w = e.w & 0xfffu; w; w >>= 4) {
-                  const int sl = pl[dzi] * p.TH + (int)(w & 0xfu) - 1;
-                  mbar_wait(tempty0 + 8 * sl, (te_bits >> sl) & 1u);
-                  te_bits ^= 1u << sl;
-                }
-                fence_after();
+          // accumulators that start with this row must have been drained (and re-zeroed) by the epilogue
+          if (e.w & 0xfffu) {
+            if (ok0 && fst0)
+              for (uint32_t w = e.w & 0xfffu; w; w >>= 4) {
+                const int sl = pl0 * p.TH + (int)(w & 0xfu) - 1;
+                mbar_wait(tempty0 + 8 * sl, (te_bits >> sl) & 1u);
+                te_bits ^= 1u << sl;
               }
-              const uint32_t dacc = tmem_base + p.acc_col0 + pl[dzi] * planeN + e.y;
-              uint64_t bd = bd_base + (uint64_t)((uint32_t)(dzi * p.NA) * blk2 + e.z);
-              if (!(p.exp & 4))
-              for (int a = 0; a < p.NA; ++a) {
-                umma_ts(dacc, a_t + a * 8, bd, e.x);
-                bd += blk2;
+            if (ok1 && fst1)
+              for (uint32_t w = e.w & 0xfffu; w; w >>= 4) {
+                const int sl = pl1 * p.TH + (int)(w & 0xfu) - 1;
+                mbar_wait(tempty0 + 8 * sl, (te_bits >> sl) & 1u);
+                te_bits ^= 1u << sl;
               }
-            }
-            umma_commit(rdone0 + 8 * (nrow & (kRowDone - 1)));   // frees the A slot AND publishes the outputs this row completed
           }
-          __syncwarp();
+          fence_after();
+          const uint32_t a_t = tmem_base + as * (p.NA * 8);
+          const uint64_t bd0 = bd_base + (uint64_t)e.z;
+          if (!(p.exp & 4)) {
+            if (ok0) {
+              const uint32_t dacc = acc0 + pl0 * planeN + e.y;
+              uint64_t bd = bd0;
+              for (int a = 0; a < p.NA; ++a, bd += blk2) umma_ts_if(leader, dacc, a_t + a * 8, bd, e.x);
+            }
+            if (ok1) {
+              const uint32_t dacc = acc0 + pl1 * planeN + e.y;
+              uint64_t bd = bd0 + dzw;
+              for (int a = 0; a < p.NA; ++a, bd += blk2) umma_ts_if(leader, dacc, a_t + a * 8, bd, e.x);
+            }
+            if (ok2) {
+              const uint32_t dacc = acc0 + pl2 * planeN + e.y;
+              uint64_t bd = bd0 + 2 * dzw;
+              for (int a = 0; a < p.NA; ++a, bd += blk2) umma_ts_if(leader, dacc, a_t + a * 8, bd, e.x);
+            }
+          }
+          umma_commit_if(leader, rdone0 + 8 * (nrow & (kRowDone - 1)));   // frees the A slot AND publishes the outputs this row completed
           DFF_RT(5, nrow);
           ++nrow;
           if (++as == p.RA) { as = 0; aphase ^= 1; }
