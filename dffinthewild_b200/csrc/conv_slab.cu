@@ -33,7 +33,7 @@ constexpr int kSlabThreads = kSlabProducers + 32 + 128;  // + warps 3-6: epilogu
 constexpr int kSlabMaxOps = 128;
 constexpr int kSlabMaxPlanes = 8;
 constexpr int kSlabTW = 8, kSlabTH = 16;
-constexpr int kSlabSmemBudget = 220 * 1024;   // per SM, shared by the co-resident CTAs
+constexpr int kSlabSmemBudget = 228 * 1024;   // per SM; every co-resident CTA also costs ~1 KB static + 1 KB reserved
 
 // DFF_SLAB_TRACE (compile-time, debugging only): CTA 0 records clock64 timestamps of its pipeline events per slice
 #ifdef DFF_SLAB_TRACE
@@ -454,7 +454,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   int occ = 4, NP = 0;
   for (; occ >= 1; --occ) {
     if (occ * p.tmem_cols > 512) continue;
-    const int budget = kSlabSmemBudget / occ - 1024;  // static shared memory + allocation granularity
+    const int budget = kSlabSmemBudget / occ - 2048 - 256;  // static shared memory, the per-CTA reservation, allocation granularity
     NP = (budget - fixed) / p.plane_bytes;
     if (NP >= np_min) break;
   }
