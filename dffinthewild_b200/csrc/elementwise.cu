@@ -37,6 +37,45 @@ __global__ void from_cl_kernel(const T* __restrict__ src, float* __restrict__ ds
   }
 }
 
+// First-layer input of the tensor-core path: (B,S,H,W+2,8) bf16, column c = [R,G,B of pixel c-2 | R,G,B of pixel c | 0 0] (zeros
+// outside the image).  The network's first convolution is 1x9x9 with dilation 2 on 3 channels (reference :144); with a pixel's
+// dilated right neighbour already in its channel vector, two horizontal taps are ONE 8-channel tap: 9 x 5 taps instead of 9 x 9 —
+// the K dimension of the implicit GEMM shrinks from 81 x 8 to 45 x 8 stored channels for the same 16 bytes per pixel.  The two
+// margin columns make the pairs whose left pixel is outside the image (but whose right pixel is inside) addressable.
+__global__ void to_cl_pair_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int S, int H, int W) {
+  const int Wp = W + 2;
+  const size_t npix = (size_t)B * S * H * Wp;
+  const size_t plane = (size_t)S * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Wp);
+    const size_t row = i / Wp;                 // (b*S + s)*H + y
+    const size_t b = row / ((size_t)S * H), sy = row % ((size_t)S * H);
+    const float* s = src + b * 3 * plane + sy * W;
+    const bool lo = c >= 2, hi = c < W;
+    float4 v0, v1;
+    v0.x = lo ? __ldg(s + c - 2) : 0.f; v0.y = lo ? __ldg(s + plane + c - 2) : 0.f; v0.z = lo ? __ldg(s + 2 * plane + c - 2) : 0.f;
+    v0.w = hi ? __ldg(s + c) : 0.f;
+    v1.x = hi ? __ldg(s + plane + c) : 0.f;
+    v1.y = hi ? __ldg(s + 2 * plane + c) : 0.f;
+    v1.z = 0.f; v1.w = 0.f;
+    Elem<__nv_bfloat16>::store4(dst + i * 8, v0);
+    Elem<__nv_bfloat16>::store4(dst + i * 8 + 4, v1);
+  }
+}
+
+// W' (Cout, 8, 1, 9, 5) fp32 for the paired input: W'[co][ci][ky][j] = W[co][ci][ky][2j] (ci < 3), W[co][ci-3][ky][2j+1] (3 <= ci < 6,
+// 2j+1 < 9), 0 otherwise.  W: (Cout, 3, 1, 9, 9).
+__global__ void pair_weight_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout) {
+  const int n = Cout * 8 * 9 * 5;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int j = i % 5, ky = (i / 5) % 9, ci = (i / 45) % 8, co = i / 360;
+    float v = 0.f;
+    if (ci < 3) v = w[((co * 3 + ci) * 9 + ky) * 9 + 2 * j];
+    else if (ci < 6 && 2 * j + 1 < 9) v = w[((co * 3 + ci - 3) * 9 + ky) * 9 + 2 * j + 1];
+    dst[i] = v;
+  }
+}
+
 static inline int grid_for(size_t n, int threads, int cap = 148 * 16) {
   size_t g = (n + threads - 1) / threads;
   return (int)(g < (size_t)cap ? (g ? g : 1) : cap);
@@ -48,6 +87,17 @@ int launch_to_cl(const float* src, int B, int C, int S, int H, int W, void* dst,
   if (bf16) to_cl_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, B, C, S, H, W, Cp);
   else to_cl_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (float*)dst, B, C, S, H, W, Cp);
   DFF_LAUNCH_CHECK("to_cl");
+  return 0;
+}
+int launch_to_cl_pair(const float* src, int B, int S, int H, int W, void* dst, cudaStream_t st) {
+  const size_t n = (size_t)B * S * H * (W + 2);
+  to_cl_pair_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, B, S, H, W);
+  DFF_LAUNCH_CHECK("to_cl_pair");
+  return 0;
+}
+int launch_pair_weight(const float* w, float* dst, int Cout, cudaStream_t st) {
+  pair_weight_kernel<<<cdiv(Cout * 360, 256), 256, 0, st>>>(w, dst, Cout);
+  DFF_LAUNCH_CHECK("pair_weight");
   return 0;
 }
 int launch_from_cl(const void* src, int B, int C, int S, int H, int W, int Cp, bool bf16, float* dst, cudaStream_t st) {

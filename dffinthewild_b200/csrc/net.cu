@@ -15,6 +15,8 @@ namespace dff {
 // ---- launchers implemented in the other translation units --------------------------------------------------
 int launch_conv_ffma(ConvArgs a, bool bf16, cudaStream_t st);
 int launch_to_cl(const float* src, int B, int C, int S, int H, int W, void* dst, int Cp, bool bf16, cudaStream_t st);
+int launch_to_cl_pair(const float* src, int B, int S, int H, int W, void* dst, cudaStream_t st);
+int launch_pair_weight(const float* w, float* dst, int Cout, cudaStream_t st);
 int launch_from_cl(const void* src, int B, int C, int S, int H, int W, int Cp, bool bf16, float* dst, cudaStream_t st);
 int launch_pool(const void* src, void* dst, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st);
 int launch_depth_head(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
@@ -82,11 +84,12 @@ struct Layer {
   std::string bn;    // state_dict prefix of its BatchNorm3d ("" = none)
   int cin, cout, kd, kh, kw, stride, dil;
   bool transposed, bias;
+  bool pair_x = false;   // tensor-core path of the first layer: input pixels carry their dilated right neighbour (9 x 5 paired taps)
   // derived
   int CinP, CoutP, ntaps;
   int CinT, Ntc;  // tensor-core path: stored input channels (multiple of 8) and MMA N (multiple of 16, >= 16)
   int64_t raw_w, raw_gamma, raw_beta, raw_mean, raw_var, raw_bias;  // element offsets in the raw buffer (-1: none)
-  size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab, pk_proj;                  // byte offsets in the packed buffer
+  size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab, pk_proj, pk_pair;                  // byte offsets in the packed buffer
 };
 struct Param {
   std::string name;
@@ -131,6 +134,8 @@ struct Net {
     packed_bytes += align_up((size_t)(l.ntaps + 1) * l.Ntc * l.CinT * 2, 256);
     l.pk_wslab = packed_bytes;
     packed_bytes += align_up((size_t)l.ntaps * l.Ntc * l.CinT * 2, 256);
+    l.pk_pair = packed_bytes;   // paired-tap fp32 weights (Cout, 8, 1, 9, 5) of the first layer
+    if (cin == 3 && kh == 9 && kw == 9 && dil == 2 && kd == 1) { l.pair_x = true; packed_bytes += align_up((size_t)cout * 360 * sizeof(float), 256); }
     l.pk_proj = packed_bytes;   // C -> 1 projections (classifiers): contiguous fp32 weights for the fused epilogue
     if (cout == 1 && l.ntaps == 1) packed_bytes += align_up((size_t)l.CinT * sizeof(float), 256);
     index[name] = (int)layers.size();
@@ -314,6 +319,17 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     a.skip_out = e.skip_out ? 1 : 0;
   }
   if (!l.transposed) {
+    if (l.pair_x && wtc) {   // 9 (dy, dilation 2) x 5 (paired dx, step 4) taps on the pair-packed input
+      a.taps.n = 0;
+      for (int b = 0; b < 9; ++b)
+        for (int c = 0; c < 5; ++c) {
+          a.taps.dz[a.taps.n] = 0;
+          a.taps.dy[a.taps.n] = (int8_t)(2 * b - 8);
+          a.taps.dx[a.taps.n] = (int8_t)(4 * c - 8 + 2);   // +2: the pair-packed input has two margin columns on the left
+          a.taps.widx[a.taps.n] = (uint8_t)(b * 5 + c);
+          ++a.taps.n;
+        }
+    } else
     conv_taps(l, a.taps);
     a.isy = a.isx = l.stride; a.osy = a.osx = 1; a.ooy = a.oox = 0;
     a.OHt = out.H; a.OWt = out.W;
@@ -322,7 +338,7 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     if (wtc) {
       if (wslab && use_row && conv_row_supported(a, l.Ntc)) return launch_conv_row(a, wslab, l.Ntc, nsm, st);
       if (wslab && conv_slab_supported(a, nullptr, 1, l.Ntc)) return launch_conv_slab(a, nullptr, 1, wslab, l.Ntc, nsm, st);
-      return launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st);
+      return launch_conv_tc(a, wtc, l.pair_x ? 45 : l.ntaps, l.Ntc, nsm, st);
     }
     return launch_conv_ffma(a, bf16, st);
   }
@@ -412,7 +428,7 @@ struct Runner {
     const Layer& l = net.layers[net.index.at(name)];
     Ten out;
     if (l.transposed) out = alloc(in.B, in.S, in.H * 2, in.W * 2, e.out_f32 ? l.cout : l.CoutP, e.out_f32);
-    else out = alloc(in.B, in.S, in.H / l.stride, in.W / l.stride, e.out_f32 ? l.cout : l.CoutP, e.out_f32);
+    else out = alloc(in.B, in.S, in.H / l.stride, (l.pair_x && use_tc ? in.W - 2 : in.W) / l.stride, e.out_f32 ? l.cout : l.CoutP, e.out_f32);
     Ten aux;
     if (e.aux_add) {
       aux = alloc(out.B, out.S, out.H, out.W, out.C);
@@ -574,9 +590,9 @@ static int forward_impl(const void* packed, const float* FS, const float* fd, co
   r.use_slab = !(mode & DFF_NO_SLAB);
   const double vox = (double)B * S * H * W;
   const int c_in = r.use_tc ? 8 : 4;  // stored channels of the converted focal stack (TMA needs 16-byte pixels)
-  Ten x0 = r.alloc(B, S, H, W, c_in);
+  Ten x0 = r.alloc(B, S, H, r.use_tc ? W + 2 : W, c_in);   // (tensor-core path: pair-packed first-layer input, see to_cl_pair_kernel)
   r.op_begin("to_channels_last", 0, vox * (12 + c_in * r.esize(false)), 1);
-  if (!dry && !r.rc) r.rc = launch_to_cl(FS, B, 3, S, H, W, x0.p, c_in, r.bf16, st);
+  if (!dry && !r.rc) r.rc = r.use_tc ? launch_to_cl_pair(FS, B, S, H, W, x0.p, st) : launch_to_cl(FS, B, 3, S, H, W, x0.p, c_in, r.bf16, st);
   r.op_end();
   Ten t = r.conv("FM_measure.Focus_extraction.0.0", x0, Runner::relu());
   Ten v1 = r.srd("FM_measure.Focus_extraction.2", t);
@@ -683,8 +699,14 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
   for (const Layer& l : n.layers) {
     DFF_TRY(launch_pack_weight(raw + l.raw_w, (float*)(pk + l.pk_w), l.cout, l.cin, l.ntaps, l.CinP, l.CoutP,
                                l.transposed ? 1 : 0, st));
-    DFF_TRY(launch_pack_weight_tc(raw + l.raw_w, pk + l.pk_wtc, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
-    DFF_TRY(launch_pack_weight_slab(raw + l.raw_w, pk + l.pk_wslab, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
+    if (l.pair_x) {   // tensor-core packs of the paired-tap form: an ordinary (Cout, 8, 1, 9, 5) convolution weight
+      DFF_TRY(launch_pair_weight(raw + l.raw_w, (float*)(pk + l.pk_pair), l.cout, st));
+      DFF_TRY(launch_pack_weight_tc((const float*)(pk + l.pk_pair), pk + l.pk_wtc, l.cout, 8, 8, 45, l.Ntc, 0, st));
+      DFF_TRY(launch_pack_weight_slab((const float*)(pk + l.pk_pair), pk + l.pk_wslab, l.cout, 8, 8, 45, l.Ntc, 0, st));
+    } else {
+      DFF_TRY(launch_pack_weight_tc(raw + l.raw_w, pk + l.pk_wtc, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
+      DFF_TRY(launch_pack_weight_slab(raw + l.raw_w, pk + l.pk_wslab, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
+    }
     if (l.cout == 1 && l.ntaps == 1)
       DFF_TRY(launch_pack_weight(raw + l.raw_w, (float*)(pk + l.pk_proj), 1, l.cin, 1, l.CinT, 1, 0, st));
     const bool bn = l.raw_gamma >= 0;
