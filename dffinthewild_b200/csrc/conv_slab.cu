@@ -48,7 +48,7 @@ struct alignas(16) SlabParams {
   const void* wslab;  // bf16 [tap][chunk][N][8]
   int C0, C1, nchunk, nch0;
   int B, S, IH, IW;
-  int st, nviews, vpy[4], vpx[4];
+  int sty, stx, nviews, vpy[4], vpx[4];   // input stride per output step (y, x); one staged view per input-coordinate residue
   int oy, ox, RX, RY, CPS, plane_bytes, NP, LA, hz;
   int N, nops, nph;          // MMA N; table entries; output phases (1 = convolution, 4 = fused transposed convolution)
   int g[12], ge[12];         // MMA groups by (phase, focal offset): table range [g[ph*3+k], ge[ph*3+k])
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
     const int c = e % p.nchunk, pix = e / p.nchunk;
     const int rx = pix % p.RX, t = pix / p.RX;
     const int ry = t % p.RY, v = t / p.RY;
-    const int gy = p.st * (p.oy + ry) + p.vpy[v], gx = p.st * (p.ox + rx) + p.vpx[v];
+    const int gy = p.sty * (p.oy + ry) + p.vpy[v], gx = p.stx * (p.ox + rx) + p.vpx[v];
     const bool second = c >= p.nch0;
     const int C = second ? p.C1 : p.C0, cc = second ? c - p.nch0 : c;
     SlabElem el;
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int r = item;
       const int isp = r % p.nsplit; r /= p.nsplit;
-      const int tx0 = (r % p.tilesX) * kSlabTW * p.st; r /= p.tilesX;   // tile origin in input coordinates
-      const int ty0 = (r % p.tilesY) * kSlabTH * p.st;
+      const int tx0 = (r % p.tilesX) * kSlabTW * p.stx; r /= p.tilesX;   // tile origin in input coordinates
+      const int ty0 = (r % p.tilesY) * kSlabTH * p.sty;
       const int b = r / p.tilesY;
       const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
       const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
@@ -349,13 +349,13 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   memset(&p, 0, sizeof(p));
   if (a.C0 % 8 || a.C1 % 8 || a.C0 < 8) return false;
   if (Ntc < 16 || Ntc > 128 || Ntc % 16) return false;
-  if (a.isy != a.isx || (a.isy != 1 && a.isy != 2)) return false;
+  if ((a.isy != 1 && a.isy != 2) || (a.isx != 1 && a.isx != 2 && a.isx != 4) || a.isy * a.isx > 4) return false;
   const int nchunk = (a.C0 + a.C1) / 8;
   if (nchunk != 1 && (nchunk & 1)) return false;
   p.in0 = a.in0; p.in1 = a.in1; p.C0 = a.C0; p.C1 = a.C1; p.nchunk = nchunk; p.nch0 = a.C0 / 8;
-  p.B = a.B; p.S = a.S; p.IH = a.IH; p.IW = a.IW; p.st = a.isy;
-  p.nviews = p.st == 2 ? 4 : 1;
-  for (int v = 0; v < 4; ++v) { p.vpy[v] = v >> 1; p.vpx[v] = v & 1; }
+  p.B = a.B; p.S = a.S; p.IH = a.IH; p.IW = a.IW; p.sty = a.isy; p.stx = a.isx;
+  p.nviews = p.sty * p.stx;
+  for (int v = 0; v < 4; ++v) { p.vpy[v] = v / p.stx; p.vpx[v] = v % p.stx; }
   // ---- taps in view coordinates -------------------------------------------------------------------------------------
   struct VT { int dz, view, vy, vx, widx, ph; };
   std::vector<VT> vt;
@@ -369,11 +369,9 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     x.ph = ph;
     x.dz = tt.dz[t]; x.widx = tt.widx[t];
     int dy = tt.dy[t], dx = tt.dx[t];
-    if (p.st == 2) {
-      const int py = dy & 1, px = dx & 1;
-      x.view = py * 2 + px; x.vy = (dy - py) / 2; x.vx = (dx - px) / 2;
-    } else {
-      x.view = 0; x.vy = dy; x.vx = dx;
+    {  // input coordinate sty*o + d  ->  view (d mod sty, d mod stx), view coordinate o + floor(d / st)
+      const int py = ((dy % p.sty) + p.sty) % p.sty, px = ((dx % p.stx) + p.stx) % p.stx;
+      x.view = py * p.stx + px; x.vy = (dy - py) / p.sty; x.vx = (dx - px) / p.stx;
     }
     vymin = std::min(vymin, x.vy); vymax = std::max(vymax, x.vy);
     vxmin = std::min(vxmin, x.vx); vxmax = std::max(vxmax, x.vx);
@@ -531,6 +529,31 @@ __global__ void pack_weight_slab_kernel(const float* __restrict__ w, __nv_bfloat
     if (co < Cout && ci < Cin) v = transposed ? w[((size_t)ci * Cout + co) * ntaps + t] : w[((size_t)co * Cin + ci) * ntaps + t];
     dst[i] = __float2bfloat16_rn(v);
   }
+}
+
+// Weights of the x-folded form of a stride-1 convolution (kernel kd x kh x kw, kw taps along x): G adjacent output pixels become
+// G*Cout output channels of ONE implicit-GEMM row, fed by kw+G-1 taps along x.  dst: bf16 [kd*kh*(kw+G-1)][Cin/8][G*Cout][8] with
+// W_G[g*Cout + co][ci][kd][kh][q] = W[co][ci][kd][kh][q - g] for 0 <= q - g < kw, else 0.
+__global__ void pack_weight_slab_fold_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin, int CinP,
+                                             int kd, int kh, int kw, int G) {
+  const int nchunk = CinP / 8, N = G * Cout, kq = kw + G - 1;
+  const int n = kd * kh * kq * nchunk * N * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int j = i & 7, nn = (i >> 3) % N, c = (i / (8 * N)) % nchunk, t = i / (8 * N * nchunk);
+    const int q = t % kq, b = (t / kq) % kh, a = t / (kq * kh);
+    const int g = nn / Cout, co = nn % Cout, ci = c * 8 + j, kx = q - g;
+    float v = 0.f;
+    if (ci < Cin && kx >= 0 && kx < kw) v = w[((((size_t)co * Cin + ci) * kd + a) * kh + b) * kw + kx];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, int CinP, int kd, int kh, int kw, int G, cudaStream_t st) {
+  const int n = kd * kh * (kw + G - 1) * CinP * G * Cout;
+  int g = cdiv(n, 256);
+  if (g > 512) g = 512;
+  pack_weight_slab_fold_kernel<<<g, 256, 0, st>>>(w, (__nv_bfloat16*)dst, Cout, Cin, CinP, kd, kh, kw, G);
+  DFF_LAUNCH_CHECK("pack_weight_slab_fold");
+  return 0;
 }
 
 int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,

@@ -623,6 +623,19 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
   shift[c] = sh;
 }
 
+// scale/shift of the x-folded form: dst[g*C + c] = scale[c], dst[G*C + g*C + c] = shift[c]
+__global__ void replicate_ss_kernel(const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ dst, int C, int G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * C) return;
+  dst[i] = scale[i % C];
+  dst[G * C + i] = shift[i % C];
+}
+int launch_replicate_ss(const float* scale, const float* shift, float* dst, int C, int G, cudaStream_t st) {
+  replicate_ss_kernel<<<cdiv(G * C, 128), 128, 0, st>>>(scale, shift, dst, C, G);
+  DFF_LAUNCH_CHECK("replicate_ss");
+  return 0;
+}
+
 int launch_pack_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int CinP, int CoutP, int transposed,
                        cudaStream_t st) {
   const int n = ntaps * CinP * CoutP;

@@ -2,6 +2,7 @@
 // the forward schedule (reference train_codes/Depth_Estimation_Network.py:77-137) and the C-ABI of
 // include/dff_b200.h.  No device memory is allocated here; activations live in the caller's workspace.
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -42,6 +43,8 @@ bool conv_slab_supported(const ConvArgs& a, const TapTable* ptaps, int nph, int 
 int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const void* wslab, int Ntc, int num_sms, cudaStream_t st);
 int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
                             cudaStream_t st);
+int launch_replicate_ss(const float* scale, const float* shift, float* dst, int C, int G, cudaStream_t st);
+int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, int CinP, int kd, int kh, int kw, int G, cudaStream_t st);
 int launch_conv_wgrad(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, int ci_base, float* dw, int ntaps_total,
                       int wt_transposed, bool bf16, cudaStream_t st);
 size_t bn_partial_bytes(int C);
@@ -84,12 +87,13 @@ struct Layer {
   std::string bn;    // state_dict prefix of its BatchNorm3d ("" = none)
   int cin, cout, kd, kh, kw, stride, dil;
   bool transposed, bias;
+  int gfold = 1;         // x-fold factor of the tensor-core path: G adjacent output pixels = G*Cout channels of one GEMM row (N' = 32)
   bool pair_x = false;   // tensor-core path of the first layer: input pixels carry their dilated right neighbour (9 x 5 paired taps)
   // derived
   int CinP, CoutP, ntaps;
   int CinT, Ntc;  // tensor-core path: stored input channels (multiple of 8) and MMA N (multiple of 16, >= 16)
   int64_t raw_w, raw_gamma, raw_beta, raw_mean, raw_var, raw_bias;  // element offsets in the raw buffer (-1: none)
-  size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab, pk_proj, pk_pair;                  // byte offsets in the packed buffer
+  size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab, pk_proj, pk_pair, pk_wfold, pk_ssfold;                  // byte offsets in the packed buffer
 };
 struct Param {
   std::string name;
@@ -134,6 +138,15 @@ struct Net {
     packed_bytes += align_up((size_t)(l.ntaps + 1) * l.Ntc * l.CinT * 2, 256);
     l.pk_wslab = packed_bytes;
     packed_bytes += align_up((size_t)l.ntaps * l.Ntc * l.CinT * 2, 256);
+    // x-folded form (see pack_weight_slab_fold_kernel): small-Cout stride-1 layers are bound by the A-operand fetch of the MMA
+    // (39 clk for any N <= 32), so N' = G*Cout = 32 output channels per row cost the same as 8 or 16
+    l.pk_wfold = l.pk_ssfold = packed_bytes;
+    if (!transposed && stride == 1 && dil == 1 && kw == 3 && (cout == 8 || cout == 16) && cin % 8 == 0) {
+      l.gfold = cout == 8 ? 4 : 2;
+      packed_bytes += align_up((size_t)kd * kh * (kw + l.gfold - 1) * l.CinT * l.gfold * cout * 2, 256);
+      l.pk_ssfold = packed_bytes;
+      packed_bytes += align_up((size_t)2 * l.gfold * cout * sizeof(float), 256);
+    }
     l.pk_pair = packed_bytes;   // paired-tap fp32 weights (Cout, 8, 1, 9, 5) of the first layer
     if (cin == 3 && kh == 9 && kw == 9 && dil == 2 && kd == 1) { l.pair_x = true; packed_bytes += align_up((size_t)cout * 360 * sizeof(float), 256); }
     l.pk_proj = packed_bytes;   // C -> 1 projections (classifiers): contiguous fp32 weights for the fused epilogue
@@ -288,7 +301,8 @@ static int num_sms_of_current_device() {
 // `wtc` != null selects the tcgen05 path (bf16 only); otherwise the FFMA kernel runs.
 static int run_conv(const Layer& l, const float* w, const float* scale, const float* shift, const Ten& in, const EpiOpt& e,
                     Ten& out, bool bf16, cudaStream_t st, const void* wtc = nullptr, const void* wslab = nullptr,
-                    int* nlaunch = nullptr, bool count_only = false, bool use_row = true, const char* packed_base = nullptr) {
+                    int* nlaunch = nullptr, bool count_only = false, bool use_row = true, const char* packed_base = nullptr,
+                    bool use_fold = false) {
   int dummy = 0;
   if (!nlaunch) nlaunch = &dummy;
   *nlaunch = 0;
@@ -335,6 +349,29 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     a.OHt = out.H; a.OWt = out.W;
     *nlaunch = 1;
     if (count_only) return 0;
+    if (wtc && use_fold && packed_base && l.gfold > 1 && !a.proj_w && a.Cout == l.cout && a.OW % (8 * l.gfold) == 0) {
+      // x-folded form: G adjacent output pixels are the G*Cout channels of one GEMM row; the input is read with x-stride G
+      // (one staged view per residue), the output is the same memory viewed as (.., W/G, G*Cout)
+      const int G = l.gfold, kq = l.kw + G - 1;
+      ConvArgs f = a;
+      f.taps.n = 0;
+      for (int ka = 0; ka < l.kd; ++ka)
+        for (int kb = 0; kb < l.kh; ++kb)
+          for (int q = 0; q < kq; ++q) {
+            f.taps.dz[f.taps.n] = (int8_t)(ka - (l.kd - 1) / 2);
+            f.taps.dy[f.taps.n] = (int8_t)(kb - (l.kh - 1) / 2);
+            f.taps.dx[f.taps.n] = (int8_t)(q - 1);
+            f.taps.widx[f.taps.n] = (uint8_t)((ka * l.kh + kb) * kq + q);
+            ++f.taps.n;
+          }
+      f.isy = 1; f.isx = G;
+      f.OW = a.OW / G; f.OWt = f.OW;
+      f.Cout = G * l.cout;
+      f.scale = (const float*)(packed_base + l.pk_ssfold);
+      f.shift = f.scale + G * l.cout;
+      if (conv_slab_supported(f, nullptr, 1, G * l.cout))
+        return launch_conv_slab(f, nullptr, 1, packed_base + l.pk_wfold, G * l.cout, nsm, st);
+    }
     if (wtc) {
       if (wslab && use_row && conv_row_supported(a, l.Ntc)) return launch_conv_row(a, wslab, l.Ntc, nsm, st);
       if (wslab && conv_slab_supported(a, nullptr, 1, l.Ntc)) return launch_conv_slab(a, nullptr, 1, wslab, l.Ntc, nsm, st);
@@ -393,6 +430,7 @@ struct Runner {
   int rc = 0;
   Profile* prof = nullptr;
   bool use_tc = false, use_slab = true;
+  bool use_fold = getenv("DFF_B200_NO_FOLD") == nullptr;   // x-folded small-Cout layers (A/B switch for measurements)
 
   void op_begin(const std::string& name, double flops, double bytes, int launches) {
     if (!prof) return;
@@ -460,7 +498,8 @@ struct Runner {
       const char* pk = dry ? reinterpret_cast<const char*>(0x1000) : packed;
       int nl = 0;
       rc = run_conv(l, (const float*)(pk + l.pk_w), (const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), in, e, out,
-                    bf16, st, use_tc ? pk + l.pk_wtc : nullptr, (use_tc && use_slab) ? pk + l.pk_wslab : nullptr, &nl, dry, true, pk);
+                    bf16, st, use_tc ? pk + l.pk_wtc : nullptr, (use_tc && use_slab) ? pk + l.pk_wslab : nullptr, &nl, dry, true, pk,
+                    use_tc && use_slab && use_fold);
       if (prof && !prof->ops.empty()) prof->ops.back().launches = nl;
     }
     op_end();
@@ -713,6 +752,11 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
     DFF_TRY(launch_bn_fold(bn ? raw + l.raw_gamma : nullptr, bn ? raw + l.raw_beta : nullptr, bn ? raw + l.raw_mean : nullptr,
                            bn ? raw + l.raw_var : nullptr, l.raw_bias >= 0 ? raw + l.raw_bias : nullptr,
                            (float*)(pk + l.pk_scale), (float*)(pk + l.pk_shift), l.cout, l.CoutP, st));
+    if (l.gfold > 1) {
+      DFF_TRY(launch_pack_weight_slab_fold(raw + l.raw_w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st));
+      DFF_TRY(launch_replicate_ss((const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), (float*)(pk + l.pk_ssfold), l.cout,
+                                  l.gfold, st));
+    }
   }
   return 0;
 }
