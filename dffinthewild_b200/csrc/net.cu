@@ -141,8 +141,11 @@ struct Net {
     // x-folded form (see pack_weight_slab_fold_kernel): small-Cout stride-1 layers are bound by the A-operand fetch of the MMA
     // (39 clk for any N <= 32), so N' = G*Cout = 32 output channels per row cost the same as 8 or 16
     l.pk_wfold = l.pk_ssfold = packed_bytes;
-    if (!transposed && stride == 1 && dil == 1 && kw == 3 && (cout == 8 || cout == 16) && cin % 8 == 0) {
-      l.gfold = cout == 8 ? 4 : 2;
+    // (measured per layer class, profiles/: the fold pays where the folded kernel keeps its occupancy — Cout = 8 with G = 4 (Cin = 8)
+    // or G = 2 (Cin >= 16), Cout = 16 only for Cin >= 32)
+    const int gsel = cout == 8 ? (cin == 8 ? 4 : 2) : (cout == 16 && cin >= 32 ? 2 : 1);
+    if (!transposed && stride == 1 && dil == 1 && kw == 3 && gsel > 1 && cin % 8 == 0) {
+      l.gfold = gsel;
       packed_bytes += align_up((size_t)kd * kh * (kw + l.gfold - 1) * l.CinT * l.gfold * cout * 2, 256);
       l.pk_ssfold = packed_bytes;
       packed_bytes += align_up((size_t)2 * l.gfold * cout * sizeof(float), 256);

@@ -8,7 +8,7 @@ rows = list(csv.reader(open(f)))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 h = rows[hdr]; data = [r for r in rows[hdr + 1:] if len(r) == len(h)]
 ki, vi = h.index('Kernel Name'), h.index('Metric Value')
-first = next(i for i, r in enumerate(data) if 'to_cl_kernel' in r[ki])  # align to the start of one forward chunk
+first = next(i for i, r in enumerate(data) if ('to_cl_kernel' in r[ki] or 'to_cl_pair_kernel' in r[ki]))  # align to the start of one forward chunk
 data = data[first:]
 times = [float(r[vi].replace(',', '')) for r in data]
 l = rt.lib(); N = 256
