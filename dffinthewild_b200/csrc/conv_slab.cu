@@ -85,6 +85,57 @@ struct SlabElem {
   int8_t gy, gx;     // input row / column relative to the tile origin (bounds check)
 };
 
+// Epilogue role of the slab kernel (4 warps, one TMEM lane quadrant each).  FAST = 0: generic epilogue (tc_epilogue_tile).
+template <int FAST, bool RELU, int RES, bool AUX, bool PROJ>
+__device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, float* ss,
+                                              uint32_t ss_s) {
+  using namespace tc;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int ty = row >> 3, tx = row & 7;
+  EpiArgs ep = p.epi;
+  ep.scale = ss;
+  ep.shift = ss + p.N;
+  const int esz = ep.out_f32 ? 4 : 2;
+  const void* const rsrc = ep.res_pre ? ep.res_pre : (ep.res_post ? ep.res_post : ep.aux_add);   // (a layer has at most one residual operand)
+  int sc = 0;
+  for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+    int r = item;
+    const int isp = r % p.nsplit; r /= p.nsplit;
+    const int ox = (r % p.tilesX) * kSlabTW + tx; r /= p.tilesX;
+    const int oy = (r % p.tilesY) * kSlabTH + ty;
+    const int b = r / p.tilesY;
+    const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
+    const bool valid = oy < p.OHt && ox < p.OWt;
+    for (int s = s_begin; s < s_end; ++s, ++sc) {
+      const int buf = sc & 1;
+      const size_t row0 = ((size_t)b * p.S + s) * p.OH;
+      if (valid && rsrc) {
+        // the residual operand does not depend on the accumulator: pull it towards L1 while the MMAs run
+        for (int ph = 0; ph < p.nph; ++ph) {
+          const size_t pix = (row0 + (oy * p.osy + (p.nph > 1 ? (ph >> 1) : p.ooy))) * p.OW + (ox * p.osx + (p.nph > 1 ? (ph & 1) : p.oox));
+          const size_t ob = pix * ep.cstore * esz;
+          for (int k = 0; k < ep.cstore * esz; k += 128) prefetch_l1(reinterpret_cast<const char*>(rsrc) + ob + k);
+        }
+      }
+      mbar_wait(tfull0 + 8 * buf, (sc >> 1) & 1);
+      fence_after();
+      if (q == 3) DFF_TR(3, sc);
+      for (int ph = 0; ph < p.nph; ++ph) {
+        const size_t pix = (row0 + (oy * p.osy + (p.nph > 1 ? (ph >> 1) : p.ooy))) * p.OW + (ox * p.osx + (p.nph > 1 ? (ph & 1) : p.oox));
+        if (p.exp & 2) continue;
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N;
+        if (FAST) tc_epilogue_fast<RELU, RES, AUX, PROJ>(ep, ss_s, tacc, valid, pix);
+        else tc_epilogue_tile(ep, tacc, valid, pix);
+      }
+      fence_before();
+      mbar_arrive_relaxed(tempty0 + 8 * buf);
+      if (q == 3) DFF_TR(4, sc);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid_constant__ SlabParams p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -287,50 +338,16 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
     }
   } else {
     // =============================== epilogue ===============================
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int ty = row >> 3, tx = row & 7;
-    EpiArgs ep = p.epi;
-    ep.scale = ss;
-    ep.shift = ss + p.N;
-    const int esz = ep.out_f32 ? 4 : 2;
-    int sc = 0;
-    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-      int r = item;
-      const int isp = r % p.nsplit; r /= p.nsplit;
-      const int ox = (r % p.tilesX) * kSlabTW + tx; r /= p.tilesX;
-      const int oy = (r % p.tilesY) * kSlabTH + ty;
-      const int b = r / p.tilesY;
-      const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
-      const bool valid = oy < p.OHt && ox < p.OWt;
-      for (int s = s_begin; s < s_end; ++s, ++sc) {
-        const int buf = sc & 1;
-        const size_t row0 = ((size_t)b * p.S + s) * p.OH;
-        if (valid && (ep.res_pre || ep.res_post || ep.aux_add)) {
-          // the residual operands do not depend on the accumulator: pull them towards L1 while the MMAs run
-          for (int ph = 0; ph < p.nph; ++ph) {
-            const size_t pix = (row0 + (oy * p.osy + (p.nph > 1 ? (ph >> 1) : p.ooy))) * p.OW + (ox * p.osx + (p.nph > 1 ? (ph & 1) : p.oox));
-            const size_t ob = pix * ep.cstore * esz;
-            for (int k = 0; k < ep.cstore * esz; k += 128) {
-              if (ep.res_pre) prefetch_l1(reinterpret_cast<const char*>(ep.res_pre) + ob + k);
-              if (ep.res_post) prefetch_l1(reinterpret_cast<const char*>(ep.res_post) + ob + k);
-              if (ep.aux_add) prefetch_l1(reinterpret_cast<const char*>(ep.aux_add) + ob + k);
-            }
-          }
-        }
-        mbar_wait(tfull0 + 8 * buf, (sc >> 1) & 1);
-        fence_after();
-        if (q == 3) DFF_TR(3, sc);
-        for (int ph = 0; ph < p.nph; ++ph) {
-          const size_t pix = (row0 + (oy * p.osy + (p.nph > 1 ? (ph >> 1) : p.ooy))) * p.OW + (ox * p.osx + (p.nph > 1 ? (ph & 1) : p.oox));
-          if (p.exp & 2) continue;
-          tc_epilogue_tile(ep, tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N, valid, pix);
-        }
-        fence_before();
-        mbar_arrive_relaxed(tempty0 + 8 * buf);
-        if (q == 3) DFF_TR(4, sc);
-      }
-    }
+    // one compiled loop per operand pattern of the network's layers (see tc_epilogue_fast); mode 0 = the generic epilogue
+    const EpiArgs& e = p.epi;
+    const int res = e.res_pre ? 1 : (e.res_post ? 2 : 0);
+    const bool aux = e.out_aux != nullptr, proj = e.proj_w != nullptr;
+    const uint32_t ss_s = smem_u32(ss);
+    if (e.out_f32 || (e.res_pre && e.res_post) || (res == 1 && aux) || (res == 2 && (aux || e.relu)) || (proj && !aux && res != 2)) slab_epilogue<0, false, 0, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s);
+    else if (aux) { if (proj) slab_epilogue<1, false, 0, true, true>(p, tmem_base, tfull0, tempty0, ss, ss_s); else slab_epilogue<1, false, 0, true, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); }
+    else if (res == 2) { if (proj) slab_epilogue<1, false, 2, false, true>(p, tmem_base, tfull0, tempty0, ss, ss_s); else slab_epilogue<1, false, 2, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); }
+    else if (res == 1) { if (e.relu) slab_epilogue<1, true, 1, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); else slab_epilogue<1, false, 1, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); }
+    else { if (e.relu) slab_epilogue<1, true, 0, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); else slab_epilogue<1, false, 0, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); }
   }
   fence_before();
   __syncthreads();

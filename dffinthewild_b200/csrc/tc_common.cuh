@@ -238,4 +238,99 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiArgs& p, uint32_t tacc
   if (p.proj_out && valid) p.proj_out[pix] = pacc;
 }
 
+
+// ---- specialised epilogue (slab / row kernels: scale/shift in shared memory) ---------------------------------------------------
+// The epilogue warps are single instruction streams and, for the layers with residual operands, the bottleneck of the kernel:
+// this variant is compiled per operand pattern (no per-group branches on absent operands), reads residuals / writes outputs as
+// 16-byte vectors, and takes scale/shift through shared-state-space loads.
+//   RES: 0 none, 1 added before the ReLU (res_pre), 2 added after it (res_post).  AUX: second output out_aux = value + aux_add.
+//   PROJ: fused C -> 1 projection of the stored value (proj_src 0) or of the second output (proj_src 1).
+__device__ __forceinline__ void unpack8(const uint4& r, float* f) {
+  f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+  f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+  f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
+  f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 w;
+  w.x = tc::pack2(f[0], f[1]); w.y = tc::pack2(f[2], f[3]); w.z = tc::pack2(f[4], f[5]); w.w = tc::pack2(f[6], f[7]);
+  return w;
+}
+template <bool RELU, int RES, bool AUX, bool PROJ>
+__device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s, uint32_t tacc, bool valid, size_t pix) {
+  using namespace tc;
+  const size_t o0 = pix * p.cstore;
+  __nv_bfloat16* const out = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
+  const __nv_bfloat16* const res = reinterpret_cast<const __nv_bfloat16*>(RES == 1 ? p.res_pre : p.res_post) + o0;
+  __nv_bfloat16* const oaux = reinterpret_cast<__nv_bfloat16*>(p.out_aux) + o0;
+  const __nv_bfloat16* const aadd = reinterpret_cast<const __nv_bfloat16*>(p.aux_add) + o0;
+  float pacc = 0.f;
+  for (int c0 = 0; c0 < p.N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tacc + c0, v);
+    if (!valid || c0 >= p.cstore) continue;
+    const bool full = p.cstore - c0 >= 16;   // 16 channels in this group, else 8
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      float4 sc, sh;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w) : "r"(ss_s + 4 * (c0 + j)));
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w) : "r"(ss_s + 4 * (p.N + c0 + j)));
+      f[j] = fmaf(__uint_as_float(v[j]), sc.x, sh.x);
+      f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+      f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
+      f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+    }
+    if (RES) {
+      float r[16];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(res + c0)), r);
+      if (full) unpack8(__ldg(reinterpret_cast<const uint4*>(res + c0 + 8)), r + 8);
+      if (RES == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = (j < 8 || full) ? f[j] + r[j] : f[j];
+      }
+      if (RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (RES == 2) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = (j < 8 || full) ? f[j] + r[j] : f[j];
+      }
+    } else if (RELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (!p.skip_out) {
+      *reinterpret_cast<uint4*>(out + c0) = pack8(f);
+      if (full) *reinterpret_cast<uint4*>(out + c0 + 8) = pack8(f + 8);
+    }
+    if (AUX) {
+      float a[16];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(aadd + c0)), a);
+      if (full) unpack8(__ldg(reinterpret_cast<const uint4*>(aadd + c0 + 8)), a + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = (j < 8 || full) ? f[j] + a[j] : 0.f;
+      *reinterpret_cast<uint4*>(oaux + c0) = pack8(a);
+      if (full) *reinterpret_cast<uint4*>(oaux + c0 + 8) = pack8(a + 8);
+      if (PROJ && p.proj_src) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = a[j];
+      }
+    }
+    if (PROJ) {   // the projection sees what the next layer will read: the bf16-rounded values
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        if (j < 8 || full) {
+          const float4 pw = __ldg(reinterpret_cast<const float4*>(p.proj_w + c0 + j));
+          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j])), pw.x, pacc);
+          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 1])), pw.y, pacc);
+          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 2])), pw.z, pacc);
+          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 3])), pw.w, pacc);
+        }
+    }
+  }
+  if (PROJ && valid) p.proj_out[pix] = pacc;
+}
+
 }  // namespace dff
