@@ -269,65 +269,63 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
     uint32_t v[16];
     tmem_ld16(tacc + c0, v);
     if (!valid || c0 >= p.cstore) continue;
-    const bool full = p.cstore - c0 >= 16;   // 16 channels in this group, else 8
-    float f[16];
+    const int nh = p.cstore - c0 >= 16 ? 2 : 1;   // 8-channel halves stored from this 16-column group
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      float4 sc, sh;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w) : "r"(ss_s + 4 * (c0 + j)));
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w) : "r"(ss_s + 4 * (p.N + c0 + j)));
-      f[j] = fmaf(__uint_as_float(v[j]), sc.x, sh.x);
-      f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
-      f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
-      f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
-    }
-    if (RES) {
-      float r[16];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(res + c0)), r);
-      if (full) unpack8(__ldg(reinterpret_cast<const uint4*>(res + c0 + 8)), r + 8);
-      if (RES == 1) {
+    for (int h = 0; h < 2; ++h) {
+      if (h >= nh) break;
+      const int c = c0 + 8 * h;
+      float f[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = (j < 8 || full) ? f[j] + r[j] : f[j];
+      for (int j = 0; j < 8; j += 4) {
+        float4 sc, sh;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w) : "r"(ss_s + 4 * (c + j)));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w) : "r"(ss_s + 4 * (p.N + c + j)));
+        f[j] = fmaf(__uint_as_float(v[8 * h + j]), sc.x, sh.x);
+        f[j + 1] = fmaf(__uint_as_float(v[8 * h + j + 1]), sc.y, sh.y);
+        f[j + 2] = fmaf(__uint_as_float(v[8 * h + j + 2]), sc.z, sh.z);
+        f[j + 3] = fmaf(__uint_as_float(v[8 * h + j + 3]), sc.w, sh.w);
       }
-      if (RELU) {
+      if (RES) {
+        float r[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(res + c)), r);
+        if (RES == 1) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+        if (RELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (RES == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+      } else if (RELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
-      if (RES == 2) {
+      if (!p.skip_out) *reinterpret_cast<uint4*>(out + c) = pack8(f);
+      if (AUX) {
+        float a[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(aadd + c)), a);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = (j < 8 || full) ? f[j] + r[j] : f[j];
+        for (int j = 0; j < 8; ++j) a[j] += f[j];
+        *reinterpret_cast<uint4*>(oaux + c) = pack8(a);
+        if (PROJ && p.proj_src) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = a[j];
+        }
       }
-    } else if (RELU) {
+      if (PROJ) {   // the projection sees what the next layer will read: the bf16-rounded values
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-    }
-    if (!p.skip_out) {
-      *reinterpret_cast<uint4*>(out + c0) = pack8(f);
-      if (full) *reinterpret_cast<uint4*>(out + c0 + 8) = pack8(f + 8);
-    }
-    if (AUX) {
-      float a[16];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(aadd + c0)), a);
-      if (full) unpack8(__ldg(reinterpret_cast<const uint4*>(aadd + c0 + 8)), a + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) a[j] = (j < 8 || full) ? f[j] + a[j] : 0.f;
-      *reinterpret_cast<uint4*>(oaux + c0) = pack8(a);
-      if (full) *reinterpret_cast<uint4*>(oaux + c0 + 8) = pack8(a + 8);
-      if (PROJ && p.proj_src) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = a[j];
-      }
-    }
-    if (PROJ) {   // the projection sees what the next layer will read: the bf16-rounded values
-#pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        if (j < 8 || full) {
-          const float4 pw = __ldg(reinterpret_cast<const float4*>(p.proj_w + c0 + j));
+        for (int j = 0; j < 8; j += 4) {
+          const float4 pw = __ldg(reinterpret_cast<const float4*>(p.proj_w + c + j));
           pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j])), pw.x, pacc);
           pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 1])), pw.y, pacc);
           pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 2])), pw.z, pacc);
           pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 3])), pw.w, pacc);
         }
+      }
     }
   }
   if (PROJ && valid) p.proj_out[pix] = pacc;
