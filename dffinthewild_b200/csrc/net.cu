@@ -922,6 +922,8 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
                const void* res_pre, const void* res_post, int relu, void* out, int elem, int use_tensor_cores, void* scratch,
                int device, void* stream) {
   if (!in0 || !weight || !out || !scratch) return fail(DFF_E_ARG, "dff_conv3d: null pointer");
+  const bool out_f32 = (elem & DFF_OUT_F32) != 0;   // fp32 output from bf16 operands (cost volumes)
+  elem &= ~DFF_OUT_F32;
   if (use_tensor_cores && (elem != DFF_BF16 || (C0 % 8) || (C1 % 8)))
     return fail(DFF_E_UNSUPPORTED, "dff_conv3d: the tensor-core path needs bf16 tensors with channel counts that are multiples of 8");
   if (kd * kh * kw > kMaxTaps) return fail(DFF_E_ARG, "dff_conv3d: too many taps");
@@ -962,6 +964,8 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
   e.res_pre = res_pre ? &rp : nullptr;
   e.res_post = res_post ? &rq : nullptr;
   e.relu = relu != 0;
+  e.out_f32 = out_f32;
+  o.f32 = out_f32;
   // use_tensor_cores: 1 = best kernel for the shape (row kernel with A in TMEM -> slab kernel -> per-tap TMA kernel),
   // 2 = force the per-tap TMA kernel, 3 = slab kernel (never the row kernel)
   return run_conv(l, (const float*)scratch, scale, shift, in, e, o, elem == DFF_BF16, st, use_tensor_cores ? scratch : nullptr,

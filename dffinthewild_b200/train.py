@@ -61,27 +61,46 @@ def _st(dev):
     return _P(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def _elem(t):
+    return rt.BF16 if t.dtype == torch.bfloat16 else rt.FP32
+
+
+OUT_F32 = 16   # DFF_OUT_F32
+
+
+def _conv_call(l, x0, x1, w, Cout, stride, dil, transposed, out, elem, tc):
+    """One dff_conv3d call on channels-last tensors (no epilogue operands)."""
+    dev = x0.device
+    B, S, IH, IW, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    kd, kh, kw = w.shape[2:]
+    scratch = torch.empty(l.dff_conv3d_scratch_bytes(C0 + C1, Cout, kd, kh, kw), dtype=torch.uint8, device=dev)
+    rt.check(l.dff_conv3d(_p(x0), C0, _p(x1), C1, B, S, IH, IW, _p(w), Cout, kd, kh, kw, stride, dil, 1 if transposed else 0, None, None,
+                          None, None, 0, _p(out), elem, tc, _p(scratch), dev.index, _st(dev)))
+
+
 class ConvFn(torch.autograd.Function):
-    """Raw convolution (no bias): x0 (B,S,IH,IW,C0) [+ x1 = virtual channel concat], weight in the reference layout."""
+    """Raw convolution (no bias): x0 (B,S,IH,IW,C0) [+ x1 = virtual channel concat], weight in the reference layout.
+    fp32 tensors: FFMA kernels.  bf16 tensors: tcgen05 kernels for the forward AND the data gradient (a data gradient is a
+    convolution with the adjoint tap table: flipped taps for stride 1, a transposed convolution for stride 2 and vice versa);
+    the weight gradient is always accumulated in fp32."""
 
     @staticmethod
     def forward(ctx, x0, x1, weight, stride, dil, transposed, cin_pad):
         l = _lib()
         dev = x0.device
+        bf16 = x0.dtype == torch.bfloat16
         B, S, IH, IW, C0 = x0.shape
-        C1 = x1.shape[-1] if x1 is not None else 0
         w = weight
-        if cin_pad:  # first layer: 3 image channels stored as 4 (zero weights for the padding channel)
+        if cin_pad:  # first layer: 3 image channels stored as 4 (fp32) / 8 (bf16); zero weights for the padding channels
             w = torch.cat([weight, weight.new_zeros(weight.shape[0], cin_pad, *weight.shape[2:])], 1)
-        w = w.contiguous()
+        w = w.detach().float().contiguous()
         Cout = w.shape[1] if transposed else w.shape[0]
-        kd, kh, kw = w.shape[2:]
         OH, OW = (IH * 2, IW * 2) if transposed else (IH // stride, IW // stride)
-        out = torch.empty((B, S, OH, OW, Cout), dtype=torch.float32, device=dev)
-        scratch = torch.empty(l.dff_conv3d_scratch_bytes(C0 + C1, Cout, kd, kh, kw), dtype=torch.uint8, device=dev)
-        rt.check(l.dff_conv3d(_p(x0), C0, _p(x1), C1, B, S, IH, IW, _p(w), Cout, kd, kh, kw, stride if not transposed else 2, dil,
-                              1 if transposed else 0, None, None, None, None, 0, _p(out), rt.FP32, 0, _p(scratch), dev.index,
-                              _st(dev)))
+        cost = Cout % 4 != 0   # C -> 1 cost volumes stay fp32 (they feed the depth head)
+        out = torch.empty((B, S, OH, OW, Cout), dtype=torch.float32 if (cost or not bf16) else torch.bfloat16, device=dev)
+        elem = (rt.BF16 | (OUT_F32 if cost else 0)) if bf16 else rt.FP32
+        _conv_call(l, x0, x1, w, Cout, 2 if transposed else stride, dil, transposed, out, elem, 1 if bf16 else 0)
         ctx.save_for_backward(x0, x1, w)
         ctx.cfg = (stride, dil, transposed, cin_pad, Cout, OH, OW)
         return out
@@ -92,6 +111,8 @@ class ConvFn(torch.autograd.Function):
         x0, x1, w = ctx.saved_tensors
         stride, dil, transposed, cin_pad, Cout, OH, OW = ctx.cfg
         dev = dy.device
+        bf16 = x0.dtype == torch.bfloat16
+        elem = rt.BF16 if bf16 else rt.FP32
         dy = dy.contiguous()
         B, S, IH, IW, C0 = x0.shape
         C1 = x1.shape[-1] if x1 is not None else 0
@@ -99,30 +120,48 @@ class ConvFn(torch.autograd.Function):
         kd, kh, kw = w.shape[2:]
         st = stride if not transposed else 2
         CoS = dy.shape[-1]
-        dx0 = dx1 = None
-        if CoS % 4:  # single-channel cost volumes: pad dy to 4 stored channels with the library's layout kernel
-            dy4 = torch.empty(dy.shape[:-1] + (4,), dtype=torch.float32, device=dev)
-            rt.check(l.dff_to_channels_last(_p(dy), B, CoS, S, OH, OW, _p(dy4), 4, rt.FP32, dev.index, _st(dev)))
-            # dy is (B,S,OH,OW,1) == (B,1,S,OH,OW) in memory
-            dy, CoS = dy4, 4
+        if CoS % 4:  # single-channel cost volumes (fp32): pad dy to 4 (fp32) / 8 (bf16) stored channels with the library's layout kernel
+            cp = 8 if bf16 else 4
+            dyp = torch.empty(dy.shape[:-1] + (cp,), dtype=x0.dtype, device=dev)
+            rt.check(l.dff_to_channels_last(_p(dy.float()), B, CoS, S, OH, OW, _p(dyp), cp, elem, dev.index, _st(dev)))
+            dy, CoS = dyp, cp       # dy (B,S,OH,OW,1) == (B,1,S,OH,OW) in memory
         needs = ctx.needs_input_grad
-        if needs[0] or (x1 is not None and needs[1]):
-            scratch = torch.empty(l.dff_conv3d_dgrad_scratch_bytes(Cin, max(Cout, CoS), kd, kh, kw), dtype=torch.uint8, device=dev)
-            for idx, (x, ci0) in enumerate(((x0, 0), (x1, C0))):
-                if x is None or not needs[idx]:
-                    continue
-                dx = torch.empty_like(x)
+        dx0 = dx1 = None
+        for idx, (x, ci0) in enumerate(((x0, 0), (x1, C0))):
+            if x is None or not needs[idx]:
+                continue
+            nci = x.shape[-1]
+            dx = torch.empty_like(x)
+            if not bf16:
+                scratch = torch.empty(l.dff_conv3d_dgrad_scratch_bytes(Cin, max(Cout, CoS), kd, kh, kw), dtype=torch.uint8, device=dev)
                 rt.check(l.dff_conv3d_dgrad(_p(dy), CoS, B, S, OH, OW, _p(w), Cin, Cout, kd, kh, kw, st, dil, 1 if transposed else 0,
-                                            ci0, x.shape[-1], _p(dx), rt.FP32, _p(scratch), dev.index, _st(dev)))
-                if idx == 0:
-                    dx0 = dx
-                else:
-                    dx1 = dx
+                                            ci0, nci, _p(dx), rt.FP32, _p(scratch), dev.index, _st(dev)))
+            else:
+                # tensor-core data gradient: the adjoint convolution, weights re-laid out on the fly (tiny tensors)
+                if transposed:      # adjoint of the transposed conv = stride-2 conv of dy, weight (Cin_t, Cout_t, k) read as (Cout_c, Cin_c, k)
+                    wa = w[ci0:ci0 + nci]
+                    if CoS > Cout:
+                        wa = torch.cat([wa, wa.new_zeros(nci, CoS - Cout, kd, kh, kw)], 1)
+                    _conv_call(l, dy, None, wa.contiguous(), nci, 2, 1, False, dx, rt.BF16, 1)
+                elif st == 2:       # adjoint of the stride-2 conv = transposed conv of dy, weight (Cout, nci, k) read as (Cin_t, Cout_t, k)
+                    wa = w[:, ci0:ci0 + nci]
+                    if CoS > Cout:
+                        wa = torch.cat([wa, wa.new_zeros(CoS - Cout, nci, kd, kh, kw)], 0)
+                    _conv_call(l, dy, None, wa.contiguous(), nci, 2, 1, True, dx, rt.BF16, 1)
+                else:               # adjoint of the stride-1 conv = stride-1 conv with flipped taps and swapped channel roles
+                    wa = w[:, ci0:ci0 + nci].flip(2, 3, 4).transpose(0, 1)
+                    if CoS > Cout:
+                        wa = torch.cat([wa, wa.new_zeros(nci, CoS - Cout, kd, kh, kw)], 1)
+                    _conv_call(l, dy, None, wa.contiguous(), nci, 1, dil, False, dx, rt.BF16, 1)
+            if idx == 0:
+                dx0 = dx
+            else:
+                dx1 = dx
         dw = None
         if needs[2]:
             dw = torch.empty_like(w)
             rt.check(l.dff_conv3d_wgrad(_p(x0), C0, _p(x1), C1, B, S, IH, IW, _p(dy), CoS, Cin, Cout, kd, kh, kw, st, dil,
-                                        1 if transposed else 0, _p(dw), rt.FP32, dev.index, _st(dev)))
+                                        1 if transposed else 0, _p(dw), elem, dev.index, _st(dev)))
             if cin_pad:
                 dw = dw[:, :Cin - cin_pad].contiguous()
         return dx0, dx1, dw, None, None, None, None
@@ -145,14 +184,14 @@ class BnActFn(torch.autograd.Function):
             ss = torch.empty(2 * C, dtype=torch.float32, device=dev)
             scratch = torch.empty(l.dff_bn_scratch_bytes(C), dtype=torch.uint8, device=dev)
             track = bn is not None and bn.track_running_stats and bn.running_mean is not None
-            rt.check(l.dff_bn_train_forward(_p(x), npix, C, rt.FP32, _p(gamma), _p(beta), _p(bn.running_mean) if track else None,
+            rt.check(l.dff_bn_train_forward(_p(x), npix, C, _elem(x), _p(gamma), _p(beta), _p(bn.running_mean) if track else None,
                                             _p(bn.running_var) if track else None, bn.momentum if bn is not None else 0.1,
                                             bn.eps if bn is not None else 1e-5, _p(res_pre), _p(res_post), 1 if relu else 0,
                                             _p(out), _p(mean), _p(invstd), _p(ss), _p(scratch), dev.index, _st(dev)))
             if track:
                 bn.num_batches_tracked += 1
         else:
-            rt.check(l.dff_bn_train_forward(_p(x), npix, C, rt.FP32, None, None, None, None, 0.0, 0.0, _p(res_pre), _p(res_post),
+            rt.check(l.dff_bn_train_forward(_p(x), npix, C, _elem(x), None, None, None, None, 0.0, 0.0, _p(res_pre), _p(res_post),
                                             1 if relu else 0, _p(out), None, None, None, None, dev.index, _st(dev)))
         # ReLU mask source: the output before res_post.  Without res_post that is `out` itself; with it, relu(x) > 0 <=> x > 0
         # (no-BN layers, reference :399-402) so the raw input serves as the mask.
@@ -165,7 +204,7 @@ class BnActFn(torch.autograd.Function):
         l = _lib()
         x, gamma, mean, invstd, y = ctx.saved_tensors
         dev = dy.device
-        dy = dy.contiguous()
+        dy = dy.to(x.dtype).contiguous()
         C = x.shape[-1]
         npix = x.numel() // C
         mask = None
@@ -181,10 +220,10 @@ class BnActFn(torch.autograd.Function):
             dgamma = torch.empty(C, dtype=torch.float32, device=dev)
             dbeta = torch.empty(C, dtype=torch.float32, device=dev)
             scratch = torch.empty(l.dff_bn_scratch_bytes(C), dtype=torch.uint8, device=dev)
-            rt.check(l.dff_bn_train_backward(_p(dy), _p(mask), _p(x), _p(mean), _p(invstd), _p(gamma), npix, C, rt.FP32, _p(dx),
+            rt.check(l.dff_bn_train_backward(_p(dy), _p(mask), _p(x), _p(mean), _p(invstd), _p(gamma), npix, C, _elem(x), _p(dx),
                                              _p(dres), _p(dgamma), _p(dbeta), _p(scratch), dev.index, _st(dev)))
         else:
-            rt.check(l.dff_bn_train_backward(_p(dy), _p(mask), None, None, None, None, npix, C, rt.FP32, _p(dx), _p(dres), None, None,
+            rt.check(l.dff_bn_train_backward(_p(dy), _p(mask), None, None, None, None, npix, C, _elem(x), _p(dx), _p(dres), None, None,
                                              None, dev.index, _st(dev)))
         return dx, dgamma, dbeta, dres, (dy if ctx.has_post else None), None, None
 
@@ -195,7 +234,7 @@ class PoolFn(torch.autograd.Function):
         l = _lib()
         B, S, H, W, C = x.shape
         out = torch.empty((B, S, H // k, W // k, C), dtype=x.dtype, device=x.device)
-        rt.check(l.dff_pool3d(_p(x), B * S, H, W, C, k, 1 if is_max else 0, rt.FP32, _p(out), x.device.index, _st(x.device)))
+        rt.check(l.dff_pool3d(_p(x), B * S, H, W, C, k, 1 if is_max else 0, _elem(x), _p(out), x.device.index, _st(x.device)))
         ctx.save_for_backward(x)
         ctx.cfg = (k, is_max)
         return out
@@ -207,7 +246,7 @@ class PoolFn(torch.autograd.Function):
         k, is_max = ctx.cfg
         B, S, H, W, C = x.shape
         dx = torch.empty_like(x)
-        rt.check(l.dff_pool3d_backward(_p(x), _p(dy.contiguous()), B * S, H, W, C, k, 1 if is_max else 0, rt.FP32, _p(dx),
+        rt.check(l.dff_pool3d_backward(_p(x), _p(dy.contiguous()), B * S, H, W, C, k, 1 if is_max else 0, _elem(x), _p(dx),
                                        x.device.index, _st(x.device)))
         return dx, None, None
 
@@ -217,7 +256,7 @@ class AddFn(torch.autograd.Function):
     def forward(ctx, a, b):
         l = _lib()
         out = torch.empty_like(a)
-        rt.check(l.dff_add(_p(a), _p(b), a.numel(), rt.FP32, _p(out), a.device.index, _st(a.device)))
+        rt.check(l.dff_add(_p(a), _p(b), a.numel(), _elem(a), _p(out), a.device.index, _st(a.device)))
         return out
 
     @staticmethod
@@ -326,8 +365,7 @@ def dff_net_train_forward(net, FS, focus_dists):
         raise rt.DffError("dff_b200: FS must be (B,3,S,H,W), got %s" % (tuple(FS.shape),))
     if FS.dtype != torch.float32 or focus_dists.dtype != torch.float32:
         raise rt.DffError("dff_b200: FS and focus_dists must be float32")
-    if getattr(net, "precision", "fp32") != "fp32":
-        raise rt.DffError("dff_b200: the train path runs in fp32 (parity) precision in this build")
+    bf16 = getattr(net, "precision", "fp32") == "bf16"
     B, _, S, H, W = FS.shape
     if H % 32 or W % 32:
         raise rt.DffError("dff_b200: H and W must be multiples of 32 (pad with -1 like the reference dataloaders)")
@@ -337,9 +375,9 @@ def dff_net_train_forward(net, FS, focus_dists):
     while fd.dim() < 4:
         fd = fd.unsqueeze(0)
     fd = fd.expand(B, S, H, W)
-    x0 = rt.to_channels_last(FS, 4, False)                      # (B,S,H,W,4), the 4th channel is zero
+    x0 = rt.to_channels_last(FS, 8 if bf16 else 4, bf16)      # (B,S,H,W,4|8): image channels + zero padding
     fm = net.FM_measure.Focus_extraction
-    v1 = _srd(fm[2], _cbn(x0, fm[0], relu=True, cin_pad=1))
+    v1 = _srd(fm[2], _cbn(x0, fm[0], relu=True, cin_pad=5 if bf16 else 1))
     v2 = _srd(net.FM_conv1[1], _efd(net.FM_conv1[0], v1))
     v3 = _srd(net.FM_conv2[1], _efd(net.FM_conv2[0], v2))
     vol = _pyramid(net.SPP_module, v3)

@@ -55,6 +55,7 @@ extern "C" {
 #define DFF_TRAIN 2 /* BatchNorm in batch-statistics mode; activations are kept for dff_backward */
 #define DFF_NO_TC 4 /* debugging aid with DFF_BF16: bf16 storage but FFMA kernels instead of tcgen05 */
 #define DFF_NO_SLAB 8 /* debugging aid with DFF_BF16: only the per-tap TMA tcgen05 kernel, never the slab kernel */
+#define DFF_OUT_F32 16 /* with DFF_BF16 as the `elem` of dff_conv3d: store the output as fp32 (C -> 1 cost volumes) */
 
 /* which parameter set a call refers to */
 #define DFF_NET_DFF 0  /* DFF_net (384-key state_dict)                                */

@@ -124,3 +124,41 @@ def test_adam_step_runs_on_module_parameters(built_lib):
     with torch.no_grad():
         o = net(FS, fd)          # eval path picks up the updated weights and running statistics
     assert all(torch.isfinite(t).all() for t in o)
+
+
+def test_bf16_train_step_tensor_cores(built_lib):
+    """bf16 training path: tcgen05 forward + tensor-core data gradients, fp32 weight gradients / BatchNorm statistics.
+    Gate (per-tensor cosine is not usable in bf16 at these weights): outputs and loss track the fp32 path,
+    gradients are finite and globally aligned with the fp32 gradients, Adam steps stay finite."""
+    from oracle import synth
+    sd = _state()
+    B, S, H, W = 2, 5, 64, 64
+    FS, fd = synth.focal_stack(B, S, H, W, seed=41).cuda(), synth.focus_dists(B, S, H, W, "defocus").cuda()
+    gt, mask = synth.gt_and_mask(B, H, W, seed=41)
+    gt, mask = gt.cuda(), mask.cuda()
+    res = {}
+    for prec in ("fp32", "bf16"):
+        net = _net(sd)
+        net.DFF_net.precision = prec
+        outs = net(FS, fd)
+        loss = _loss(outs, gt, mask)
+        loss.backward()
+        res[prec] = (loss.item(), [o.detach().float() for o in outs],
+                     torch.cat([p.grad.float().flatten() for p in net.parameters() if p.grad is not None]))
+    l32, o32, g32 = res["fp32"]
+    l16, o16, g16 = res["bf16"]
+    assert abs(l16 - l32) <= 3e-2 * abs(l32), (l16, l32)
+    for a, b in zip(o16, o32):
+        assert ((a - b).abs().mean() / b.abs().mean()).item() <= 5e-2
+    assert torch.isfinite(g16).all()
+    cos = float(torch.dot(g16.double(), g32.double()) / (g16.double().norm() * g32.double().norm()))
+    assert cos >= 0.8, cos
+    net = _net(sd)
+    net.DFF_net.precision = "bf16"
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    for _ in range(3):
+        opt.zero_grad()
+        loss = _loss(net(FS, fd), gt, mask)
+        loss.backward()
+        opt.step()
+        assert np.isfinite(loss.item())
