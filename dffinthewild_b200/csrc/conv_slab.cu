@@ -50,7 +50,8 @@ struct alignas(16) SlabParams {
   int B, S, IH, IW;
   int sty, stx, nviews, vpy[4], vpx[4];   // input stride per output step (y, x); one staged view per input-coordinate residue
   int oy, ox, RX, RY, CPS, plane_bytes, NP, LA, hz;
-  int N, nops, nph;          // MMA N; table entries; output phases (1 = convolution, 4 = fused transposed convolution)
+  int N, nops, nph;          // MMA N; table entries; output phases (1 = convolution, 4 = fused transposed convolution, 2 = x-folded one)
+  int phy[4], phx[4];        // output offset of each phase
   int g[12], ge[12];         // MMA groups by (phase, focal offset): table range [g[ph*3+k], ge[ph*3+k])
   int tilesX, tilesY, nsplit, slen, nitems;
   int OHt, OWt, OH, OW, osy, osx, ooy, oox;
@@ -114,7 +115,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
       if (valid && rsrc) {
         // the residual operand does not depend on the accumulator: pull it towards L1 while the MMAs run
         for (int ph = 0; ph < p.nph; ++ph) {
-          const size_t pix = (row0 + (oy * p.osy + (p.nph > 1 ? (ph >> 1) : p.ooy))) * p.OW + (ox * p.osx + (p.nph > 1 ? (ph & 1) : p.oox));
+          const size_t pix = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
           const size_t ob = pix * ep.cstore * esz;
           for (int k = 0; k < ep.cstore * esz; k += 128) prefetch_l1(reinterpret_cast<const char*>(rsrc) + ob + k);
         }
@@ -123,7 +124,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
       fence_after();
       if (q == 3) DFF_TR(3, sc);
       for (int ph = 0; ph < p.nph; ++ph) {
-        const size_t pix = (row0 + (oy * p.osy + (p.nph > 1 ? (ph >> 1) : p.ooy))) * p.OW + (ox * p.osx + (p.nph > 1 ? (ph & 1) : p.oox));
+        const size_t pix = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
         if (p.exp & 2) continue;
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N;
         if (FAST) tc_epilogue_fast<RELU, RES, AUX, PROJ>(ep, ss_s, tacc, valid, pix);
@@ -377,8 +378,12 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   struct VT { int dz, view, vy, vx, widx, ph; };
   std::vector<VT> vt;
   int vymin = 1000, vymax = -1000, vxmin = 1000, vxmax = -1000, dzmin = 1000, dzmax = -1000;
-  if (nph != 1 && nph != 4) return false;
+  if (nph != 1 && nph != 2 && nph != 4) return false;
   p.nph = nph;
+  for (int ph = 0; ph < 4; ++ph) {
+    p.phy[ph] = nph == 4 ? (ph >> 1) : (nph == 2 ? ph : a.ooy);   // nph == 2: the two row phases of an x-folded transposed conv
+    p.phx[ph] = nph == 4 ? (ph & 1) : (nph == 2 ? 0 : a.oox);
+  }
   for (int ph = 0; ph < nph; ++ph)
   for (int t = 0; t < ptaps[ph].n; ++t) {
     const TapTable& tt = ptaps[ph];
@@ -494,6 +499,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.epi.out = a.out; p.epi.out_aux = a.out_aux; p.epi.aux_add = a.aux_add;
   p.epi.cstore = a.Cout; p.epi.relu = a.relu; p.epi.out_f32 = a.out_f32; p.epi.N = Ntc;
   p.epi.proj_w = a.proj_w; p.epi.proj_out = a.proj_out; p.epi.proj_src = a.proj_src; p.epi.skip_out = a.skip_out;
+  p.epi.proj_c = a.proj_c;
   return true;
 }
 
@@ -570,6 +576,34 @@ int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, i
   if (g > 512) g = 512;
   pack_weight_slab_fold_kernel<<<g, 256, 0, st>>>(w, (__nv_bfloat16*)dst, Cout, Cin, CinP, kd, kh, kw, G);
   DFF_LAUNCH_CHECK("pack_weight_slab_fold");
+  return 0;
+}
+
+// x-folded transposed convolution (k = 3, stride (1,2,2)): the two column phases px = 0, 1 of an output row are adjacent pixels, so
+// they become 2*Cout channels of one GEMM row fed by the input taps dx in {0, +1}:  dst bf16 [(kd*3+kh)*2 + dxq][Cin/8][2*Cout][8],
+//   px = 0: dxq == 0 ? Wt[ci][co][kd][kh][1] : 0          px = 1: dxq == 1 ? Wt[ci][co][kd][kh][0] : Wt[ci][co][kd][kh][2]
+__global__ void pack_weight_slab_deconv_fold_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
+                                                    int CinP) {
+  const int nchunk = CinP / 8, N = 2 * Cout;
+  const int n = 18 * nchunk * N * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int j = i & 7, nn = (i >> 3) % N, c = (i / (8 * N)) % nchunk, t = i / (8 * N * nchunk);
+    const int dxq = t & 1, kk = t >> 1;   // kk = kd*3 + kh
+    const int px = nn / Cout, co = nn % Cout, ci = c * 8 + j;
+    int kw = -1;
+    if (px == 0) kw = dxq == 0 ? 1 : -1;
+    else kw = dxq == 1 ? 0 : 2;
+    float v = 0.f;
+    if (ci < Cin && kw >= 0) v = w[(((size_t)ci * Cout + co) * 9 + kk) * 3 + kw];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+int launch_pack_weight_slab_deconv_fold(const float* w, void* dst, int Cout, int Cin, int CinP, cudaStream_t st) {
+  const int n = 18 * CinP * 2 * Cout;
+  int g = cdiv(n, 256);
+  if (g > 512) g = 512;
+  pack_weight_slab_deconv_fold_kernel<<<g, 256, 0, st>>>(w, (__nv_bfloat16*)dst, Cout, Cin, CinP);
+  DFF_LAUNCH_CHECK("pack_weight_slab_deconv_fold");
   return 0;
 }
 

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     EpiArgs ep;
     ep.scale = p.scale; ep.shift = p.shift; ep.res_pre = p.res_pre; ep.res_post = p.res_post; ep.out = p.out;
     ep.out_aux = p.out_aux; ep.aux_add = p.aux_add; ep.cstore = p.cstore; ep.relu = p.relu; ep.out_f32 = p.out_f32; ep.N = p.N;
-    ep.proj_w = p.proj_w; ep.proj_out = p.proj_out; ep.proj_src = p.proj_src; ep.skip_out = p.skip_out;
+    ep.proj_w = p.proj_w; ep.proj_out = p.proj_out; ep.proj_src = p.proj_src; ep.skip_out = p.skip_out; ep.proj_c = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;

@@ -43,6 +43,7 @@ bool conv_slab_supported(const ConvArgs& a, const TapTable* ptaps, int nph, int 
 int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const void* wslab, int Ntc, int num_sms, cudaStream_t st);
 int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
                             cudaStream_t st);
+int launch_pack_weight_slab_deconv_fold(const float* w, void* dst, int Cout, int Cin, int CinP, cudaStream_t st);
 int launch_replicate_ss(const float* scale, const float* shift, float* dst, int C, int G, cudaStream_t st);
 int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, int CinP, int kd, int kh, int kw, int G, cudaStream_t st);
 int launch_conv_wgrad(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, int ci_base, float* dw, int ntaps_total,
@@ -149,6 +150,13 @@ struct Net {
       packed_bytes += align_up((size_t)kd * kh * (kw + l.gfold - 1) * l.CinT * l.gfold * cout * 2, 256);
       l.pk_ssfold = packed_bytes;
       packed_bytes += align_up((size_t)2 * l.gfold * cout * sizeof(float), 256);
+    }
+    if (transposed && cout <= 32 && cout % 8 == 0 && cin % 8 == 0) {   // x-folded transposed conv: the two column phases in one GEMM row
+      l.gfold = 2;
+      l.pk_wfold = packed_bytes;
+      packed_bytes += align_up((size_t)18 * l.CinT * 2 * cout * 2, 256);
+      l.pk_ssfold = packed_bytes;
+      packed_bytes += align_up((size_t)2 * 2 * cout * sizeof(float), 256);
     }
     l.pk_pair = packed_bytes;   // paired-tap fp32 weights (Cout, 8, 1, 9, 5) of the first layer
     if (cin == 3 && kh == 9 && kw == 9 && dil == 2 && kd == 1) { l.pair_x = true; packed_bytes += align_up((size_t)cout * 360 * sizeof(float), 256); }
@@ -381,6 +389,38 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
       return launch_conv_tc(a, wtc, l.pair_x ? 45 : l.ntaps, l.Ntc, nsm, st);
     }
     return launch_conv_ffma(a, bf16, st);
+  }
+  if (wtc && wslab && use_fold && packed_base && l.gfold == 2 && a.Cout == l.cout) {
+    // x-folded transposed conv: two row phases, each GEMM row = the two adjacent output pixels (2j, 2j+1) as 2*Cout channels
+    TapTable pt[2];
+    for (int py = 0; py < 2; ++py) {
+      TapTable& t = pt[py];
+      t.n = 0;
+      for (int kd = 0; kd < 3; ++kd)
+        for (int kh = 0; kh < 3; ++kh) {
+          if ((kh == 1) != (py == 0)) continue;   // row phase 0 uses kh = 1, row phase 1 uses kh = 0 (offset +1) and 2 (offset 0)
+          for (int dxq = 0; dxq < 2; ++dxq) {
+            t.dz[t.n] = (int8_t)(1 - kd);
+            t.dy[t.n] = (int8_t)(kh == 0 ? 1 : 0);
+            t.dx[t.n] = (int8_t)dxq;
+            t.widx[t.n] = (uint8_t)((kd * 3 + kh) * 2 + dxq);
+            ++t.n;
+          }
+        }
+    }
+    ConvArgs f = a;
+    f.taps = pt[1];
+    f.isy = f.isx = 1; f.osy = 2; f.osx = 1; f.ooy = f.oox = 0;
+    f.OHt = in.H; f.OWt = in.W;
+    f.OW = in.W;                 // output viewed as (.., 2*IH, IW, 2*Cout)
+    f.Cout = 2 * l.cout;
+    f.scale = (const float*)(packed_base + l.pk_ssfold);
+    f.shift = f.scale + 2 * l.cout;
+    f.proj_c = a.proj_w ? l.cout : 0;
+    if (conv_slab_supported(f, pt, 2, 2 * l.cout)) {
+      *nlaunch = 1;
+      return count_only ? 0 : launch_conv_slab(f, pt, 2, packed_base + l.pk_wfold, 2 * l.cout, nsm, st);
+    }
   }
   if (wtc && wslab) {  // all four output-parity phases in one launch: the input planes are staged once
     TapTable pt[4];
@@ -756,7 +796,8 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
                            bn ? raw + l.raw_var : nullptr, l.raw_bias >= 0 ? raw + l.raw_bias : nullptr,
                            (float*)(pk + l.pk_scale), (float*)(pk + l.pk_shift), l.cout, l.CoutP, st));
     if (l.gfold > 1) {
-      DFF_TRY(launch_pack_weight_slab_fold(raw + l.raw_w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st));
+      if (l.transposed) DFF_TRY(launch_pack_weight_slab_deconv_fold(raw + l.raw_w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, st));
+      else DFF_TRY(launch_pack_weight_slab_fold(raw + l.raw_w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st));
       DFF_TRY(launch_replicate_ss((const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), (float*)(pk + l.pk_ssfold), l.cout,
                                   l.gfold, st));
     }

@@ -140,6 +140,7 @@ struct EpiArgs {
   const float* proj_w;
   float* proj_out;
   int proj_src, skip_out;
+  int proj_c;   // x-folded rows hold cstore / proj_c pixels: one projection per pixel, proj_out[pix * (cstore / proj_c) + g]; 0 = one pixel
 };
 
 // `tacc`: TMEM address of the accumulator (lane quadrant and buffer column included).  Warp-collective (tcgen05.ld).
@@ -264,7 +265,8 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
   const __nv_bfloat16* const res = reinterpret_cast<const __nv_bfloat16*>(RES == 1 ? p.res_pre : p.res_post) + o0;
   __nv_bfloat16* const oaux = reinterpret_cast<__nv_bfloat16*>(p.out_aux) + o0;
   const __nv_bfloat16* const aadd = reinterpret_cast<const __nv_bfloat16*>(p.aux_add) + o0;
-  float pacc = 0.f;
+  float pacc = 0.f, pacc1 = 0.f;   // (x-folded rows: pixel 0 / pixel 1 of the row)
+  const int pc = (PROJ && p.proj_c) ? p.proj_c : p.cstore;
   for (int c0 = 0; c0 < p.N; c0 += 16) {
     uint32_t v[16];
     tmem_ld16(tacc + c0, v);
@@ -317,18 +319,24 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
         }
       }
       if (PROJ) {   // the projection sees what the next layer will read: the bf16-rounded values
+        const int g = c >= pc ? 1 : 0, cw = c - g * pc;
+        float t = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j += 4) {
-          const float4 pw = __ldg(reinterpret_cast<const float4*>(p.proj_w + c + j));
-          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j])), pw.x, pacc);
-          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 1])), pw.y, pacc);
-          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 2])), pw.z, pacc);
-          pacc = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 3])), pw.w, pacc);
+          const float4 pw = __ldg(reinterpret_cast<const float4*>(p.proj_w + cw + j));
+          t = fmaf(__bfloat162float(__float2bfloat16_rn(f[j])), pw.x, t);
+          t = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 1])), pw.y, t);
+          t = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 2])), pw.z, t);
+          t = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 3])), pw.w, t);
         }
+        if (g) pacc1 += t; else pacc += t;
       }
     }
   }
-  if (PROJ && valid) p.proj_out[pix] = pacc;
+  if (PROJ && valid) {
+    if (p.proj_c) { p.proj_out[2 * pix] = pacc; p.proj_out[2 * pix + 1] = pacc1; }
+    else p.proj_out[pix] = pacc;
+  }
 }
 
 }  // namespace dff
