@@ -1,5 +1,7 @@
 // Bandwidth kernels of the depth-from-focus path: layout conversion, pooling, the depth head, the FOV warp and the
 // weight/BatchNorm packing.  All are coalesced, vectorised where alignment allows, and read every byte once.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dff {
@@ -207,20 +209,22 @@ __device__ __forceinline__ float softplus_p(float v) {
   if (FAST) return (v > 20.f ? v : __logf(1.f + __expf(v))) + 1e-6f;
   return softplus_ref(v) + 1e-6f;
 }
-template <bool FAST>
-__global__ void __launch_bounds__(128) depth_head4_kernel(const __grid_constant__ Head4 a, const float* __restrict__ fd, long long sb,
-                                                          long long ss, long long sy, long long sx, int B, int S, int H, int W) {
+// One thread = one output pixel x one PAIR of heads (blockIdx.z parity): half the registers per thread, twice the threads —
+// the kernel is latency-bound, occupancy is what it needs (the second read of focus_dists hits L1/L2).
+template <bool FAST, int HP>
+__global__ void __launch_bounds__(128, 10) depth_head4_kernel(const __grid_constant__ Head4 a, const float* __restrict__ fd, long long sb,
+                                                              long long ss, long long sy, long long sx, int B, int S, int H, int W) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y, b = blockIdx.z;
+  const int y = blockIdx.y, b = blockIdx.z / (4 / HP), hp = blockIdx.z % (4 / HP);
   if (x >= W) return;
-  // heads 0-2 are bilinearly upsampled (align_corners=False); head 3 is at full resolution.  Per head: the four tap offsets
-  // inside a slice and the two interpolation weights.
-  int o00[3], o01[3], o10[3], o11[3];
-  float ly1[3], lx1[3];
-  size_t sl[3];
+  // per head of the pair: the four bilinear tap offsets inside a slice (align_corners=False) and the interpolation weights;
+  // a full-resolution head degenerates to one tap with weight 1
+  int o00[HP], o01[HP], o10[HP], o11[HP], sl[HP];
+  float ly1[HP], lx1[HP];
+  const float* c[HP];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int h = a.h[k], w = a.w[k];
+  for (int k = 0; k < HP; ++k) {
+    const int hd = HP * hp + k, h = a.h[hd], w = a.w[hd];
     const float ry = (float)h / (float)H, rx = (float)w / (float)W;
     float fy = ry * ((float)y + 0.5f) - 0.5f, fx = rx * ((float)x + 0.5f) - 0.5f;
     fy = fy < 0.f ? 0.f : fy;
@@ -229,44 +233,29 @@ __global__ void __launch_bounds__(128) depth_head4_kernel(const __grid_constant_
     const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
     ly1[k] = fy - (float)y0; lx1[k] = fx - (float)x0;
     o00[k] = y0 * w + x0; o01[k] = y0 * w + x1; o10[k] = y1 * w + x0; o11[k] = y1 * w + x1;
-    sl[k] = (size_t)h * w;
+    sl[k] = h * w;
+    c[k] = a.cost[hd] + (size_t)b * S * sl[k];
   }
-  const size_t sl3 = (size_t)H * W;
-  const float* c0 = a.cost[0] + (size_t)b * S * sl[0];
-  const float* c1 = a.cost[1] + (size_t)b * S * sl[1];
-  const float* c2 = a.cost[2] + (size_t)b * S * sl[2];
-  const float* c3 = a.cost[3] + (size_t)b * S * sl3 + (size_t)y * W + x;
-  float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+  float num[HP], den[HP];
+#pragma unroll
+  for (int k = 0; k < HP; ++k) num[k] = den[k] = 0.f;
   const float* fp = fd + b * sb + y * sy + x * sx;
 #pragma unroll 2
   for (int s = 0; s < S; ++s) {
     const float f = __ldg(fp + s * ss);
-    float v[4];
-    {
-      const float* c = c0 + s * sl[0];
-      v[0] = (1.f - ly1[0]) * ((1.f - lx1[0]) * __ldg(c + o00[0]) + lx1[0] * __ldg(c + o01[0])) +
-             ly1[0] * ((1.f - lx1[0]) * __ldg(c + o10[0]) + lx1[0] * __ldg(c + o11[0]));
-    }
-    {
-      const float* c = c1 + s * sl[1];
-      v[1] = (1.f - ly1[1]) * ((1.f - lx1[1]) * __ldg(c + o00[1]) + lx1[1] * __ldg(c + o01[1])) +
-             ly1[1] * ((1.f - lx1[1]) * __ldg(c + o10[1]) + lx1[1] * __ldg(c + o11[1]));
-    }
-    {
-      const float* c = c2 + s * sl[2];
-      v[2] = (1.f - ly1[2]) * ((1.f - lx1[2]) * __ldg(c + o00[2]) + lx1[2] * __ldg(c + o01[2])) +
-             ly1[2] * ((1.f - lx1[2]) * __ldg(c + o10[2]) + lx1[2] * __ldg(c + o11[2]));
-    }
-    v[3] = __ldg(c3 + s * sl3);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float p = softplus_p<FAST>(v[k]);
-      den[k] += p;
-      num[k] = fmaf(f, p, num[k]);
+    for (int k = 0; k < HP; ++k) {
+      const float* p = c[k];
+      const float v = (1.f - ly1[k]) * ((1.f - lx1[k]) * __ldg(p + o00[k]) + lx1[k] * __ldg(p + o01[k])) +
+                      ly1[k] * ((1.f - lx1[k]) * __ldg(p + o10[k]) + lx1[k] * __ldg(p + o11[k]));
+      c[k] += sl[k];
+      const float pr = softplus_p<FAST>(v);
+      den[k] += pr;
+      num[k] = fmaf(f, pr, num[k]);
     }
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) a.depth[k][((size_t)b * H + y) * W + x] = num[k] / den[k];
+  for (int k = 0; k < HP; ++k) a.depth[HP * hp + k][((size_t)b * H + y) * W + x] = num[k] / den[k];
 }
 
 // cost[0..2]: upsampled heads (any resolution dividing H, W) ; cost[3]: the full-resolution head.  fast: SFU exp/log.
@@ -277,10 +266,10 @@ int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4
     if (h[k] <= 0 || w[k] <= 0 || H % h[k] || W % w[k]) return fail(-1, "depth_head: H,W must be multiples of the cost resolution");
     a.cost[k] = cost[k]; a.h[k] = h[k]; a.w[k] = w[k]; a.depth[k] = depth[k];
   }
-  dim3 grid(cdiv(W, 128), H, B);
-  if (h[3] != H || w[3] != W) return fail(-1, "depth_head4: the last head must be at full resolution");
-  if (fast) depth_head4_kernel<true><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
-  else depth_head4_kernel<false><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
+  static const int hp = getenv("DFF_HEAD_HP") ? atoi(getenv("DFF_HEAD_HP")) : 2;
+  dim3 grid(cdiv(W, 128), H, B * (4 / hp));
+  if (fast) { if (hp == 1) depth_head4_kernel<true, 1><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W); else depth_head4_kernel<true, 2><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W); }
+  else depth_head4_kernel<false, 2><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
   DFF_LAUNCH_CHECK("depth_head4");
   return 0;
 }
