@@ -919,8 +919,11 @@ int dff_forward_host(const void* packed, const float* FS_host, const float* fd_h
   };
   if (fd_span(mb) > (size_t)mb * S * H * W) return fail(DFF_E_ARG, "dff_forward_host: focus_dists strides exceed (B,S,H,W)");
   int rc = 0, nchunk = 0;
-  for (int i0 = 0; i0 < B && !rc; i0 += mb, ++nchunk) {
-    const int n = (B - i0) < mb ? (B - i0) : mb, k = nchunk & 1;
+  // chunk sizes ramp up (mb/4, mb/2, mb, mb, ...): the first host->device copy cannot overlap anything, so it is kept short
+  for (int i0 = 0, n = 0; i0 < B && !rc; i0 += n, ++nchunk) {
+    n = nchunk == 0 ? (mb >= 4 ? mb / 4 : mb) : (nchunk == 1 ? (mb >= 2 ? mb / 2 : mb) : mb);
+    if (n > B - i0) n = B - i0;
+    const int k = nchunk & 1;
     char* io = (char*)dev_io + k * stage;
     float* dFS = (float*)io;
     float* dfd = (float*)(io + align_up((size_t)mb * fs_stack * 4, 256));
