@@ -25,6 +25,8 @@ int launch_depth_head(const float* cost, int h, int w, const float* fd, const in
 int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4], const float* fd, const int64_t* st4, int B, int S,
                        int H, int W, float* const depth[4], bool fast, cudaStream_t st);
 int launch_srd_attention(const void* F, const float* w0, const float* w1, void* out, int B, int S, int H, int W, int C, cudaStream_t st);
+int launch_srd_attention_mma(const void* F, const float* w0, const float* w1, void* out, int B, int S, int H, int W, int C, int num_sms,
+                             cudaStream_t st);
 int launch_fov_warp_cl(const void* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
                        cudaStream_t st);
 int launch_pair_volume(const void* feat, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
@@ -570,15 +572,24 @@ struct Runner {
     Ten f = conv(p + ".Focus_Measure.conv.2.0", t, e);
     const Layer& l0 = net.layers[net.index.at(p + ".N_ch_attention.0")];
     const Layer& l1 = net.layers[net.index.at(p + ".N_ch_attention.2")];
-    if (use_tc && f.C == 8 && l0.CinP == f.C && l0.CoutP == f.C) {   // (C = 16 needs 111 registers per pixel-thread: slower than the two MMAs)
-      // both attention convolutions, both ReLUs and the residual in one bandwidth pass (the intermediate stays in registers)
-      Ten o = alloc(f.B, f.S, f.H, f.W, f.C);
-      const double vox = (double)f.B * f.S * f.H * f.W;
-      op_begin(p + ".N_ch_attention(fused)", 2.0 * vox * f.C * f.C * 4, 2.0 * vox * f.C * esize(false) + 4.0 * f.C * f.C * 4, 1);
-      if (!dry && !rc)
-        rc = launch_srd_attention(f.p, (const float*)(packed + l0.pk_w), (const float*)(packed + l1.pk_w), o.p, f.B, f.S, f.H, f.W, f.C, st);
-      op_end();
-      return o;
+    if (use_tc && (f.C == 8 || f.C == 16 || f.C == 32) && l0.CinP == f.C && l0.CoutP == f.C && (f.H * f.W) % 16 == 0) {
+      // both attention convolutions, both ReLUs and the residual in one bandwidth pass (the intermediate stays in registers):
+      // warp-level tensor-core kernel (attention.cu); DFF_B200_ATTN=ffma selects the scalar C = 8 kernel, =mma2 the two slab launches
+      static const char* mode = getenv("DFF_B200_ATTN");
+      const bool scalar = mode && !strcmp(mode, "ffma") && f.C == 8;
+      if (!(mode && !strcmp(mode, "mma2"))) {
+        Ten o = alloc(f.B, f.S, f.H, f.W, f.C);
+        const double vox = (double)f.B * f.S * f.H * f.W;
+        op_begin(p + ".N_ch_attention(fused)", 2.0 * vox * f.C * f.C * 4, 2.0 * vox * f.C * esize(false) + 4.0 * f.C * f.C * 4, 1);
+        if (!dry && !rc) {
+          const float* w0 = (const float*)(packed + l0.pk_w);
+          const float* w1 = (const float*)(packed + l1.pk_w);
+          rc = scalar ? launch_srd_attention(f.p, w0, w1, o.p, f.B, f.S, f.H, f.W, f.C, st)
+                      : launch_srd_attention_mma(f.p, w0, w1, o.p, f.B, f.S, f.H, f.W, f.C, num_sms_of_current_device(), st);
+        }
+        op_end();
+        return o;
+      }
     }
     Ten a = conv(p + ".N_ch_attention.0", f, relu());
     EpiOpt e2 = relu();
@@ -1014,6 +1025,22 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
   // 2 = force the per-tap TMA kernel, 3 = slab kernel (never the row kernel)
   return run_conv(l, (const float*)scratch, scale, shift, in, e, o, elem == DFF_BF16, st, use_tensor_cores ? scratch : nullptr,
                   use_tensor_cores != 2 ? (char*)scratch + tcb : nullptr, nullptr, false, use_tensor_cores == 1);
+}
+
+// SRD channel-attention branch as one operator (reference train_codes/Depth_Estimation_Network.py:399-407)
+int dff_srd_attention(const void* F, int B, int S, int H, int W, int C, const float* w_a, const float* w_b, void* out, void* scratch,
+                      int device, void* stream) {
+  if (!F || !w_a || !w_b || !out || !scratch) return fail(DFF_E_ARG, "dff_srd_attention: null pointer");
+  if (C != 8 && C != 16 && C != 32) return fail(DFF_E_UNSUPPORTED, "dff_srd_attention: C must be 8, 16 or 32");
+  if (((size_t)H * W) % 16) return fail(DFF_E_ARG, "dff_srd_attention: H*W must be a multiple of 16");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* w0 = (float*)scratch;            // [dz][ci][co]
+  float* w1 = w0 + (size_t)3 * C * C;     // [c][co]
+  DFF_TRY(launch_pack_weight(w_a, w0, C, C, 3, C, C, 0, st));
+  DFF_TRY(launch_pack_weight(w_b, w1, C, C, 1, C, C, 0, st));
+  return launch_srd_attention_mma(F, w0, w1, out, B, S, H, W, C, num_sms_of_current_device(), st);
 }
 
 int dff_depth_head(const float* cost, int h, int w, const float* fd, const int64_t fd_strides[4], int B, int S, int H, int W,

@@ -47,6 +47,7 @@ def _declare(lib):
         "dff_conv3d_scratch_bytes": (sz, [i, i, i, i, i]),
         "dff_conv3d": (i, [vp, i, vp, i, i, i, i, i, fp, i, i, i, i, i, i, i, fp, fp, vp, vp, i, vp, i, i, vp, i, vp]),
         "dff_depth_head": (i, [fp, i, i, fp, c.POINTER(i64), i, i, i, i, fp, i, vp]),
+        "dff_srd_attention": (i, [vp, i, i, i, i, i, fp, fp, vp, vp, i, vp]),
         "dff_fov_warp": (i, [fp, fp, fp, i, i, i, i, i, fp, fp, i, vp]),
         "dff_fov_warp_cl": (i, [vp, fp, fp, i, i, i, i, i, vp, i, i, vp]),
         "dff_pair_volume": (i, [vp, fp, fp, i, i, i, i, i, vp, i, i, vp]),
@@ -296,6 +297,20 @@ def _with(shape, axis, n):
     s = list(shape)
     s[axis] = n
     return s
+
+
+def srd_attention(x, w_a, w_b):
+    """SRD channel-attention branch (reference Depth_Estimation_Network.py:399-407) in one pass on bf16 channels-last data:
+    x (B,C,S,H,W) fp32, w_a (C,C,3,1,1), w_b (C,C,1,1,1) -> x + relu(conv1x1x1(relu(conv3x1x1(x)))) as (B,C,S,H,W) fp32."""
+    _require_cuda(x, "x")
+    B, C, S, H, W = x.shape
+    a = to_channels_last(x, C, True)
+    out = torch.empty_like(a)
+    scratch = torch.empty(4 * C * C, dtype=torch.float32, device=x.device)
+    check(lib().dff_srd_attention(_ptr(a), B, S, H, W, C, _ptr(w_a.detach().to(x.device, torch.float32).contiguous()),
+                                  _ptr(w_b.detach().to(x.device, torch.float32).contiguous()), _ptr(out), _ptr(scratch),
+                                  x.device.index, _stream(x.device)))
+    return from_channels_last(out, C)
 
 
 def depth_head(cost, focus_dists, H, W):

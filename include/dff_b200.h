@@ -124,6 +124,13 @@ int dff_conv3d(const void *in0, int C0, const void *in1, int C1, int B, int S, i
                const float *shift, const void *res_pre, const void *res_post, int relu, void *out, int elem,
                int use_tensor_cores, void *scratch, int device, void *stream);
 
+/* SRD / Feature_Extraction channel-attention branch (reference train_codes/Depth_Estimation_Network.py:399-407), one pass:
+ *   out = F + relu( conv1x1x1( relu( conv3x1x1(F; w_a) ); w_b ) )      (no BatchNorm, no bias)
+ * F, out: channels-last (B,S,H,W,C) bf16, C in {8,16,32}, H*W % 16 == 0; w_a (C,C,3,1,1), w_b (C,C,1,1,1) fp32 in the
+ * reference layout; scratch >= 4*C*C floats.  The intermediate is rounded to bf16 (as every activation of the bf16 mode). */
+int dff_srd_attention(const void *F, int B, int S, int H, int W, int C, const float *w_a, const float *w_b, void *out,
+                      void *scratch, int device, void *stream);
+
 /* cost (B,S,h,w) fp32 with H % h == 0 -> depth (B,H,W) fp32 */
 int dff_depth_head(const float *cost, int h, int w, const float *fd, const int64_t fd_strides[4], int B, int S, int H,
                    int W, float *depth, int device, void *stream);

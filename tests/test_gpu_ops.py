@@ -212,6 +212,29 @@ def test_conv_bf16_storage(rt):
     assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("C,S,H,W", [(8, 10, 32, 40), (8, 1, 16, 16), (8, 2, 16, 24), (16, 5, 16, 48), (16, 3, 32, 32), (32, 4, 16, 24),
+                                     (32, 10, 32, 32)])
+def test_srd_attention_one_pass(rt, C, S, H, W):
+    """Fused attention branch (mma.sync kernel) against torch fp64 on the same bf16-rounded operands: the only differences are
+    fp32 accumulation order, the bf16 rounding of the intermediate and of the result."""
+    B = 3
+    bf = lambda t: t.to(torch.bfloat16).float()
+    x = bf(_rand(B, C, S, H, W, seed=11, scale=2.0))
+    wa = bf(_rand(C, C, 3, 1, 1, seed=12, scale=(2.0 / (3 * C)) ** 0.5 * 1.7))
+    wb = bf(_rand(C, C, 1, 1, 1, seed=13, scale=(2.0 / C) ** 0.5 * 1.7))
+    mid = F.relu(F.conv3d(x.double(), wa.double(), None, 1, (1, 0, 0)))
+    mid_bf = mid.float().to(torch.bfloat16).double()
+    ref = x.double() + F.relu(F.conv3d(mid_bf, wb.double()))
+    out = rt.srd_attention(x.cuda(), wa.cuda(), wb.cuda()).cpu().double()
+    # the intermediate may round to a neighbouring bf16 value (fp32 vs fp64 accumulation): one ulp of one term of the second sum
+    tol = 2.0 ** -8 * (ref.abs().max().item() + mid.abs().max().item() * wb.abs().max().item())
+    err = (out - ref).abs().max().item()
+    assert err <= tol, (err, tol)
+    # and the bulk must be exact to output rounding (half an ulp of bf16)
+    frac_exact = ((out - ref).abs() <= 2.0 ** -8 * ref.abs().clamp_min(1e-3)).double().mean().item()
+    assert frac_exact > 0.99, frac_exact
+
+
 @pytest.mark.parametrize("r", [1, 2, 4, 8])
 def test_depth_head(rt, r):
     from oracle import dff_oracle as O
