@@ -92,6 +92,7 @@ struct ConvArgs {
   const float* proj_w;     // optional fused C -> 1 projection in the tensor-core epilogues (see EpiArgs)
   float* proj_out;
   int proj_src, skip_out;
+  int no_wstream;          // slab kernel: do not fall back to streamed weights (the caller has a better form for this layer)
   int proj_c;              // channels per pixel of the projection when a GEMM row holds several pixels (x-folded layers), 0 = all
   TapTable taps;
 };

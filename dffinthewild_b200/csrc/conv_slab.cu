@@ -30,6 +30,9 @@ namespace dff {
 constexpr int kSlabProducers = 64;                     // warps 0-1: cp.async producers
 constexpr int kSlabMmaWarp = kSlabProducers / 32;      // warp 2: MMA issuer (+TMEM alloc)
 constexpr int kSlabThreads = kSlabProducers + 32 + 128;  // + warps 3-6: epilogue (one per TMEM lane quadrant)
+constexpr int kSlabThreadsWS = kSlabThreads + 32;        // weight-streaming variant: + warp 7, the weight producer
+constexpr int kSlabMaxWSlot = 40 * 1024;                 // largest slot of the streamed-weight ring (bytes)
+constexpr int kSlabMaxWSlots = 8;
 constexpr int kSlabMaxOps = 128;
 constexpr int kSlabMaxPlanes = 8;
 constexpr int kSlabTW = 8, kSlabTH = 16;
@@ -59,6 +62,11 @@ struct alignas(16) SlabParams {
   long long* trace;
   int exp;                   // timing experiments only (DFF_SLAB_EXPERIMENT bit mask; results are wrong): 1 no loads, 2 no stores, 4 no MMAs
   EpiArgs epi;
+  // streamed weights (layers whose weights do not fit in shared memory next to the plane ring): the MMA table is cut into blocks of
+  // consecutive MMAs whose weights are one contiguous range of `wslab`; warp 7 streams them through a ring of `nwslots` slots
+  int wstream, nwslots, nblk, wslot_bytes;
+  int gb[12], gbe[12];              // block range per MMA group
+  uint8_t bop[kSlabMaxOps], bn[kSlabMaxOps];   // first MMA / number of MMAs of each block
   alignas(16) uint64_t tab[kSlabMaxOps + 4];  // (+1 quad: the issuer prefetches one quad ahead) per MMA, zero-extended to 64 bits (added to the descriptor): (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
   int16_t wsrc[2 * kSlabMaxOps];  // per MMA and K half: 8-channel weight block (tap * nchunk + chunk) in `wslab`, -1 = zeros
 };
@@ -137,10 +145,12 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
   }
 }
 
-__global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid_constant__ SlabParams p) {
+template <bool WS>
+__global__ void __launch_bounds__(WS ? kSlabThreadsWS : kSlabThreads, WS ? 1 : 4) conv_slab_kernel(const __grid_constant__ SlabParams p) {
   using namespace tc;
+  constexpr int kThreads = WS ? kSlabThreadsWS : kSlabThreads;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kSlabMaxPlanes + 4];
+  __shared__ __align__(8) uint64_t bars[2 * kSlabMaxPlanes + 4 + (WS ? 2 * kSlabMaxWSlots : 0)];
   __shared__ uint32_t tmem_base_s;
   const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
@@ -151,8 +161,14 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kSlabMaxPlanes]);
   const uint32_t tfull0 = smem_u32(&bars[2 * kSlabMaxPlanes]), tempty0 = smem_u32(&bars[2 * kSlabMaxPlanes + 2]);
+  const uint32_t wfull0 = smem_u32(&bars[2 * kSlabMaxPlanes + 4]), wempty0 = wfull0 + 8 * kSlabMaxWSlots;   // (WS only)
 
   if (threadIdx.x == 0) {
+    if (WS)
+      for (int i = 0; i < p.nwslots; ++i) {
+        mbar_init(wfull0 + 8 * i, 1);
+        mbar_init(wempty0 + 8 * i, 1);
+      }
     for (int i = 0; i < p.NP; ++i) {
       mbar_init(full0 + 8 * i, kSlabProducers);
       mbar_init(empty0 + 8 * i, 1);
@@ -169,10 +185,10 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // ---- one-time: MMA table, weights (MMA order), BatchNorm scale/shift and the staging table into shared memory --------
-  {
+  if (!WS) {
     const int total = 2 * p.nops * p.N;  // 16-byte rows
     const uint4* wg = reinterpret_cast<const uint4*>(p.wslab);
-    for (int i = threadIdx.x; i < total; i += kSlabThreads) {
+    for (int i = threadIdx.x; i < total; i += kThreads) {
       const int blk = i / p.N, r = i - blk * p.N;
       const int src = p.wsrc[blk];
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -180,11 +196,11 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
       asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_s + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
   }
-  for (int i = threadIdx.x; i < p.N; i += kSlabThreads) {
+  for (int i = threadIdx.x; i < p.N; i += kThreads) {
     ss[i] = p.epi.scale ? __ldg(p.epi.scale + i) : 1.f;
     ss[p.N + i] = p.epi.shift ? __ldg(p.epi.shift + i) : 0.f;
   }
-  for (int e = threadIdx.x; e < p.nelem; e += kSlabThreads) {
+  for (int e = threadIdx.x; e < p.nelem; e += kThreads) {
     const int c = e % p.nchunk, pix = e / p.nchunk;
     const int rx = pix % p.RX, t = pix / p.RX;
     const int ry = t % p.RY, v = t / p.RY;
@@ -262,6 +278,8 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
     const int NP = p.NP, ngrp = 3 * p.nph;
     int wslot = 0, sc = 0;
     uint32_t wphase = 0;
+    int wsl = 0;          // (WS) slot / parity of the streamed-weight ring
+    uint32_t wsph = 0;
     uint64_t a_prev = 0, a_cur = 0, a_next = 0;   // descriptor bases of the planes of slices s-1, s, s+1
     uint32_t e_prev = 0, e_cur = 0, e_next = 0;   // their `empty` barriers
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
@@ -286,10 +304,65 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
         mbar_wait(tempty0 + 8 * buf, ((sc >> 1) & 1) ^ 1);
         fence_after();
         DFF_TR(1, sc);
+        if (WS) {
+          // streamed weights: the whole warp waits for a block's ring slot (warp-uniform control flow keeps the descriptors in uniform
+          // registers), the elected lane issues the block's MMAs and hands the slot back when they have read it
+          uint32_t dacc = tmem_base + buf * p.nph * p.N;
+          uint32_t acc = 0;
+          int k = 0;
+#pragma unroll 1
+          for (int gi = 0; gi < ngrp; ++gi) {
+            const int b0 = p.gb[gi], b1 = p.gbe[gi];
+            const int z = s + k - 1;
+            if (b1 > b0 && z >= 0 && z < p.S && !(p.exp & 4)) {
+              const uint64_t ad0 = k == 0 ? a_prev : (k == 1 ? a_cur : a_next);
+#pragma unroll 1
+              for (int b = b0; b < b1; ++b) {
+#ifdef DFF_SLAB_TRACE
+                const long long tw0 = clock64();
+#endif
+                mbar_wait(wfull0 + 8 * wsl, wsph);
+#ifdef DFF_SLAB_TRACE
+                if (p.trace && blockIdx.x == 0 && sc < 64 && lane == 0) p.trace[sc * 8 + 7] += clock64() - tw0;   // clocks spent waiting for weights
+#endif
+                fence_after();
+                if (leader) {
+                  const int o0 = p.bop[b];
+                  int n = p.bn[b];
+                  uint64_t bd = bd_base + (uint64_t)((uint32_t)(wsl * p.wslot_bytes) >> 4);
+                  const ulonglong2* tq = reinterpret_cast<const ulonglong2*>(p.tab + o0);  // blocks start on quad boundaries
+                  ulonglong2 t01 = tq[0], t23 = tq[1];
+#pragma unroll 1
+                  for (; n >= 4; n -= 4) {
+                    tq += 2;
+                    const ulonglong2 n01 = tq[0], n23 = tq[1];
+                    umma(dacc, ad0 + t01.x, bd, idesc, acc);
+                    umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
+                    umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
+                    umma_acc(dacc, ad0 + t23.y, bd + 3 * b_step, idesc);
+                    acc = 1;
+                    bd += 4 * b_step;
+                    t01 = n01; t23 = n23;
+                  }
+                  if (n > 0) {
+                    umma(dacc, ad0 + t01.x, bd, idesc, acc);
+                    if (n > 1) umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
+                    if (n > 2) umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
+                  }
+                  umma_commit(wempty0 + 8 * wsl);
+                }
+                acc = 1;
+                if (++wsl == p.nwslots) { wsl = 0; wsph ^= 1; }
+              }
+            }
+            if (++k == 3) { k = 0; dacc += p.N; acc = 0; }
+          }
+        }
         if (leader) {
           uint32_t dacc = tmem_base + buf * p.nph * p.N;
           uint32_t acc = 0;
           int k = 0;
+          if (!WS)
 #pragma unroll 1
           for (int gi = 0; gi < ngrp; ++gi) {
             const int i0 = p.g[gi], n0 = p.ge[gi] - i0;
@@ -335,6 +408,40 @@ __global__ void __launch_bounds__(kSlabThreads, 4) conv_slab_kernel(const __grid
         }
         __syncwarp();
         DFF_TR(2, sc);
+      }
+    }
+  } else if (WS && warp == kSlabThreads / 32) {
+    // =============================== weight producer (streaming variant) ===============================
+    // walks exactly the issuer's schedule; one bulk copy (global -> shared, completion on the slot's `full` barrier) per block
+    if (lane == 0) {
+      const char* const wg = reinterpret_cast<const char*>(p.wslab);
+      const int ngrp = 3 * p.nph;
+      int wsl = 0;
+      uint32_t eph = 1;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        const int isp = item % p.nsplit;
+        const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
+        for (int s = s_begin; s < s_end; ++s) {
+          int k = 0;
+          for (int gi = 0; gi < ngrp; ++gi) {
+            const int b0 = p.gb[gi], b1 = p.gbe[gi];
+            const int z = s + k - 1;
+            if (b1 > b0 && z >= 0 && z < p.S && !(p.exp & 4)) {
+              for (int b = b0; b < b1; ++b) {
+                mbar_wait(wempty0 + 8 * wsl, eph);
+                const uint32_t bytes = (uint32_t)p.bn[b] * (uint32_t)p.N * 32u;
+                const char* src = wg + (size_t)p.wsrc[2 * p.bop[b]] * p.N * 16;
+                mbar_expect_tx(wfull0 + 8 * wsl, bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 w_s + (uint32_t)(wsl * p.wslot_bytes)),
+                             "l"(src), "r"(bytes), "r"(wfull0 + 8 * wsl)
+                             : "memory");
+                if (++wsl == p.nwslots) { wsl = 0; eph ^= 1; }
+              }
+            }
+            if (++k == 3) k = 0;
+          }
+        }
       }
     }
   } else {
@@ -460,25 +567,77 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.w_bytes = nops * Ntc * 32;
   // ---- shared memory: table + weights + scale/shift + staging table + ring; as many co-resident CTAs as fit -----------------
   p.nelem = p.nviews * p.RY * p.RX * nchunk;
-  int off = 1024 + ((p.w_bytes + 127) & ~127);
-  p.ss_off = off;
-  off += (2 * Ntc * 4 + 127) & ~127;
-  p.elem_off = off;
-  off += (p.nelem * 8 + 127) & ~127;
-  p.planes_off = off;
-  const int fixed = off + 128;  // + slack for the 128-byte alignment of the dynamic window
   const int np_min = 2 * p.hz + 2;
   const int cols = 2 * nph * Ntc;
   if (cols > 512) return false;
   p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  int fixed = 0;
+  auto lay_out = [&](int wregion) {   // offsets for a weight region of `wregion` bytes; returns the fixed part
+    int off = 1024 + ((wregion + 127) & ~127);
+    p.ss_off = off;
+    off += (2 * Ntc * 4 + 127) & ~127;
+    p.elem_off = off;
+    off += (p.nelem * 8 + 127) & ~127;
+    p.planes_off = off;
+    return off + 128;  // + slack for the 128-byte alignment of the dynamic window
+  };
   int occ = 4, NP = 0;
+  fixed = lay_out(p.w_bytes);
   for (; occ >= 1; --occ) {
     if (occ * p.tmem_cols > 512) continue;
     const int budget = kSlabSmemBudget / occ - 2048 - 256;  // static shared memory, the per-CTA reservation, allocation granularity
     NP = (budget - fixed) / p.plane_bytes;
     if (NP >= np_min) break;
   }
-  if (occ < 1) return false;
+  if (occ < 1) {
+    // Resident weights do not fit next to the plane ring: stream them (one CTA per SM, warp 7 feeds a ring of 3-4 slots with bulk
+    // copies).  Blocks = runs of MMAs of one group whose weights are contiguous in `wslab` (consecutive chunk pairs / taps).
+    static const bool no_ws = getenv("DFF_B200_NO_WSTREAM") != nullptr;
+    if (no_ws || a.no_wstream || nchunk < 2) return false;
+    // one CTA per SM leaves nothing to hide partially filled tiles behind: very sparsely filled tile grids stay on the per-tap kernel (measured: 1/16 and 1/32 resolution still gain)
+    // (a fused transposed convolution competes with four launches of this same kernel, not with the per-tap kernel)
+    static const double min_fill = getenv("DFF_B200_WS_FILL") ? atof(getenv("DFF_B200_WS_FILL")) : 0.5;
+    if (nph != 4 && (double)a.OHt * a.OWt < min_fill * (double)(cdiv(a.OHt, kSlabTH) * kSlabTH) * (cdiv(a.OWt, kSlabTW) * kSlabTW)) return false;
+    // Every block costs the issuing warp a barrier wait and a tcgen05.commit (~250 clk that the tensor pipe idles), so blocks are made
+    // as large as the ring allows: a group of MMAs is cut into the fewest blocks whose slot (<= 40 KB) still leaves room for three
+    // slots and the minimal plane ring.
+    const int opb = Ntc * 32;
+    int gmax = 0;
+    for (int gi = 0; gi < 3 * nph; ++gi) gmax = std::max(gmax, p.ge[gi] - p.g[gi]);
+    const int budget = kSlabSmemBudget - 2048 - 256 - 256;
+    int per_slot = 0, nw = 0;
+    for (int parts = 1; parts <= 16 && !per_slot; ++parts) {
+      const int ps = (cdiv(gmax, parts) + 3) & ~3;   // (blocks start on quad boundaries of the MMA table)
+      if (ps * opb > kSlabMaxWSlot) continue;
+      for (nw = 4; nw >= 3; --nw) {
+        fixed = lay_out(nw * ps * opb);
+        NP = (budget - fixed) / p.plane_bytes;
+        if (NP >= np_min + (nw > 3 ? 1 : 0)) { per_slot = ps; break; }   // a fourth slot only if the plane ring keeps one plane of look-ahead
+      }
+    }
+    if (!per_slot) return false;
+    int nb = 0;
+    for (int gi = 0; gi < 3 * nph; ++gi) {
+      p.gb[gi] = nb;
+      int o = p.g[gi];
+      while (o < p.ge[gi]) {
+        int n = 1;
+        while (o + n < p.ge[gi] && n < per_slot && p.wsrc[2 * (o + n)] == p.wsrc[2 * (o + n - 1)] + 2 && p.wsrc[2 * (o + n) + 1] == p.wsrc[2 * (o + n)] + 1) ++n;
+        if (p.wsrc[2 * o] < 0 || p.wsrc[2 * o + 1] != p.wsrc[2 * o] + 1) return false;
+        if (n < per_slot && o + n < p.ge[gi] && (n & 3)) return false;   // a discontinuity off a quad boundary: not expressible
+        p.bop[nb] = (uint8_t)o; p.bn[nb] = (uint8_t)n;
+        ++nb;
+        o += n;
+      }
+      p.gbe[gi] = nb;
+    }
+    p.nblk = nb;
+    occ = 1;
+    p.wslot_bytes = per_slot * opb;
+    p.wstream = 1;
+    p.nwslots = nw;
+    p.w_bytes = nw * p.wslot_bytes;
+  }
   if (NP > kSlabMaxPlanes) NP = kSlabMaxPlanes;
   p.NP = NP;
   p.LA = std::min(5, NP - 2 * p.hz - 1);
@@ -523,9 +682,14 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
 #ifdef DFF_SLAB_TRACE
   if (getenv("DFF_SLAB_TRACE")) { cudaMalloc(&p.trace, 64 * 8 * 8); cudaMemset(p.trace, 0, 64 * 8 * 8); }
 #endif
-  DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.nitems < num_sms * occ ? p.nitems : num_sms * occ;
-  conv_slab_kernel<<<grid, kSlabThreads, smem, st>>>(p);
+  if (p.wstream) {
+    DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_slab_kernel<true><<<grid, kSlabThreadsWS, smem, st>>>(p);
+  } else {
+    DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_slab_kernel<false><<<grid, kSlabThreads, smem, st>>>(p);
+  }
   DFF_LAUNCH_CHECK("conv_slab");
 #ifdef DFF_SLAB_TRACE
   if (p.trace) {
@@ -533,9 +697,9 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
     cudaDeviceSynchronize();
     cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(p.trace);
-    printf("trace C0=%d C1=%d N=%d nops=%d NP=%d occ=%d grid=%d (clk since first event): full-wait tempty-wait issued | tfull-wait epi-done | empty-wait loads-issued\n", p.C0, p.C1, p.N, p.nops, p.NP, occ, grid);
+    printf("trace C0=%d C1=%d N=%d nops=%d NP=%d occ=%d grid=%d wstream=%d nwslots=%d nblk=%d (clk since first event): full-wait tempty-wait issued | tfull-wait epi-done | empty-wait loads-issued\n", p.C0, p.C1, p.N, p.nops, p.NP, occ, grid, p.wstream, p.nwslots, p.nblk);
     long long t0 = h[5] ? h[5] : h[0];
-    for (int i = 0; i < 40; ++i) { for (int j = 0; j < 7; ++j) printf("%8lld", h[i * 8 + j] ? h[i * 8 + j] - t0 : -1); printf("\n"); }
+    for (int i = 0; i < 40; ++i) { for (int j = 0; j < 7; ++j) printf("%8lld", h[i * 8 + j] ? h[i * 8 + j] - t0 : -1); printf(" | w-wait %6lld\n", h[i * 8 + 7]); }
   }
 #endif
   return 0;

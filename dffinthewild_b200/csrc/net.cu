@@ -419,6 +419,7 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     f.scale = (const float*)(packed_base + l.pk_ssfold);
     f.shift = f.scale + 2 * l.cout;
     f.proj_c = a.proj_w ? l.cout : 0;
+    f.no_wstream = a.proj_w ? 0 : 1;   // (measured: with streamed weights the fold only pays when it also halves the classifier epilogue)
     if (conv_slab_supported(f, pt, 2, 2 * l.cout)) {
       *nlaunch = 1;
       return count_only ? 0 : launch_conv_slab(f, pt, 2, packed_base + l.pk_wfold, 2 * l.cout, nsm, st);
