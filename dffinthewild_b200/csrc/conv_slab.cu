@@ -200,11 +200,15 @@ __global__ void __launch_bounds__(WS ? kSlabThreadsWS : kSlabThreads, WS ? 1 : 4
     ss[i] = p.epi.scale ? __ldg(p.epi.scale + i) : 1.f;
     ss[p.N + i] = p.epi.shift ? __ldg(p.epi.shift + i) : 0.f;
   }
+  // (table order = global address order: consecutive producer threads copy consecutive 16-byte pieces — the chunks of a pixel, then
+  // the next pixel of the row — whatever view the pixel belongs to; the shared-memory destination is free-form anyway.  With
+  // strided views (stride-2 and x-folded layers) a view-major order would have every thread touch its own 32-byte sector.)
   for (int e = threadIdx.x; e < p.nelem; e += kThreads) {
-    const int c = e % p.nchunk, pix = e / p.nchunk;
-    const int rx = pix % p.RX, t = pix / p.RX;
-    const int ry = t % p.RY, v = t / p.RY;
-    const int gy = p.sty * (p.oy + ry) + p.vpy[v], gx = p.stx * (p.ox + rx) + p.vpx[v];
+    const int c = e % p.nchunk, t = e / p.nchunk;
+    const int gxi = t % (p.stx * p.RX), gyi = t / (p.stx * p.RX);
+    const int rx = gxi / p.stx, vx = gxi % p.stx, ry = gyi / p.sty, vy = gyi % p.sty;
+    const int pix = ((vy * p.stx + vx) * p.RY + ry) * p.RX + rx;
+    const int gy = p.sty * p.oy + gyi, gx = p.stx * p.ox + gxi;
     const bool second = c >= p.nch0;
     const int C = second ? p.C1 : p.C0, cc = second ? c - p.nch0 : c;
     SlabElem el;
