@@ -30,7 +30,9 @@ namespace dff {
 constexpr int kSlabProducers = 64;                     // warps 0-1: cp.async producers
 constexpr int kSlabMmaWarp = kSlabProducers / 32;      // warp 2: MMA issuer (+TMEM alloc)
 constexpr int kSlabThreads = kSlabProducers + 32 + 128;  // + warps 3-6: epilogue (one per TMEM lane quadrant)
-constexpr int kSlabThreadsWS = kSlabThreads + 32;        // weight-streaming variant: + warp 7, the weight producer
+// variants: E2 = a second group of four epilogue warps (warps 7-10; the groups take alternate output phases) for multi-phase layers
+// whose shared-memory footprint leaves at most two CTAs per SM; WS = weight streaming: + one last warp, the weight producer
+__host__ __device__ constexpr int slab_threads(bool ws, bool e2) { return kSlabThreads + (e2 ? 128 : 0) + (ws ? 32 : 0); }
 constexpr int kSlabMaxWSlot = 40 * 1024;                 // largest slot of the streamed-weight ring (bytes)
 constexpr int kSlabMaxWSlots = 8;
 constexpr int kSlabMaxOps = 128;
@@ -65,6 +67,7 @@ struct alignas(16) SlabParams {
   // streamed weights (layers whose weights do not fit in shared memory next to the plane ring): the MMA table is cut into blocks of
   // consecutive MMAs whose weights are one contiguous range of `wslab`; warp 7 streams them through a ring of `nwslots` slots
   int wstream, nwslots, nblk, wslot_bytes;
+  int egroups;                      // epilogue warp groups (1 or 2)
   int gb[12], gbe[12];              // block range per MMA group
   uint8_t bop[kSlabMaxOps], bn[kSlabMaxOps];   // first MMA / number of MMAs of each block
   alignas(16) uint64_t tab[kSlabMaxOps + 4];  // (+1 quad: the issuer prefetches one quad ahead) per MMA, zero-extended to 64 bits (added to the descriptor): (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
@@ -97,10 +100,11 @@ struct SlabElem {
 // Epilogue role of the slab kernel (4 warps, one TMEM lane quadrant each).  FAST = 0: generic epilogue (tc_epilogue_tile).
 template <int FAST, bool RELU, int RES, bool AUX, bool PROJ>
 __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, float* ss,
-                                              uint32_t ss_s) {
+                                              uint32_t ss_s, const int neg) {
   using namespace tc;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = warp & 3;
+  const int q = warp & 3;                                   // TMEM lane quadrant of this warp
+  const int eg = (warp - (kSlabMmaWarp + 1)) >> 2;          // epilogue group: takes the output phases eg, eg + neg, ...
   const int row = q * 32 + lane;
   const int ty = row >> 3, tx = row & 7;
   EpiArgs ep = p.epi;
@@ -122,7 +126,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
       const size_t row0 = ((size_t)b * p.S + s) * p.OH;
       if (valid && rsrc) {
         // the residual operand does not depend on the accumulator: pull it towards L1 while the MMAs run
-        for (int ph = 0; ph < p.nph; ++ph) {
+        for (int ph = eg; ph < p.nph; ph += neg) {
           const size_t pix = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
           const size_t ob = pix * ep.cstore * esz;
           for (int k = 0; k < ep.cstore * esz; k += 128) prefetch_l1(reinterpret_cast<const char*>(rsrc) + ob + k);
@@ -130,8 +134,8 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
       }
       mbar_wait(tfull0 + 8 * buf, (sc >> 1) & 1);
       fence_after();
-      if (q == 3) DFF_TR(3, sc);
-      for (int ph = 0; ph < p.nph; ++ph) {
+      if (q == 3 && eg == 0) DFF_TR(3, sc);
+      for (int ph = eg; ph < p.nph; ph += neg) {
         const size_t pix = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
         if (p.exp & 2) continue;
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N;
@@ -140,15 +144,16 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
       }
       fence_before();
       mbar_arrive_relaxed(tempty0 + 8 * buf);
-      if (q == 3) DFF_TR(4, sc);
+      if (q == 3 && eg == 0) DFF_TR(4, sc);
     }
   }
 }
 
-template <bool WS>
-__global__ void __launch_bounds__(WS ? kSlabThreadsWS : kSlabThreads, WS ? 1 : 4) conv_slab_kernel(const __grid_constant__ SlabParams p) {
+template <bool WS, bool E2>
+__global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) conv_slab_kernel(const __grid_constant__ SlabParams p) {
   using namespace tc;
-  constexpr int kThreads = WS ? kSlabThreadsWS : kSlabThreads;
+  constexpr int kThreads = slab_threads(WS, E2);
+  constexpr int kEG = E2 ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kSlabMaxPlanes + 4 + (WS ? 2 * kSlabMaxWSlots : 0)];
   __shared__ uint32_t tmem_base_s;
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(WS ? kSlabThreadsWS : kSlabThreads, WS ? 1 : 4
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, 128);
+      mbar_init(tempty0 + 8 * i, 128 * kEG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(WS ? kSlabThreadsWS : kSlabThreads, WS ? 1 : 4
         DFF_TR(2, sc);
       }
     }
-  } else if (WS && warp == kSlabThreads / 32) {
+  } else if (WS && warp == kThreads / 32 - 1) {
     // =============================== weight producer (streaming variant) ===============================
     // walks exactly the issuer's schedule; one bulk copy (global -> shared, completion on the slot's `full` barrier) per block
     if (lane == 0) {
@@ -455,11 +460,11 @@ __global__ void __launch_bounds__(WS ? kSlabThreadsWS : kSlabThreads, WS ? 1 : 4
     const int res = e.res_pre ? 1 : (e.res_post ? 2 : 0);
     const bool aux = e.out_aux != nullptr, proj = e.proj_w != nullptr;
     const uint32_t ss_s = smem_u32(ss);
-    if (e.out_f32 || (e.res_pre && e.res_post) || (res == 1 && aux) || (res == 2 && (aux || e.relu)) || (proj && !aux && res != 2)) slab_epilogue<0, false, 0, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s);
-    else if (aux) { if (proj) slab_epilogue<1, false, 0, true, true>(p, tmem_base, tfull0, tempty0, ss, ss_s); else slab_epilogue<1, false, 0, true, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); }
-    else if (res == 2) { if (proj) slab_epilogue<1, false, 2, false, true>(p, tmem_base, tfull0, tempty0, ss, ss_s); else slab_epilogue<1, false, 2, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); }
-    else if (res == 1) { if (e.relu) slab_epilogue<1, true, 1, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); else slab_epilogue<1, false, 1, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); }
-    else { if (e.relu) slab_epilogue<1, true, 0, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); else slab_epilogue<1, false, 0, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s); }
+    if (e.out_f32 || (e.res_pre && e.res_post) || (res == 1 && aux) || (res == 2 && (aux || e.relu)) || (proj && !aux && res != 2)) slab_epilogue<0, false, 0, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s, kEG);
+    else if (aux) { if (proj) slab_epilogue<1, false, 0, true, true>(p, tmem_base, tfull0, tempty0, ss, ss_s, kEG); else slab_epilogue<1, false, 0, true, false>(p, tmem_base, tfull0, tempty0, ss, ss_s, kEG); }
+    else if (res == 2) { if (proj) slab_epilogue<1, false, 2, false, true>(p, tmem_base, tfull0, tempty0, ss, ss_s, kEG); else slab_epilogue<1, false, 2, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s, kEG); }
+    else if (res == 1) { if (e.relu) slab_epilogue<1, true, 1, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s, kEG); else slab_epilogue<1, false, 1, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s, kEG); }
+    else { if (e.relu) slab_epilogue<1, true, 0, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s, kEG); else slab_epilogue<1, false, 0, false, false>(p, tmem_base, tfull0, tempty0, ss, ss_s, kEG); }
   }
   fence_before();
   __syncthreads();
@@ -644,6 +649,9 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   }
   if (NP > kSlabMaxPlanes) NP = kSlabMaxPlanes;
   p.NP = NP;
+  // multi-phase layers (transposed convolutions) at one or two CTAs per SM are bound by their four epilogue warps: give them eight
+  static const bool no_e2 = getenv("DFF_B200_NO_EPI2") != nullptr;
+  p.egroups = (nph >= 2 && occ <= 2 && !no_e2) ? 2 : 1;
   p.LA = std::min(5, NP - 2 * p.hz - 1);
   *smem_out = (size_t)fixed + (size_t)NP * p.plane_bytes;
   *occ_out = occ;
@@ -687,13 +695,14 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
   if (getenv("DFF_SLAB_TRACE")) { cudaMalloc(&p.trace, 64 * 8 * 8); cudaMemset(p.trace, 0, 64 * 8 * 8); }
 #endif
   const int grid = p.nitems < num_sms * occ ? p.nitems : num_sms * occ;
-  if (p.wstream) {
-    DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_slab_kernel<true><<<grid, kSlabThreadsWS, smem, st>>>(p);
-  } else {
-    DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_slab_kernel<false><<<grid, kSlabThreads, smem, st>>>(p);
-  }
+#define DFF_SLAB_LAUNCH(WS_, E2_)                                                                                              \
+  do {                                                                                                                             \
+    DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<WS_, E2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    conv_slab_kernel<WS_, E2_><<<grid, slab_threads(WS_, E2_), smem, st>>>(p);                                                     \
+  } while (0)
+  if (p.wstream) { if (p.egroups == 2) DFF_SLAB_LAUNCH(true, true); else DFF_SLAB_LAUNCH(true, false); }
+  else { if (p.egroups == 2) DFF_SLAB_LAUNCH(false, true); else DFF_SLAB_LAUNCH(false, false); }
+#undef DFF_SLAB_LAUNCH
   DFF_LAUNCH_CHECK("conv_slab");
 #ifdef DFF_SLAB_TRACE
   if (p.trace) {
