@@ -246,13 +246,16 @@ def run_ours(args):
     hfd = torch.empty((n_local, S, H, W), dtype=torch.float32).pin_memory()
     hfd.copy_(fd)
     houts = [torch.empty((n_local, H, W), dtype=torch.float32).pin_memory() for _ in range(4)]
-    dev_io = torch.empty(lib.dff_host_io_bytes(mb, S, H, W), dtype=torch.uint8, device=dev)
+    emb = min(args.e2e_micro_batch, n_local)
+    dev_io = torch.empty(lib.dff_host_io_bytes(emb, S, H, W), dtype=torch.uint8, device=dev)
+    if emb > mb:
+        ws = torch.empty(lib.dff_workspace_bytes(emb, S, H, W, mode), dtype=torch.uint8, device=dev)
     hstrides = (ctypes.c_int64 * 4)(*hfd.stride())
     hp = (ctypes.c_void_p * 4)(*[o.data_ptr() for o in houts])
 
     def e2e_step():
         # ONE C-ABI call per step: the library pipelines H2D copies / kernels / D2H reads over micro-batches internally
-        rt.check(lib.dff_forward_host(packed.data_ptr(), hFS.data_ptr(), hfd.data_ptr(), hstrides, n_local, mb, S, H, W, hp,
+        rt.check(lib.dff_forward_host(packed.data_ptr(), hFS.data_ptr(), hfd.data_ptr(), hstrides, n_local, emb, S, H, W, hp,
                                       dev_io.data_ptr(), ws.data_ptr(), ws.numel(), mode, local, sp))
 
     e2e_step()
@@ -278,7 +281,7 @@ def run_ours(args):
         "config": workload_config(world, mb, args.precision),
         "clocks": clk.summary(),
         "e2e": {"value": e2e_val, "unit": "stacks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "dff_forward_host (C-ABI, pinned host buffers; copies pipelined with kernels over micro-batches)",
+                "steps": e2e_steps, "api": "dff_forward_host (C-ABI, pinned host buffers; copies pipelined with kernels over micro-batches of <= %d)" % emb,
                 "matches_device_run": bool(same)},
         "gpu_launches": launches_per_chunk * (n_local // mb) * args.steps,
         "roofline": roof,
@@ -301,8 +304,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DFF_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--micro-batch", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-micro-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -875,19 +875,22 @@ int dff_forward_profiled(const void* packed, const float* FS, const float* fd, c
   return rc;
 }
 
-// ---- host-buffer entry point: a two-stage software pipeline over micro-batches ------------------------------------------------
-// stage k holds one micro-batch: FS | focus_dists | 4 depth maps.  Chunk i+1's host->device copies and chunk i-1's device->host
-// reads run on two private copy streams while chunk i computes on the caller's stream (PCIe is full duplex).
+// ---- host-buffer entry point: a three-stage software pipeline over micro-batches ----------------------------------------------
+// stage k holds one micro-batch: FS | focus_dists | 4 depth maps.  The host->device copies of the next two chunks and chunk i-1's
+// device->host reads run on two private copy streams while chunk i computes on the caller's stream (PCIe is full duplex).  The
+// copies of a DDFF stack take 0.64 ms, its kernels 0.68 ms + 1.3 ms per launch sequence: with three stages the copy stream never
+// idles, so only the first chunk's copy is exposed.
+constexpr int kHostStages = 3;
 static size_t host_stage_bytes(int mb, int S, int H, int W) {
   return align_up((size_t)mb * 3 * S * H * W * 4, 256) + align_up((size_t)mb * S * H * W * 4, 256) +
          4 * align_up((size_t)mb * H * W * 4, 256);
 }
-size_t dff_host_io_bytes(int micro_batch, int S, int H, int W) { return 2 * host_stage_bytes(micro_batch, S, H, W); }
+size_t dff_host_io_bytes(int micro_batch, int S, int H, int W) { return kHostStages * host_stage_bytes(micro_batch, S, H, W); }
 
 namespace {
 struct HostPipe {
   cudaStream_t h2d = nullptr, d2h = nullptr;
-  cudaEvent_t in_ready[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+  cudaEvent_t in_ready[kHostStages] = {}, computed[kHostStages] = {}, out_done[kHostStages] = {};
   bool ok = false;
 };
 // one pipe per (host thread, device): nn.DataParallel drives each GPU from its own thread
@@ -897,7 +900,7 @@ HostPipe* host_pipe(int device) {
   if (!hp.ok) {
     if (cudaStreamCreateWithFlags(&hp.h2d, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaStreamCreateWithFlags(&hp.d2h, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kHostStages; ++k) {
       if (cudaEventCreateWithFlags(&hp.in_ready[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&hp.computed[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&hp.out_done[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -931,19 +934,20 @@ int dff_forward_host(const void* packed, const float* FS_host, const float* fd_h
   };
   if (fd_span(mb) > (size_t)mb * S * H * W) return fail(DFF_E_ARG, "dff_forward_host: focus_dists strides exceed (B,S,H,W)");
   int rc = 0, nchunk = 0;
-  // chunk sizes ramp up (mb/4, mb/2, mb, mb, ...): the first host->device copy cannot overlap anything, so it is kept short
+  // chunk sizes ramp up (mb/4, mb/4, mb/2, mb/2, mb/2, mb, mb, ...): the first host->device copy cannot overlap anything, and the
+  // copy stream is only ~1.2x faster than the kernels, so the kernels catch up with it through small chunks first
   for (int i0 = 0, n = 0; i0 < B && !rc; i0 += n, ++nchunk) {
-    n = nchunk == 0 ? (mb >= 4 ? mb / 4 : mb) : (nchunk == 1 ? (mb >= 2 ? mb / 2 : mb) : mb);
+    n = nchunk < 2 ? (mb >= 4 ? mb / 4 : mb) : (nchunk < 5 ? (mb >= 2 ? mb / 2 : mb) : mb);
     if (n > B - i0) n = B - i0;
-    const int k = nchunk & 1;
+    const int k = nchunk % kHostStages;
     char* io = (char*)dev_io + k * stage;
     float* dFS = (float*)io;
     float* dfd = (float*)(io + align_up((size_t)mb * fs_stack * 4, 256));
     char* o = (char*)dfd + align_up((size_t)mb * S * H * W * 4, 256);
     float* dout[4];
     for (int j = 0; j < 4; ++j) dout[j] = (float*)(o + j * align_up((size_t)mb * map_px * 4, 256));
-    // stage k is free again once chunk i-2's maps have left it
-    if (nchunk >= 2) DFF_CUDA(cudaStreamWaitEvent(hp->h2d, hp->out_done[k], 0));
+    // stage k is free again once the maps of the chunk that used it last have left it
+    if (nchunk >= kHostStages) DFF_CUDA(cudaStreamWaitEvent(hp->h2d, hp->out_done[k], 0));
     DFF_CUDA(cudaMemcpyAsync(dFS, FS_host + (size_t)i0 * fs_stack, (size_t)n * fs_stack * 4, cudaMemcpyHostToDevice, hp->h2d));
     DFF_CUDA(cudaMemcpyAsync(dfd, fd_host + (size_t)i0 * fd_strides[0], fd_span(n) * 4, cudaMemcpyHostToDevice, hp->h2d));
     DFF_CUDA(cudaEventRecord(hp->in_ready[k], hp->h2d));

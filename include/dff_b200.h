@@ -102,7 +102,7 @@ int dff_forward_profiled(const void *packed, const float *FS, const float *fd, c
                          int *op_launches_host, char *op_names_host, int *n_ops);
 
 /* Same computation with HOST buffers (pinned for full speed; pageable works): B stacks are processed in micro-batches of
- * `micro_batch` through a two-stage pipeline — the host->device copies of chunk i+1 and the device->host reads of chunk i-1
+ * `micro_batch` through a three-stage pipeline — the host->device copies of chunks i+1, i+2 and the device->host reads of chunk i-1
  * overlap chunk i's kernels (two private copy streams per calling thread and device).  Returns after every map is in host
  * memory.  FS_host (B,3,S,H,W); fd_host + strides as in dff_forward; out4_host[j] (B,H,W) or NULL.  `dev_io` is caller-owned
  * device scratch of dff_host_io_bytes(micro_batch, ...) bytes; `workspace` >= dff_workspace_bytes(micro_batch, ...).
