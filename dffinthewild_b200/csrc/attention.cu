@@ -58,11 +58,13 @@ __global__ void __launch_bounds__(kAttnThreads) srd_attention_mma8_kernel(const 
                                                                           const float* __restrict__ w1, __nv_bfloat16* __restrict__ out,
                                                                           int S, size_t plane, size_t ntiles) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  pdl_trigger();
   // B fragments (k = 2t, 2t+1 ; n = g) straight from the fp32 packs w0 [dz][ci][co], w1 [c][co]
   const uint32_t bm = pack_bf2(__ldg(w0 + (0 * 8 + 2 * t) * 8 + g), __ldg(w0 + (0 * 8 + 2 * t + 1) * 8 + g));
   const uint32_t bc = pack_bf2(__ldg(w0 + (1 * 8 + 2 * t) * 8 + g), __ldg(w0 + (1 * 8 + 2 * t + 1) * 8 + g));
   const uint32_t bp = pack_bf2(__ldg(w0 + (2 * 8 + 2 * t) * 8 + g), __ldg(w0 + (2 * 8 + 2 * t + 1) * 8 + g));
   const uint32_t b2 = pack_bf2(__ldg(w1 + (2 * t) * 8 + g), __ldg(w1 + (2 * t + 1) * 8 + g));
+  pdl_wait();   // F is the previous layer's output
   const size_t zs = plane * 8;   // elements between slices
   const size_t warp0 = (size_t)blockIdx.x * (kAttnThreads / 32) + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * (kAttnThreads / 32);
   for (size_t tile = warp0; tile < ntiles; tile += nwarps) {
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(kAttnThreads) srd_attention_mma_kernel(const _
                                                                          int S, size_t plane, size_t ntiles) {
   constexpr int KC = C / 16, NT = C / 8;
   __shared__ uint2 sB1[3 * KC * NT * 32], sB2[KC * NT * 32];
+  pdl_trigger();
   // B fragments in MMA order.  First product: logical k = 2t, 2t+1 | 2t+8, 2t+9 of block (dz, i) <-> input channels 16i+4t, +1 | +2, +3;
   // n = 8j + g natural.  Second product: k natural (the first product's accumulator fragment), output column g of tile j = 2i'+h
   // <-> channel 16i' + 4(g >> 1) + 2h + (g & 1), so the thread's accumulators are channels 16i'+4t .. 4t+3.
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(kAttnThreads) srd_attention_mma_kernel(const _
     sB2[e] = make_uint2(pack_bf2(__ldg(w), __ldg(w + C)), pack_bf2(__ldg(w + 8 * C), __ldg(w + 9 * C)));
   }
   __syncthreads();
+  pdl_wait();   // F is the previous layer's output
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const size_t zs = plane * C;
   const size_t warp0 = (size_t)blockIdx.x * (kAttnThreads / 32) + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * (kAttnThreads / 32);
@@ -193,11 +197,10 @@ int launch_srd_attention_mma(const void* F, const float* w0, const float* w1, vo
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   const __nv_bfloat16* f = (const __nv_bfloat16*)F;
   __nv_bfloat16* o = (__nv_bfloat16*)out;
-  if (C == 8) srd_attention_mma8_kernel<<<grid, kAttnThreads, 0, st>>>(f, w0, w1, o, S, plane, ntiles);
-  else if (C == 16) srd_attention_mma_kernel<16><<<grid, kAttnThreads, 0, st>>>(f, w0, w1, o, S, plane, ntiles);
-  else if (C == 32) srd_attention_mma_kernel<32><<<grid, kAttnThreads, 0, st>>>(f, w0, w1, o, S, plane, ntiles);
+  if (C == 8) DFF_CUDA(launch_pdl(srd_attention_mma8_kernel, dim3(grid), dim3(kAttnThreads), 0, st, f, w0, w1, o, S, plane, ntiles));
+  else if (C == 16) DFF_CUDA(launch_pdl(srd_attention_mma_kernel<16>, dim3(grid), dim3(kAttnThreads), 0, st, f, w0, w1, o, S, plane, ntiles));
+  else if (C == 32) DFF_CUDA(launch_pdl(srd_attention_mma_kernel<32>, dim3(grid), dim3(kAttnThreads), 0, st, f, w0, w1, o, S, plane, ntiles));
   else return fail(-5, "srd_attention: C must be 8, 16 or 32");
-  DFF_LAUNCH_CHECK("srd_attention_mma");
   return 0;
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 
 namespace dff {
 
@@ -52,6 +53,27 @@ int check_cuda(cudaError_t e, const char* what);
     int _rc = (x);          \
     if (_rc) return _rc;    \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// A kernel launched through launch_pdl may become resident while its predecessor in the stream is still draining: it runs its
+// prologue (weights -> shared memory, tables, TMEM allocation — nothing a predecessor writes) and then blocks in pdl_wait() until
+// the predecessor grid has completed and its memory is visible.  Every such kernel calls pdl_trigger() when it starts its last
+// work item so that ITS successor may do the same while the tail drains (triggering at kernel start made early-resident successors
+// compete with the running kernel: -9 % at 2 stacks but +2..4 % at 16..64).  Kernels launched the ordinary way in between simply serialise as usual.  DFF_B200_NO_PDL=1 turns it off.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

@@ -114,6 +114,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
   const void* const rsrc = ep.res_pre ? ep.res_pre : (ep.res_post ? ep.res_post : ep.aux_add);   // (a layer has at most one residual operand)
   int sc = 0;
   for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+    if (item + (int)gridDim.x >= p.nitems) pdl_trigger();
     int r = item;
     const int isp = r % p.nsplit; r /= p.nsplit;
     const int ox = (r % p.tilesX) * kSlabTW + tx; r /= p.tilesX;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   if (!WS) {
     const int total = 2 * p.nops * p.N;  // 16-byte rows
     const uint4* wg = reinterpret_cast<const uint4*>(p.wslab);
+#pragma unroll 4
     for (int i = threadIdx.x; i < total; i += kThreads) {
       const int blk = i / p.N, r = i - blk * p.N;
       const int src = p.wsrc[blk];
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   fence_before();
   __syncthreads();
   fence_after();
+  pdl_wait();      // everything above touched only weights and tables; from here on the previous layer's output is read
   const uint32_t tmem_base = tmem_base_s;
   const int hz = p.hz;
 
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
     int np = 0;
     uint32_t ephase = 1;      // parity to wait for on its `empty` barrier (a fresh barrier passes parity 1)
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      if (item + (int)gridDim.x >= p.nitems) pdl_trigger();   // last item of this CTA: the next kernel may start filling drained SMs
       int r = item;
       const int isp = r % p.nsplit; r /= p.nsplit;
       const int tx0 = (r % p.tilesX) * kSlabTW * p.stx; r /= p.tilesX;   // tile origin in input coordinates
@@ -292,6 +296,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
     uint64_t a_prev = 0, a_cur = 0, a_next = 0;   // descriptor bases of the planes of slices s-1, s, s+1
     uint32_t e_prev = 0, e_cur = 0, e_next = 0;   // their `empty` barriers
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      if (item + (int)gridDim.x >= p.nitems) pdl_trigger();
       const int isp = item % p.nsplit;
       const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
       const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
@@ -422,6 +427,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   } else if (WS && warp == kThreads / 32 - 1) {
     // =============================== weight producer (streaming variant) ===============================
     // walks exactly the issuer's schedule; one bulk copy (global -> shared, completion on the slot's `full` barrier) per block
+    pdl_trigger();
     if (lane == 0) {
       const char* const wg = reinterpret_cast<const char*>(p.wslab);
       const int ngrp = 3 * p.nph;
@@ -698,7 +704,7 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
 #define DFF_SLAB_LAUNCH(WS_, E2_)                                                                                              \
   do {                                                                                                                             \
     DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<WS_, E2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-    conv_slab_kernel<WS_, E2_><<<grid, slab_threads(WS_, E2_), smem, st>>>(p);                                                     \
+    DFF_CUDA(launch_pdl(conv_slab_kernel<WS_, E2_>, dim3(grid), dim3(slab_threads(WS_, E2_)), smem, st, p));                        \
   } while (0)
   if (p.wstream) { if (p.egroups == 2) DFF_SLAB_LAUNCH(true, true); else DFF_SLAB_LAUNCH(true, false); }
   else { if (p.egroups == 2) DFF_SLAB_LAUNCH(false, true); else DFF_SLAB_LAUNCH(false, false); }

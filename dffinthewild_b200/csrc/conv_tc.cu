@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   // dynamic smem base aligned to 1024 B (128B-swizzle atoms and UMMA base_offset = 0 need it)
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kTcMaxStages]);
   const uint32_t tfull0 = smem_u32(&bars[2 * kTcMaxStages]), tempty0 = smem_u32(&bars[2 * kTcMaxStages + 2]);
 
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   fence_before();
   __syncthreads();
   fence_after();
+  pdl_wait();   // (barriers, TMEM and descriptor prefetch above do not depend on the previous layer)
   const uint32_t tmem_base = tmem_base_s;
   const int tiles_per_bs = p.tilesX * p.tilesY;
 
@@ -320,7 +322,7 @@ int launch_conv_tc(const ConvArgs& a, const void* wtc, int ntaps_total, int Ntc,
   const size_t smem = (size_t)p.nstages * p.stage_bytes + 1024;
   DFF_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;
-  conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
+  DFF_CUDA(launch_pdl(conv_tc_kernel, dim3(grid), dim3(kTcThreads), smem, st, p));
   DFF_LAUNCH_CHECK("conv_tc");
   return 0;
 }

@@ -77,6 +77,13 @@ int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+// Programmatic dependent launch pays while per-launch fixed costs matter (measured on DDFF stacks: -10 % at 2 stacks per call, -5 % at
+// 4, +1 % at 16, +2 % at 64), so dff_forward switches it per call on the amount of work; DFF_B200_PDL=0/1 forces it off/on.
+static thread_local bool g_pdl_call = true;
+bool pdl_enabled() {
+  static const int forced = getenv("DFF_B200_PDL") ? atoi(getenv("DFF_B200_PDL")) : (getenv("DFF_B200_NO_PDL") ? 0 : -1);
+  return forced >= 0 ? forced != 0 : g_pdl_call;
+}
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return 0;
   g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
@@ -678,6 +685,7 @@ static int forward_impl(const void* packed, const float* FS, const float* fd, co
   if (B < 1 || S < 1 || H < 32 || W < 32 || H % 32 || W % 32)
     return fail(DFF_E_ARG, "dff_forward: need B,S >= 1 and H,W positive multiples of 32 (pad with -1 like the reference dataloaders)");
   if (mode & DFF_TRAIN) return fail(DFF_E_UNSUPPORTED, "dff_forward: DFF_TRAIN is not available in this build");
+  g_pdl_call = (double)B * S * H * W <= 8.0 * 10 * 384 * 576;   // up to 8 DDFF stacks' worth of voxels per call
   Runner r{net_of(DFF_NET_DFF), (const char*)packed, (char*)ws, ws_bytes, 0, dry, (mode & DFF_BF16) != 0, st};
   r.prof = prof;
   r.use_tc = r.bf16 && !(mode & DFF_NO_TC);
