@@ -115,6 +115,9 @@ struct ConvArgs {
   float* proj_out;
   int proj_src, skip_out;
   int no_wstream;          // slab kernel: do not fall back to streamed weights (the caller has a better form for this layer)
+  int row_step;            // > 0: consecutive tile rows are `row_step` input rows apart and the y stride is taken by the MMA descriptor
+                           // (no row-parity views): the row-folded first layer.  Output: 8-channel groups `grp_rows` rows apart.
+  int grp_rows;
   int proj_c;              // channels per pixel of the projection when a GEMM row holds several pixels (x-folded layers), 0 = all
   TapTable taps;
 };

@@ -469,7 +469,7 @@ static bool row_plan(const ConvArgs& a, int Ntc, RowParams& p, size_t* smem_out,
   p.epi.out = a.out; p.epi.out_aux = a.out_aux; p.epi.aux_add = a.aux_add;
   p.epi.cstore = a.Cout; p.epi.relu = a.relu; p.epi.out_f32 = a.out_f32; p.epi.N = Ntc;
   p.epi.proj_w = a.proj_w; p.epi.proj_out = a.proj_out; p.epi.proj_src = a.proj_src; p.epi.skip_out = a.skip_out;
-  p.epi.proj_c = 0;
+  p.epi.proj_c = 0; p.epi.grp_stride = 0; p.epi.pix_c = 0;
   *smem_out = (size_t)p.rows_off + (size_t)p.NR * p.row_bytes + 1024;
   *occ_out = best_occ;
   return true;

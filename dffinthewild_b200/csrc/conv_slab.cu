@@ -47,12 +47,14 @@ constexpr int kSlabSmemBudget = 228 * 1024;   // per SM; every co-resident CTA a
 #define DFF_TR(slot, idx) do { } while (0)
 #endif
 
-struct alignas(16) SlabParams {
+struct alignas(64) SlabParams {
+  CUtensorMap tmap;   // (tma) in0 as (C0, IW, IH, S*B) bf16
   const void* in0;
   const void* in1;
   const void* wslab;  // bf16 [tap][chunk][N][8]
   int C0, C1, nchunk, nch0;
   int B, S, IH, IW;
+  int tile_sy, sbo;   // input rows per tile step; A-descriptor stride between 8-row groups (bytes)
   int sty, stx, nviews, vpy[4], vpx[4];   // input stride per output step (y, x); one staged view per input-coordinate residue
   int oy, ox, RX, RY, CPS, plane_bytes, NP, LA, hz;
   int N, nops, nph;          // MMA N; table entries; output phases (1 = convolution, 4 = fused transposed convolution, 2 = x-folded one)
@@ -68,6 +70,7 @@ struct alignas(16) SlabParams {
   // consecutive MMAs whose weights are one contiguous range of `wslab`; warp 7 streams them through a ring of `nwslots` slots
   int wstream, nwslots, nblk, wslot_bytes;
   int egroups;                      // epilogue warp groups (1 or 2)
+  int tma;                          // planes staged by ONE tiled TMA load each (single-chunk, single-view layers: box 8 ch x RX x RY)
   int gb[12], gbe[12];              // block range per MMA group
   uint8_t bop[kSlabMaxOps], bn[kSlabMaxOps];   // first MMA / number of MMAs of each block
   alignas(16) uint64_t tab[kSlabMaxOps + 4];  // (+1 quad: the issuer prefetches one quad ahead) per MMA, zero-extended to 64 bits (added to the descriptor): (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
@@ -91,10 +94,11 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // staged-element table entry (built once per CTA): where one 16-byte piece of a slice plane comes from / goes to
+constexpr int kSlabElemBias = 64;
 struct SlabElem {
   int32_t rel;       // element offset from the tile-origin pixel of the slice, in the source's own channel stride
   uint16_t dst16;    // (byte offset inside the ring slot) >> 4, bit 15 = second source
-  int8_t gy, gx;     // input row / column relative to the tile origin (bounds check)
+  uint8_t gy, gx;    // input row / column relative to the tile origin, biased by kSlabElemBias (bounds check)
 };
 
 // Epilogue role of the slab kernel (4 warps, one TMEM lane quadrant each).  FAST = 0: generic epilogue (tc_epilogue_tile).
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
         mbar_init(wempty0 + 8 * i, 1);
       }
     for (int i = 0; i < p.NP; ++i) {
-      mbar_init(full0 + 8 * i, kSlabProducers);
+      mbar_init(full0 + 8 * i, p.tma ? 1 : kSlabProducers);
       mbar_init(empty0 + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   // (table order = global address order: consecutive producer threads copy consecutive 16-byte pieces — the chunks of a pixel, then
   // the next pixel of the row — whatever view the pixel belongs to; the shared-memory destination is free-form anyway.  With
   // strided views (stride-2 and x-folded layers) a view-major order would have every thread touch its own 32-byte sector.)
-  for (int e = threadIdx.x; e < p.nelem; e += kThreads) {
+  for (int e = threadIdx.x; e < (p.tma ? 0 : p.nelem); e += kThreads) {
     const int c = e % p.nchunk, t = e / p.nchunk;
     const int gxi = t % (p.stx * p.RX), gyi = t / (p.stx * p.RX);
     const int rx = gxi / p.stx, vx = gxi % p.stx, ry = gyi / p.sty, vy = gyi % p.sty;
@@ -221,8 +225,8 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
     SlabElem el;
     el.rel = (gy * p.IW + gx) * C + cc * 8;
     el.dst16 = (uint16_t)(((c * p.CPS + pix * 16) >> 4) | (second ? 0x8000 : 0));
-    el.gy = (int8_t)gy;
-    el.gx = (int8_t)gx;
+    el.gy = (uint8_t)(gy + kSlabElemBias);
+    el.gx = (uint8_t)(gx + kSlabElemBias);
     const_cast<SlabElem*>(elems)[e] = el;
   }
   fence_proxy_async();
@@ -233,7 +237,35 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   const uint32_t tmem_base = tmem_base_s;
   const int hz = p.hz;
 
-  if (warp < kSlabMmaWarp) {
+  if (warp < kSlabMmaWarp && p.tma) {
+    // =============================== producer: one tiled TMA load per slice plane ===============================
+    // box = 8 channels x RX pixels x RY rows lands in shared memory as [row][pixel][16 B] — the plane layout itself; out-of-bounds
+    // rows / columns (the convolution's zero padding) are filled by the TMA unit.  One thread, no per-element work.
+    if (threadIdx.x == 0) {
+      prefetch_tmap(&p.tmap);
+      int slot = 0;
+      uint32_t ephase = 1;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        if (item + (int)gridDim.x >= p.nitems) pdl_trigger();
+        int r = item;
+        const int isp = r % p.nsplit; r /= p.nsplit;
+        const int tx0 = (r % p.tilesX) * kSlabTW * p.stx; r /= p.tilesX;
+        const int ty0 = (r % p.tilesY) * p.tile_sy;
+        const int b = r / p.tilesY;
+        const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
+        const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
+        for (int z = zlo; z < zhi; ++z) {
+          mbar_wait(empty0 + 8 * slot, ephase);
+          mbar_expect_tx(full0 + 8 * slot, (uint32_t)p.CPS);
+          if (!(p.exp & 1)) tma_load_4d(planes_s + slot * p.plane_bytes, &p.tmap, full0 + 8 * slot, 0, tx0 + p.ox, ty0 + p.oy, b * p.S + z);
+          else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * slot), "r"((uint32_t)p.CPS) : "memory");
+          if (++slot == p.NP) { slot = 0; ephase ^= 1; }
+        }
+      }
+    } else {
+      pdl_trigger();
+    }
+  } else if (warp < kSlabMmaWarp) {
     // =============================== producers: stage slice planes with cp.async ===============================
     const int ptid = threadIdx.x;
     const char* const base0 = reinterpret_cast<const char*>(p.in0);
@@ -246,7 +278,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
       int r = item;
       const int isp = r % p.nsplit; r /= p.nsplit;
       const int tx0 = (r % p.tilesX) * kSlabTW * p.stx; r /= p.tilesX;   // tile origin in input coordinates
-      const int ty0 = (r % p.tilesY) * kSlabTH * p.sty;
+      const int ty0 = (r % p.tilesY) * p.tile_sy;
       const int b = r / p.tilesY;
       const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
       const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
@@ -260,7 +292,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
         if (!(p.exp & 1))
         for (int e = ptid; e < p.nelem; e += kSlabProducers) {
           const SlabElem el = elems[e];
-          const int gy = ty0 + el.gy, gx = tx0 + el.gx;
+          const int gy = ty0 + (int)el.gy - kSlabElemBias, gx = tx0 + (int)el.gx - kSlabElemBias;
           const bool ok = gy >= 0 && gy < p.IH && gx >= 0 && gx < p.IW;
           const char* src = ((el.dst16 & 0x8000) ? o1 : o0) + (ptrdiff_t)el.rel * 2;
           cp_async16(dst0 + ((uint32_t)(el.dst16 & 0x7fff) << 4), ok ? src : base0, ok ? 16u : 0u);
@@ -283,7 +315,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
     const bool leader = elect_one();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
     // descriptor high words: SBO (8-row group stride) | version 1 | no swizzle
-    const uint64_t a_hi = (uint64_t)(((uint32_t)(p.RX * 16) >> 4) | (1u << 14)) << 32;
+    const uint64_t a_hi = (uint64_t)(((uint32_t)p.sbo >> 4) | (1u << 14)) << 32;
     const uint64_t b_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
     const uint64_t b_step = (uint32_t)(p.N * 32) >> 4;
     const uint64_t bd_base = b_hi | (uint64_t)((w_s >> 4) | (((uint32_t)(p.N * 16) >> 4) << 16));
@@ -484,23 +516,24 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
 // host side: plan (geometry, MMA table, ring depth) + launch
 // ------------------------------------------------------------------------------------------------------------------
 // `ptaps`/`nph`: tap table per output phase (nph = 1: a.taps; nph = 4: the parity phases of a transposed convolution).
+#define return_false do { if (getenv("DFF_B200_DEBUG_PLAN")) fprintf(stderr, "slab_plan: fail at line %d\n", __LINE__); return false; } while (0)
 static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc, int num_sms, SlabParams& p, size_t* smem_out,
                       int* occ_out) {
   memset(&p, 0, sizeof(p));
-  if (a.C0 % 8 || a.C1 % 8 || a.C0 < 8) return false;
-  if (Ntc < 16 || Ntc > 128 || Ntc % 16) return false;
-  if ((a.isy != 1 && a.isy != 2) || (a.isx != 1 && a.isx != 2 && a.isx != 4) || a.isy * a.isx > 4) return false;
+  if (a.C0 % 8 || a.C1 % 8 || a.C0 < 8) return_false;
+  if (Ntc < 16 || Ntc > 128 || Ntc % 16) return_false;
+  if ((a.isy != 1 && a.isy != 2) || (a.isx != 1 && a.isx != 2 && a.isx != 4) || a.isy * a.isx > 4) return_false;
   const int nchunk = (a.C0 + a.C1) / 8;
-  if (nchunk != 1 && (nchunk & 1)) return false;
+  if (nchunk != 1 && (nchunk & 1)) return_false;
   p.in0 = a.in0; p.in1 = a.in1; p.C0 = a.C0; p.C1 = a.C1; p.nchunk = nchunk; p.nch0 = a.C0 / 8;
-  p.B = a.B; p.S = a.S; p.IH = a.IH; p.IW = a.IW; p.sty = a.isy; p.stx = a.isx;
+  p.B = a.B; p.S = a.S; p.IH = a.IH; p.IW = a.IW; p.sty = a.row_step > 0 ? 1 : a.isy; p.stx = a.isx;
   p.nviews = p.sty * p.stx;
   for (int v = 0; v < 4; ++v) { p.vpy[v] = v / p.stx; p.vpx[v] = v % p.stx; }
   // ---- taps in view coordinates -------------------------------------------------------------------------------------
   struct VT { int dz, view, vy, vx, widx, ph; };
   std::vector<VT> vt;
   int vymin = 1000, vymax = -1000, vxmin = 1000, vxmax = -1000, dzmin = 1000, dzmax = -1000;
-  if (nph != 1 && nph != 2 && nph != 4) return false;
+  if (nph != 1 && nph != 2 && nph != 4) return_false;
   p.nph = nph;
   for (int ph = 0; ph < 4; ++ph) {
     p.phy[ph] = nph == 4 ? (ph >> 1) : (nph == 2 ? ph : a.ooy);   // nph == 2: the two row phases of an x-folded transposed conv
@@ -522,10 +555,10 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     dzmin = std::min(dzmin, x.dz); dzmax = std::max(dzmax, x.dz);
     vt.push_back(x);
   }
-  if (dzmin < -1 || dzmax > 1) return false;
+  if (dzmin < -1 || dzmax > 1) return_false;
   p.hz = (dzmin < 0 || dzmax > 0) ? 1 : 0;
   p.oy = vymin; p.ox = vxmin;
-  p.RY = kSlabTH + (vymax - vymin);
+  p.RY = (a.row_step > 0 ? (kSlabTH - 1) * a.row_step + 1 : kSlabTH) + (vymax - vymin);
   p.RX = kSlabTW + (vxmax - vxmin);
   // DFF_SLAB_EXPERIMENT=aligned: timing experiment only (wrong results) — force 128-byte aligned core matrices
   static const bool exp_aligned = getenv("DFF_SLAB_EXPERIMENT") && !strcmp(getenv("DFF_SLAB_EXPERIMENT"), "aligned");
@@ -533,7 +566,12 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   if (exp_aligned) p.RX = (p.RX + 7) & ~7;
   p.CPS = p.nviews * p.RY * p.RX * 16;
   p.plane_bytes = (nchunk * p.CPS + 127) & ~127;
-  if ((p.CPS >> 4) >= (1 << 14) || p.RX * 16 >= (1 << 18)) return false;
+  if (p.sty * p.oy < -kSlabElemBias || p.stx * p.ox < -kSlabElemBias || p.sty * (p.oy + p.RY) > 255 - kSlabElemBias ||
+      p.stx * (p.ox + p.RX) > 255 - kSlabElemBias)
+    return_false;   // (staging-table coordinates are biased bytes)
+  p.tile_sy = a.row_step > 0 ? kSlabTH * a.row_step : kSlabTH * p.sty;
+  p.sbo = (a.row_step > 0 ? a.row_step : 1) * p.RX * 16;
+  if ((p.CPS >> 4) >= (1 << 14) || p.sbo >= (1 << 18)) return_false;
   auto aoff = [&](const VT& x, int chunk) {
     int o = chunk * p.CPS + ((x.view * p.RY + (x.vy - p.oy)) * p.RX + (x.vx - p.ox)) * 16;
     if (exp_aligned) o &= ~127;
@@ -544,7 +582,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   for (int ph = 0; ph < nph; ++ph)
   for (int k = 0; k < 3; ++k) {
     while (nops & 3) {  // groups start on a 16-byte table boundary (the issuer reads four entries per load); pads never run
-      if (nops >= kSlabMaxOps) return false;
+      if (nops >= kSlabMaxOps) return_false;
       p.tab[nops] = 0; p.wsrc[2 * nops] = -1; p.wsrc[2 * nops + 1] = -1;
       ++nops;
     }
@@ -555,7 +593,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     if (nchunk > 1) {
       for (auto& x : grp)
         for (int j = 0; j < nchunk; j += 2) {
-          if (nops >= kSlabMaxOps) return false;
+          if (nops >= kSlabMaxOps) return_false;
           p.tab[nops] = (uint32_t)(aoff(x, j) >> 4) | ((uint32_t)(p.CPS >> 4) << 16);
           p.wsrc[2 * nops] = (int16_t)(x.widx * nchunk + j);
           p.wsrc[2 * nops + 1] = (int16_t)(x.widx * nchunk + j + 1);
@@ -564,10 +602,10 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     } else {  // 8-channel tensor: K = 16 is two taps; an odd tap is paired with zero weights
       std::sort(grp.begin(), grp.end(), [&](const VT& l, const VT& r) { return aoff(l, 0) < aoff(r, 0); });
       for (size_t i = 0; i < grp.size(); i += 2) {
-        if (nops >= kSlabMaxOps) return false;
+        if (nops >= kSlabMaxOps) return_false;
         const bool pair = i + 1 < grp.size();
         const int o1 = aoff(grp[i], 0), o2 = pair ? aoff(grp[i + 1], 0) : o1;
-        if (((o2 - o1) >> 4) >= (1 << 14)) return false;
+        if (((o2 - o1) >> 4) >= (1 << 14)) return_false;
         p.tab[nops] = (uint32_t)(o1 >> 4) | ((uint32_t)((o2 - o1) >> 4) << 16);
         p.wsrc[2 * nops] = (int16_t)grp[i].widx;
         p.wsrc[2 * nops + 1] = pair ? (int16_t)grp[i + 1].widx : (int16_t)-1;
@@ -577,14 +615,14 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     p.ge[ph * 3 + k] = nops;
   }
   p.nops = nops;
-  if (nops == 0) return false;
+  if (nops == 0) return_false;
   p.N = Ntc;
   p.w_bytes = nops * Ntc * 32;
   // ---- shared memory: table + weights + scale/shift + staging table + ring; as many co-resident CTAs as fit -----------------
   p.nelem = p.nviews * p.RY * p.RX * nchunk;
   const int np_min = 2 * p.hz + 2;
   const int cols = 2 * nph * Ntc;
-  if (cols > 512) return false;
+  if (cols > 512) return_false;
   p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   int fixed = 0;
   auto lay_out = [&](int wregion) {   // offsets for a weight region of `wregion` bytes; returns the fixed part
@@ -608,11 +646,11 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     // Resident weights do not fit next to the plane ring: stream them (one CTA per SM, warp 7 feeds a ring of 3-4 slots with bulk
     // copies).  Blocks = runs of MMAs of one group whose weights are contiguous in `wslab` (consecutive chunk pairs / taps).
     static const bool no_ws = getenv("DFF_B200_NO_WSTREAM") != nullptr;
-    if (no_ws || a.no_wstream || nchunk < 2) return false;
+    if (no_ws || a.no_wstream || nchunk < 2) return_false;
     // one CTA per SM leaves nothing to hide partially filled tiles behind: very sparsely filled tile grids stay on the per-tap kernel (measured: 1/16 and 1/32 resolution still gain)
     // (a fused transposed convolution competes with four launches of this same kernel, not with the per-tap kernel)
     static const double min_fill = getenv("DFF_B200_WS_FILL") ? atof(getenv("DFF_B200_WS_FILL")) : 0.5;
-    if (nph != 4 && (double)a.OHt * a.OWt < min_fill * (double)(cdiv(a.OHt, kSlabTH) * kSlabTH) * (cdiv(a.OWt, kSlabTW) * kSlabTW)) return false;
+    if (nph != 4 && (double)a.OHt * a.OWt < min_fill * (double)(cdiv(a.OHt, kSlabTH) * kSlabTH) * (cdiv(a.OWt, kSlabTW) * kSlabTW)) return_false;
     // Every block costs the issuing warp a barrier wait and a tcgen05.commit (~250 clk that the tensor pipe idles), so blocks are made
     // as large as the ring allows: a group of MMAs is cut into the fewest blocks whose slot (<= 40 KB) still leaves room for three
     // slots and the minimal plane ring.
@@ -630,7 +668,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
         if (NP >= np_min + (nw > 3 ? 1 : 0)) { per_slot = ps; break; }   // a fourth slot only if the plane ring keeps one plane of look-ahead
       }
     }
-    if (!per_slot) return false;
+    if (!per_slot) return_false;
     int nb = 0;
     for (int gi = 0; gi < 3 * nph; ++gi) {
       p.gb[gi] = nb;
@@ -638,8 +676,8 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
       while (o < p.ge[gi]) {
         int n = 1;
         while (o + n < p.ge[gi] && n < per_slot && p.wsrc[2 * (o + n)] == p.wsrc[2 * (o + n - 1)] + 2 && p.wsrc[2 * (o + n) + 1] == p.wsrc[2 * (o + n)] + 1) ++n;
-        if (p.wsrc[2 * o] < 0 || p.wsrc[2 * o + 1] != p.wsrc[2 * o] + 1) return false;
-        if (n < per_slot && o + n < p.ge[gi] && (n & 3)) return false;   // a discontinuity off a quad boundary: not expressible
+        if (p.wsrc[2 * o] < 0 || p.wsrc[2 * o + 1] != p.wsrc[2 * o] + 1) return_false;
+        if (n < per_slot && o + n < p.ge[gi] && (n & 3)) return_false;   // a discontinuity off a quad boundary: not expressible
         p.bop[nb] = (uint8_t)o; p.bn[nb] = (uint8_t)n;
         ++nb;
         o += n;
@@ -655,6 +693,9 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   }
   if (NP > kSlabMaxPlanes) NP = kSlabMaxPlanes;
   p.NP = NP;
+  // single-chunk, single-view layers whose plane is a multiple of 128 bytes: staged by TMA (descriptor encoded at launch)
+  static const bool no_tma = getenv("DFF_B200_NO_SLAB_TMA") != nullptr;
+  p.tma = (!no_tma && a.row_step > 0 && nchunk == 1 && p.nviews == 1 && a.C0 == 8 && !a.in1 && p.CPS % 128 == 0 && p.RX <= 256 && p.RY <= 256) ? 1 : 0;
   // multi-phase layers (transposed convolutions) at one or two CTAs per SM are bound by their four epilogue warps: give them eight
   static const bool no_e2 = getenv("DFF_B200_NO_EPI2") != nullptr;
   p.egroups = (nph >= 2 && occ <= 2 && !no_e2) ? 2 : 1;
@@ -677,9 +718,12 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.epi.cstore = a.Cout; p.epi.relu = a.relu; p.epi.out_f32 = a.out_f32; p.epi.N = Ntc;
   p.epi.proj_w = a.proj_w; p.epi.proj_out = a.proj_out; p.epi.proj_src = a.proj_src; p.epi.skip_out = a.skip_out;
   p.epi.proj_c = a.proj_c;
+  p.epi.grp_stride = a.grp_rows > 0 ? (long long)a.grp_rows * a.OW * 8 : 0;
+  p.epi.pix_c = 8;
   return true;
 }
 
+#undef return_false
 bool conv_slab_supported(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc) {
   SlabParams p;
   size_t smem;
@@ -697,6 +741,12 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
   if (!slab_plan(a, ptaps ? ptaps : &a.taps, ptaps ? nph : 1, Ntc, num_sms, p, &smem, &occ))
     return fail(-5, "conv_slab: unsupported layer shape");
   p.wslab = wslab;
+  if (p.tma) {
+    const unsigned long long dims[4] = {8ull, (unsigned long long)a.IW, (unsigned long long)a.IH, (unsigned long long)a.S * a.B};
+    const unsigned long long strides[3] = {16ull, (unsigned long long)a.IW * 16, (unsigned long long)a.IH * a.IW * 16};
+    const unsigned box[4] = {8u, (unsigned)p.RX, (unsigned)p.RY, 1u};
+    DFF_TRY(encode_tmap_bf16(&p.tmap, a.in0, 4, dims, strides, box));
+  }
 #ifdef DFF_SLAB_TRACE
   if (getenv("DFF_SLAB_TRACE")) { cudaMalloc(&p.trace, 64 * 8 * 8); cudaMemset(p.trace, 0, 64 * 8 * 8); }
 #endif
@@ -787,6 +837,25 @@ int launch_pack_weight_slab_deconv_fold(const float* w, void* dst, int Cout, int
   if (g > 512) g = 512;
   pack_weight_slab_deconv_fold_kernel<<<g, 256, 0, st>>>(w, (__nv_bfloat16*)dst, Cout, Cin, CinP);
   DFF_LAUNCH_CHECK("pack_weight_slab_deconv_fold");
+  return 0;
+}
+
+// Row-folded first layer (1 x 9 x 9, dilation 2, on the pair-packed input): the G = 4 output rows y, y+2, y+4, y+6 are the 4 x Cout
+// channels of one GEMM row fed by the 12 x 5 taps (q, c) at input rows y + 2q - 8:  dst bf16 [q*5 + c][1][G*Cout][8] with
+//   W_G[g*Cout + co][ci][q][c] = Wpair[co][ci][q - g][c] for 0 <= q - g < 9, else 0.     Wpair: (Cout, 8, 1, 9, 5) fp32.
+__global__ void pack_weight_slab_rowfold_kernel(const float* __restrict__ wp, __nv_bfloat16* __restrict__ dst, int Cout) {
+  const int N = 4 * Cout, n = 60 * N * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int ci = i & 7, nn = (i >> 3) % N, t = i / (8 * N);
+    const int c = t % 5, q = t / 5, g = nn / Cout, co = nn % Cout, ky = q - g;
+    float v = 0.f;
+    if (ky >= 0 && ky < 9) v = wp[((co * 8 + ci) * 9 + ky) * 5 + c];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+int launch_pack_weight_slab_rowfold(const float* wpair, void* dst, int Cout, cudaStream_t st) {
+  pack_weight_slab_rowfold_kernel<<<cdiv(60 * 4 * Cout * 8, 256), 256, 0, st>>>(wpair, (__nv_bfloat16*)dst, Cout);
+  DFF_LAUNCH_CHECK("pack_weight_slab_rowfold");
   return 0;
 }
 

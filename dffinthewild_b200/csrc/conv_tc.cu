@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     EpiArgs ep;
     ep.scale = p.scale; ep.shift = p.shift; ep.res_pre = p.res_pre; ep.res_post = p.res_post; ep.out = p.out;
     ep.out_aux = p.out_aux; ep.aux_add = p.aux_add; ep.cstore = p.cstore; ep.relu = p.relu; ep.out_f32 = p.out_f32; ep.N = p.N;
-    ep.proj_w = p.proj_w; ep.proj_out = p.proj_out; ep.proj_src = p.proj_src; ep.skip_out = p.skip_out; ep.proj_c = 0;
+    ep.proj_w = p.proj_w; ep.proj_out = p.proj_out; ep.proj_src = p.proj_src; ep.skip_out = p.skip_out; ep.proj_c = 0; ep.grp_stride = 0; ep.pix_c = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -204,6 +204,15 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return 0;
+}
+
+int encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                     const unsigned* box) {
+  cuuint64_t d[5], sb[4];
+  cuuint32_t bx[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) sb[i] = strides_bytes[i];
+  return encode(m, base, rank, d, sb, bx, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 bool conv_tc_supported(const ConvArgs& a, int Ntc) {

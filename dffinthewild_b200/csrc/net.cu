@@ -48,6 +48,7 @@ int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int Ci
 int launch_pack_weight_slab_deconv_fold(const float* w, void* dst, int Cout, int Cin, int CinP, cudaStream_t st);
 int launch_replicate_ss(const float* scale, const float* shift, float* dst, int C, int G, cudaStream_t st);
 int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, int CinP, int kd, int kh, int kw, int G, cudaStream_t st);
+int launch_pack_weight_slab_rowfold(const float* wpair, void* dst, int Cout, cudaStream_t st);
 int launch_conv_wgrad(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, int ci_base, float* dw, int ntaps_total,
                       int wt_transposed, bool bf16, cudaStream_t st);
 size_t bn_partial_bytes(int C);
@@ -168,7 +169,16 @@ struct Net {
       packed_bytes += align_up((size_t)2 * 2 * cout * sizeof(float), 256);
     }
     l.pk_pair = packed_bytes;   // paired-tap fp32 weights (Cout, 8, 1, 9, 5) of the first layer
-    if (cin == 3 && kh == 9 && kw == 9 && dil == 2 && kd == 1) { l.pair_x = true; packed_bytes += align_up((size_t)cout * 360 * sizeof(float), 256); }
+    if (cin == 3 && kh == 9 && kw == 9 && dil == 2 && kd == 1) {
+      l.pair_x = true;
+      packed_bytes += align_up((size_t)cout * 360 * sizeof(float), 256);
+      if (cout == 8) {   // row-folded form (pack_weight_slab_rowfold_kernel): 60 taps x 32 output channels; scale/shift replicated 4x
+        l.pk_wfold = packed_bytes;
+        packed_bytes += align_up((size_t)60 * 32 * 8 * 2, 256);
+        l.pk_ssfold = packed_bytes;
+        packed_bytes += align_up((size_t)2 * 32 * sizeof(float), 256);
+      }
+    }
     l.pk_proj = packed_bytes;   // C -> 1 projections (classifiers): contiguous fp32 weights for the fused epilogue
     if (cout == 1 && l.ntaps == 1) packed_bytes += align_up((size_t)l.CinT * sizeof(float), 256);
     index[name] = (int)layers.size();
@@ -353,6 +363,39 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     a.skip_out = e.skip_out ? 1 : 0;
   }
   if (!l.transposed) {
+    static const bool no_rowfold = getenv("DFF_B200_NO_ROWFOLD") != nullptr;
+    if (l.pair_x && wtc && use_fold && packed_base && l.pk_wfold != l.pk_ssfold && !no_rowfold && !a.proj_w && a.Cout == 8 && out.H % 8 == 0) {
+      // Row-folded first layer: with dilation 2 the output rows y, y+2, y+4, y+6 share 12 of their 4 x 9 tap rows, so they become the
+      // 32 channels of ONE GEMM row (3x fewer MMAs, whose cost does not depend on N <= 32).  GEMM row (R, x) of phase p = 0, 1 holds the
+      // output rows 8R + p + 2g: tile rows are 8 input rows apart (the A descriptor's row-group stride), the two row parities are the two
+      // phases of the launch and share the staged plane; the epilogue stores group g two rows below group g-1.
+      ConvArgs f = a;
+      TapTable pt[2];
+      for (int ph = 0; ph < 2; ++ph) {
+        TapTable& t = pt[ph];
+        t.n = 0;
+        for (int q = 0; q < 12; ++q)
+          for (int c = 0; c < 5; ++c) {
+            t.dz[t.n] = 0;
+            t.dy[t.n] = (int8_t)(2 * q - 8 + ph);
+            t.dx[t.n] = (int8_t)(4 * c - 8 + 2);
+            t.widx[t.n] = (uint8_t)(q * 5 + c);
+            ++t.n;
+          }
+      }
+      f.taps = pt[0];
+      f.isy = f.isx = 1; f.row_step = 8; f.grp_rows = 2;
+      f.osy = 8; f.osx = 1; f.ooy = f.oox = 0;
+      f.OHt = out.H / 8; f.OWt = out.W;
+      f.Cout = 32;
+      f.scale = (const float*)(packed_base + l.pk_ssfold);
+      f.shift = f.scale + 32;
+      if (getenv("DFF_B200_DEBUG_PLAN")) fprintf(stderr, "rowfold: supported=%d\n", (int)conv_slab_supported(f, pt, 2, 32));
+      if (conv_slab_supported(f, pt, 2, 32)) {
+        *nlaunch = 1;
+        return count_only ? 0 : launch_conv_slab(f, pt, 2, packed_base + l.pk_wfold, 32, nsm, st);
+      }
+    }
     if (l.pair_x && wtc) {   // 9 (dy, dilation 2) x 5 (paired dx, step 4) taps on the pair-packed input
       a.taps.n = 0;
       for (int b = 0; b < 9; ++b)
@@ -805,6 +848,7 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
       DFF_TRY(launch_pair_weight(raw + l.raw_w, (float*)(pk + l.pk_pair), l.cout, st));
       DFF_TRY(launch_pack_weight_tc((const float*)(pk + l.pk_pair), pk + l.pk_wtc, l.cout, 8, 8, 45, l.Ntc, 0, st));
       DFF_TRY(launch_pack_weight_slab((const float*)(pk + l.pk_pair), pk + l.pk_wslab, l.cout, 8, 8, 45, l.Ntc, 0, st));
+      if (l.pk_wfold != l.pk_ssfold) DFF_TRY(launch_pack_weight_slab_rowfold((const float*)(pk + l.pk_pair), pk + l.pk_wfold, l.cout, st));
     } else {
       DFF_TRY(launch_pack_weight_tc(raw + l.raw_w, pk + l.pk_wtc, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
       DFF_TRY(launch_pack_weight_slab(raw + l.raw_w, pk + l.pk_wslab, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
@@ -815,6 +859,8 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
     DFF_TRY(launch_bn_fold(bn ? raw + l.raw_gamma : nullptr, bn ? raw + l.raw_beta : nullptr, bn ? raw + l.raw_mean : nullptr,
                            bn ? raw + l.raw_var : nullptr, l.raw_bias >= 0 ? raw + l.raw_bias : nullptr,
                            (float*)(pk + l.pk_scale), (float*)(pk + l.pk_shift), l.cout, l.CoutP, st));
+    if (l.pair_x && l.pk_wfold != l.pk_ssfold)
+      DFF_TRY(launch_replicate_ss((const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), (float*)(pk + l.pk_ssfold), l.cout, 4, st));
     if (l.gfold > 1) {
       if (l.transposed) DFF_TRY(launch_pack_weight_slab_deconv_fold(raw + l.raw_w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, st));
       else DFF_TRY(launch_pack_weight_slab_fold(raw + l.raw_w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st));

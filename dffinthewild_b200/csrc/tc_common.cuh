@@ -53,6 +53,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -123,6 +129,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 }  // namespace tc
 
+// host: bf16 tiled tensor map without swizzle (conv_tc.cu); out-of-bounds elements read as zero
+int encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                     const unsigned* box);
+
 // ---- fused epilogue of one 128-pixel x N accumulator tile --------------------------------------------------------------
 // y = acc*scale[c] + shift[c] (BatchNorm eval / bias; scale and shift are both given or both null, 16-byte aligned) ; += res_pre ; ReLU ; += res_post ; store bf16 channels-last (or fp32
 // for cost volumes) ; optional second output out_aux = y + aux_add.  (epilogue classes E1-E9.)
@@ -140,6 +150,8 @@ struct EpiArgs {
   const float* proj_w;
   float* proj_out;
   int proj_src, skip_out;
+  long long grp_stride;   // != 0: 8-channel group g of a GEMM row is stored at pixel base + g * grp_stride elements (row-folded first layer)
+  int pix_c;              // channels per stored pixel when grp_stride != 0
   int proj_c;   // x-folded rows hold cstore / proj_c pixels: one projection per pixel, proj_out[pix * (cstore / proj_c) + g]; 0 = one pixel
 };
 
@@ -260,7 +272,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 template <bool RELU, int RES, bool AUX, bool PROJ>
 __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s, uint32_t tacc, bool valid, size_t pix) {
   using namespace tc;
-  const size_t o0 = pix * p.cstore;
+  const size_t o0 = p.grp_stride ? pix * p.pix_c : pix * p.cstore;
   __nv_bfloat16* const out = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
   const __nv_bfloat16* const res = reinterpret_cast<const __nv_bfloat16*>(RES == 1 ? p.res_pre : p.res_post) + o0;
   __nv_bfloat16* const oaux = reinterpret_cast<__nv_bfloat16*>(p.out_aux) + o0;
@@ -306,7 +318,8 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
-      if (!p.skip_out) *reinterpret_cast<uint4*>(out + c) = pack8(f);
+      if (p.grp_stride) *reinterpret_cast<uint4*>(out + (size_t)(c >> 3) * p.grp_stride) = pack8(f);   // (no residual operands in this form)
+      else if (!p.skip_out) *reinterpret_cast<uint4*>(out + c) = pack8(f);
       if (AUX) {
         float a[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(aadd + c)), a);
