@@ -48,7 +48,7 @@ constexpr int kSlabSmemBudget = 228 * 1024;   // per SM; every co-resident CTA a
 #endif
 
 struct alignas(64) SlabParams {
-  CUtensorMap tmap;   // (tma) in0 as (C0, IW, IH, S*B) bf16
+  CUtensorMap tmap[8];   // (tma) per source (x4) and view: the view's pixels as a (C, W/stx, H/sty, S*B) bf16 tensor
   const void* in0;
   const void* in1;
   const void* wslab;  // bf16 [tap][chunk][N][8]
@@ -56,7 +56,7 @@ struct alignas(64) SlabParams {
   int B, S, IH, IW;
   int tile_sy, sbo;   // input rows per tile step; A-descriptor stride between 8-row groups (bytes)
   int sty, stx, nviews, vpy[4], vpx[4];   // input stride per output step (y, x); one staged view per input-coordinate residue
-  int oy, ox, RX, RY, CPS, plane_bytes, NP, LA, hz;
+  int oy, ox, RX, RY, VB, CPS, plane_bytes, NP, LA, hz;   // VB: bytes of one (chunk, view) block of a plane (RY*RX*16 rounded up to 128)
   int N, nops, nph;          // MMA N; table entries; output phases (1 = convolution, 4 = fused transposed convolution, 2 = x-folded one)
   int phy[4], phx[4];        // output offset of each phase
   int g[12], ge[12];         // MMA groups by (phase, focal offset): table range [g[ph*3+k], ge[ph*3+k])
@@ -214,17 +214,17 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   // (table order = global address order: consecutive producer threads copy consecutive 16-byte pieces — the chunks of a pixel, then
   // the next pixel of the row — whatever view the pixel belongs to; the shared-memory destination is free-form anyway.  With
   // strided views (stride-2 and x-folded layers) a view-major order would have every thread touch its own 32-byte sector.)
-  for (int e = threadIdx.x; e < (p.tma ? 0 : p.nelem); e += kThreads) {
+  for (int e = threadIdx.x; e < p.nelem; e += kThreads) {
     const int c = e % p.nchunk, t = e / p.nchunk;
     const int gxi = t % (p.stx * p.RX), gyi = t / (p.stx * p.RX);
     const int rx = gxi / p.stx, vx = gxi % p.stx, ry = gyi / p.sty, vy = gyi % p.sty;
-    const int pix = ((vy * p.stx + vx) * p.RY + ry) * p.RX + rx;
+    const int pixo = (vy * p.stx + vx) * p.VB + (ry * p.RX + rx) * 16;   // byte offset inside the chunk's block
     const int gy = p.sty * p.oy + gyi, gx = p.stx * p.ox + gxi;
     const bool second = c >= p.nch0;
     const int C = second ? p.C1 : p.C0, cc = second ? c - p.nch0 : c;
     SlabElem el;
     el.rel = (gy * p.IW + gx) * C + cc * 8;
-    el.dst16 = (uint16_t)(((c * p.CPS + pix * 16) >> 4) | (second ? 0x8000 : 0));
+    el.dst16 = (uint16_t)(((c * p.CPS + pixo) >> 4) | (second ? 0x8000 : 0));
     el.gy = (uint8_t)(gy + kSlabElemBias);
     el.gx = (uint8_t)(gx + kSlabElemBias);
     const_cast<SlabElem*>(elems)[e] = el;
@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
     // box = 8 channels x RX pixels x RY rows lands in shared memory as [row][pixel][16 B] — the plane layout itself; out-of-bounds
     // rows / columns (the convolution's zero padding) are filled by the TMA unit.  One thread, no per-element work.
     if (threadIdx.x == 0) {
-      prefetch_tmap(&p.tmap);
+      for (int i = 0; i < (p.C1 ? 8 : 4); ++i)
+        if ((i & 3) < p.nviews) prefetch_tmap(&p.tmap[i]);
       int slot = 0;
       uint32_t ephase = 1;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
@@ -256,9 +257,19 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
         const int zlo = max(0, s_begin - hz), zhi = min(p.S, s_end + hz);
         for (int z = zlo; z < zhi; ++z) {
           mbar_wait(empty0 + 8 * slot, ephase);
-          mbar_expect_tx(full0 + 8 * slot, (uint32_t)p.CPS);
-          if (!(p.exp & 1)) tma_load_4d(planes_s + slot * p.plane_bytes, &p.tmap, full0 + 8 * slot, 0, tx0 + p.ox, ty0 + p.oy, b * p.S + z);
-          else asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * slot), "r"((uint32_t)p.CPS) : "memory");
+          const uint32_t total = (uint32_t)(p.nchunk * p.nviews * p.RY * p.RX * 16);
+          mbar_expect_tx(full0 + 8 * slot, total);
+          if (!(p.exp & 1)) {
+            const uint32_t dst0 = planes_s + slot * p.plane_bytes;
+            const int x0 = tx0 / p.stx + p.ox, y0 = ty0 / p.sty + p.oy, bz = b * p.S + z;   // view coordinates of the staged region
+            for (int c = 0; c < p.nchunk; ++c) {
+              const int src = c >= p.nch0 ? 1 : 0, cc = src ? c - p.nch0 : c;
+              for (int v = 0; v < p.nviews; ++v)
+                tma_load_4d(dst0 + c * p.CPS + v * p.VB, &p.tmap[src * 4 + v], full0 + 8 * slot, cc * 8, x0, y0, bz);
+            }
+          } else {
+            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * slot), "r"(total) : "memory");
+          }
           if (++slot == p.NP) { slot = 0; ephase ^= 1; }
         }
       }
@@ -564,8 +575,9 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   static const bool exp_aligned = getenv("DFF_SLAB_EXPERIMENT") && !strcmp(getenv("DFF_SLAB_EXPERIMENT"), "aligned");
   p.exp = (getenv("DFF_SLAB_EXPERIMENT") && !exp_aligned) ? atoi(getenv("DFF_SLAB_EXPERIMENT")) : 0;
   if (exp_aligned) p.RX = (p.RX + 7) & ~7;
-  p.CPS = p.nviews * p.RY * p.RX * 16;
-  p.plane_bytes = (nchunk * p.CPS + 127) & ~127;
+  p.VB = (p.RY * p.RX * 16 + 127) & ~127;   // (each (chunk, view) block is the destination of one TMA box: 128-byte aligned)
+  p.CPS = p.nviews * p.VB;
+  p.plane_bytes = nchunk * p.CPS;
   if (p.sty * p.oy < -kSlabElemBias || p.stx * p.ox < -kSlabElemBias || p.sty * (p.oy + p.RY) > 255 - kSlabElemBias ||
       p.stx * (p.ox + p.RX) > 255 - kSlabElemBias)
     return_false;   // (staging-table coordinates are biased bytes)
@@ -573,7 +585,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.sbo = (a.row_step > 0 ? a.row_step : 1) * p.RX * 16;
   if ((p.CPS >> 4) >= (1 << 14) || p.sbo >= (1 << 18)) return_false;
   auto aoff = [&](const VT& x, int chunk) {
-    int o = chunk * p.CPS + ((x.view * p.RY + (x.vy - p.oy)) * p.RX + (x.vx - p.ox)) * 16;
+    int o = chunk * p.CPS + x.view * p.VB + ((x.vy - p.oy) * p.RX + (x.vx - p.ox)) * 16;
     if (exp_aligned) o &= ~127;
     return o;
   };
@@ -619,7 +631,11 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.N = Ntc;
   p.w_bytes = nops * Ntc * 32;
   // ---- shared memory: table + weights + scale/shift + staging table + ring; as many co-resident CTAs as fit -----------------
-  p.nelem = p.nviews * p.RY * p.RX * nchunk;
+  // planes staged by TMA: one box (8 channels x RX x RY) per chunk and view (descriptors encoded at launch); DFF_B200_SLAB_TMA=0 keeps
+  // the cp.async producers, =1 restricts TMA to the row-folded first layer
+  static const int tma_mode = getenv("DFF_B200_SLAB_TMA") ? atoi(getenv("DFF_B200_SLAB_TMA")) : 2;
+  p.tma = (tma_mode > 0 && (a.row_step > 0 || tma_mode > 1) && p.RX <= 256 && p.RY <= 256 && a.IW % p.stx == 0 && a.IH % p.sty == 0) ? 1 : 0;
+  p.nelem = p.tma ? 0 : p.nviews * p.RY * p.RX * nchunk;   // (staging table of the cp.async producers)
   const int np_min = 2 * p.hz + 2;
   const int cols = 2 * nph * Ntc;
   if (cols > 512) return_false;
@@ -693,9 +709,6 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   }
   if (NP > kSlabMaxPlanes) NP = kSlabMaxPlanes;
   p.NP = NP;
-  // single-chunk, single-view layers whose plane is a multiple of 128 bytes: staged by TMA (descriptor encoded at launch)
-  static const bool no_tma = getenv("DFF_B200_NO_SLAB_TMA") != nullptr;
-  p.tma = (!no_tma && a.row_step > 0 && nchunk == 1 && p.nviews == 1 && a.C0 == 8 && !a.in1 && p.CPS % 128 == 0 && p.RX <= 256 && p.RY <= 256) ? 1 : 0;
   // multi-phase layers (transposed convolutions) at one or two CTAs per SM are bound by their four epilogue warps: give them eight
   static const bool no_e2 = getenv("DFF_B200_NO_EPI2") != nullptr;
   p.egroups = (nph >= 2 && occ <= 2 && !no_e2) ? 2 : 1;
@@ -742,10 +755,17 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
     return fail(-5, "conv_slab: unsupported layer shape");
   p.wslab = wslab;
   if (p.tma) {
-    const unsigned long long dims[4] = {8ull, (unsigned long long)a.IW, (unsigned long long)a.IH, (unsigned long long)a.S * a.B};
-    const unsigned long long strides[3] = {16ull, (unsigned long long)a.IW * 16, (unsigned long long)a.IH * a.IW * 16};
-    const unsigned box[4] = {8u, (unsigned)p.RX, (unsigned)p.RY, 1u};
-    DFF_TRY(encode_tmap_bf16(&p.tmap, a.in0, 4, dims, strides, box));
+    for (int src = 0; src < (a.C1 ? 2 : 1); ++src) {
+      const unsigned long long C = src ? a.C1 : a.C0;
+      const char* base = (const char*)(src ? a.in1 : a.in0);
+      for (int v = 0; v < p.nviews; ++v) {
+        const int vy = v / p.stx, vx = v % p.stx;
+        const unsigned long long dims[4] = {C, (unsigned long long)(a.IW / p.stx), (unsigned long long)(a.IH / p.sty), (unsigned long long)a.S * a.B};
+        const unsigned long long strides[3] = {C * 2 * p.stx, (unsigned long long)a.IW * C * 2 * p.sty, (unsigned long long)a.IH * a.IW * C * 2};
+        const unsigned box[4] = {8u, (unsigned)p.RX, (unsigned)p.RY, 1u};
+        DFF_TRY(encode_tmap_bf16(&p.tmap[src * 4 + v], base + ((size_t)vy * a.IW + vx) * C * 2, 4, dims, strides, box));
+      }
+    }
   }
 #ifdef DFF_SLAB_TRACE
   if (getenv("DFF_SLAB_TRACE")) { cudaMalloc(&p.trace, 64 * 8 * 8); cudaMemset(p.trace, 0, 64 * 8 * 8); }
