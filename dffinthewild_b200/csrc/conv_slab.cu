@@ -27,10 +27,10 @@
 
 namespace dff {
 
-constexpr int kSlabProducers = 64;                     // warps 0-1: cp.async producers
-constexpr int kSlabMmaWarp = kSlabProducers / 32;      // warp 2: MMA issuer (+TMEM alloc)
-constexpr int kSlabThreads = kSlabProducers + 32 + 128;  // + warps 3-6: epilogue (one per TMEM lane quadrant)
-// variants: E2 = a second group of four epilogue warps (warps 7-10; the groups take alternate output phases) for multi-phase layers
+constexpr int kSlabProducers = 32;                     // warp 0: producer (one thread drives the TMA; all 32 in the cp.async fallback)
+constexpr int kSlabMmaWarp = kSlabProducers / 32;      // warp 1: MMA issuer (+TMEM alloc)
+constexpr int kSlabThreads = kSlabProducers + 32 + 128;  // + warps 2-5: epilogue (one per TMEM lane quadrant)
+// variants: E2 = a second group of four epilogue warps (warps 6-9; the groups take alternate output phases) for multi-phase layers
 // whose shared-memory footprint leaves at most two CTAs per SM; WS = weight streaming: + one last warp, the weight producer
 __host__ __device__ constexpr int slab_threads(bool ws, bool e2) { return kSlabThreads + (e2 ? 128 : 0) + (ws ? 32 : 0); }
 constexpr int kSlabMaxWSlot = 40 * 1024;                 // largest slot of the streamed-weight ring (bytes)
@@ -129,12 +129,17 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
     for (int s = s_begin; s < s_end; ++s, ++sc) {
       const int buf = sc & 1;
       const size_t row0 = ((size_t)b * p.S + s) * p.OH;
-      if (valid && rsrc) {
-        // the residual operand does not depend on the accumulator: pull it towards L1 while the MMAs run
-        for (int ph = eg; ph < p.nph; ph += neg) {
-          const size_t pix = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
-          const size_t ob = pix * ep.cstore * esz;
-          for (int k = 0; k < ep.cstore * esz; k += 128) prefetch_l1(reinterpret_cast<const char*>(rsrc) + ob + k);
+      uint4 rv[4];
+      {
+        // the residual / second-output operand does not depend on the accumulator: its first 32 columns are requested before the wait
+        const size_t pix = (row0 + (oy * p.osy + p.phy[eg])) * p.OW + (ox * p.osx + p.phx[eg]);
+        if (FAST && eg < p.nph) tc_epilogue_preload<RES, AUX>(ep, valid, pix, 0, rv);
+        else if (valid && rsrc) {
+          for (int ph = eg; ph < p.nph; ph += neg) {
+            const size_t px = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
+            const size_t ob = px * ep.cstore * esz;
+            for (int k = 0; k < ep.cstore * esz; k += 128) prefetch_l1(reinterpret_cast<const char*>(rsrc) + ob + k);
+          }
         }
       }
       mbar_wait(tfull0 + 8 * buf, (sc >> 1) & 1);
@@ -144,8 +149,10 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
         const size_t pix = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
         if (p.exp & 2) continue;
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N;
-        if (FAST) tc_epilogue_fast<RELU, RES, AUX, PROJ>(ep, ss_s, tacc, valid, pix);
-        else tc_epilogue_tile(ep, tacc, valid, pix);
+        if (FAST) {
+          if (ph != eg) tc_epilogue_preload<RES, AUX>(ep, valid, pix, 0, rv);
+          tc_epilogue_fast<RELU, RES, AUX, PROJ>(ep, ss_s, tacc, valid, pix, rv);
+        } else tc_epilogue_tile(ep, tacc, valid, pix);
       }
       fence_before();
       mbar_arrive_relaxed(tempty0 + 8 * buf);
@@ -155,6 +162,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
 }
 
 template <bool WS, bool E2>
+// (192 threads x 4 CTAs per SM: 85 registers per thread)
 __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) conv_slab_kernel(const __grid_constant__ SlabParams p) {
   using namespace tc;
   constexpr int kThreads = slab_threads(WS, E2);

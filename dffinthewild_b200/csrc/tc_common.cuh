@@ -269,17 +269,32 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   w.x = tc::pack2(f[0], f[1]); w.y = tc::pack2(f[2], f[3]); w.z = tc::pack2(f[4], f[5]); w.w = tc::pack2(f[6], f[7]);
   return w;
 }
+// Residual / second-output operand of one GEMM row, 32 columns (four 16-byte vectors) at a time: issued as ONE batch of loads — by the
+// caller before it waits for the accumulator (first batch) or at the start of the next 32 columns — instead of one exposed round trip
+// per 8-channel half (the operand is a full-size activation tensor: DRAM latency).
+template <int RES, bool AUX>
+__device__ __forceinline__ void tc_epilogue_preload(const EpiArgs& p, bool valid, size_t pix, int c32, uint4* rv) {
+  if (!(RES || AUX) || !valid) return;
+  const __nv_bfloat16* const src =
+      reinterpret_cast<const __nv_bfloat16*>(AUX ? p.aux_add : (RES == 1 ? p.res_pre : p.res_post)) + (p.grp_stride ? pix * p.pix_c : pix * p.cstore);
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+    if (c32 + 8 * h < p.cstore) rv[h] = __ldg(reinterpret_cast<const uint4*>(src + c32 + 8 * h));
+}
 template <bool RELU, int RES, bool AUX, bool PROJ>
-__device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s, uint32_t tacc, bool valid, size_t pix) {
+__device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s, uint32_t tacc, bool valid, size_t pix, uint4* rv) {
   using namespace tc;
   const size_t o0 = p.grp_stride ? pix * p.pix_c : pix * p.cstore;
   __nv_bfloat16* const out = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
-  const __nv_bfloat16* const res = reinterpret_cast<const __nv_bfloat16*>(RES == 1 ? p.res_pre : p.res_post) + o0;
   __nv_bfloat16* const oaux = reinterpret_cast<__nv_bfloat16*>(p.out_aux) + o0;
-  const __nv_bfloat16* const aadd = reinterpret_cast<const __nv_bfloat16*>(p.aux_add) + o0;
   float pacc = 0.f, pacc1 = 0.f;   // (x-folded rows: pixel 0 / pixel 1 of the row)
   const int pc = (PROJ && p.proj_c) ? p.proj_c : p.cstore;
-  for (int c0 = 0; c0 < p.N; c0 += 16) {
+  for (int c32 = 0; c32 < p.N; c32 += 32) {
+    if (c32 > 0) tc_epilogue_preload<RES, AUX>(p, valid, pix, c32, rv);   // (the first 32 columns come preloaded)
+#pragma unroll
+   for (int g16 = 0; g16 < 2; ++g16) {
+    const int c0 = c32 + 16 * g16;
+    if (c0 >= p.N) break;
     uint32_t v[16];
     tmem_ld16(tacc + c0, v);
     if (!valid || c0 >= p.cstore) continue;
@@ -299,9 +314,10 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
         f[j + 2] = fmaf(__uint_as_float(v[8 * h + j + 2]), sc.z, sh.z);
         f[j + 3] = fmaf(__uint_as_float(v[8 * h + j + 3]), sc.w, sh.w);
       }
+      const uint4 rvec = rv[g16 * 2 + h];
       if (RES) {
         float r[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(res + c)), r);
+        unpack8(rvec, r);
         if (RES == 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += r[j];
@@ -322,7 +338,7 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
       else if (!p.skip_out) *reinterpret_cast<uint4*>(out + c) = pack8(f);
       if (AUX) {
         float a[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(aadd + c)), a);
+        unpack8(rvec, a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] += f[j];
         *reinterpret_cast<uint4*>(oaux + c) = pack8(a);
@@ -345,6 +361,7 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
         if (g) pacc1 += t; else pacc += t;
       }
     }
+   }
   }
   if (PROJ && valid) {
     if (p.proj_c) { p.proj_out[2 * pix] = pacc; p.proj_out[2 * pix + 1] = pacc1; }
