@@ -142,8 +142,39 @@ __global__ void pool_kernel(const T* __restrict__ src, T* __restrict__ dst, int 
   }
 }
 
+// MaxPool3d((1,2,2)) on bf16 channels-last volumes, 8 channels (16 bytes) per thread: four 16-byte loads, packed bf16x2 maxima (exact),
+// one 16-byte store — the generic kernel above spends its time on 8-byte accesses and fp32 conversions.
+__global__ void __launch_bounds__(256) maxpool2_bf16x8_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int BS, int H, int W, int C8) {
+  const int OH = H / 2, OW = W / 2;
+  const size_t n = (size_t)BS * OH * OW * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    size_t r = i / C8;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const size_t bs = r / OH;
+    const uint4* p = src + ((bs * H + 2 * oy) * W + 2 * ox) * C8 + c8;
+    const uint4 a = __ldg(p), b = __ldg(p + C8), c = __ldg(p + (size_t)W * C8), d = __ldg(p + (size_t)W * C8 + C8);
+    auto mx = [](uint32_t x, uint32_t y) {
+      const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&x), *reinterpret_cast<const __nv_bfloat162*>(&y));
+      return *reinterpret_cast<const uint32_t*>(&m);
+    };
+    uint4 o;
+    o.x = mx(mx(a.x, b.x), mx(c.x, d.x)); o.y = mx(mx(a.y, b.y), mx(c.y, d.y));
+    o.z = mx(mx(a.z, b.z), mx(c.z, d.z)); o.w = mx(mx(a.w, b.w), mx(c.w, d.w));
+    dst[i] = o;
+  }
+}
+
 int launch_pool(const void* src, void* dst, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st) {
   if (C % 4 || H % k || W % k) return fail(-1, "pool: C % 4, H % k, W % k must be 0");
+  if (bf16 && is_max && k == 2 && C % 8 == 0) {
+    const size_t n8 = (size_t)BS * (H / 2) * (W / 2) * (C / 8);
+    maxpool2_bf16x8_kernel<<<grid_for(n8, 256, 148 * 32), 256, 0, st>>>((const uint4*)src, (uint4*)dst, BS, H, W, C / 8);
+    DFF_LAUNCH_CHECK("maxpool2");
+    return 0;
+  }
   const size_t n = (size_t)BS * (H / k) * (W / k) * (C / 4);
   const int g = grid_for(n, 256);
   if (bf16) {

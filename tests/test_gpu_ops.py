@@ -235,6 +235,28 @@ def test_srd_attention_one_pass(rt, C, S, H, W):
     assert frac_exact > 0.99, frac_exact
 
 
+@pytest.mark.parametrize("C,k,is_max", [(8, 2, True), (16, 2, True), (32, 2, False), (32, 4, False), (32, 8, False)])
+def test_pool_bf16_exact(rt, C, k, is_max):
+    """(1,k,k) pooling on bf16 channels-last volumes (MaxPool3d of EFD, reference :387; AvgPool3d pyramid, :248-250): the maximum of
+    bf16 values is exact; the average is one rounding of the fp32 mean."""
+    import ctypes
+    from dffinthewild_b200 import train as tr
+    l = tr._lib() if hasattr(tr, "_lib") else rt.lib()
+    BS, H, W = 6, 16, 48
+    x = _rand(BS, H, W, C, seed=21, scale=3.0).to(torch.bfloat16).cuda()
+    out = torch.empty((BS, H // k, W // k, C), dtype=torch.bfloat16, device="cuda")
+    f = rt.lib().dff_pool3d
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    rt.check(f(x.data_ptr(), BS, H, W, C, k, 1 if is_max else 0, rt.BF16, out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+    xr = x.float().view(BS, H // k, k, W // k, k, C)
+    ref = xr.amax(dim=(2, 4)) if is_max else xr.mean(dim=(2, 4))
+    if is_max:
+        assert torch.equal(out.float(), ref)
+    else:
+        assert (out.float() - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item()
+
+
 @pytest.mark.parametrize("r", [1, 2, 4, 8])
 def test_depth_head(rt, r):
     from oracle import dff_oracle as O
