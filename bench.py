@@ -5,7 +5,7 @@
 
 One step = one pass of the hot path (DFF_net forward, reference train_codes/Depth_Estimation_Network.py:77-137)
 over 64 synthetic DDFF full-resolution stacks PER GPU (10 x 3 x 383 x 552, padded to 384 x 576 with -1 like
-Depth_Estimation_Test/test_Dataloader.py:128-140).  Focal stacks are independent, so ranks share nothing: weak scaling,
+Depth_Estimation_Test/test_Dataloader.py:128-140), one dff_forward call per step (--micro-batch 64; 49 GB of workspace).  Focal stacks are independent, so ranks share nothing: weak scaling,
 no collective on the data path (N=1 is exactly BASELINE.json configs[1]: batch 64).
 
 `value`   stacks/s, inputs resident in HBM, CUDA-event timed, max over ranks.
@@ -300,12 +300,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DFF_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--micro-batch", type=int, default=64)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-micro-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

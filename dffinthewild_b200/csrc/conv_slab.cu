@@ -1,22 +1,31 @@
-// "Slab" implicit-GEMM convolution on tcgen05/TMEM — the main bf16 kernel of the network.
+// "Slab" implicit-GEMM convolution on tcgen05/TMEM fed by TMA — the main bf16 kernel of the network.
 //
 // Replaces the cuDNN conv3d / conv_transpose3d calls of the reference (train_codes/Depth_Estimation_Network.py:352-355,
-// 43-50, 278-301) for every layer whose weights fit in shared memory (all full-, half- and quarter-resolution layers).
+// 43-50, 278-301) for every layer but the five with >= 128 input channels or stride 2 on 64 (those stay on conv_tc.cu).
 //
 // What bounds a focal-volume convolution on B200 is not the tensor pipe but how often the activation tile is re-read: a
 // per-tap TMA implicit GEMM (conv_tc.cu) pulls the same 128 pixels 27 times from L2.  Here one CTA owns an 8 x 16 pixel
 // column of the focal volume and walks the S slices:
-//   * 4 producer warps stage each slice's halo'd tile ONCE in shared memory with 16-byte cp.async (zero-fill = padding,
-//     second source pointer = torch.cat, parity views = stride 2) in the UMMA no-swizzle K-major layout: per 8-channel chunk
-//     a plane of [row][pixel] x 16 B, so 8 horizontally adjacent pixels form one 128-byte core matrix.  A ring of NP
-//     planes holds slices s-1, s, s+1 (the 3-tap focal dimension) plus look-ahead;
+//   * one producer thread stages each slice's halo'd tile ONCE in shared memory with tiled TMA loads — one box of
+//     8 channels x RX pixels x RY rows per 8-channel chunk and input-stride residue ("view": stride-2 and x-folded layers),
+//     out-of-bounds = the convolution's zero padding, second tensor map = torch.cat — which lands as [row][pixel] x 16 B: the UMMA
+//     no-swizzle K-major layout in which 8 horizontally adjacent pixels form one 128-byte core matrix.  A ring of NP planes holds
+//     slices s-1, s, s+1 (the 3-tap focal dimension) plus look-ahead.  (Per-element 16-byte cp.async by two producer warps, the
+//     first implementation and still the DFF_B200_SLAB_TMA=0 fallback, sustained only ~8 B/clk per SM and bounded a third of the
+//     layers: profiles/r1_slab_roles.txt.)
 //   * a convolution tap is then nothing but a byte offset added to the matrix-descriptor start address (dy rows, dx pixels,
 //     dz = which ring slot) — no data movement per tap; the K=16 of one tcgen05.mma is two 8-channel chunk planes (LBO = plane
 //     stride) or, for 8-channel tensors, two neighbouring taps (LBO = their distance);
-//   * the layer's weights are loaded once per CTA into shared memory, already ordered by MMA;
-//   * one thread issues the MMAs of a slice (taps x Cin/16) into a double-buffered TMEM accumulator; 4 epilogue warps apply
-//     BatchNorm/bias, residuals, ReLU and store while the next slice is being multiplied.
+//   * the layer's weights are loaded once per CTA into shared memory, already ordered by MMA — or, when they do not fit next to
+//     the plane ring (64-channel 3x3x3 layers, stride-2 layers), STREAMED: one more warp feeds a ring of 3-4 slots with
+//     cp.async.bulk copies of the next block of MMAs' weights (template parameter WS);
+//   * one warp issues the MMAs of a slice (taps x Cin/16) from uniform registers into a double-buffered TMEM accumulator; 4 epilogue
+//     warps (8 for multi-phase layers at <= 2 CTAs/SM, template parameter E2) apply BatchNorm/bias, residuals, ReLU, the fused
+//     classifier and store while the next slice is being multiplied; residual operands are requested before the accumulator wait.
+//   * row-folded first layer (a.row_step): tile rows 8 input rows apart through the descriptor's row-group stride, two row-parity
+//     phases over one staged plane, 32 = 4 rows x 8 output channels per GEMM row (net.cu::run_conv).
 // HBM/L2 traffic per output pixel drops from taps x Cin to ~1.4 x Cin, and there is no per-tap barrier round trip.
+// Kernels launch with programmatic dependent launch: the prologue (weights, barriers, TMEM) overlaps the previous layer's tail.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -535,7 +544,8 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
 // host side: plan (geometry, MMA table, ring depth) + launch
 // ------------------------------------------------------------------------------------------------------------------
 // `ptaps`/`nph`: tap table per output phase (nph = 1: a.taps; nph = 4: the parity phases of a transposed convolution).
-#define return_false do { if (getenv("DFF_B200_DEBUG_PLAN")) fprintf(stderr, "slab_plan: fail at line %d\n", __LINE__); return false; } while (0)
+// DFF_B200_DEBUG_PLAN=1 (works in a dry run without a GPU): report which rule of the plan rejected a layer
+#define return_false do { if (getenv("DFF_B200_DEBUG_PLAN")) fprintf(stderr, "slab_plan: rejected at line %d\n", __LINE__); return false; } while (0)
 static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc, int num_sms, SlabParams& p, size_t* smem_out,
                       int* occ_out) {
   memset(&p, 0, sizeof(p));

@@ -390,7 +390,6 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
       f.Cout = 32;
       f.scale = (const float*)(packed_base + l.pk_ssfold);
       f.shift = f.scale + 32;
-      if (getenv("DFF_B200_DEBUG_PLAN")) fprintf(stderr, "rowfold: supported=%d\n", (int)conv_slab_supported(f, pt, 2, 32));
       if (conv_slab_supported(f, pt, 2, 32)) {
         *nlaunch = 1;
         return count_only ? 0 : launch_conv_slab(f, pt, 2, packed_base + l.pk_wfold, 32, nsm, st);
