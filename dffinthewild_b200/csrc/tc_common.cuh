@@ -272,14 +272,27 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // Residual / second-output operand of one GEMM row, 32 columns (four 16-byte vectors) at a time: issued as ONE batch of loads — by the
 // caller before it waits for the accumulator (first batch) or at the start of the next 32 columns — instead of one exposed round trip
 // per 8-channel half (the operand is a full-size activation tensor: DRAM latency).
+// 32-byte global accesses (sm_100: LDG/STG.256): a GEMM row's 16 bf16 channels in one instruction — full 32-byte sectors per request
+__device__ __forceinline__ void ldg_nc_v8(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
 template <int RES, bool AUX>
 __device__ __forceinline__ void tc_epilogue_preload(const EpiArgs& p, bool valid, size_t pix, int c32, uint4* rv) {
   if (!(RES || AUX) || !valid) return;
   const __nv_bfloat16* const src =
       reinterpret_cast<const __nv_bfloat16*>(AUX ? p.aux_add : (RES == 1 ? p.res_pre : p.res_post)) + (p.grp_stride ? pix * p.pix_c : pix * p.cstore);
 #pragma unroll
-  for (int h = 0; h < 4; ++h)
-    if (c32 + 8 * h < p.cstore) rv[h] = __ldg(reinterpret_cast<const uint4*>(src + c32 + 8 * h));
+  for (int h = 0; h < 4; h += 2) {
+    if (c32 + 8 * h + 16 <= p.cstore) ldg_nc_v8(src + c32 + 8 * h, rv[h], rv[h + 1]);   // (rows of >= 16 channels are 32-byte aligned)
+    else if (c32 + 8 * h < p.cstore) rv[h] = __ldg(reinterpret_cast<const uint4*>(src + c32 + 8 * h));
+  }
 }
 template <bool RELU, int RES, bool AUX, bool PROJ>
 __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s, uint32_t tacc, bool valid, size_t pix, uint4* rv) {
@@ -299,6 +312,7 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
     tmem_ld16(tacc + c0, v);
     if (!valid || c0 >= p.cstore) continue;
     const int nh = p.cstore - c0 >= 16 ? 2 : 1;   // 8-channel halves stored from this 16-column group
+    uint4 po[2], pa[2];                           // packed output / second output of the two halves
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h >= nh) break;
@@ -334,14 +348,14 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
-      if (p.grp_stride) *reinterpret_cast<uint4*>(out + (size_t)(c >> 3) * p.grp_stride) = pack8(f);   // (no residual operands in this form)
-      else if (!p.skip_out) *reinterpret_cast<uint4*>(out + c) = pack8(f);
+      po[h] = pack8(f);
+      if (p.grp_stride) *reinterpret_cast<uint4*>(out + (size_t)(c >> 3) * p.grp_stride) = po[h];   // (no residual operands in this form)
       if (AUX) {
         float a[8];
         unpack8(rvec, a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] += f[j];
-        *reinterpret_cast<uint4*>(oaux + c) = pack8(a);
+        pa[h] = pack8(a);
         if (PROJ && p.proj_src) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = a[j];
@@ -360,6 +374,13 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
         }
         if (g) pacc1 += t; else pacc += t;
       }
+    }
+    if (nh == 2) {   // 16 channels = 32 bytes per row and instruction
+      if (!p.grp_stride && !p.skip_out) stg_v8(out + c0, po[0], po[1]);
+      if (AUX) stg_v8(oaux + c0, pa[0], pa[1]);
+    } else {
+      if (!p.grp_stride && !p.skip_out) *reinterpret_cast<uint4*>(out + c0) = po[0];
+      if (AUX) *reinterpret_cast<uint4*>(oaux + c0) = pa[0];
     }
    }
   }
