@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   const uint32_t w_s = smem0 + 1024;               // weights, MMA order: [op][half][N][8] bf16
   const uint32_t planes_s = smem0 + p.planes_off;  // ring of NP slice planes
   const SlabElem* const elems = reinterpret_cast<const SlabElem*>(smem_gen + p.elem_off);
-  float* const ss = reinterpret_cast<float*>(smem_gen + p.ss_off);  // scale[N], shift[N]
+  float* const ss = reinterpret_cast<float*>(smem_gen + p.ss_off);  // scale[N], shift[N], classifier weights[N]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kSlabMaxPlanes]);
   const uint32_t tfull0 = smem_u32(&bars[2 * kSlabMaxPlanes]), tempty0 = smem_u32(&bars[2 * kSlabMaxPlanes + 2]);
@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   for (int i = threadIdx.x; i < p.N; i += kThreads) {
     ss[i] = p.epi.scale ? __ldg(p.epi.scale + i) : 1.f;
     ss[p.N + i] = p.epi.shift ? __ldg(p.epi.shift + i) : 0.f;
+    const int pc = p.epi.proj_c ? p.epi.proj_c : p.epi.cstore;   // (x-folded rows hold cstore / proj_c pixels)
+    ss[2 * p.N + i] = (p.epi.proj_w && i < p.epi.cstore) ? __ldg(p.epi.proj_w + i % pc) : 0.f;
   }
   // (table order = global address order: consecutive producer threads copy consecutive 16-byte pieces — the chunks of a pixel, then
   // the next pixel of the row — whatever view the pixel belongs to; the shared-memory destination is free-form anyway.  With
@@ -662,7 +664,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   auto lay_out = [&](int wregion) {   // offsets for a weight region of `wregion` bytes; returns the fixed part
     int off = 1024 + ((wregion + 127) & ~127);
     p.ss_off = off;
-    off += (2 * Ntc * 4 + 127) & ~127;
+    off += (3 * Ntc * 4 + 127) & ~127;   // scale | shift | fused-classifier weights
     p.elem_off = off;
     off += (p.nelem * 8 + 127) & ~127;
     p.planes_off = off;

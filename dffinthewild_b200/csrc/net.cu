@@ -987,10 +987,11 @@ int dff_forward_host(const void* packed, const float* FS_host, const float* fd_h
   };
   if (fd_span(mb) > (size_t)mb * S * H * W) return fail(DFF_E_ARG, "dff_forward_host: focus_dists strides exceed (B,S,H,W)");
   int rc = 0, nchunk = 0;
-  // chunk sizes ramp up (mb/4, mb/4, mb/2, mb/2, mb/2, mb, mb, ...): the first host->device copy cannot overlap anything, and the
-  // copy stream is only ~1.2x faster than the kernels, so the kernels catch up with it through small chunks first
+  // chunk sizes: mb/4, mb/4, then mb/2 throughout.  The first host->device copy cannot overlap anything, so it is short; after that the
+  // copy stream (0.64 ms per DDFF stack) is the slower side (kernels: ~1 ms + 0.6 ms per stack per call), so what is exposed at the
+  // end is the LAST chunk's kernels — half-size chunks halve that, and their launch overhead hides under the copies.
   for (int i0 = 0, n = 0; i0 < B && !rc; i0 += n, ++nchunk) {
-    n = nchunk < 2 ? (mb >= 4 ? mb / 4 : mb) : (nchunk < 5 ? (mb >= 2 ? mb / 2 : mb) : mb);
+    n = nchunk < 2 ? (mb >= 4 ? mb / 4 : mb) : (mb >= 2 ? mb / 2 : mb);
     if (n > B - i0) n = B - i0;
     const int k = nchunk % kHostStages;
     char* io = (char*)dev_io + k * stage;

@@ -362,11 +362,12 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
         }
       }
       if (PROJ) {   // the projection sees what the next layer will read: the bf16-rounded values
-        const int g = c >= pc ? 1 : 0, cw = c - g * pc;
+        const int g = c >= pc ? 1 : 0;
         float t = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; j += 4) {
-          const float4 pw = __ldg(reinterpret_cast<const float4*>(p.proj_w + cw + j));
+          float4 pw;   // classifier weights, replicated per pixel of the row, live behind scale/shift in shared memory
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pw.x), "=f"(pw.y), "=f"(pw.z), "=f"(pw.w) : "r"(ss_s + 4 * (2 * p.N + c + j)));
           t = fmaf(__bfloat162float(__float2bfloat16_rn(f[j])), pw.x, t);
           t = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 1])), pw.y, t);
           t = fmaf(__bfloat162float(__float2bfloat16_rn(f[j + 2])), pw.z, t);
