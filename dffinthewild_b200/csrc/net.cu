@@ -1036,6 +1036,7 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
                const void* res_pre, const void* res_post, int relu, void* out, int elem, int use_tensor_cores, void* scratch,
                int device, void* stream) {
   if (!in0 || !weight || !out || !scratch) return fail(DFF_E_ARG, "dff_conv3d: null pointer");
+  g_pdl_call = false;   // the weights are packed by kernels launched just before the convolution: its prologue must not run ahead of them
   const bool out_f32 = (elem & DFF_OUT_F32) != 0;   // fp32 output from bf16 operands (cost volumes)
   elem &= ~DFF_OUT_F32;
   if (use_tensor_cores && (elem != DFF_BF16 || (C0 % 8) || (C1 % 8)))
@@ -1090,6 +1091,7 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
 int dff_srd_attention(const void* F, int B, int S, int H, int W, int C, const float* w_a, const float* w_b, void* out, void* scratch,
                       int device, void* stream) {
   if (!F || !w_a || !w_b || !out || !scratch) return fail(DFF_E_ARG, "dff_srd_attention: null pointer");
+  g_pdl_call = false;   // (weights packed just before the launch, see dff_conv3d)
   if (C != 8 && C != 16 && C != 32) return fail(DFF_E_UNSUPPORTED, "dff_srd_attention: C must be 8, 16 or 32");
   if (((size_t)H * W) % 16) return fail(DFF_E_ARG, "dff_srd_attention: H*W must be a multiple of 16");
   DeviceGuard g(device);
