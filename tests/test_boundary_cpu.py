@@ -96,3 +96,28 @@ def test_workspace_size_and_shape_errors(built_lib):
     assert a > 0 and abs(b - 2 * a) <= 1 << 16 and h < a
     assert l.dff_workspace_bytes(1, 10, 100, 224, rt.FP32) == 0  # H not a multiple of 32
     assert b"multiples of 32" in l.dff_last_error()
+
+
+def test_operator_plan_dry_run(built_lib):
+    """The library plans a forward without a GPU (`dff_forward_profiled` with null pointers): the operator list is what bench.py's
+    roofline divides by — its algorithmic FLOPs must be SURVEY.md §8(d)'s 93,563 FLOP/voxel (2*MACs of the 70 executed conv layers,
+    classifier and attention products included) and the bf16 plan must stay at one launch per fused operator."""
+    import ctypes
+    from dffinthewild_b200 import runtime as rt
+    l = rt.lib()
+    N = 256
+    ms, fl, by = (ctypes.c_float * N)(), (ctypes.c_double * N)(), (ctypes.c_double * N)()
+    la, nm, n = (ctypes.c_int * N)(), ctypes.create_string_buffer(N * 64), ctypes.c_int(0)
+    B, S, H, W = 2, 10, 384, 576
+    for mode, max_launches in ((rt.BF16, 80), (rt.FP32, 140)):
+        rc = l.dff_forward_profiled(None, None, None, None, B, S, H, W, None, None, 0, mode, 0, None, N, ms, fl, by, la, nm, ctypes.byref(n))
+        assert rc == 0, l.dff_last_error()
+        names = [nm.raw[k * 64:(k + 1) * 64].split(b"\0")[0].decode() for k in range(n.value)]
+        assert names[0] == "to_channels_last" and names[-1] == "depth_heads"
+        assert "dres4.conv6.0" in names and "FM_measure.Focus_extraction.0.0" in names
+        flops = sum(fl[k] for k in range(n.value))
+        vox = B * S * H * W
+        assert abs(flops / vox - 93563.0) / 93563.0 < 0.01, flops / vox
+        launches = sum(la[k] for k in range(n.value))
+        assert n.value <= launches <= max_launches, launches
+        assert all(by[k] > 0 for k in range(n.value))
