@@ -1,5 +1,5 @@
 // tcgen05 / TMEM / TMA / mbarrier primitives (inline PTX) and the fused convolution epilogue shared by the
-// tensor-core convolution kernels (conv_tc.cu: per-tap TMA streaming; conv_slab.cu: shared-memory slab + resident weights).
+// tensor-core convolution kernels (conv_tc.cu: per-tap TMA streaming; conv_slab.cu: TMA-staged shared-memory slab, resident or streamed weights).
 #pragma once
 #include <cuda.h>
 
