@@ -232,6 +232,13 @@ def run_ours(args):
             "hbm_view": {"achieved_gbs": ach_gbs, "peak_gbs": pk["hbm"], "frac": ach_gbs / pk["hbm"]},
             "whole_step": {"tflops_per_gpu": FLOP_PER_VOXEL * S * H * W * PER_GPU_BATCH / (ms_per_step / 1000.0) / 1e12,
                            "frac_of_tensor_peak": FLOP_PER_VOXEL * S * H * W * PER_GPU_BATCH / (ms_per_step / 1000.0) / 1e12 / pk["tf_sustained"]}}
+    try:   # BASELINE.json's second figure: tensor-pipe utilisation of the 3-D aggregation convs (hourglasses, pyramid, dres0, deconvs)
+        sel = [a for n, a in agg.items() if n.startswith(("dres", "SPP_module", "deconv_", "confidence"))]
+        t_s, f_s = sum(a["ms"] for a in sel) / 1000.0, sum(a["flops"] for a in sel)
+        roof["aggregation_convs"] = {"tflops": f_s / t_s / 1e12, "frac_of_tensor_peak": f_s / t_s / 1e12 / pk["tf_sustained"],
+                                     "share_of_step": 1000.0 * t_s / total_prof_ms, "operators": len(sel)}
+    except Exception as ex:   # (a reporting extra must never take the bench line down)
+        roof["aggregation_convs"] = {"error": str(ex)}
     tr = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")   # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
     if os.path.exists(tr):
         t = json.load(open(tr))
