@@ -7,15 +7,21 @@
  *
  *   dff_forward            <- DFF_net.forward        train_codes/Depth_Estimation_Network.py:77-137
  *                                                    Depth_Estimation_Test/Depth_Estimation_Network.py:74-127
- *   dff_backward           <- autograd of the above  (invoked at train_codes/train_code_Defocus.py:167)
+ *   dff_forward_host       <- the eval loop's `.cuda()` uploads + forward + `.cpu()` reads, Depth_Estimation_Test/test.py:115-121
  *   dff_pack_weights       <- nn.Module parameter/buffer storage read by every conv/BN call
  *                             (convbn_3d, train_codes/Depth_Estimation_Network.py:352-355)
  *   dff_conv3d             <- one nn.Conv3d / nn.ConvTranspose3d (+BatchNorm3d eval +ReLU +residual) call site,
  *                             e.g. train_codes/Depth_Estimation_Network.py:144-148, 278-301
+ *   dff_srd_attention      <- the channel-attention branch of Feature_Extraction / SRD, train_codes/Depth_Estimation_Network.py:399-407
  *   dff_depth_head         <- upsample + softplus-normalise + expected focus distance,
  *                             train_codes/Depth_Estimation_Network.py:92-98, 118-136
- *   dff_fov_warp           <- FlowNetwork.FOV_warp    End_to_End/End_to_End.py:106-134
- *   dff_flow_forward       <- FlowNetwork.forward     End_to_End/End_to_End.py:63-104
+ *   dff_conv3d_dgrad, dff_conv3d_wgrad, dff_bn_train_forward/backward, dff_pool3d(_backward), dff_add,
+ *   dff_depth_head_backward <- autograd of DFF_net.forward in train mode (invoked at train_codes/train_code_Defocus.py:167;
+ *                             BatchNorm3d with batch statistics, train_codes/Depth_Estimation_Network.py:355); PyTorch's autograd
+ *                             stays the tape (dffinthewild_b200/train.py), every computation is one of these calls
+ *   dff_fov_warp(_cl)      <- FlowNetwork.FOV_warp    End_to_End/End_to_End.py:106-134
+ *   dff_pair_volume, dff_spatial_mean_accum (+ dff_conv3d)
+ *                          <- FlowNetwork.forward     End_to_End/End_to_End.py:63-104 (composed in dffinthewild_b200/End_to_End.py)
  *
  * Conventions
  *   - All pointers are DEVICE pointers unless the name ends in `_host`.  The library never allocates or frees
@@ -52,7 +58,7 @@ extern "C" {
 /* precision / mode flags (bit-or) */
 #define DFF_FP32 0  /* fp32 activations, FFMA kernels: parity mode (<= 1e-4 relative per pixel) */
 #define DFF_BF16 1  /* bf16 activations, tcgen05/TMEM implicit-GEMM kernels, fp32 accumulate */
-#define DFF_TRAIN 2 /* BatchNorm in batch-statistics mode; activations are kept for dff_backward */
+#define DFF_TRAIN 2 /* BatchNorm in batch-statistics mode; reserved: train mode runs through the operator calls below */
 #define DFF_NO_TC 4 /* debugging aid with DFF_BF16: bf16 storage but FFMA kernels instead of tcgen05 */
 #define DFF_NO_SLAB 8 /* debugging aid with DFF_BF16: only the per-tap TMA tcgen05 kernel, never the slab kernel */
 #define DFF_OUT_F32 16 /* with DFF_BF16 as the `elem` of dff_conv3d: store the output as fp32 (C -> 1 cost volumes) */
