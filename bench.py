@@ -81,7 +81,7 @@ class ClockSampler:
 def make_net(precision):
     import torch
     from dffinthewild_b200.Depth_Estimation_Network import Network
-    from oracle import synth
+    from dffinthewild_b200 import synth
     torch.manual_seed(0)
     net = Network()
     sd = synth.synthetic_state(net.state_dict(), seed=1)
@@ -94,7 +94,8 @@ def cpu_reference_time(sd, n_runs, warmup):
     """The reference's CPU implementation of the path (oracle port: same torch CPU ops in the same order) on one
     stack of the workload, all host threads."""
     import torch
-    from oracle import dff_oracle, synth
+    from oracle import dff_oracle
+    from dffinthewild_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     FS = synth.focal_stack(1, S, H, W, seed=0, valid_hw=VALID_HW)
@@ -142,7 +143,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from dffinthewild_b200 import runtime as rt
-    from oracle import synth
+    from dffinthewild_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -167,7 +168,7 @@ def run_ours(args):
         FS[i:i + mb] = one.to(dev).roll(i, dims=-1)   # distinct content per chunk
     fd = synth.focus_dists(n_local, S, H, W, "ddff").to(dev)
     outs = [torch.empty((n_local, H, W), dtype=torch.float32, device=dev) for _ in range(4)]
-    packed = rt.PackedWeights(dff).get(dff, dev)
+    packed = rt.packed_weights(dff, dev)
     ws = torch.empty(lib.dff_workspace_bytes(mb, S, H, W, mode), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)

@@ -164,7 +164,7 @@ def reference_init_(net):
             m.bias.data.zero_()
 
 
-class DFF_net(nn.Module):
+class DFF_net(_rt.PackedOwnerMixin, nn.Module):
     """Depth-from-focus network (reference `DFF_net`, :17-137).  Forward = one C-ABI call."""
 
     def __init__(self):

@@ -65,6 +65,68 @@ __global__ void to_cl_pair_kernel(const float* __restrict__ src, __nv_bfloat16* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Input staging from the datasets' own format: uint8 focal stacks (B,S,H0,W0,3) exactly as the reference's
+// dataloaders read them (Depth_Estimation_Test/test_Dataloader.py:122-147: hdf5 stack S x H x W x C uint8 -> `/127.5 - 1.0` in
+// fp32 -> -1 padding of H, W to multiples of 32 -> transpose to C x S x H x W).  One pass does all of it and writes the layout the
+// first convolution reads, so a quarter of the bytes cross PCIe and the fp32 (B,3,S,H,W) tensor never exists.
+//   v = fl32(fl32(u8) / 127.5f) - 1.0f   (IEEE division and subtraction: bit-identical to numpy's float32 arithmetic)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u8_norm(unsigned char u) { return __fsub_rn(__fdiv_rn((float)u, 127.5f), 1.0f); }
+
+// -> pair-packed bf16 (B,S,H,W+2,8): the u8 twin of to_cl_pair_kernel (pixels with y >= H0 or x >= W0 are the -1 padding)
+__global__ void u8_to_cl_pair_kernel(const unsigned char* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int S, int H0, int W0,
+                                     int H, int W) {
+  const int Wp = W + 2;
+  const size_t npix = (size_t)B * S * H * Wp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Wp);
+    const size_t row = i / Wp;                 // (b*S + s)*H + y
+    const int y = (int)(row % H);
+    const size_t bs = row / H;
+    const bool yin = y < H0;
+    const unsigned char* s = src + ((bs * H0 + (yin ? y : 0)) * (size_t)W0) * 3;
+    float l[3], r[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int xl = c - 2;
+      l[k] = xl < 0 ? 0.f : ((yin && xl < W0) ? u8_norm(__ldg(s + (size_t)xl * 3 + k)) : -1.f);
+      r[k] = c >= W ? 0.f : ((yin && c < W0) ? u8_norm(__ldg(s + (size_t)c * 3 + k)) : -1.f);
+    }
+    Elem<__nv_bfloat16>::store4(dst + i * 8, make_float4(l[0], l[1], l[2], r[0]));
+    Elem<__nv_bfloat16>::store4(dst + i * 8 + 4, make_float4(r[1], r[2], 0.f, 0.f));
+  }
+}
+
+// -> channels-last (B,S,H,W,Cp) fp32 | bf16 (fp32 parity mode, FFMA kernels), and -> the reference layout (B,3,S,H,W) fp32
+template <typename T>
+__global__ void u8_to_cl_kernel(const unsigned char* __restrict__ src, T* __restrict__ dst, int B, int S, int H0, int W0, int H, int W,
+                                int Cp) {
+  const size_t npix = (size_t)B * S * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const size_t bs = i / ((size_t)W * H);
+    const bool in = y < H0 && x < W0;
+    const unsigned char* s = src + ((bs * H0 + (in ? y : 0)) * (size_t)W0 + (in ? x : 0)) * 3;
+    float4 v;
+    v.x = in ? u8_norm(__ldg(s)) : -1.f; v.y = in ? u8_norm(__ldg(s + 1)) : -1.f; v.z = in ? u8_norm(__ldg(s + 2)) : -1.f; v.w = 0.f;
+    Elem<T>::store4(dst + i * Cp, v);
+    for (int c = 4; c < Cp; c += 4) Elem<T>::store4(dst + i * Cp + c, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+__global__ void u8_to_planar_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int B, int S, int H0, int W0, int H,
+                                    int W) {
+  const size_t plane = (size_t)S * H * W, npix = (size_t)B * plane;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const size_t bs = i / ((size_t)W * H), b = i / plane, r = i % plane;
+    const bool in = y < H0 && x < W0;
+    const unsigned char* s = src + ((bs * H0 + (in ? y : 0)) * (size_t)W0 + (in ? x : 0)) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dst[(b * 3 + k) * plane + r] = in ? u8_norm(__ldg(s + k)) : -1.f;
+  }
+}
+
 // W' (Cout, 8, 1, 9, 5) fp32 for the paired input: W'[co][ci][ky][j] = W[co][ci][ky][2j] (ci < 3), W[co][ci-3][ky][2j+1] (3 <= ci < 6,
 // 2j+1 < 9), 0 otherwise.  W: (Cout, 3, 1, 9, 9).
 __global__ void pair_weight_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout) {
@@ -95,6 +157,26 @@ int launch_to_cl_pair(const float* src, int B, int S, int H, int W, void* dst, c
   const size_t n = (size_t)B * S * H * (W + 2);
   to_cl_pair_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, B, S, H, W);
   DFF_LAUNCH_CHECK("to_cl_pair");
+  return 0;
+}
+int launch_u8_to_cl_pair(const unsigned char* src, int B, int S, int H0, int W0, int H, int W, void* dst, cudaStream_t st) {
+  const size_t n = (size_t)B * S * H * (W + 2);
+  u8_to_cl_pair_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, B, S, H0, W0, H, W);
+  DFF_LAUNCH_CHECK("u8_to_cl_pair");
+  return 0;
+}
+int launch_u8_to_cl(const unsigned char* src, int B, int S, int H0, int W0, int H, int W, void* dst, int Cp, bool bf16, cudaStream_t st) {
+  if (Cp % 4 || Cp < 4) return fail(-1, "u8_to_channels_last: Cp must be a multiple of 4");
+  const size_t n = (size_t)B * S * H * W;
+  if (bf16) u8_to_cl_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, B, S, H0, W0, H, W, Cp);
+  else u8_to_cl_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (float*)dst, B, S, H0, W0, H, W, Cp);
+  DFF_LAUNCH_CHECK("u8_to_cl");
+  return 0;
+}
+int launch_u8_to_planar(const unsigned char* src, int B, int S, int H0, int W0, int H, int W, float* dst, cudaStream_t st) {
+  const size_t n = (size_t)B * S * H * W;
+  u8_to_planar_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, dst, B, S, H0, W0, H, W);
+  DFF_LAUNCH_CHECK("u8_to_planar");
   return 0;
 }
 int launch_pair_weight(const float* w, float* dst, int Cout, cudaStream_t st) {

@@ -18,6 +18,9 @@ int launch_conv_ffma(ConvArgs a, bool bf16, cudaStream_t st);
 int launch_to_cl(const float* src, int B, int C, int S, int H, int W, void* dst, int Cp, bool bf16, cudaStream_t st);
 int launch_to_cl_pair(const float* src, int B, int S, int H, int W, void* dst, cudaStream_t st);
 int launch_pair_weight(const float* w, float* dst, int Cout, cudaStream_t st);
+int launch_u8_to_cl_pair(const unsigned char* src, int B, int S, int H0, int W0, int H, int W, void* dst, cudaStream_t st);
+int launch_u8_to_cl(const unsigned char* src, int B, int S, int H0, int W0, int H, int W, void* dst, int Cp, bool bf16, cudaStream_t st);
+int launch_u8_to_planar(const unsigned char* src, int B, int S, int H0, int W0, int H, int W, float* dst, cudaStream_t st);
 int launch_from_cl(const void* src, int B, int C, int S, int H, int W, int Cp, bool bf16, float* dst, cudaStream_t st);
 int launch_pool(const void* src, void* dst, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st);
 int launch_depth_head(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
@@ -59,7 +62,9 @@ int launch_bn_apply(const void* x, const float* scale, const float* shift, const
                     size_t npix, int C, bool bf16, void* out, cudaStream_t st);
 int launch_bn_backward(const void* dy, const void* y, const void* x, const float* mean, const float* invstd, const float* gamma,
                        size_t npix, int C, bool bf16, void* dx, void* g_out, float* dgamma, float* dbeta, void* partial,
-                       cudaStream_t st);
+                       cudaStream_t st, bool fixed_stats = false);
+int launch_bn_eval_stats(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C, float* scale,
+                         float* shift, float* mean, float* invstd, cudaStream_t st);
 int launch_add(const void* a, const void* b, size_t n, bool bf16, void* out, cudaStream_t st);
 int launch_pool_bwd(const void* x, const void* dy, void* dx, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st);
 int launch_depth_head_bwd(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
@@ -721,12 +726,25 @@ struct Runner {
   }
 };
 
-static int forward_impl(const void* packed, const float* FS, const float* fd, const int64_t* fds, int B, int S, int H, int W,
+// The focal stacks of a call: the reference's fp32 (B,3,S,H,W) tensor, or the datasets' uint8 (B,S,H0,W0,3) stacks (H0 <= H, W0 <= W;
+// normalisation and the -1 padding happen in the staging kernel).
+struct FwdIn {
+  const float* FS = nullptr;
+  const unsigned char* u8 = nullptr;
+  int H0 = 0, W0 = 0;
+  FwdIn() = default;
+  FwdIn(const float* f) : FS(f) {}
+  FwdIn(const unsigned char* u, int h0, int w0) : u8(u), H0(h0), W0(w0) {}
+};
+
+static int forward_impl(const void* packed, const FwdIn& fin, const float* fd, const int64_t* fds, int B, int S, int H, int W,
                         float* const* out4, float* const* cost4, void* ws, size_t ws_bytes, int mode, cudaStream_t st,
                         bool dry, size_t* need, Profile* prof = nullptr) {
   if (B < 1 || S < 1 || H < 32 || W < 32 || H % 32 || W % 32)
     return fail(DFF_E_ARG, "dff_forward: need B,S >= 1 and H,W positive multiples of 32 (pad with -1 like the reference dataloaders)");
   if (mode & DFF_TRAIN) return fail(DFF_E_UNSUPPORTED, "dff_forward: DFF_TRAIN is not available in this build");
+  if (fin.u8 && (fin.H0 < 1 || fin.W0 < 1 || fin.H0 > H || fin.W0 > W))
+    return fail(DFF_E_ARG, "dff_forward_u8: need 1 <= H0 <= H and 1 <= W0 <= W (H, W = the padded extent)");
   g_pdl_call = (double)B * S * H * W <= 8.0 * 10 * 384 * 576;   // up to 8 DDFF stacks' worth of voxels per call
   Runner r{net_of(DFF_NET_DFF), (const char*)packed, (char*)ws, ws_bytes, 0, dry, (mode & DFF_BF16) != 0, st};
   r.prof = prof;
@@ -735,8 +753,15 @@ static int forward_impl(const void* packed, const float* FS, const float* fd, co
   const double vox = (double)B * S * H * W;
   const int c_in = r.use_tc ? 8 : 4;  // stored channels of the converted focal stack (TMA needs 16-byte pixels)
   Ten x0 = r.alloc(B, S, H, r.use_tc ? W + 2 : W, c_in);   // (tensor-core path: pair-packed first-layer input, see to_cl_pair_kernel)
-  r.op_begin("to_channels_last", 0, vox * (12 + c_in * r.esize(false)), 1);
-  if (!dry && !r.rc) r.rc = r.use_tc ? launch_to_cl_pair(FS, B, S, H, W, x0.p, st) : launch_to_cl(FS, B, 3, S, H, W, x0.p, c_in, r.bf16, st);
+  if (fin.u8 || (dry && fin.H0)) {
+    r.op_begin("to_channels_last(u8)", 0, 3.0 * B * S * fin.H0 * fin.W0 + vox * c_in * r.esize(false), 1);
+    if (!dry && !r.rc)
+      r.rc = r.use_tc ? launch_u8_to_cl_pair(fin.u8, B, S, fin.H0, fin.W0, H, W, x0.p, st)
+                      : launch_u8_to_cl(fin.u8, B, S, fin.H0, fin.W0, H, W, x0.p, c_in, r.bf16, st);
+  } else {
+    r.op_begin("to_channels_last", 0, vox * (12 + c_in * r.esize(false)), 1);
+    if (!dry && !r.rc) r.rc = r.use_tc ? launch_to_cl_pair(fin.FS, B, S, H, W, x0.p, st) : launch_to_cl(fin.FS, B, 3, S, H, W, x0.p, c_in, r.bf16, st);
+  }
   r.op_end();
   Ten t = r.conv("FM_measure.Focus_extraction.0.0", x0, Runner::relu());
   Ten v1 = r.srd("FM_measure.Focus_extraction.2", t);
@@ -872,7 +897,7 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
 
 size_t dff_workspace_bytes(int B, int S, int H, int W, int mode) {
   size_t need = 0;
-  if (forward_impl(nullptr, nullptr, nullptr, nullptr, B, S, H, W, nullptr, nullptr, nullptr, 0, mode, nullptr, true, &need))
+  if (forward_impl(nullptr, FwdIn(), nullptr, nullptr, B, S, H, W, nullptr, nullptr, nullptr, 0, mode, nullptr, true, &need))
     return 0;
   return need;
 }
@@ -883,8 +908,26 @@ int dff_forward(const void* packed, const float* FS, const float* fd, const int6
   if (!packed || !FS || !fd || !fd_strides || !out4 || !workspace) return fail(DFF_E_ARG, "dff_forward: null pointer");
   DeviceGuard g(device);
   if (g.rc) return g.rc;
-  return forward_impl(packed, FS, fd, fd_strides, B, S, H, W, out4, cost4, workspace, workspace_bytes, mode,
+  return forward_impl(packed, FwdIn(FS), fd, fd_strides, B, S, H, W, out4, cost4, workspace, workspace_bytes, mode,
                       (cudaStream_t)stream, false, nullptr);
+}
+
+int dff_forward_u8(const void* packed, const uint8_t* FS_u8, int H0, int W0, const float* fd, const int64_t fd_strides[4], int B,
+                   int S, int H, int W, float* const out4[4], float* const cost4[4], void* workspace, size_t workspace_bytes,
+                   int mode, int device, void* stream) {
+  if (!packed || !FS_u8 || !fd || !fd_strides || !out4 || !workspace) return fail(DFF_E_ARG, "dff_forward_u8: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return forward_impl(packed, FwdIn(FS_u8, H0, W0), fd, fd_strides, B, S, H, W, out4, cost4, workspace, workspace_bytes, mode,
+                      (cudaStream_t)stream, false, nullptr);
+}
+
+int dff_stage_u8(const uint8_t* FS_u8, int H0, int W0, int B, int S, int H, int W, float* FS, int device, void* stream) {
+  if (!FS_u8 || !FS) return fail(DFF_E_ARG, "dff_stage_u8: null pointer");
+  if (H0 < 1 || W0 < 1 || H0 > H || W0 > W) return fail(DFF_E_ARG, "dff_stage_u8: need 1 <= H0 <= H and 1 <= W0 <= W");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_u8_to_planar(FS_u8, B, S, H0, W0, H, W, FS, (cudaStream_t)stream);
 }
 
 int dff_forward_profiled(const void* packed, const float* FS, const float* fd, const int64_t fd_strides[4], int B, int S,
@@ -897,13 +940,13 @@ int dff_forward_profiled(const void* packed, const float* FS, const float* fd, c
   prof.events = !dry;
   int rc = 0;
   if (dry) {
-    rc = forward_impl(nullptr, nullptr, nullptr, nullptr, B, S, H, W, nullptr, nullptr, nullptr, 0, mode, nullptr, true,
+    rc = forward_impl(nullptr, FwdIn(), nullptr, nullptr, B, S, H, W, nullptr, nullptr, nullptr, 0, mode, nullptr, true,
                       nullptr, &prof);
   } else {
     if (!FS || !fd || !fd_strides || !out4 || !workspace) return fail(DFF_E_ARG, "dff_forward_profiled: null pointer");
     DeviceGuard g(device);
     if (g.rc) return g.rc;
-    rc = forward_impl(packed, FS, fd, fd_strides, B, S, H, W, out4, nullptr, workspace, workspace_bytes, mode,
+    rc = forward_impl(packed, FwdIn(FS), fd, fd_strides, B, S, H, W, out4, nullptr, workspace, workspace_bytes, mode,
                       (cudaStream_t)stream, false, nullptr, &prof);
     if (!rc) rc = check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
   }
@@ -934,23 +977,57 @@ int dff_forward_profiled(const void* packed, const float* FS, const float* fd, c
 // copies of a DDFF stack take 0.64 ms, its kernels 0.68 ms + 1.3 ms per launch sequence: with three stages the copy stream never
 // idles, so only the first chunk's copy is exposed.
 constexpr int kHostStages = 3;
-static size_t host_stage_bytes(int mb, int S, int H, int W) {
-  return align_up((size_t)mb * 3 * S * H * W * 4, 256) + align_up((size_t)mb * S * H * W * 4, 256) +
-         4 * align_up((size_t)mb * H * W * 4, 256);
+// focus-distance elements one chunk of n stacks addresses through the strides
+static size_t fd_span(const int64_t* fds, int n, int S, int H, int W) {
+  const int dims[4] = {n, S, H, W};
+  size_t e = 1;
+  for (int i = 0; i < 4; ++i) e += (size_t)(dims[i] - 1) * (size_t)fds[i];
+  return e;
 }
-size_t dff_host_io_bytes(int micro_batch, int S, int H, int W) { return kHostStages * host_stage_bytes(micro_batch, S, H, W); }
+// one stage: input stacks (in_stack_bytes each) | focus_dists (fd_elems) | 4 depth maps
+static size_t host_stage_bytes(int mb, size_t in_stack_bytes, size_t fd_elems, int H, int W) {
+  return align_up((size_t)mb * in_stack_bytes, 256) + align_up(fd_elems * 4, 256) + 4 * align_up((size_t)mb * H * W * 4, 256);
+}
+size_t dff_host_io_bytes(int micro_batch, int S, int H, int W) {
+  return kHostStages * host_stage_bytes(micro_batch, (size_t)3 * S * H * W * 4, (size_t)micro_batch * S * H * W, H, W);
+}
+size_t dff_host_io_bytes_u8(int micro_batch, int S, int H0, int W0, int H, int W, const int64_t fd_strides[4]) {
+  if (!fd_strides || micro_batch < 1) return 0;
+  return kHostStages * host_stage_bytes(micro_batch, (size_t)3 * S * H0 * W0, fd_span(fd_strides, micro_batch, S, H, W), H, W);
+}
 
 namespace {
 struct HostPipe {
   cudaStream_t h2d = nullptr, d2h = nullptr;
   cudaEvent_t in_ready[kHostStages] = {}, computed[kHostStages] = {}, out_done[kHostStages] = {};
   bool ok = false;
+  int device = -1;
+  HostPipe() = default;
+  HostPipe(const HostPipe&) = delete;
+  HostPipe& operator=(const HostPipe&) = delete;
+  // the calling thread ends (nn.DataParallel's worker threads are short-lived): give the streams and events back.  At process
+  // exit the runtime may already be gone; the calls then fail harmlessly.
+  ~HostPipe() {
+    if (device < 0) return;
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
+    for (int k = 0; k < kHostStages; ++k) {
+      if (in_ready[k]) cudaEventDestroy(in_ready[k]);
+      if (computed[k]) cudaEventDestroy(computed[k]);
+      if (out_done[k]) cudaEventDestroy(out_done[k]);
+    }
+    if (h2d) cudaStreamDestroy(h2d);
+    if (d2h) cudaStreamDestroy(d2h);
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+  }
 };
 // one pipe per (host thread, device): nn.DataParallel drives each GPU from its own thread
 HostPipe* host_pipe(int device) {
   thread_local std::map<int, HostPipe> pipes;
   HostPipe& hp = pipes[device];
   if (!hp.ok) {
+    hp.device = device;
     if (cudaStreamCreateWithFlags(&hp.h2d, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaStreamCreateWithFlags(&hp.d2h, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     for (int k = 0; k < kHostStages; ++k) {
@@ -962,51 +1039,43 @@ HostPipe* host_pipe(int device) {
   }
   return &hp;
 }
-}  // namespace
 
-int dff_forward_host(const void* packed, const float* FS_host, const float* fd_host, const int64_t fd_strides[4], int B,
-                     int micro_batch, int S, int H, int W, float* const out4_host[4], void* dev_io, void* workspace,
-                     size_t workspace_bytes, int mode, int device, void* stream) {
-  if (!packed || !FS_host || !fd_host || !fd_strides || !out4_host || !dev_io || !workspace)
-    return fail(DFF_E_ARG, "dff_forward_host: null pointer");
+// `in_host`: fp32 (B,3,S,H,W) stacks (u8 == false) or uint8 (B,S,H0,W0,3) stacks
+int forward_host_impl(const void* packed, const void* in_host, bool u8, int H0, int W0, const float* fd_host, const int64_t* fd_strides,
+                      int B, int micro_batch, int S, int H, int W, float* const* out4_host, void* dev_io, void* workspace,
+                      size_t workspace_bytes, int mode, int device, cudaStream_t st) {
   if (B < 1 || micro_batch < 1) return fail(DFF_E_ARG, "dff_forward_host: B and micro_batch must be >= 1");
+  if (u8 && (H0 < 1 || W0 < 1 || H0 > H || W0 > W)) return fail(DFF_E_ARG, "dff_forward_host_u8: need 1 <= H0 <= H and 1 <= W0 <= W");
   DeviceGuard g(device);
   if (g.rc) return g.rc;
   HostPipe* hp = host_pipe(device);
   if (!hp) return fail(DFF_E_CUDA, "dff_forward_host: cannot create the copy streams");
-  cudaStream_t st = (cudaStream_t)stream;
   const int mb = micro_batch < B ? micro_batch : B;
-  const size_t stage = host_stage_bytes(mb, S, H, W);
-  const size_t fs_stack = (size_t)3 * S * H * W, map_px = (size_t)H * W;
-  // focus-distance elements one chunk of n stacks addresses through the strides
-  auto fd_span = [&](int n) {
-    const int dims[4] = {n, S, H, W};
-    size_t e = 1;
-    for (int i = 0; i < 4; ++i) e += (size_t)(dims[i] - 1) * (size_t)fd_strides[i];
-    return e;
-  };
-  if (fd_span(mb) > (size_t)mb * S * H * W) return fail(DFF_E_ARG, "dff_forward_host: focus_dists strides exceed (B,S,H,W)");
+  const size_t in_stack = u8 ? (size_t)3 * S * H0 * W0 : (size_t)3 * S * H * W * 4, map_px = (size_t)H * W;
+  if (fd_span(fd_strides, mb, S, H, W) > (size_t)mb * S * H * W) return fail(DFF_E_ARG, "dff_forward_host: focus_dists strides exceed (B,S,H,W)");
+  const size_t fd_elems = u8 ? fd_span(fd_strides, mb, S, H, W) : (size_t)mb * S * H * W;
+  const size_t stage = host_stage_bytes(mb, in_stack, fd_elems, H, W);
   int rc = 0, nchunk = 0;
-  // chunk sizes: mb/4, mb/4, then mb/2 throughout.  The first host->device copy cannot overlap anything, so it is short; after that the
-  // copy stream (0.64 ms per DDFF stack) is the slower side (kernels: ~1 ms + 0.6 ms per stack per call), so what is exposed at the
-  // end is the LAST chunk's kernels — half-size chunks halve that, and their launch overhead hides under the copies.
+  // chunk sizes: mb/4, mb/4, then mb/2 throughout.  The first host->device copy cannot overlap anything, so it is short; after that
+  // whichever side is slower (fp32 stacks: the copies, 0.64 ms per DDFF stack; uint8 stacks: the kernels) leaves the LAST chunk's
+  // kernels exposed — half-size chunks halve that, and their launch overhead hides under the other side.
   for (int i0 = 0, n = 0; i0 < B && !rc; i0 += n, ++nchunk) {
     n = nchunk < 2 ? (mb >= 4 ? mb / 4 : mb) : (mb >= 2 ? mb / 2 : mb);
     if (n > B - i0) n = B - i0;
     const int k = nchunk % kHostStages;
     char* io = (char*)dev_io + k * stage;
-    float* dFS = (float*)io;
-    float* dfd = (float*)(io + align_up((size_t)mb * fs_stack * 4, 256));
-    char* o = (char*)dfd + align_up((size_t)mb * S * H * W * 4, 256);
+    float* dfd = (float*)(io + align_up((size_t)mb * in_stack, 256));
+    char* o = (char*)dfd + align_up(fd_elems * 4, 256);
     float* dout[4];
     for (int j = 0; j < 4; ++j) dout[j] = (float*)(o + j * align_up((size_t)mb * map_px * 4, 256));
     // stage k is free again once the maps of the chunk that used it last have left it
     if (nchunk >= kHostStages) DFF_CUDA(cudaStreamWaitEvent(hp->h2d, hp->out_done[k], 0));
-    DFF_CUDA(cudaMemcpyAsync(dFS, FS_host + (size_t)i0 * fs_stack, (size_t)n * fs_stack * 4, cudaMemcpyHostToDevice, hp->h2d));
-    DFF_CUDA(cudaMemcpyAsync(dfd, fd_host + (size_t)i0 * fd_strides[0], fd_span(n) * 4, cudaMemcpyHostToDevice, hp->h2d));
+    DFF_CUDA(cudaMemcpyAsync(io, (const char*)in_host + (size_t)i0 * in_stack, (size_t)n * in_stack, cudaMemcpyHostToDevice, hp->h2d));
+    DFF_CUDA(cudaMemcpyAsync(dfd, fd_host + (size_t)i0 * fd_strides[0], fd_span(fd_strides, n, S, H, W) * 4, cudaMemcpyHostToDevice, hp->h2d));
     DFF_CUDA(cudaEventRecord(hp->in_ready[k], hp->h2d));
     DFF_CUDA(cudaStreamWaitEvent(st, hp->in_ready[k], 0));
-    rc = forward_impl(packed, dFS, dfd, fd_strides, n, S, H, W, dout, nullptr, workspace, workspace_bytes, mode, st, false, nullptr);
+    const FwdIn fin = u8 ? FwdIn((const unsigned char*)io, H0, W0) : FwdIn((const float*)io);
+    rc = forward_impl(packed, fin, dfd, fd_strides, n, S, H, W, dout, nullptr, workspace, workspace_bytes, mode, st, false, nullptr);
     if (rc) break;
     DFF_CUDA(cudaEventRecord(hp->computed[k], st));
     DFF_CUDA(cudaStreamWaitEvent(hp->d2h, hp->computed[k], 0));
@@ -1022,6 +1091,25 @@ int dff_forward_host(const void* packed, const float* FS_host, const float* fd_h
   DFF_CUDA(e2);
   DFF_CUDA(e3);
   return 0;
+}
+}  // namespace
+
+int dff_forward_host(const void* packed, const float* FS_host, const float* fd_host, const int64_t fd_strides[4], int B,
+                     int micro_batch, int S, int H, int W, float* const out4_host[4], void* dev_io, void* workspace,
+                     size_t workspace_bytes, int mode, int device, void* stream) {
+  if (!packed || !FS_host || !fd_host || !fd_strides || !out4_host || !dev_io || !workspace)
+    return fail(DFF_E_ARG, "dff_forward_host: null pointer");
+  return forward_host_impl(packed, FS_host, false, 0, 0, fd_host, fd_strides, B, micro_batch, S, H, W, out4_host, dev_io, workspace,
+                           workspace_bytes, mode, device, (cudaStream_t)stream);
+}
+
+int dff_forward_host_u8(const void* packed, const uint8_t* FS_u8_host, int H0, int W0, const float* fd_host, const int64_t fd_strides[4],
+                        int B, int micro_batch, int S, int H, int W, float* const out4_host[4], void* dev_io, void* workspace,
+                        size_t workspace_bytes, int mode, int device, void* stream) {
+  if (!packed || !FS_u8_host || !fd_host || !fd_strides || !out4_host || !dev_io || !workspace)
+    return fail(DFF_E_ARG, "dff_forward_host_u8: null pointer");
+  return forward_host_impl(packed, FS_u8_host, true, H0, W0, fd_host, fd_strides, B, micro_batch, S, H, W, out4_host, dev_io, workspace,
+                           workspace_bytes, mode, device, (cudaStream_t)stream);
 }
 
 size_t dff_conv3d_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw) {
@@ -1250,6 +1338,28 @@ int dff_bn_train_backward(const void* dy, const void* y_relu, const void* x, con
   if (g.rc) return g.rc;
   return launch_bn_backward(dy, y_relu, x, save_mean, save_invstd, gamma, (size_t)npix, C, elem == DFF_BF16, dx, dres, dgamma, dbeta,
                             scratch, (cudaStream_t)stream);
+}
+
+int dff_bn_eval_forward(const void* x, int64_t npix, int C, int elem, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, const void* res_pre, const void* res_post, int relu, void* out,
+                        float* save_mean, float* save_invstd, float* scale_shift, int device, void* stream) {
+  if (!x || !out || !running_mean || !running_var || !save_mean || !save_invstd || !scale_shift)
+    return fail(DFF_E_ARG, "dff_bn_eval_forward: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DFF_TRY(launch_bn_eval_stats(gamma, beta, running_mean, running_var, eps, C, scale_shift, scale_shift + C, save_mean, save_invstd, st));
+  return launch_bn_apply(x, scale_shift, scale_shift + C, res_pre, res_post, relu, (size_t)npix, C, elem == DFF_BF16, out, st);
+}
+
+int dff_bn_eval_backward(const void* dy, const void* y_relu, const void* x, const float* save_mean, const float* save_invstd,
+                         const float* gamma, int64_t npix, int C, int elem, void* dx, void* dres, float* dgamma, float* dbeta,
+                         void* scratch, int device, void* stream) {
+  if (!dy || !x || !save_mean || !save_invstd || !dgamma || !dbeta || !scratch) return fail(DFF_E_ARG, "dff_bn_eval_backward: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_bn_backward(dy, y_relu, x, save_mean, save_invstd, gamma, (size_t)npix, C, elem == DFF_BF16, dx, dres, dgamma, dbeta,
+                            scratch, (cudaStream_t)stream, true);
 }
 
 int dff_add(const void* a, const void* b, int64_t n, int elem, void* out, int device, void* stream) {

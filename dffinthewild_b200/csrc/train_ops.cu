@@ -99,6 +99,21 @@ __global__ void bn_finalize_kernel(const double2* __restrict__ partial, int nblo
   }
 }
 
+// BatchNorm3d with its RUNNING statistics inside a differentiable (taped) forward — frozen-BN fine-tuning, gradients w.r.t. the
+// input of an eval-mode network: mean = running_mean, invstd = 1/sqrt(running_var + eps); nothing is updated.
+__global__ void bn_eval_stats_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rm,
+                                     const float* __restrict__ rv, float eps, int C, float* __restrict__ scale, float* __restrict__ shift,
+                                     float* __restrict__ mean, float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double inv = 1.0 / sqrt((double)rv[c] + (double)eps);
+  const double g = gamma ? (double)gamma[c] : 1.0, bt = beta ? (double)beta[c] : 0.0, m = rm[c];
+  scale[c] = (float)(g * inv);
+  shift[c] = (float)(bt - m * g * inv);
+  mean[c] = (float)m;
+  invstd[c] = (float)inv;
+}
+
 // y = x*scale[c] + shift[c] (+ res_pre) ; ReLU ; (+ res_post)        (scale/shift null: identity)
 template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -298,6 +313,13 @@ int launch_bn_stats(const void* x, size_t npix, int C, bool bf16, const float* g
   return 0;
 }
 
+int launch_bn_eval_stats(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C, float* scale,
+                         float* shift, float* mean, float* invstd, cudaStream_t st) {
+  bn_eval_stats_kernel<<<cdiv(C, 128), 128, 0, st>>>(gamma, beta, rm, rv, eps, C, scale, shift, mean, invstd);
+  DFF_LAUNCH_CHECK("bn_eval_stats");
+  return 0;
+}
+
 int launch_bn_apply(const void* x, const float* scale, const float* shift, const void* res_pre, const void* res_post, int relu,
                     size_t npix, int C, bool bf16, void* out, cudaStream_t st) {
   if (C % 4) return fail(-1, "bn_apply: C must be a multiple of 4");
@@ -311,9 +333,10 @@ int launch_bn_apply(const void* x, const float* scale, const float* shift, const
 // Backward of  out = [relu]( BN(x) + res_pre ) (+ res_post is handled by the caller: its gradient is dy itself).
 // y != null: ReLU mask from the stored (pre-res_post) output.  mean == null: no BatchNorm (dx = g).
 // Writes dx (may be null), g_out (may be null: gradient of res_pre), dgamma/dbeta (with BN).
+// fixed_stats: the statistics were constants of the forward (running statistics): dx = gamma*invstd*g, no batch-mean terms.
 int launch_bn_backward(const void* dy, const void* y, const void* x, const float* mean, const float* invstd, const float* gamma,
                        size_t npix, int C, bool bf16, void* dx, void* g_out, float* dgamma, float* dbeta, void* partial,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool fixed_stats) {
   if (C % 4 || C > 4 * kRedThreads) return fail(-1, "bn_backward: C must be a multiple of 4 (<= 1024)");
   const size_t n4 = npix * C / 4;
   if (mean) {
@@ -328,7 +351,7 @@ int launch_bn_backward(const void* dy, const void* y, const void* x, const float
                                                      0.f, dgamma, dbeta, nullptr, nullptr);
     DFF_LAUNCH_CHECK("bn_bwd_finalize");
   }
-  const float inv_m = 1.f / (float)npix;
+  const float inv_m = fixed_stats ? 0.f : 1.f / (float)npix;
   if (bf16) bn_bwd_apply_kernel<<<ew_grid(n4, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)x, mean, invstd, gamma, dgamma, dbeta, inv_m, n4, C, (__nv_bfloat16*)dx, (__nv_bfloat16*)g_out);
   else bn_bwd_apply_kernel<<<ew_grid(n4, 256), 256, 0, st>>>((const float*)dy, (const float*)y, (const float*)x, mean, invstd, gamma, dgamma, dbeta, inv_m, n4, C, (float*)dx, (float*)g_out);
   DFF_LAUNCH_CHECK("bn_bwd_apply");

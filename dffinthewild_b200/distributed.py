@@ -38,14 +38,35 @@ class GradBucket:
         """`optimizer.zero_grad(set_to_none=False)` equivalent that keeps the views alive."""
         self.flat.zero_()
 
+    def rebind(self):
+        """Make every `.grad` a view of the flat buffer again.  `optimizer.zero_grad()` / `model.zero_grad()` default to
+        `set_to_none=True`, which drops the views: a gradient autograd then allocated on its own is copied into its slot and
+        re-bound; a parameter without a gradient contributes zeros."""
+        o = 0
+        for p in self.params:
+            n = p.numel()
+            view = self.flat[o:o + n].view_as(p)
+            g = p.grad
+            if g is None:
+                view.zero_()
+                p.grad = view
+            elif g.data_ptr() != view.data_ptr() or g.dtype != torch.float32:
+                if g.shape != p.shape:
+                    raise ValueError("GradBucket: foreign gradient of shape %s for a parameter of shape %s" % (tuple(g.shape), tuple(p.shape)))
+                view.copy_(g)
+                p.grad = view
+            o += n
+
     def allreduce_gradients(self, weight=1.0, group=None):
         """Weighted average of the gradients over all ranks, in place, with ONE all-reduce."""
+        self.rebind()
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         self.flat[:self.numel].mul_(float(weight))
         self.flat[self.numel] = float(weight)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.flat[:self.numel].div_(self.flat[self.numel])
+        # (no rank has a valid pixel: the summed weight is 0 and so is every gradient — keep the zeros instead of 0/0)
+        self.flat[:self.numel].div_(self.flat[self.numel].clamp_min(torch.finfo(torch.float32).tiny))
 
 
 def unused_parameter_names(module):

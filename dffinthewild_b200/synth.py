@@ -1,4 +1,4 @@
-"""Deterministic synthetic weights and inputs — TEST INFRASTRUCTURE (shared by tests/, bench.py, gen_golden.py).
+"""Deterministic synthetic weights and inputs for tests/, bench.py and oracle/gen_golden.py (generators only: no arithmetic of the path).
 
 Everything is drawn from numpy's PCG64 (stable across numpy versions), keyed by name, so the same tensors can be
 rebuilt on the GPU box without shipping a 16 MB state_dict.  Input recipes follow SURVEY.md §8(d):

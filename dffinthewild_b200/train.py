@@ -40,6 +40,8 @@ def _declare_train(lib):
         "dff_bn_scratch_bytes": (sz, [i]),
         "dff_bn_train_forward": (i, [vp, i64, i, i, vp, vp, vp, vp, f, f, vp, vp, i, vp, vp, vp, vp, vp, i, vp]),
         "dff_bn_train_backward": (i, [vp, vp, vp, vp, vp, vp, i64, i, i, vp, vp, vp, vp, vp, i, vp]),
+        "dff_bn_eval_forward": (i, [vp, i64, i, i, vp, vp, vp, vp, f, vp, vp, i, vp, vp, vp, vp, i, vp]),
+        "dff_bn_eval_backward": (i, [vp, vp, vp, vp, vp, vp, i64, i, i, vp, vp, vp, vp, vp, i, vp]),
         "dff_add": (i, [vp, vp, i64, i, vp, i, vp]),
         "dff_pool3d": (i, [vp, i, i, i, i, i, i, i, vp, i, vp]),
         "dff_pool3d_backward": (i, [vp, vp, i, i, i, i, i, i, i, vp, i, vp]),
@@ -178,24 +180,37 @@ class BnActFn(torch.autograd.Function):
         npix = x.numel() // C
         out = torch.empty_like(x)
         mean = invstd = None
+        batch_stats = bn is None or bn.training or bn.running_mean is None   # (torch: no running statistics => batch statistics)
         if gamma is not None:
             mean = torch.empty(C, dtype=torch.float32, device=dev)
             invstd = torch.empty(C, dtype=torch.float32, device=dev)
             ss = torch.empty(2 * C, dtype=torch.float32, device=dev)
-            scratch = torch.empty(l.dff_bn_scratch_bytes(C), dtype=torch.uint8, device=dev)
-            track = bn is not None and bn.track_running_stats and bn.running_mean is not None
-            rt.check(l.dff_bn_train_forward(_p(x), npix, C, _elem(x), _p(gamma), _p(beta), _p(bn.running_mean) if track else None,
-                                            _p(bn.running_var) if track else None, bn.momentum if bn is not None else 0.1,
-                                            bn.eps if bn is not None else 1e-5, _p(res_pre), _p(res_post), 1 if relu else 0,
-                                            _p(out), _p(mean), _p(invstd), _p(ss), _p(scratch), dev.index, _st(dev)))
-            if track:
-                bn.num_batches_tracked += 1
+            if batch_stats:
+                scratch = torch.empty(l.dff_bn_scratch_bytes(C), dtype=torch.uint8, device=dev)
+                track = bn is not None and bn.track_running_stats and bn.running_mean is not None
+                momentum = 0.1
+                if bn is not None and track:
+                    # nn.BatchNorm3d: momentum=None means a cumulative moving average over num_batches_tracked
+                    momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
+                rt.check(l.dff_bn_train_forward(_p(x), npix, C, _elem(x), _p(gamma), _p(beta), _p(bn.running_mean) if track else None,
+                                                _p(bn.running_var) if track else None, momentum,
+                                                bn.eps if bn is not None else 1e-5, _p(res_pre), _p(res_post), 1 if relu else 0,
+                                                _p(out), _p(mean), _p(invstd), _p(ss), _p(scratch), dev.index, _st(dev)))
+                if track:
+                    bn.num_batches_tracked += 1
+                    # the library wrote the running statistics through raw pointers: make the update visible to version-keyed caches
+                    torch.autograd.graph.increment_version(bn.running_mean)
+                    torch.autograd.graph.increment_version(bn.running_var)
+            else:   # eval-mode BatchNorm inside a taped forward: running statistics, no update
+                rt.check(l.dff_bn_eval_forward(_p(x), npix, C, _elem(x), _p(gamma), _p(beta), _p(bn.running_mean), _p(bn.running_var),
+                                               bn.eps, _p(res_pre), _p(res_post), 1 if relu else 0, _p(out), _p(mean), _p(invstd),
+                                               _p(ss), dev.index, _st(dev)))
         else:
             rt.check(l.dff_bn_train_forward(_p(x), npix, C, _elem(x), None, None, None, None, 0.0, 0.0, _p(res_pre), _p(res_post),
                                             1 if relu else 0, _p(out), None, None, None, None, dev.index, _st(dev)))
         # ReLU mask source: the output before res_post.  Without res_post that is `out` itself; with it, relu(x) > 0 <=> x > 0
         # (no-BN layers, reference :399-402) so the raw input serves as the mask.
-        ctx.relu, ctx.has_post = relu, res_post is not None
+        ctx.relu, ctx.has_post, ctx.batch_stats = relu, res_post is not None, batch_stats
         ctx.save_for_backward(x, gamma, mean, invstd, out if (relu and res_post is None) else None)
         return out
 
@@ -220,8 +235,9 @@ class BnActFn(torch.autograd.Function):
             dgamma = torch.empty(C, dtype=torch.float32, device=dev)
             dbeta = torch.empty(C, dtype=torch.float32, device=dev)
             scratch = torch.empty(l.dff_bn_scratch_bytes(C), dtype=torch.uint8, device=dev)
-            rt.check(l.dff_bn_train_backward(_p(dy), _p(mask), _p(x), _p(mean), _p(invstd), _p(gamma), npix, C, _elem(x), _p(dx),
-                                             _p(dres), _p(dgamma), _p(dbeta), _p(scratch), dev.index, _st(dev)))
+            fn = l.dff_bn_train_backward if ctx.batch_stats else l.dff_bn_eval_backward
+            rt.check(fn(_p(dy), _p(mask), _p(x), _p(mean), _p(invstd), _p(gamma), npix, C, _elem(x), _p(dx), _p(dres), _p(dgamma), _p(dbeta),
+                        _p(scratch), dev.index, _st(dev)))
         else:
             rt.check(l.dff_bn_train_backward(_p(dy), _p(mask), None, None, None, None, npix, C, _elem(x), _p(dx), _p(dres), None, None,
                                              None, dev.index, _st(dev)))

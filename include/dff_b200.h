@@ -118,6 +118,24 @@ int dff_forward_host(const void *packed, const float *FS_host, const float *fd_h
                      int micro_batch, int S, int H, int W, float *const out4_host[4], void *dev_io, void *workspace,
                      size_t workspace_bytes, int mode, int device, void *stream);
 
+/* ---- uint8 input staging (reference Depth_Estimation_Test/test_Dataloader.py:122-147, 105-113) ---------------
+ * The datasets store focal stacks as uint8 (S, H0, W0, 3); the reference's dataloader turns them into fp32 `x/127.5 - 1.0`, pads
+ * H, W to multiples of 32 with -1, transposes to (3, S, H, W) and tiles the S focus distances to (S, H, W).  These entry points
+ * take the stacks as stored — FS_u8 (B, S, H0, W0, 3) uint8, H0 <= H, W0 <= W with H, W the padded extent — and do the
+ * normalisation (IEEE fp32, bit-identical to numpy's), the padding and the layout change in the first kernel of the forward;
+ * focus_dists may be the S scalars per stack (strides {S, 1, 0, 0}).  Results are bit-identical to dff_forward on the fp32 tensor
+ * the dataloader would have produced.  A quarter of the bytes cross PCIe (6.3 instead of 35.4 MB per DDFF stack). */
+int dff_forward_u8(const void *packed, const uint8_t *FS_u8, int H0, int W0, const float *fd, const int64_t fd_strides[4], int B,
+                   int S, int H, int W, float *const out4[4], float *const cost4[4], void *workspace, size_t workspace_bytes,
+                   int mode, int device, void *stream);
+/* host-buffer variant: same pipeline as dff_forward_host; dev_io >= dff_host_io_bytes_u8(...) */
+size_t dff_host_io_bytes_u8(int micro_batch, int S, int H0, int W0, int H, int W, const int64_t fd_strides[4]);
+int dff_forward_host_u8(const void *packed, const uint8_t *FS_u8_host, int H0, int W0, const float *fd_host,
+                        const int64_t fd_strides[4], int B, int micro_batch, int S, int H, int W, float *const out4_host[4],
+                        void *dev_io, void *workspace, size_t workspace_bytes, int mode, int device, void *stream);
+/* the dataloader tail alone: FS_u8 (B,S,H0,W0,3) -> FS (B,3,S,H,W) fp32, normalised and -1 padded (the tensor the reference feeds) */
+int dff_stage_u8(const uint8_t *FS_u8, int H0, int W0, int B, int S, int H, int W, float *FS, int device, void *stream);
+
 /* ---- single operators (unit-parity surface; also what dff_forward is made of) ----------------------------- */
 /* Generic 3-D convolution on channels-last activations.
  *   in0 (B,S,IH,IW,C0) [+ in1 (B,S,IH,IW,C1): virtual channel concat]  ->  out (B,S,OH,OW,Cout)
@@ -183,6 +201,15 @@ int dff_bn_train_forward(const void *x, int64_t npix, int C, int elem, const flo
 int dff_bn_train_backward(const void *dy, const void *y_relu, const void *x, const float *save_mean, const float *save_invstd,
                           const float *gamma, int64_t npix, int C, int elem, void *dx, void *dres, float *dgamma, float *dbeta,
                           void *scratch, int device, void *stream);
+/* The same operator with the module's RUNNING statistics (a BatchNorm3d in eval mode inside a differentiable forward: frozen-BN
+ * fine-tuning, input gradients of an eval-mode network).  Nothing is updated; save_mean / save_invstd receive running_mean and
+ * 1/sqrt(running_var + eps) for the backward, which has no batch-mean terms: dx = gamma * invstd * g. */
+int dff_bn_eval_forward(const void *x, int64_t npix, int C, int elem, const float *gamma, const float *beta,
+                        const float *running_mean, const float *running_var, float eps, const void *res_pre, const void *res_post,
+                        int relu, void *out, float *save_mean, float *save_invstd, float *scale_shift, int device, void *stream);
+int dff_bn_eval_backward(const void *dy, const void *y_relu, const void *x, const float *save_mean, const float *save_invstd,
+                         const float *gamma, int64_t npix, int C, int elem, void *dx, void *dres, float *dgamma, float *dbeta,
+                         void *scratch, int device, void *stream);
 int dff_add(const void *a, const void *b, int64_t n, int elem, void *out, int device, void *stream);
 /* (1,k,k) pooling of (BS,H,W,C) channels-last volumes, forward and backward (max: first maximum in row-major order). */
 int dff_pool3d(const void *x, int BS, int H, int W, int C, int k, int is_max, int elem, void *out, int device, void *stream);

@@ -6,8 +6,8 @@ A functional restatement of the reference's depth-from-focus forward pass, writt
 384-key layout) plus inputs and evaluates the network with `torch.nn.functional` primitives on the CPU in
 fp32 or fp64.  The arithmetic primitives (conv3d, conv_transpose3d, batch_norm, pooling, bilinear
 interpolate, softplus, grid_sample) live in PyTorch, a third-party dependency the reference pins as
-torch==1.6.0 (README.md:16) and that is installed here as 2.11.0; `oracle/ops_ref.c` restates those
-primitives independently in plain C for the kernel-level tests.
+torch==1.6.0 (README.md:16) and that is installed here as 2.11.0; the kernel-level tests check each primitive
+against the same torch CPU call in fp64 (`tests/test_gpu_ops.py`).
 
 Pinning: the reference ships no tests, golden vectors or checkpoints, so this oracle is
 pinned against the *live reference module* imported from `/root/reference` in the build container:

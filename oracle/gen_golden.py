@@ -17,7 +17,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import dff_oracle as O  # noqa: E402
-from oracle import synth  # noqa: E402
+from dffinthewild_b200 import synth  # noqa: E402
 
 REF = "/root/reference"
 OUT = os.path.join(ROOT, "tests", "golden")

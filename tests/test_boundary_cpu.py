@@ -121,3 +121,122 @@ def test_operator_plan_dry_run(built_lib):
         launches = sum(la[k] for k in range(n.value))
         assert n.value <= launches <= max_launches, launches
         assert all(by[k] > 0 for k in range(n.value))
+
+
+def _fake_replica(net):
+    """What torch.nn.parallel.replicate builds for one device (torch/nn/parallel/replicate.py), without needing a GPU:
+    per-module `_replicate_for_data_parallel()` shells, children re-linked, parameters re-attached as plain tensors."""
+    mods = list(net.modules())
+    idx = {m: i for i, m in enumerate(mods)}
+    reps = [m._replicate_for_data_parallel() for m in mods]
+    for m, r in zip(mods, reps):
+        for k, child in m._modules.items():
+            r._modules[k] = None if child is None else reps[idx[child]]
+        for k, p in m._parameters.items():
+            if p is not None:
+                t = p.detach().clone()      # broadcast copy: a plain tensor, not an nn.Parameter
+                setattr(r, k, t)
+        for k, b in m._buffers.items():
+            r._buffers[k] = None if b is None else b.clone()
+    return reps[0]
+
+
+def test_dataparallel_replica_resolves_every_tensor(built_lib):
+    """nn.DataParallel replicas have empty `_parameters` (weights are plain attributes) and a shallow copy of the owner's
+    `__dict__`: the weight pack must find every tensor by attribute path and keep its cache on the owner
+    (reference call sites Depth_Estimation_Test/test.py:30-32, train_codes/train_code_Defocus.py:63)."""
+    from dffinthewild_b200 import runtime as rt
+    net = _net()
+    rep = _fake_replica(net)
+    assert len(list(rep.DFF_net.named_parameters())) == 0           # the situation round 1 broke on
+    assert rt.owner_of(rep.DFF_net) is net.DFF_net
+    assert rt.owner_of(net.DFF_net) is net.DFF_net
+    for n in rt.param_names(rt.NET_DFF):
+        a, b = rt.PackedWeights._resolve(rep.DFF_net, n), rt.PackedWeights._resolve(net.DFF_net, n)
+        assert a.data_ptr() != b.data_ptr() and torch.equal(a, b), n
+    assert rt.packed_cache(rep.DFF_net) is rt.packed_cache(net.DFF_net)
+    assert rt._any_requires_grad(rep.DFF_net)
+
+
+def test_weight_cache_key_and_invalidation(built_lib):
+    import copy
+    from dffinthewild_b200 import runtime as rt
+    net = _net().DFF_net
+    cache = rt.packed_cache(net)
+    dev = torch.device("cuda", 0)   # (only the index is used by the key)
+    k0 = cache._key(net, dev)
+    assert cache._key(net, dev) == k0
+    with torch.no_grad():
+        net.classif3[0].weight.mul_(2.0)
+    k1 = cache._key(net, dev)
+    assert k1 != k0
+    bn = net.dres4.conv2[1]
+    bn.num_batches_tracked += 1            # what a train-mode forward does
+    k2 = cache._key(net, dev)
+    assert k2 != k1
+    torch.autograd.graph.increment_version(bn.running_mean)   # what train.py does after the library updated the buffer in place
+    assert cache._key(net, dev) != k2
+    # mode flips invalidate; deep copies and pickles start empty and do not share the lock
+    cache._slots[0] = ("k", None, None)
+    net.eval()
+    assert not cache._slots
+    cache._slots[0] = ("k", None, None)
+    net.invalidate_packed_weights()
+    assert not cache._slots
+    twin = copy.deepcopy(net)
+    assert rt.packed_cache(twin) is not cache and not rt.packed_cache(twin)._slots
+    import pickle
+    assert isinstance(pickle.loads(pickle.dumps(cache)), rt.PackedWeights)
+
+
+def test_dispatch_follows_mode_and_grad(built_lib, monkeypatch):
+    """BatchNorm behaviour follows module.training; the tape follows grad mode.  Only eval + no tape is the single-call path."""
+    from dffinthewild_b200 import runtime as rt
+    from dffinthewild_b200 import train as tr
+    seen = []
+    monkeypatch.setattr(rt, "_require_cuda", lambda t, what: None)
+    monkeypatch.setattr(tr, "dff_net_train_forward", lambda net, FS, fd: seen.append("train") or ())
+    monkeypatch.setattr(rt, "_check_device", lambda i: (_ for _ in ()).throw(rt.DffError("inference path")))
+    net = _net().DFF_net
+    FS, fd = torch.zeros(1, 3, 2, 32, 32), torch.zeros(1, 2, 32, 32)
+
+    def path(**kw):
+        seen.clear()
+        try:
+            rt.dff_net_forward(net, FS, fd)
+        except rt.DffError as e:
+            assert "inference path" in str(e)
+            return "infer"
+        return seen[0]
+
+    net.train()
+    assert path() == "train"
+    with torch.no_grad():
+        assert path() == "train"              # batch statistics + running-stat updates, no tape
+    net.eval()
+    assert path() == "train"                  # eval statistics, but parameters require grad: differentiable outputs
+    with torch.no_grad():
+        assert path() == "infer"
+    for p in net.parameters():
+        p.requires_grad_(False)
+    assert path() == "infer"
+    FS.requires_grad_(True)
+    assert path() == "train"                  # input gradients of a frozen eval network
+    FS.requires_grad_(False)
+    net.dres2.conv2[1].train()
+    assert path() == "train"                  # one BatchNorm3d in batch-statistics mode
+
+
+def test_grad_bucket_survives_zero_grad():
+    from dffinthewild_b200 import distributed as D
+    net = _net()
+    skip = D.unused_parameter_names(net)
+    bucket = D.GradBucket(net, skip=skip)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    opt.zero_grad()                            # set_to_none=True: drops the views
+    p0, p1 = bucket.params[0], bucket.params[1]
+    assert p0.grad is None
+    p0.grad = torch.full_like(p0, 3.0)         # autograd allocates a fresh gradient
+    bucket.rebind()
+    assert p0.grad.data_ptr() == bucket.flat.data_ptr() and float(bucket.flat[0]) == 3.0
+    assert p1.grad is not None and float(p1.grad.abs().sum()) == 0.0

@@ -32,7 +32,7 @@ def test_e2e_refuses_cpu_and_wrong_slice_count(built_lib):
 
 @pytest.mark.gpu
 def test_e2e_matches_reference_golden(built_lib):
-    from oracle import synth
+    from dffinthewild_b200 import synth
     g = golden("g4_e2e_synth.npz")
     net = _net()
     sd = synth.synthetic_state(net.state_dict(), seed=2)
@@ -53,7 +53,7 @@ def test_e2e_matches_reference_golden(built_lib):
 def test_e2e_alignment_vs_fp64_oracle_batch2(built_lib):
     """B = 2 exercises the reference's broadcast quirk (sample 0's scale correction applied to every sample)."""
     from oracle import dff_oracle as O
-    from oracle import synth
+    from dffinthewild_b200 import synth
     net = _net()
     sd = synth.synthetic_state(net.state_dict(), seed=2)
     net.load_state_dict(sd, strict=True)

@@ -27,7 +27,7 @@ def _rel(a, b):
 
 
 def test_golden_g1_asbuilt_fp32(built_lib):
-    from oracle import synth
+    from dffinthewild_b200 import synth
     g = golden("g1_eval_asbuilt.npz")
     net = _net()
     FS, fd = synth.focal_stack(1, 3, 32, 64, seed=11), synth.focus_dists(1, 3, 32, 64, "ddff")
@@ -42,7 +42,7 @@ def test_golden_g1_asbuilt_fp32(built_lib):
 
 
 def test_golden_g2_synth_fp32(built_lib):
-    from oracle import synth
+    from dffinthewild_b200 import synth
     g = golden("g2_eval_synth.npz")
     net0 = _net()
     sd = synth.synthetic_state(net0.state_dict(), seed=1)
@@ -58,7 +58,7 @@ def test_golden_g2_synth_fp32(built_lib):
 @pytest.mark.parametrize("B,S,H,W,kind", [(1, 10, 96, 128, "ddff"), (3, 1, 32, 32, "defocus"), (1, 15, 64, 96, "ddff")])
 def test_fp32_vs_fp64_oracle(built_lib, B, S, H, W, kind):
     from oracle import dff_oracle as O
-    from oracle import synth
+    from dffinthewild_b200 import synth
     sd = synth.synthetic_state(_net().state_dict(), seed=4)
     net = _net(sd)
     FS = synth.focal_stack(B, S, H, W, seed=40 + S)
@@ -74,7 +74,7 @@ def test_bf16_mode_on_reference_metrics(built_lib):
     """bf16 mode: tolerance on the reference's own depth metrics (metrics.py:90-97, 41-61), oracle as ground truth.
     Gates from SURVEY.md §7.3 for trained-like (calibrated) weights: AbsRel <= 1e-2, MSE <= 3e-6 x (range/0.26)^2."""
     from oracle import dff_oracle as O
-    from oracle import synth
+    from dffinthewild_b200 import synth
     sd = synth.synthetic_state(_net().state_dict(), seed=4)
     net = _net(sd, "bf16")
     B, S, H, W = 1, 10, 96, 128
@@ -91,7 +91,7 @@ def test_bf16_mode_on_reference_metrics(built_lib):
 
 
 def test_weight_cache_follows_parameter_updates(built_lib):
-    from oracle import synth
+    from dffinthewild_b200 import synth
     net = _net(synth.synthetic_state(_net().state_dict(), seed=4))
     FS, fd = synth.focal_stack(1, 2, 32, 32, seed=60).cuda(), synth.focus_dists(1, 2, 32, 32, "defocus").cuda()
     with torch.no_grad():

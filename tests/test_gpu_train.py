@@ -27,13 +27,13 @@ def _loss(outs, gt, mask):
 
 def _state():
     from dffinthewild_b200.Depth_Estimation_Network import Network
-    from oracle import synth
+    from dffinthewild_b200 import synth
     torch.manual_seed(0)
     return synth.synthetic_state(Network().state_dict(), seed=1)
 
 
 def test_golden_g3_train_step(built_lib):
-    from oracle import synth
+    from dffinthewild_b200 import synth
     g = golden("g3_train_synth.npz")
     sd = _state()
     net = _net(sd)
@@ -75,7 +75,7 @@ def test_golden_g3_train_step(built_lib):
 def test_gradients_vs_fp64_oracle(built_lib):
     """fp32-mode gradient gate of SURVEY.md §8d: per-tensor cosine >= 0.9999 against the fp64 CPU oracle."""
     from oracle import dff_oracle as O
-    from oracle import synth
+    from dffinthewild_b200 import synth
     sd = _state()
     net = _net(sd)
     B, S, H, W = 2, 5, 64, 32
@@ -104,7 +104,7 @@ def test_gradients_vs_fp64_oracle(built_lib):
 
 def test_adam_step_runs_on_module_parameters(built_lib):
     """train_code_Defocus.py:67,159-168: zero_grad / backward / Adam.step on the drop-in module's own parameters."""
-    from oracle import synth
+    from dffinthewild_b200 import synth
     net = _net(_state())
     opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99))
     FS, fd = synth.focal_stack(1, 3, 32, 32, seed=31).cuda(), synth.focus_dists(1, 3, 32, 32, "defocus").cuda()
@@ -130,7 +130,7 @@ def test_bf16_train_step_tensor_cores(built_lib):
     """bf16 training path: tcgen05 forward + tensor-core data gradients, fp32 weight gradients / BatchNorm statistics.
     Gate (per-tensor cosine is not usable in bf16 at these weights): outputs and loss track the fp32 path,
     gradients are finite and globally aligned with the fp32 gradients, Adam steps stay finite."""
-    from oracle import synth
+    from dffinthewild_b200 import synth
     sd = _state()
     B, S, H, W = 2, 5, 64, 64
     FS, fd = synth.focal_stack(B, S, H, W, seed=41).cuda(), synth.focus_dists(B, S, H, W, "defocus").cuda()

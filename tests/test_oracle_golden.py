@@ -6,7 +6,7 @@ import torch
 
 from conftest import golden
 from oracle import dff_oracle as O
-from oracle import synth
+from dffinthewild_b200 import synth
 
 RTOL = 2e-5
 

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 from dffinthewild_b200 import distributed as D
 from dffinthewild_b200.Depth_Estimation_Network import Network
-from oracle import synth
+from dffinthewild_b200 import synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=5)

@@ -4,7 +4,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dffinthewild_b200.End_to_End import Network
-from oracle import synth
+from dffinthewild_b200 import synth
 
 H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) >= 3 else (512, 768)
 prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"

@@ -4,7 +4,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dffinthewild_b200.Depth_Estimation_Network import Network
-from oracle import synth
+from dffinthewild_b200 import synth
 
 B, S, H, W = [int(a) for a in sys.argv[1:5]] if len(sys.argv) >= 5 else (16, 10, 384, 576)
 prec = sys.argv[5] if len(sys.argv) > 5 else "bf16"
