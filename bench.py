@@ -8,9 +8,14 @@ over 64 synthetic DDFF full-resolution stacks PER GPU (10 x 3 x 383 x 552, padde
 Depth_Estimation_Test/test_Dataloader.py:128-140), one dff_forward call per step (--micro-batch 64; 49 GB of workspace).  Focal stacks are independent, so ranks share nothing: weak scaling,
 no collective on the data path (N=1 is exactly BASELINE.json configs[1]: batch 64).
 
-`value`   stacks/s, inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`     the same metric through the C-ABI call that takes HOST buffers (`dff_forward_host`): pinned-host -> device
-          copies of FS / focus_dists and device -> host reads of the four depth maps are inside the timed region.
+Inputs are the datasets' own format: uint8 stacks (S,383,552,3) + the S focus distances per stack; the
+`/127.5-1` normalisation, the -1 padding to 384x576 and the layout change are the first kernel of the forward.
+`value`   stacks/s through `dff_forward_u8`, inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     the same metric through the C-ABI call that takes HOST buffers (`dff_forward_host_u8`): pinned-host -> device
+          copies of the stacks / focus distances and device -> host reads of the four depth maps are inside the timed region.
+`parity`  stack 0 of the benchmarked batch against the CPU oracle (the same run that times `cpu_baseline`).
+`train`   BASELINE.json configs[2]: DefocusNet-shaped training step (4 stacks of 5x3x256x256 per GPU, fwd + loss + bwd +
+          gradient all-reduce + Adam), stacks/s and the all-reduce time.
 `roofline` the dominant kernel (largest share of the step): algorithmic FLOPs / its CUDA-event time vs the measured
           bf16 tensor peak of MEASURED_PEAKS.json.
 `cpu_baseline` the oracle port (the reference's torch CPU ops) on this box's host cores, one stack of the workload.
@@ -90,39 +95,63 @@ def make_net(precision):
     return net, sd
 
 
-def cpu_reference_time(sd, n_runs, warmup):
+def u8_stacks(n, seed):
+    """n synthetic DDFF-12 stacks as the dataset stores them: uint8 (n, S, 383, 552, 3)."""
+    import numpy as np
+    import torch
+    g = np.random.Generator(np.random.PCG64(seed))
+    return torch.from_numpy(g.integers(0, 256, (n, S) + VALID_HW + (3,), dtype=np.uint8))
+
+
+def dataloader_tail(u8):
+    """What the reference's dataloader makes of uint8 stacks (Depth_Estimation_Test/test_Dataloader.py:122-141): the oracle's input."""
+    import numpy as np
+    import torch
+    fs = u8.numpy().astype(np.float32) / 127.5 - 1.0
+    fs = np.pad(fs, ((0, 0), (0, 0), (0, H - VALID_HW[0]), (0, W - VALID_HW[1]), (0, 0)), mode="constant", constant_values=-1)
+    return torch.from_numpy(np.ascontiguousarray(np.transpose(fs, (0, 4, 1, 2, 3))))
+
+
+def cpu_reference_time(sd, n_runs, warmup, FS=None, fd=None, hw=None):
     """The reference's CPU implementation of the path (oracle port: same torch CPU ops in the same order) on one
-    stack of the workload, all host threads."""
+    stack of the workload, all host threads.  Returns (times, cores, outputs of the last run)."""
     import torch
     from oracle import dff_oracle
     from dffinthewild_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    FS = synth.focal_stack(1, S, H, W, seed=0, valid_hw=VALID_HW)
-    fd = synth.focus_dists(1, S, H, W, "ddff")
-    times = []
+    h, w = hw or (H, W)
+    if FS is None:
+        FS = synth.focal_stack(1, S, h, w, seed=0, valid_hw=VALID_HW if hw is None else None)
+    if fd is None:
+        fd = synth.focus_dists(1, S, h, w, "ddff")
+    times, outs = [], None
     with torch.no_grad():
         for i in range(warmup + n_runs):
             t0 = time.perf_counter()
-            dff_oracle.dff_forward(sd, FS, fd)
+            outs = dff_oracle.dff_forward(sd, FS, fd)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return times, cores
+    return times, cores, outs
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (the oracle port: the reference is pure Python on torch
+    ops, so the port IS its op sequence) on the box's host cores, one stack of the workload per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     _, sd = make_net("fp32")
-    steps = max(1, args.steps)
-    times, cores = cpu_reference_time(sd, steps, min(args.warmup, 1))
+    steps = max(1, min(args.steps, 20))     # (bounded sample: ~1 s per DDFF stack on 16 cores)
+    warm = max(1, min(args.warmup, 3))
+    times, cores, _ = cpu_reference_time(sd, steps, warm)
     total = sum(times)
     val = len(times) / total
-    sample = "1 stack (10x3x384x576) per step, oracle port of the reference's torch CPU path, %d torch threads" % cores
+    sample = ("%d timed forwards of 1 stack (10x3x384x576) after %d warm-up, oracle port of the reference's torch CPU path, %d torch "
+              "threads; the GPU arm runs 64 such stacks per step — the metric is stacks/s either way" % (steps, warm, cores))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "stacks/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1000 * total / len(times), "higher_is_better": True,
+        "warmup": warm, "ms_per_step": 1000 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus, 1, "cpu"),
         "cpu_baseline": {"value": val, "unit": "stacks/s", "cores": cores, "kind": "port", "sample": sample},
@@ -135,15 +164,75 @@ def workload_config(n_gpus, micro_batch, precision):
                         "per GPU, independent stacks partitioned across GPUs",
             "stacks_per_gpu": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus, "slices": S, "padded_hw": [H, W],
             "micro_batch": micro_batch, "precision": precision,
+            "input": "uint8 stacks (S,383,552,3) + S focus distances per stack; normalise/pad/transpose on the GPU",
             "parallelism": "stack-partitioned x%d, no collective" % n_gpus,
-            "l2": "inputs (%.1f GB per rank) exceed the 126 MB L2; no explicit flush" % (PER_GPU_BATCH * 4 * 4 * S * H * W / 1e9)}
+            "l2": "per step each rank reads %.2f GB of input and streams ~45 GB of activations: far beyond the 126 MB L2; no explicit flush"
+                  % (PER_GPU_BATCH * S * VALID_HW[0] * VALID_HW[1] * 3 / 1e9)}
+
+
+def train_record(args, dev, world, rank):
+    """BASELINE.json configs[2]: DefocusNet-shaped training step, 4 stacks of 5x3x256x256 per GPU (global batch 32 at
+    8 GPUs), reference loss recipe (train_code_Defocus.py:160-165), ONE gradient all-reduce, Adam(0.9, 0.99)."""
+    import torch
+    import torch.distributed as dist
+    from dffinthewild_b200 import distributed as D
+    from dffinthewild_b200 import synth
+    from dffinthewild_b200 import train_step as TS
+    B, S3, H3, W3 = 4, 5, 256, 256
+    net, _ = make_net(args.precision)
+    net = net.to(dev).train()
+    FS, fd = synth.focal_stack(B, S3, H3, W3, seed=300 + rank).to(dev), synth.focus_dists(B, S3, H3, W3, "defocus", tiled=False).to(dev)
+    gt, mask = synth.gt_and_mask(B, H3, W3, seed=300 + rank)
+    gt, mask = gt.to(dev), mask.to(dev)
+    stepper = TS.TrainStep(net, lr=1e-4, betas=(0.9, 0.99), weights=(0.3, 0.5, 0.7, 1.0))
+    steps, warm = max(2, min(args.train_steps, args.steps)), 2
+    for _ in range(warm):
+        stepper.step(FS, fd, gt, mask)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        info = stepper.step(FS, fd, gt, mask, time_allreduce=True)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / steps, stepper.allreduce_ms()], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar = float(t[0]), float(t[1])
+    V = S3 * H3 * W3
+    return {"metric": "DefocusNet-shape training focal stacks/sec (fwd + loss + bwd + all-reduce + Adam)",
+            "value": B * world / (ms / 1e3), "unit": "stacks/s", "ms_per_step": ms, "allreduce_ms": ar, "steps": steps,
+            "tflops_per_gpu": 276801.0 * V * B / (ms / 1e3) / 1e12, "flop_per_voxel": 276801,
+            "loss": float(info["loss"]), "stacks_per_gpu": B, "shape": [S3, 3, H3, W3], "precision": args.precision,
+            "allreduce_bytes": stepper.allreduce_bytes}
+
+
+def dataparallel_check(sd):
+    """The reference's unchanged `nn.DataParallel` call site (Depth_Estimation_Test/test.py:30-32,115-121) over two devices against the
+    single-device result (rank 0 only, after the timed regions)."""
+    import torch
+    from dffinthewild_b200 import synth
+    from dffinthewild_b200.Depth_Estimation_Network import Network
+    torch.manual_seed(0)
+    model = torch.nn.DataParallel(Network().cpu(), device_ids=[0, 1])
+    model.module.load_state_dict(sd)
+    model = model.cuda().eval()
+    FS, fd = synth.focal_stack(2, 3, 32, 64, seed=83), synth.focus_dists(2, 3, 32, 64, "defocus")
+    with torch.no_grad():
+        outs = model(FS.cuda(0), fd.cuda(0))
+        ref = model.module(FS.cuda(0), fd.cuda(0))
+    return {"devices": [0, 1], "bit_identical_to_single_device": all(torch.equal(o, r) for o, r in zip(outs, ref))}
 
 
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from dffinthewild_b200 import runtime as rt
-    from dffinthewild_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -152,6 +241,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # every rank waits for rank 0's build before it loads the library (a clean checkout has no .so yet)
+    import __graft_entry__ as g
+    if local == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
     n_local = PER_GPU_BATCH
     mb = min(args.micro_batch, n_local)
     assert n_local % mb == 0
@@ -160,27 +255,28 @@ def run_ours(args):
     dff = net.DFF_net
     lib = rt.lib()
     mode = rt.BF16 if args.precision == "bf16" else rt.FP32
+    H0, W0 = VALID_HW
 
-    # ---- synthetic inputs, resident in HBM -----------------------------------------------------------------
-    one = synth.focal_stack(mb, S, H, W, seed=100 + rank, valid_hw=VALID_HW)
-    FS = torch.empty((n_local, 3, S, H, W), dtype=torch.float32, device=dev)
-    for i in range(0, n_local, mb):
-        FS[i:i + mb] = one.to(dev).roll(i, dims=-1)   # distinct content per chunk
-    fd = synth.focus_dists(n_local, S, H, W, "ddff").to(dev)
+    # ---- synthetic inputs: uint8 stacks as the dataset stores them, pinned on the host and resident in HBM ----------------------
+    hU8 = u8_stacks(n_local, 100 + rank).pin_memory()
+    U8 = hU8.to(dev)
+    from dffinthewild_b200 import synth
+    hfd = synth.focus_dists(n_local, S, H, W, "ddff", tiled=False).pin_memory()      # (n, S, 1, 1): the S scalars per stack
+    fd = hfd.to(dev)
     outs = [torch.empty((n_local, H, W), dtype=torch.float32, device=dev) for _ in range(4)]
     packed = rt.packed_weights(dff, dev)
     ws = torch.empty(lib.dff_workspace_bytes(mb, S, H, W, mode), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
-    strides = (ctypes.c_int64 * 4)(*fd[:mb].stride())
+    strides = (ctypes.c_int64 * 4)(S, 1, 0, 0)
 
     def chunk_ptrs(i):
         return (ctypes.c_void_p * 4)(*[o[i:i + mb].data_ptr() for o in outs])
 
     def step():
         for i in range(0, n_local, mb):
-            rt.check(lib.dff_forward(packed.data_ptr(), FS[i:i + mb].data_ptr(), fd[i:i + mb].data_ptr(), strides, mb, S, H, W,
-                                     chunk_ptrs(i), None, ws.data_ptr(), ws.numel(), mode, local, sp))
+            rt.check(lib.dff_forward_u8(packed.data_ptr(), U8[i:i + mb].data_ptr(), H0, W0, fd[i:i + mb].data_ptr(), strides, mb, S, H, W,
+                                        chunk_ptrs(i), None, ws.data_ptr(), ws.numel(), mode, local, sp))
 
     def barrier():
         if world > 1:
@@ -206,20 +302,23 @@ def run_ours(args):
     value = PER_GPU_BATCH * world / (ms_per_step / 1000.0)
 
     # ---- per-operator profile (CUDA events on the launching stream) -> dominant kernel + roofline ---------------
+    # (the profiled entry point takes the reference's fp32 tensor: only the staging kernel differs from the timed loop)
+    FS32 = rt.stage_u8(U8[:mb])
+    fdt = fd[:mb].expand(mb, S, H, W).contiguous()
+    tstr = (ctypes.c_int64 * 4)(*fdt.stride())
     NOPS = 256
     op_ms, op_fl, op_by = (ctypes.c_float * NOPS)(), (ctypes.c_double * NOPS)(), (ctypes.c_double * NOPS)()
     op_la, op_nm, n_ops = (ctypes.c_int * NOPS)(), ctypes.create_string_buffer(NOPS * 64), ctypes.c_int(0)
     agg = {}
-    prof_chunks = min(3, n_local // mb)
-    for j in range(prof_chunks):
-        i = j * mb
-        rt.check(lib.dff_forward_profiled(packed.data_ptr(), FS[i:i + mb].data_ptr(), fd[i:i + mb].data_ptr(), strides, mb, S, H,
-                                          W, chunk_ptrs(i), ws.data_ptr(), ws.numel(), mode, local, sp, NOPS, op_ms, op_fl, op_by,
+    for j in range(3):
+        rt.check(lib.dff_forward_profiled(packed.data_ptr(), FS32.data_ptr(), fdt.data_ptr(), tstr, mb, S, H,
+                                          W, chunk_ptrs(0), ws.data_ptr(), ws.numel(), mode, local, sp, NOPS, op_ms, op_fl, op_by,
                                           op_la, op_nm, ctypes.byref(n_ops)))
         for k in range(n_ops.value):
             name = op_nm.raw[k * 64:(k + 1) * 64].split(b"\0")[0].decode()
             a = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0, "calls": 0})
             a["ms"] += op_ms[k]; a["flops"] += op_fl[k]; a["bytes"] += op_by[k]; a["launches"] += op_la[k]; a["calls"] += 1
+    del FS32, fdt
     launches_per_chunk = sum(op_la[k] for k in range(n_ops.value))
     total_prof_ms = sum(a["ms"] for a in agg.values())
     top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
@@ -238,6 +337,13 @@ def run_ours(args):
         t_s, f_s = sum(a["ms"] for a in sel) / 1000.0, sum(a["flops"] for a in sel)
         roof["aggregation_convs"] = {"tflops": f_s / t_s / 1e12, "frac_of_tensor_peak": f_s / t_s / 1e12 / pk["tf_sustained"],
                                      "share_of_step": 1000.0 * t_s / total_prof_ms, "operators": len(sel)}
+        # the bandwidth kernels against the measured HBM peak (north_star (c)): algorithmic bytes / CUDA-event time
+        bw = {}
+        for n, a in agg.items():
+            if n in ("depth_heads", "maxpool", "avgpool", "avgpool_pyramid", "to_channels_last") or "N_ch_attention(fused)" in n:
+                gbs = a["bytes"] / (a["ms"] / 1000.0) / 1e9
+                bw[n] = {"gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm"], "ms_per_call": a["ms"] / a["calls"]}
+        roof["bandwidth_kernels"] = bw
     except Exception as ex:   # (a reporting extra must never take the bench line down)
         roof["aggregation_convs"] = {"error": str(ex)}
     tr = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")   # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
@@ -249,24 +355,20 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    hFS = torch.empty((n_local, 3, S, H, W), dtype=torch.float32).pin_memory()
-    hFS.copy_(FS)
-    hfd = torch.empty((n_local, S, H, W), dtype=torch.float32).pin_memory()
-    hfd.copy_(fd)
     houts = [torch.empty((n_local, H, W), dtype=torch.float32).pin_memory() for _ in range(4)]
     emb = min(args.e2e_micro_batch, n_local)
-    dev_io = torch.empty(lib.dff_host_io_bytes(emb, S, H, W), dtype=torch.uint8, device=dev)
+    dev_io = torch.empty(lib.dff_host_io_bytes_u8(emb, S, H0, W0, H, W, strides), dtype=torch.uint8, device=dev)
     if emb > mb:
         ws = torch.empty(lib.dff_workspace_bytes(emb, S, H, W, mode), dtype=torch.uint8, device=dev)
-    hstrides = (ctypes.c_int64 * 4)(*hfd.stride())
     hp = (ctypes.c_void_p * 4)(*[o.data_ptr() for o in houts])
 
     def e2e_step():
         # ONE C-ABI call per step: the library pipelines H2D copies / kernels / D2H reads over micro-batches internally
-        rt.check(lib.dff_forward_host(packed.data_ptr(), hFS.data_ptr(), hfd.data_ptr(), hstrides, n_local, emb, S, H, W, hp,
-                                      dev_io.data_ptr(), ws.data_ptr(), ws.numel(), mode, local, sp))
+        rt.check(lib.dff_forward_host_u8(packed.data_ptr(), hU8.data_ptr(), H0, W0, hfd.data_ptr(), strides, n_local, emb, S, H, W, hp,
+                                         dev_io.data_ptr(), ws.data_ptr(), ws.numel(), mode, local, sp))
 
-    e2e_step()
+    for _ in range(2):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -278,7 +380,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = PER_GPU_BATCH * world * e2e_steps / e2e_s
-    h2d = n_local * (3 * S * H * W + S * H * W) * 4
+    h2d = n_local * (3 * S * H0 * W0 + S * 4)
     d2h = n_local * 4 * H * W * 4
     same = all(torch.equal(h.to(dev), o) for h, o in zip(houts, outs))
 
@@ -289,40 +391,74 @@ def run_ours(args):
         "config": workload_config(world, mb, args.precision),
         "clocks": clk.summary(),
         "e2e": {"value": e2e_val, "unit": "stacks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "dff_forward_host (C-ABI, pinned host buffers; copies pipelined with kernels over micro-batches of <= %d)" % emb,
+                "steps": e2e_steps, "api": "dff_forward_host_u8 (C-ABI, pinned host buffers: uint8 stacks + S focus distances in, four "
+                                           "fp32 maps out; copies pipelined with kernels over micro-batches of <= %d)" % emb,
                 "matches_device_run": bool(same)},
         "gpu_launches": launches_per_chunk * (n_local // mb) * args.steps,
         "roofline": roof,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, cores = cpu_reference_time(sd, 2, 1)
-        line["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "stacks/s", "cores": cores, "kind": "port",
-                                "sample": "2 timed forwards of 1 stack (10x3x384x576) after 1 warm-up, oracle port of the "
-                                          "reference's torch CPU path, %d torch threads" % cores}
+    del dev_io, ws
+    torch.cuda.empty_cache()
+    if not args.no_train:
+        try:
+            line["train"] = train_record(args, dev, world, rank)
+        except Exception as ex:   # (reported, never fatal for the headline)
+            line["train"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    if rank == 0 and not args.no_cpu_baseline:
+        # the oracle on stack 0 of the benchmarked batch: the CPU baseline AND the parity gate of the benchmarked code path
+        FS0 = dataloader_tail(hU8[:1])
+        fd0 = hfd[:1].expand(1, S, H, W).contiguous()
+        times, cores, ref = cpu_reference_time(sd, 2, 1, FS0, fd0)
+        from oracle import dff_oracle as O
+        mask = np.ones((H, W), dtype=bool)
+        par = {}
+        for o, r, n in zip(outs, ref, ("mid_out", "pred1", "pred2", "pred3")):
+            est, gt = o[0].cpu().numpy(), r[0].numpy()
+            par[n] = {"absrel": float(O.mask_abs_rel(est, gt, mask)), "mse": float(O.mask_mse(est, gt, mask)),
+                      "max_rel": float((np.abs(est - gt) / np.abs(gt)).max())}
+        gate = {"absrel": 1e-2, "mse": 3e-6} if args.precision == "bf16" else {"max_rel": 1e-4}
+        ok = all(all(v[k] <= lim for k, lim in gate.items()) for v in par.values())
+        line["parity"] = {"against": "CPU oracle (fp32) on stack 0 of the benchmarked 64-stack call", "gate": gate, "pass": bool(ok),
+                          "absrel": max(v["absrel"] for v in par.values()), "mse": max(v["mse"] for v in par.values()), "heads": par}
+        if world == 1:
+            line["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "stacks/s", "cores": cores, "kind": "port",
+                                    "sample": "2 timed forwards of 1 stack (10x3x384x576) after 1 warm-up, oracle port of the "
+                                              "reference's torch CPU path, %d torch threads" % cores}
+            t1, _, _ = cpu_reference_time(sd, 2, 1, hw=(224, 224))
+            line["cpu_baseline"]["c1"] = {"value": len(t1) / sum(t1), "unit": "stacks/s",
+                                          "sample": "BASELINE.json configs[0]: batch 1, 10x3x224x224, 2 timed forwards after 1 warm-up"}
     if rank == 0:
+        inc = os.path.join(ROOT, "profiles", "r2_gpu_incumbent.json")
+        if os.path.exists(inc):   # torch-eager / cuDNN on this pool's B200 (tools/incumbent.py; measured separately, not in this run)
+            line["gpu_incumbent"] = json.load(open(inc))
+        if world > 1 and torch.cuda.device_count() >= 2:
+            try:
+                line["dataparallel_check"] = dataparallel_check(sd)
+            except Exception as ex:
+                line["dataparallel_check"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DFF_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--micro-batch", type=int, default=64)
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-micro-batch", type=int, default=16)
+    ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
-        import __graft_entry__ as g
-        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-            g.build()
         run_ours(args)
 
 

@@ -371,6 +371,108 @@ __global__ void __launch_bounds__(128, 10) depth_head4_kernel(const __grid_const
   for (int k = 0; k < HP; ++k) a.depth[HP * hp + k][((size_t)b * H + y) * W + x] = num[k] / den[k];
 }
 
+
+// ---- the four heads of DFF_net, four pixels per thread (bf16 throughput mode) ------------------------------------------------------
+// The one-pixel-per-thread kernel above is instruction-bound (~60 instructions per softplus evaluation: four scalar taps with 64-bit
+// address arithmetic and a separate bilinear blend per pixel, head and slice).  The heads' resolutions are fixed — 1/8, 1/4, 1/2, 1/1
+// (reference :92-98, 118-121) — so for four horizontally adjacent output pixels the source columns and blend weights are a fixed
+// pattern per ratio: a thread loads the 2-4 source columns of its two source rows once per slice, blends vertically per column, then
+// horizontally per pixel (2 FMAs each), and evaluates softplus with two SFU operations.  Edge behaviour (ATen's clamped source index)
+// = replicate-edge column loads with the blend weight forced to 0 where ATen's taps coincide.  focus_dists is read once for all four
+// heads: as float4 when it is contiguous in x, as one broadcast scalar per slice when it is the S focus distances of the stack.
+template <int R> struct QuadTaps {
+  static constexpr int NC = R == 1 ? 4 : (R == 2 ? 4 : (R == 4 ? 3 : 2));   // source columns touched by 4 adjacent output pixels
+  int col[NC];        // clamped source columns
+  int o0, o1;         // source row offsets (elements)
+  float ly, lx[4];
+  __device__ __forceinline__ void init(int t, int y, int h, int w, int H) {
+    // rows: ATen's upsample_bilinear2d (align_corners=False): src = scale*(dst+0.5)-0.5, clamped at 0
+    float fy = (float)h / (float)H * ((float)y + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+    ly = fy - (float)y0;
+    o0 = y0 * w; o1 = y1 * w;
+    const int x = 4 * t;
+    const int c0 = R == 1 ? x : (int)floorf(((float)x + 0.5f) / (float)R - 0.5f);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) col[j] = min(max(c0 + j, 0), w - 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float fx = ((float)(x + k) + 0.5f) / (float)R - 0.5f;     // exact: R is a power of two
+      const float x0 = floorf(fx);
+      lx[k] = (R == 1 || x0 < 0.f || x0 >= (float)(w - 1)) ? 0.f : fx - x0;
+    }
+  }
+  // column index (relative to col[0]) of the left tap of output pixel k
+  static __device__ __forceinline__ constexpr int idx(int k) { return R == 1 ? k : (R == 2 ? (k + 1) / 2 : (R == 4 ? k / 2 : 0)); }
+  __device__ __forceinline__ void eval(const float* __restrict__ c, float* v) const {
+    if (R == 1) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(c + o0 + col[0]));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      return;
+    }
+    float cv[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const float a = __ldg(c + o0 + col[j]), b = __ldg(c + o1 + col[j]);
+      cv[j] = fmaf(ly, b - a, a);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = idx(k);
+      v[k] = fmaf(lx[k], cv[i + 1 < NC ? i + 1 : NC - 1] - cv[i], cv[i]);
+    }
+  }
+};
+
+template <int FDMODE>   // 0: generic strides, 1: contiguous in x (float4), 2: one scalar per slice
+__global__ void __launch_bounds__(128) depth_head4_quad_kernel(const __grid_constant__ Head4 a, const float* __restrict__ fd, long long sb,
+                                                               long long ss, long long sy, long long sx, int B, int S, int H, int W) {
+  const int W4 = W >> 2;
+  const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (q >= (size_t)B * H * W4) return;
+  const int t = (int)(q % W4), y = (int)((q / W4) % H), b = (int)(q / ((size_t)W4 * H));
+  QuadTaps<8> t0; QuadTaps<4> t1; QuadTaps<2> t2; QuadTaps<1> t3;
+  t0.init(t, y, a.h[0], a.w[0], H); t1.init(t, y, a.h[1], a.w[1], H); t2.init(t, y, a.h[2], a.w[2], H); t3.init(t, y, a.h[3], a.w[3], H);
+  const int sl0 = a.h[0] * a.w[0], sl1 = a.h[1] * a.w[1], sl2 = a.h[2] * a.w[2], sl3 = a.h[3] * a.w[3];
+  const float* c0 = a.cost[0] + (size_t)b * S * sl0;
+  const float* c1 = a.cost[1] + (size_t)b * S * sl1;
+  const float* c2 = a.cost[2] + (size_t)b * S * sl2;
+  const float* c3 = a.cost[3] + (size_t)b * S * sl3;
+  const float* fp = fd + b * sb + y * sy + (long long)(4 * t) * sx;
+  float num[4][4], den[4][4];
+#pragma unroll
+  for (int hd = 0; hd < 4; ++hd)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) num[hd][k] = den[hd][k] = 0.f;
+  for (int s = 0; s < S; ++s) {
+    float f[4];
+    if (FDMODE == 2) { f[0] = f[1] = f[2] = f[3] = __ldg(fp); }
+    else if (FDMODE == 1) { const float4 v = __ldg(reinterpret_cast<const float4*>(fp)); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+    else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) f[k] = __ldg(fp + k * sx);
+    }
+    fp += ss;
+    float v[4][4];
+    t0.eval(c0, v[0]); t1.eval(c1, v[1]); t2.eval(c2, v[2]); t3.eval(c3, v[3]);
+    c0 += sl0; c1 += sl1; c2 += sl2; c3 += sl3;
+#pragma unroll
+    for (int hd = 0; hd < 4; ++hd)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float pr = softplus_p<true>(v[hd][k]);
+        den[hd][k] += pr;
+        num[hd][k] = fmaf(f[k], pr, num[hd][k]);
+      }
+  }
+  const size_t o = ((size_t)b * H + y) * W + 4 * t;
+#pragma unroll
+  for (int hd = 0; hd < 4; ++hd)
+    *reinterpret_cast<float4*>(a.depth[hd] + o) = make_float4(__fdividef(num[hd][0], den[hd][0]), __fdividef(num[hd][1], den[hd][1]),
+                                                              __fdividef(num[hd][2], den[hd][2]), __fdividef(num[hd][3], den[hd][3]));
+}
+
 // cost[0..2]: upsampled heads (any resolution dividing H, W) ; cost[3]: the full-resolution head.  fast: SFU exp/log.
 int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4], const float* fd, const int64_t* st4, int B, int S,
                        int H, int W, float* const depth[4], bool fast, cudaStream_t st) {
@@ -380,6 +482,22 @@ int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4
     a.cost[k] = cost[k]; a.h[k] = h[k]; a.w[k] = w[k]; a.depth[k] = depth[k];
   }
   static const int hp = getenv("DFF_HEAD_HP") ? atoi(getenv("DFF_HEAD_HP")) : 2;
+  static const bool no_quad = getenv("DFF_HEAD_NO_QUAD") != nullptr;
+  const bool pyramid = H == 8 * h[0] && W == 8 * w[0] && H == 4 * h[1] && W == 4 * w[1] && H == 2 * h[2] && W == 2 * w[2] && H == h[3] &&
+                       W == w[3] && w[0] >= 2 && h[0] >= 1;
+  bool aligned = (reinterpret_cast<uintptr_t>(cost[3]) % 16 == 0);
+  for (int k = 0; k < 4; ++k) aligned = aligned && (reinterpret_cast<uintptr_t>(depth[k]) % 16 == 0);
+  if (fast && pyramid && aligned && !no_quad) {
+    const size_t nq = (size_t)B * H * (W / 4);
+    const unsigned g = (unsigned)((nq + 127) / 128);
+    const bool fd_scalar = st4[2] == 0 && st4[3] == 0;
+    const bool fd_vec = st4[3] == 1 && st4[2] % 4 == 0 && st4[1] % 4 == 0 && st4[0] % 4 == 0 && reinterpret_cast<uintptr_t>(fd) % 16 == 0;
+    if (fd_scalar) depth_head4_quad_kernel<2><<<g, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
+    else if (fd_vec) depth_head4_quad_kernel<1><<<g, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
+    else depth_head4_quad_kernel<0><<<g, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);
+    DFF_LAUNCH_CHECK("depth_head4_quad");
+    return 0;
+  }
   dim3 grid(cdiv(W, 128), H, B * (4 / hp));
   if (fast) { if (hp == 1) depth_head4_kernel<true, 1><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W); else depth_head4_kernel<true, 2><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W); }
   else depth_head4_kernel<false, 2><<<grid, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);

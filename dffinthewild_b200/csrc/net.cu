@@ -66,6 +66,10 @@ int launch_bn_backward(const void* dy, const void* y, const void* x, const float
 int launch_bn_eval_stats(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C, float* scale,
                          float* shift, float* mean, float* invstd, cudaStream_t st);
 int launch_add(const void* a, const void* b, size_t n, bool bf16, void* out, cudaStream_t st);
+int launch_masked_mse(const float* const pred[4], const float* gt, const unsigned char* mask, size_t n, const float w[4],
+                      float* const grad[4], float* stats, double* scratch, cudaStream_t st);
+int launch_adam_flat(float* p, const float* g, float* m, float* v, size_t n, double lr, double b1, double b2, double eps, int step,
+                     const float* gscale, cudaStream_t st);
 int launch_pool_bwd(const void* x, const void* dy, void* dx, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st);
 int launch_depth_head_bwd(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
                           const float* ddepth, float* dcost, cudaStream_t st);
@@ -111,6 +115,54 @@ struct Layer {
   int64_t raw_w, raw_gamma, raw_beta, raw_mean, raw_var, raw_bias;  // element offsets in the raw buffer (-1: none)
   size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab, pk_proj, pk_pair, pk_wfold, pk_ssfold;                  // byte offsets in the packed buffer
 };
+// Where each kernel layout of one layer lives inside a packed buffer (byte offsets from its start); `packed_bytes` is advanced.
+// Shared by the network's layer table and the single-operator entry point (dff_conv3d with the forward's plan).
+static void layout_layer(Layer& l, size_t& packed_bytes) {
+  l.pk_w = packed_bytes;
+  packed_bytes += align_up((size_t)l.ntaps * l.CinP * l.CoutP * sizeof(float), 256);
+  l.pk_scale = packed_bytes;
+  packed_bytes += align_up(l.CoutP * sizeof(float), 256);
+  l.pk_shift = packed_bytes;
+  packed_bytes += align_up(l.CoutP * sizeof(float), 256);
+  l.pk_wtc = packed_bytes;
+  packed_bytes += align_up((size_t)(l.ntaps + 1) * l.Ntc * l.CinT * 2, 256);
+  l.pk_wslab = packed_bytes;
+  packed_bytes += align_up((size_t)l.ntaps * l.Ntc * l.CinT * 2, 256);
+  // x-folded form (see pack_weight_slab_fold_kernel): small-Cout stride-1 layers are bound by the A-operand fetch of the MMA
+  // (39 clk for any N <= 32), so N' = G*Cout = 32 output channels per row cost the same as 8 or 16
+  l.pk_wfold = l.pk_ssfold = packed_bytes;
+  // (measured per layer class, profiles/: the fold pays where the folded kernel keeps its occupancy — Cout = 8 with G = 4 (Cin = 8)
+  // or G = 2 (Cin >= 16), Cout = 16 only for Cin >= 32)
+  const int cin = l.cin, cout = l.cout, kd = l.kd, kh = l.kh, kw = l.kw, stride = l.stride, dil = l.dil;
+  const bool transposed = l.transposed;
+  const int gsel = cout == 8 ? (cin == 8 ? 4 : 2) : (cout == 16 && cin >= 32 ? 2 : 1);
+  if (!transposed && stride == 1 && dil == 1 && kw == 3 && gsel > 1 && cin % 8 == 0) {
+    l.gfold = gsel;
+    packed_bytes += align_up((size_t)kd * kh * (kw + l.gfold - 1) * l.CinT * l.gfold * cout * 2, 256);
+    l.pk_ssfold = packed_bytes;
+    packed_bytes += align_up((size_t)2 * l.gfold * cout * sizeof(float), 256);
+  }
+  if (transposed && cout <= 32 && cout % 8 == 0 && cin % 8 == 0) {   // x-folded transposed conv: the two column phases in one GEMM row
+    l.gfold = 2;
+    l.pk_wfold = packed_bytes;
+    packed_bytes += align_up((size_t)18 * l.CinT * 2 * cout * 2, 256);
+    l.pk_ssfold = packed_bytes;
+    packed_bytes += align_up((size_t)2 * 2 * cout * sizeof(float), 256);
+  }
+  l.pk_pair = packed_bytes;   // paired-tap fp32 weights (Cout, 8, 1, 9, 5) of the first layer
+  if (cin == 3 && kh == 9 && kw == 9 && dil == 2 && kd == 1) {
+    l.pair_x = true;
+    packed_bytes += align_up((size_t)cout * 360 * sizeof(float), 256);
+    if (cout == 8) {   // row-folded form (pack_weight_slab_rowfold_kernel): 60 taps x 32 output channels; scale/shift replicated 4x
+      l.pk_wfold = packed_bytes;
+      packed_bytes += align_up((size_t)60 * 32 * 8 * 2, 256);
+      l.pk_ssfold = packed_bytes;
+      packed_bytes += align_up((size_t)2 * 32 * sizeof(float), 256);
+    }
+  }
+  l.pk_proj = packed_bytes;   // C -> 1 projections (classifiers): contiguous fp32 weights for the fused epilogue
+  if (cout == 1 && l.ntaps == 1) packed_bytes += align_up((size_t)l.CinT * sizeof(float), 256);
+}
 struct Param {
   std::string name;
   int64_t numel, offset;
@@ -144,48 +196,7 @@ struct Net {
       l.raw_mean = reg(bn + ".running_mean", cout);
       l.raw_var = reg(bn + ".running_var", cout);
     }
-    l.pk_w = packed_bytes;
-    packed_bytes += align_up((size_t)l.ntaps * l.CinP * l.CoutP * sizeof(float), 256);
-    l.pk_scale = packed_bytes;
-    packed_bytes += align_up(l.CoutP * sizeof(float), 256);
-    l.pk_shift = packed_bytes;
-    packed_bytes += align_up(l.CoutP * sizeof(float), 256);
-    l.pk_wtc = packed_bytes;
-    packed_bytes += align_up((size_t)(l.ntaps + 1) * l.Ntc * l.CinT * 2, 256);
-    l.pk_wslab = packed_bytes;
-    packed_bytes += align_up((size_t)l.ntaps * l.Ntc * l.CinT * 2, 256);
-    // x-folded form (see pack_weight_slab_fold_kernel): small-Cout stride-1 layers are bound by the A-operand fetch of the MMA
-    // (39 clk for any N <= 32), so N' = G*Cout = 32 output channels per row cost the same as 8 or 16
-    l.pk_wfold = l.pk_ssfold = packed_bytes;
-    // (measured per layer class, profiles/: the fold pays where the folded kernel keeps its occupancy — Cout = 8 with G = 4 (Cin = 8)
-    // or G = 2 (Cin >= 16), Cout = 16 only for Cin >= 32)
-    const int gsel = cout == 8 ? (cin == 8 ? 4 : 2) : (cout == 16 && cin >= 32 ? 2 : 1);
-    if (!transposed && stride == 1 && dil == 1 && kw == 3 && gsel > 1 && cin % 8 == 0) {
-      l.gfold = gsel;
-      packed_bytes += align_up((size_t)kd * kh * (kw + l.gfold - 1) * l.CinT * l.gfold * cout * 2, 256);
-      l.pk_ssfold = packed_bytes;
-      packed_bytes += align_up((size_t)2 * l.gfold * cout * sizeof(float), 256);
-    }
-    if (transposed && cout <= 32 && cout % 8 == 0 && cin % 8 == 0) {   // x-folded transposed conv: the two column phases in one GEMM row
-      l.gfold = 2;
-      l.pk_wfold = packed_bytes;
-      packed_bytes += align_up((size_t)18 * l.CinT * 2 * cout * 2, 256);
-      l.pk_ssfold = packed_bytes;
-      packed_bytes += align_up((size_t)2 * 2 * cout * sizeof(float), 256);
-    }
-    l.pk_pair = packed_bytes;   // paired-tap fp32 weights (Cout, 8, 1, 9, 5) of the first layer
-    if (cin == 3 && kh == 9 && kw == 9 && dil == 2 && kd == 1) {
-      l.pair_x = true;
-      packed_bytes += align_up((size_t)cout * 360 * sizeof(float), 256);
-      if (cout == 8) {   // row-folded form (pack_weight_slab_rowfold_kernel): 60 taps x 32 output channels; scale/shift replicated 4x
-        l.pk_wfold = packed_bytes;
-        packed_bytes += align_up((size_t)60 * 32 * 8 * 2, 256);
-        l.pk_ssfold = packed_bytes;
-        packed_bytes += align_up((size_t)2 * 32 * sizeof(float), 256);
-      }
-    }
-    l.pk_proj = packed_bytes;   // C -> 1 projections (classifiers): contiguous fp32 weights for the fused epilogue
-    if (cout == 1 && l.ntaps == 1) packed_bytes += align_up((size_t)l.CinT * sizeof(float), 256);
+    layout_layer(l, packed_bytes);
     index[name] = (int)layers.size();
     layers.push_back(l);
   }
@@ -822,6 +833,34 @@ struct DeviceGuard {
   }
 };
 
+
+// every kernel layout of one layer's weights (`w`: the reference layout) at its offsets inside `pk`
+static int pack_layer_weights(const Layer& l, const float* w, char* pk, cudaStream_t st) {
+  DFF_TRY(launch_pack_weight(w, (float*)(pk + l.pk_w), l.cout, l.cin, l.ntaps, l.CinP, l.CoutP, l.transposed ? 1 : 0, st));
+  if (l.pair_x) {   // tensor-core packs of the paired-tap form: an ordinary (Cout, 8, 1, 9, 5) convolution weight
+    DFF_TRY(launch_pair_weight(w, (float*)(pk + l.pk_pair), l.cout, st));
+    DFF_TRY(launch_pack_weight_tc((const float*)(pk + l.pk_pair), pk + l.pk_wtc, l.cout, 8, 8, 45, l.Ntc, 0, st));
+    DFF_TRY(launch_pack_weight_slab((const float*)(pk + l.pk_pair), pk + l.pk_wslab, l.cout, 8, 8, 45, l.Ntc, 0, st));
+    if (l.pk_wfold != l.pk_ssfold) DFF_TRY(launch_pack_weight_slab_rowfold((const float*)(pk + l.pk_pair), pk + l.pk_wfold, l.cout, st));
+  } else {
+    DFF_TRY(launch_pack_weight_tc(w, pk + l.pk_wtc, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
+    DFF_TRY(launch_pack_weight_slab(w, pk + l.pk_wslab, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
+  }
+  if (l.cout == 1 && l.ntaps == 1) DFF_TRY(launch_pack_weight(w, (float*)(pk + l.pk_proj), 1, l.cin, 1, l.CinT, 1, 0, st));
+  if (l.gfold > 1) {
+    if (l.transposed) DFF_TRY(launch_pack_weight_slab_deconv_fold(w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, st));
+    else DFF_TRY(launch_pack_weight_slab_fold(w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st));
+  }
+  return 0;
+}
+// scale/shift of the folded forms (replicated per pixel of the GEMM row) from the layer's scale/shift in `pk`
+static int pack_layer_folded_ss(const Layer& l, char* pk, cudaStream_t st) {
+  const int G = (l.pair_x && l.pk_wfold != l.pk_ssfold) ? 4 : l.gfold;
+  if (G > 1)
+    DFF_TRY(launch_replicate_ss((const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), (float*)(pk + l.pk_ssfold), l.cout, G, st));
+  return 0;
+}
+
 }  // namespace dff
 
 using namespace dff;
@@ -866,31 +905,12 @@ int dff_pack_weights(int net, const float* raw, void* packed, int device, void* 
   const Net& n = net_of(net);
   char* pk = (char*)packed;
   for (const Layer& l : n.layers) {
-    DFF_TRY(launch_pack_weight(raw + l.raw_w, (float*)(pk + l.pk_w), l.cout, l.cin, l.ntaps, l.CinP, l.CoutP,
-                               l.transposed ? 1 : 0, st));
-    if (l.pair_x) {   // tensor-core packs of the paired-tap form: an ordinary (Cout, 8, 1, 9, 5) convolution weight
-      DFF_TRY(launch_pair_weight(raw + l.raw_w, (float*)(pk + l.pk_pair), l.cout, st));
-      DFF_TRY(launch_pack_weight_tc((const float*)(pk + l.pk_pair), pk + l.pk_wtc, l.cout, 8, 8, 45, l.Ntc, 0, st));
-      DFF_TRY(launch_pack_weight_slab((const float*)(pk + l.pk_pair), pk + l.pk_wslab, l.cout, 8, 8, 45, l.Ntc, 0, st));
-      if (l.pk_wfold != l.pk_ssfold) DFF_TRY(launch_pack_weight_slab_rowfold((const float*)(pk + l.pk_pair), pk + l.pk_wfold, l.cout, st));
-    } else {
-      DFF_TRY(launch_pack_weight_tc(raw + l.raw_w, pk + l.pk_wtc, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
-      DFF_TRY(launch_pack_weight_slab(raw + l.raw_w, pk + l.pk_wslab, l.cout, l.cin, l.CinT, l.ntaps, l.Ntc, l.transposed ? 1 : 0, st));
-    }
-    if (l.cout == 1 && l.ntaps == 1)
-      DFF_TRY(launch_pack_weight(raw + l.raw_w, (float*)(pk + l.pk_proj), 1, l.cin, 1, l.CinT, 1, 0, st));
+    DFF_TRY(pack_layer_weights(l, raw + l.raw_w, pk, st));
     const bool bn = l.raw_gamma >= 0;
     DFF_TRY(launch_bn_fold(bn ? raw + l.raw_gamma : nullptr, bn ? raw + l.raw_beta : nullptr, bn ? raw + l.raw_mean : nullptr,
                            bn ? raw + l.raw_var : nullptr, l.raw_bias >= 0 ? raw + l.raw_bias : nullptr,
                            (float*)(pk + l.pk_scale), (float*)(pk + l.pk_shift), l.cout, l.CoutP, st));
-    if (l.pair_x && l.pk_wfold != l.pk_ssfold)
-      DFF_TRY(launch_replicate_ss((const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), (float*)(pk + l.pk_ssfold), l.cout, 4, st));
-    if (l.gfold > 1) {
-      if (l.transposed) DFF_TRY(launch_pack_weight_slab_deconv_fold(raw + l.raw_w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, st));
-      else DFF_TRY(launch_pack_weight_slab_fold(raw + l.raw_w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st));
-      DFF_TRY(launch_replicate_ss((const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), (float*)(pk + l.pk_ssfold), l.cout,
-                                  l.gfold, st));
-    }
+    DFF_TRY(pack_layer_folded_ss(l, pk, st));
   }
   return 0;
 }
@@ -1112,56 +1132,97 @@ int dff_forward_host_u8(const void* packed, const uint8_t* FS_u8_host, int H0, i
                            workspace_bytes, mode, device, (cudaStream_t)stream);
 }
 
-size_t dff_conv3d_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw) {
-  const size_t CinP = align_up(Cin, 4), CoutP = align_up(Cout, 8);
-  const size_t ffma = align_up((size_t)kd * kh * kw * CinP * CoutP * 4, 256);
-  const size_t tcb = align_up(((size_t)kd * kh * kw + 1) * align_up(Cout, 16) * align_up(Cin, 8) * 2, 256);
-  return (ffma > 2 * tcb ? ffma : 2 * tcb);  // tensor-core path keeps two layouts (per-tap TMA + slab)
+static Layer adhoc_layer(int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, bool transposed, bool tc, size_t* bytes) {
+  Layer l{"adhoc", "", Cin, Cout, kd, kh, kw, stride_hw, dil_hw, transposed, false};
+  l.ntaps = kd * kh * kw;
+  l.CinP = tc ? (int)align_up(Cin, 8) : (int)align_up(Cin, 4);   // (stored channels: the caller's tensors are already padded)
+  l.CoutP = (int)align_up(Cout, 8);
+  l.CinT = (int)align_up(Cin, 8);
+  l.Ntc = (int)align_up(Cout, 16);
+  l.raw_w = l.raw_gamma = l.raw_beta = l.raw_mean = l.raw_var = l.raw_bias = -1;
+  size_t n = 0;
+  layout_layer(l, n);
+  if (bytes) *bytes = n;
+  return l;
 }
 
-int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const float* weight, int Cout,
-               int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, const float* scale, const float* shift,
-               const void* res_pre, const void* res_post, int relu, void* out, int elem, int use_tensor_cores, void* scratch,
-               int device, void* stream) {
+size_t dff_conv3d_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw) {
+  // every kernel layout of the layer (FFMA, per-tap TMA, slab, folded forms) + a fused classifier's weights
+  size_t n = 0, m = 0;
+  adhoc_layer(Cin, Cout, kd, kh, kw, 1, kh == 9 ? 2 : 1, false, true, &n);
+  adhoc_layer(Cin, Cout, 3, 3, 3, 2, 1, true, true, &m);
+  return (n > m ? n : m) + align_up((size_t)align_up(Cout, 16) * 4 * sizeof(float), 256) + 1024;
+}
+
+int dff_conv3d_ex(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const float* weight, int Cout,
+                  int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, const float* scale, const float* shift,
+                  const void* res_pre, const void* res_post, int relu, void* out, int elem, int plan, int pair_input,
+                  const void* aux_add, void* aux_out, const float* proj_w, float* proj_out, int proj_on_aux, int skip_out,
+                  void* scratch, int device, void* stream) {
   if (!in0 || !weight || !out || !scratch) return fail(DFF_E_ARG, "dff_conv3d: null pointer");
   g_pdl_call = false;   // the weights are packed by kernels launched just before the convolution: its prologue must not run ahead of them
   const bool out_f32 = (elem & DFF_OUT_F32) != 0;   // fp32 output from bf16 operands (cost volumes)
   elem &= ~DFF_OUT_F32;
-  if (use_tensor_cores && (elem != DFF_BF16 || (C0 % 8) || (C1 % 8)))
+  const bool tc = plan != 0;
+  if (tc && (elem != DFF_BF16 || (C0 % 8) || (C1 % 8)))
     return fail(DFF_E_UNSUPPORTED, "dff_conv3d: the tensor-core path needs bf16 tensors with channel counts that are multiples of 8");
   if (kd * kh * kw > kMaxTaps) return fail(DFF_E_ARG, "dff_conv3d: too many taps");
-  if (use_tensor_cores && ((scale == nullptr) != (shift == nullptr)))
+  if (tc && ((scale == nullptr) != (shift == nullptr)))
     return fail(DFF_E_ARG, "dff_conv3d: the tensor-core path takes scale and shift together (or neither)");
   if (transposed && !(kd == 3 && kh == 3 && kw == 3 && stride_hw == 2 && dil_hw == 1))
     return fail(DFF_E_ARG, "dff_conv3d: transposed conv must be k=3, stride (1,2,2)");
   if (C0 % 4 || C1 % 4) return fail(DFF_E_ARG, "dff_conv3d: stored channels must be multiples of 4");
+  if ((aux_add == nullptr) != (aux_out == nullptr)) return fail(DFF_E_ARG, "dff_conv3d: aux_add and aux_out go together");
+  if ((proj_w == nullptr) != (proj_out == nullptr)) return fail(DFF_E_ARG, "dff_conv3d: proj_w and proj_out go together");
+  if ((aux_add || proj_w || pair_input) && plan != 4)
+    return fail(DFF_E_UNSUPPORTED, "dff_conv3d: second output / fused classifier / pair-packed input exist only in the forward's plan (plan 4)");
+  if (pair_input && !(C0 == 8 && C1 == 0 && kd == 1 && kh == 9 && kw == 9 && dil_hw == 2 && stride_hw == 1 && !transposed))
+    return fail(DFF_E_ARG, "dff_conv3d: the pair-packed input belongs to the 1x9x9 dilation-2 first layer");
   DeviceGuard g(device);
   if (g.rc) return g.rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int Cin = C0 + C1;
-  Layer l{"adhoc", "", Cin, Cout, kd, kh, kw, stride_hw, dil_hw, transposed != 0, false};
-  l.CinP = Cin;
-  l.CoutP = (int)align_up(Cout, 8);
-  l.ntaps = kd * kh * kw;
-  l.CinT = Cin;
-  l.Ntc = (int)align_up(Cout, 16);
-  const size_t tcb = align_up(((size_t)l.ntaps + 1) * l.Ntc * Cin * 2, 256);
-  if (use_tensor_cores) {
-    DFF_TRY(launch_pack_weight_tc(weight, scratch, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
-    DFF_TRY(launch_pack_weight_slab(weight, (char*)scratch + tcb, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
-  } else
-    DFF_TRY(launch_pack_weight(weight, (float*)scratch, Cout, Cin, l.ntaps, l.CinP, l.CoutP, transposed ? 1 : 0, st));
+  const int Cin = pair_input ? 3 : C0 + C1;
+  size_t nbytes = 0;
+  Layer l = adhoc_layer(Cin, Cout, kd, kh, kw, stride_hw, dil_hw, transposed != 0, tc, &nbytes);
+  if (!pair_input) { l.CinP = Cin; l.CinT = Cin; l.pair_x = false; }
+  char* pk = (char*)scratch;
+  if (plan == 4) {
+    DFF_TRY(pack_layer_weights(l, weight, pk, st));
+    // per-channel scale/shift as the forward keeps them (padded to CoutP; identity when absent), then the replicated folded forms
+    DFF_TRY(launch_bn_fold(nullptr, nullptr, nullptr, nullptr, nullptr, (float*)(pk + l.pk_scale), (float*)(pk + l.pk_shift), Cout, l.CoutP, st));
+    if (scale) {
+      DFF_CUDA(cudaMemcpyAsync(pk + l.pk_scale, scale, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      DFF_CUDA(cudaMemcpyAsync(pk + l.pk_shift, shift, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    DFF_TRY(pack_layer_folded_ss(l, pk, st));
+  } else if (tc) {
+    DFF_TRY(launch_pack_weight_tc(weight, pk + l.pk_wtc, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
+    DFF_TRY(launch_pack_weight_slab(weight, pk + l.pk_wslab, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
+  } else {
+    DFF_TRY(launch_pack_weight(weight, (float*)(pk + l.pk_w), Cout, Cin, l.ntaps, l.CinP, l.CoutP, transposed ? 1 : 0, st));
+  }
+  Layer pl = l;   // the fused classifier: its weights sit behind the layer's own packs
+  if (proj_w) {
+    pl.cin = Cout; pl.cout = 1; pl.CinT = (int)align_up(Cout, 8);
+    pl.pk_proj = align_up(nbytes, 256);
+    DFF_CUDA(cudaMemsetAsync(pk + pl.pk_proj, 0, (size_t)align_up(Cout, 16) * sizeof(float), st));
+    DFF_CUDA(cudaMemcpyAsync(pk + pl.pk_proj, proj_w, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   Ten in;
   in.p = const_cast<void*>(in0); in.B = B; in.S = S; in.H = IH; in.W = IW; in.C = C0;
   Ten t1;
   t1.p = const_cast<void*>(in1); t1.C = C1;
   Ten o;
   o.p = out; o.B = B; o.S = S; o.C = Cout;
+  const int IWl = pair_input ? IW - 2 : IW;   // (the pair-packed input has two margin columns)
   o.H = transposed ? IH * 2 : IH / stride_hw;
-  o.W = transposed ? IW * 2 : IW / stride_hw;
-  Ten rp, rq;
+  o.W = transposed ? IWl * 2 : IWl / stride_hw;
+  Ten rp, rq, ax, ao, po;
   rp.p = const_cast<void*>(res_pre);
   rq.p = const_cast<void*>(res_post);
+  ax.p = const_cast<void*>(aux_add);
+  ao.p = aux_out;
+  po.p = proj_out;
   EpiOpt e;
   e.in1 = (in1 && C1) ? &t1 : nullptr;
   e.res_pre = res_pre ? &rp : nullptr;
@@ -1169,10 +1230,26 @@ int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, i
   e.relu = relu != 0;
   e.out_f32 = out_f32;
   o.f32 = out_f32;
-  // use_tensor_cores: 1 = best kernel for the shape (row kernel with A in TMEM -> slab kernel -> per-tap TMA kernel),
-  // 2 = force the per-tap TMA kernel, 3 = slab kernel (never the row kernel)
-  return run_conv(l, (const float*)scratch, scale, shift, in, e, o, elem == DFF_BF16, st, use_tensor_cores ? scratch : nullptr,
-                  use_tensor_cores != 2 ? (char*)scratch + tcb : nullptr, nullptr, false, use_tensor_cores == 1);
+  if (aux_add) { e.aux_add = &ax; e.aux_out = &ao; }
+  if (proj_w) { e.proj = &pl; e.proj_out = &po; e.proj_aux = proj_on_aux != 0; e.skip_out = skip_out != 0; }
+  // plan: 0 = FFMA; 1 = best tensor-core kernel for the plain form (row kernel with A in TMEM -> slab kernel -> per-tap TMA kernel);
+  // 2 = force the per-tap TMA kernel; 3 = slab kernel (never the row kernel); 4 = what dff_forward runs for this layer: the folded forms
+  // (x-fold, deconv-fold, row-folded first layer), the second output and the fused classifier included
+  if (plan == 4) {
+    static const bool no_fold = getenv("DFF_B200_NO_FOLD") != nullptr;
+    return run_conv(l, (const float*)(pk + l.pk_w), (const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), in, e, o, true, st,
+                    pk + l.pk_wtc, pk + l.pk_wslab, nullptr, false, true, pk, !no_fold);
+  }
+  return run_conv(l, (const float*)(pk + l.pk_w), scale, shift, in, e, o, elem == DFF_BF16, st, tc ? pk + l.pk_wtc : nullptr,
+                  (tc && plan != 2) ? pk + l.pk_wslab : nullptr, nullptr, false, plan == 1);
+}
+
+int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const float* weight, int Cout,
+               int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, const float* scale, const float* shift,
+               const void* res_pre, const void* res_post, int relu, void* out, int elem, int use_tensor_cores, void* scratch,
+               int device, void* stream) {
+  return dff_conv3d_ex(in0, C0, in1, C1, B, S, IH, IW, weight, Cout, kd, kh, kw, stride_hw, dil_hw, transposed, scale, shift, res_pre,
+                       res_post, relu, out, elem, use_tensor_cores, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, scratch, device, stream);
 }
 
 // SRD channel-attention branch as one operator (reference train_codes/Depth_Estimation_Network.py:399-407)
@@ -1200,6 +1277,16 @@ int dff_depth_head(const float* cost, int h, int w, const float* fd, const int64
   return launch_depth_head(cost, h, w, fd, fd_strides, B, S, H, W, depth, (cudaStream_t)stream);
 }
 
+int dff_depth_heads4(const float* const cost4[4], const float* fd, const int64_t fd_strides[4], int B, int S, int H, int W,
+                     float* const depth4[4], int fast, int device, void* stream) {
+  if (!cost4 || !fd || !fd_strides || !depth4) return fail(DFF_E_ARG, "dff_depth_heads4: null pointer");
+  if (H % 8 || W % 8) return fail(DFF_E_ARG, "dff_depth_heads4: H and W must be multiples of 8");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  const int h[4] = {H / 8, H / 4, H / 2, H}, w[4] = {W / 8, W / 4, W / 2, W};
+  return launch_depth_head4(cost4, h, w, fd, fd_strides, B, S, H, W, depth4, fast != 0, (cudaStream_t)stream);
+}
+
 int dff_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
                  float* flow, int device, void* stream) {
   if (!x || !fov || !out) return fail(DFF_E_ARG, "dff_fov_warp: null pointer");
@@ -1213,6 +1300,12 @@ int dff_to_channels_last(const float* src, int B, int C, int S, int H, int W, vo
   DeviceGuard g(device);
   if (g.rc) return g.rc;
   return launch_to_cl(src, B, C, S, H, W, dst, Cp, elem == DFF_BF16, (cudaStream_t)stream);
+}
+int dff_to_pair_packed(const float* FS, int B, int S, int H, int W, void* dst, int device, void* stream) {
+  if (!FS || !dst) return fail(DFF_E_ARG, "dff_to_pair_packed: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_to_cl_pair(FS, B, S, H, W, dst, (cudaStream_t)stream);
 }
 int dff_from_channels_last(const void* src, int B, int C, int S, int H, int W, int Cp, int elem, float* dst, int device,
                            void* stream) {
@@ -1360,6 +1453,25 @@ int dff_bn_eval_backward(const void* dy, const void* y_relu, const void* x, cons
   if (g.rc) return g.rc;
   return launch_bn_backward(dy, y_relu, x, save_mean, save_invstd, gamma, (size_t)npix, C, elem == DFF_BF16, dx, dres, dgamma, dbeta,
                             scratch, (cudaStream_t)stream, true);
+}
+
+int dff_masked_mse(const float* const pred4[4], const float* gt, const uint8_t* mask, int64_t n, const float weights[4],
+                   float* const grad4[4], float* stats, void* scratch, int device, void* stream) {
+  if (!pred4 || !gt || !mask || !weights || !grad4 || !stats || !scratch) return fail(DFF_E_ARG, "dff_masked_mse: null pointer");
+  for (int k = 0; k < 4; ++k)
+    if (!pred4[k] || !grad4[k]) return fail(DFF_E_ARG, "dff_masked_mse: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_masked_mse(pred4, gt, mask, (size_t)n, weights, grad4, stats, (double*)scratch, (cudaStream_t)stream);
+}
+
+int dff_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
+                  double eps, int step, const float* grad_scale, int device, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return fail(DFF_E_ARG, "dff_adam_flat: null pointer");
+  if (step < 1) return fail(DFF_E_ARG, "dff_adam_flat: step counts from 1");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_adam_flat(param, grad, exp_avg, exp_avg_sq, (size_t)n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
 }
 
 int dff_add(const void* a, const void* b, int64_t n, int elem, void* out, int device, void* stream) {

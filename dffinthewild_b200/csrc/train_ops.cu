@@ -358,6 +358,127 @@ int launch_bn_backward(const void* dy, const void* y, const void* x, const float
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Loss + optimizer of the reference's training loop (train_codes/train_code_Defocus.py:17-19, 67, 160-168).
+//   Total = sum_k w_k * mean_{mask} (pred_k - gt)^2 over the four heads.  The reference gathers `pred[mask]` / `gt[mask]` four times
+//   (nonzero + index, and an index_put_ with a radix sort in the backward); here one pass reduces the four masked sums and the count,
+//   a one-block finalise turns them into the loss, and one pass writes d Total / d pred_k = 2 w_k (pred_k - gt) mask / count.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kLossBlocks = 592;
+struct Ptr4 { const float* p[4]; };
+struct MPtr4 { float* p[4]; };
+
+__global__ void __launch_bounds__(256) masked_mse_reduce_kernel(Ptr4 pred, const float* __restrict__ gt, const unsigned char* __restrict__ mask,
+                                                                size_t n, double* __restrict__ partial) {
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (!mask[i]) continue;
+    const float g = __ldg(gt + i);
+    acc[4] += 1.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = __ldg(pred.p[k] + i) - g;
+      acc[k] += (double)d * (double)d;
+    }
+  }
+  __shared__ double sh[5][256];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) sh[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 5) partial[(size_t)blockIdx.x * 5 + threadIdx.x] = sh[threadIdx.x][0];
+}
+// stats: [0] valid count, [1] Total, [2..5] per-head masked MSE, [6] 1/count (0 when there is no valid pixel: zero loss, zero gradients)
+__global__ void masked_mse_finalize_kernel(const double* __restrict__ partial, int nblocks, float w0, float w1, float w2, float w3,
+                                           float* __restrict__ stats) {
+  __shared__ double tot[5];
+  if (threadIdx.x < 5) {
+    double a = 0;
+    for (int i = 0; i < nblocks; ++i) a += partial[(size_t)i * 5 + threadIdx.x];
+    tot[threadIdx.x] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double cnt = tot[4], inv = cnt > 0 ? 1.0 / cnt : 0.0;
+    const double w[4] = {w0, w1, w2, w3};
+    double total = 0;
+    for (int k = 0; k < 4; ++k) {
+      stats[2 + k] = (float)(tot[k] * inv);
+      total += w[k] * tot[k] * inv;
+    }
+    stats[0] = (float)cnt;
+    stats[1] = (float)total;
+    stats[6] = (float)inv;
+  }
+}
+__global__ void __launch_bounds__(256) masked_mse_grad_kernel(Ptr4 pred, const float* __restrict__ gt, const unsigned char* __restrict__ mask,
+                                                              size_t n, float w0, float w1, float w2, float w3,
+                                                              const float* __restrict__ stats, MPtr4 grad) {
+  const float inv = stats[6];
+  const float w[4] = {2.f * w0 * inv, 2.f * w1 * inv, 2.f * w2 * inv, 2.f * w3 * inv};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const bool m = mask[i] != 0;
+    const float g = __ldg(gt + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) grad.p[k][i] = m ? w[k] * (__ldg(pred.p[k] + i) - g) : 0.f;
+  }
+}
+
+int launch_masked_mse(const float* const pred[4], const float* gt, const unsigned char* mask, size_t n, const float w[4],
+                      float* const grad[4], float* stats, double* scratch, cudaStream_t st) {
+  Ptr4 pp; MPtr4 gp;
+  for (int k = 0; k < 4; ++k) { pp.p[k] = pred[k]; gp.p[k] = grad[k]; }
+  int nb = (int)((n + 255) / 256);
+  if (nb > kLossBlocks) nb = kLossBlocks;
+  if (nb < 1) nb = 1;
+  masked_mse_reduce_kernel<<<nb, 256, 0, st>>>(pp, gt, mask, n, scratch);
+  DFF_LAUNCH_CHECK("masked_mse_reduce");
+  masked_mse_finalize_kernel<<<1, 32, 0, st>>>(scratch, nb, w[0], w[1], w[2], w[3], stats);
+  DFF_LAUNCH_CHECK("masked_mse_finalize");
+  masked_mse_grad_kernel<<<ew_grid(n, 256), 256, 0, st>>>(pp, gt, mask, n, w[0], w[1], w[2], w[3], stats, gp);
+  DFF_LAUNCH_CHECK("masked_mse_grad");
+  return 0;
+}
+
+// Adam over ONE flat fp32 buffer (parameters, gradients, exp_avg, exp_avg_sq all flat and aligned): the element-wise arithmetic of
+// torch.optim.Adam's default CUDA (foreach) implementation in the same order and rounding —
+//   m = lerp(m, g, 1-b1) ; v = v*b2 + (1-b2)*g*g ; denom = sqrt(v)/sqrt(1-b2^t) + eps ; p = p + (-lr/(1-b1^t)) * (m/denom)
+// — so optimizer states stay interchangeable with the reference's `torch.optim.Adam(model.parameters(), betas=(0.9, 0.99))`.
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, size_t n, float one_minus_b1, float b2, float one_minus_b2,
+                                                        float bc2_sqrt, float eps, float neg_step, const float* __restrict__ gscale) {
+  const float gs = gscale ? __ldg(gscale) : 1.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gr = g[i];
+    if (gscale) gr *= gs;
+    float mi = m[i], vi = v[i];
+    mi = mi + one_minus_b1 * (gr - mi);                 // lerp, weight < 0.5
+    vi = __fmul_rn(vi, b2);
+    vi = vi + __fmul_rn(one_minus_b2, gr) * gr;         // addcmul: self + (value * t1) * t2
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+    p[i] = p[i] + neg_step * __fdiv_rn(mi, denom);      // addcdiv: self + value * (t1 / t2)
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+int launch_adam_flat(float* p, const float* g, float* m, float* v, size_t n, double lr, double b1, double b2, double eps, int step,
+                     const float* gscale, cudaStream_t st) {
+  // scalars are computed in double on the host exactly as the Python optimizer does, then narrowed to fp32 as ATen narrows them
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  const float one_minus_b1 = (float)(1.0 - b1), one_minus_b2 = (float)(1.0 - b2);
+  const float neg_step = (float)(-(lr / bc1)), bc2_sqrt = (float)sqrt(bc2);
+  adam_flat_kernel<<<ew_grid(n, 256), 256, 0, st>>>(p, g, m, v, n, one_minus_b1, (float)b2, one_minus_b2, bc2_sqrt, (float)eps, neg_step, gscale);
+  DFF_LAUNCH_CHECK("adam_flat");
+  return 0;
+}
+
 int launch_add(const void* a, const void* b, size_t n, bool bf16, void* out, cudaStream_t st) {
   if (n % 4) return fail(-1, "add: element count must be a multiple of 4");
   if (bf16) add_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n / 4, (__nv_bfloat16*)out);

@@ -50,6 +50,9 @@ def _declare(lib):
         "dff_stage_u8": (i, [vp, i, i, i, i, i, i, fp, i, vp]),
         "dff_conv3d_scratch_bytes": (sz, [i, i, i, i, i]),
         "dff_conv3d": (i, [vp, i, vp, i, i, i, i, i, fp, i, i, i, i, i, i, i, fp, fp, vp, vp, i, vp, i, i, vp, i, vp]),
+        "dff_conv3d_ex": (i, [vp, i, vp, i, i, i, i, i, fp, i, i, i, i, i, i, i, fp, fp, vp, vp, i, vp, i, i, i, vp, vp, fp, fp, i, i, vp,
+                              i, vp]),
+        "dff_to_pair_packed": (i, [fp, i, i, i, i, vp, i, vp]),
         "dff_depth_head": (i, [fp, i, i, fp, c.POINTER(i64), i, i, i, i, fp, i, vp]),
         "dff_srd_attention": (i, [vp, i, i, i, i, i, fp, fp, vp, vp, i, vp]),
         "dff_fov_warp": (i, [fp, fp, fp, i, i, i, i, i, fp, fp, i, vp]),
@@ -513,6 +516,51 @@ def conv3d(x, weight, stride_hw=1, dil_hw=1, transposed=False, scale=None, shift
                        1 if transposed else 0, _ptr(sc), _ptr(sh), _ptr(rp), _ptr(rq), 1 if relu else 0, _ptr(out),
                        _elem(bf16), int(tensor_cores), _ptr(scratch), dev.index, _stream(dev)))
     return from_channels_last(out, Cout)
+
+
+def conv3d_forward_plan(x, weight, stride_hw=1, dil_hw=1, transposed=False, scale=None, shift=None, res_pre=None, res_post=None,
+                        relu=False, x2=None, aux_add=None, proj_w=None, proj_on_aux=False, skip_out=False):
+    """One conv exactly as `dff_forward` would run a layer of this shape in bf16 (plan 4 of `dff_conv3d_ex`: folded forms, second
+    output, fused classifier).  Reference-layout fp32 tensors in, dict of reference-layout fp32 tensors out:
+    out (B,Cout,S,OH,OW) [unless skip_out], aux = out + aux_add, proj (B,S,OH,OW)."""
+    l = lib()
+    dev = x.device
+    B, Cx, S, IH, IW = x.shape
+    Cout = weight.shape[1] if transposed else weight.shape[0]
+    kd, kh, kw = weight.shape[2:]
+    w = weight.detach().to(dev, torch.float32).contiguous()
+    pair = (not transposed) and Cx == 3 and (kd, kh, kw) == (1, 9, 9) and dil_hw == 2
+    if pair:
+        a = torch.empty((B, S, IH, IW + 2, 8), dtype=torch.bfloat16, device=dev)
+        check(l.dff_to_pair_packed(_ptr(x.contiguous()), B, S, IH, IW, _ptr(a), dev.index, _stream(dev)))
+        C0p, IWs = 8, IW + 2
+    else:
+        if Cx % 8:
+            raise DffError("conv3d_forward_plan: channel counts must be multiples of 8")
+        a, C0p, IWs = to_channels_last(x, Cx, True), Cx, IW
+    b, C1p = (to_channels_last(x2, x2.shape[1], True), x2.shape[1]) if x2 is not None else (None, 0)
+    OH, OW = (IH * 2, IW * 2) if transposed else (IH // stride_hw, IW // stride_hw)
+    out = torch.zeros((B, S, OH, OW, Cout), dtype=torch.bfloat16, device=dev)
+    cl = lambda t: to_channels_last(t, Cout, True) if t is not None else None
+    rp, rq, ax = cl(res_pre), cl(res_post), cl(aux_add)
+    aux = torch.empty_like(out) if ax is not None else None
+    pw = proj_w.detach().to(dev, torch.float32).contiguous() if proj_w is not None else None
+    pout = torch.empty((B, S, OH, OW), dtype=torch.float32, device=dev) if pw is not None else None
+    sc = scale.detach().to(dev, torch.float32).contiguous() if scale is not None else None
+    sh = shift.detach().to(dev, torch.float32).contiguous() if shift is not None else None
+    scratch = torch.empty(l.dff_conv3d_scratch_bytes(max(C0p + C1p, 8), Cout, kd, kh, kw), dtype=torch.uint8, device=dev)
+    check(l.dff_conv3d_ex(_ptr(a), C0p, _ptr(b), C1p, B, S, IH, IWs, _ptr(w), Cout, kd, kh, kw, stride_hw, dil_hw, 1 if transposed else 0,
+                          _ptr(sc), _ptr(sh), _ptr(rp), _ptr(rq), 1 if relu else 0, _ptr(out), BF16, 4, 1 if pair else 0, _ptr(ax),
+                          _ptr(aux), _ptr(pw), _ptr(pout), 1 if proj_on_aux else 0, 1 if skip_out else 0, _ptr(scratch), dev.index,
+                          _stream(dev)))
+    res = {}
+    if not skip_out:
+        res["out"] = from_channels_last(out, Cout)
+    if aux is not None:
+        res["aux"] = from_channels_last(aux, Cout)
+    if pout is not None:
+        res["proj"] = pout
+    return res
 
 
 def _with(shape, axis, n):

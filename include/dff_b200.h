@@ -148,6 +148,21 @@ int dff_conv3d(const void *in0, int C0, const void *in1, int C1, int B, int S, i
                const float *shift, const void *res_pre, const void *res_post, int relu, void *out, int elem,
                int use_tensor_cores, void *scratch, int device, void *stream);
 
+/* The same operator with the forward's own kernel selection and fusions, so that every form dff_forward can pick is testable in
+ * isolation.  `plan`: 0 FFMA; 1 best tensor-core kernel for the plain form; 2 per-tap TMA kernel; 3 slab kernel; 4 = exactly what
+ * dff_forward runs for a layer of this shape — x-folded small-Cout layers, x-folded transposed convolutions, the row-folded
+ * pair-packed first layer (`pair_input`: in0 is the (B,S,H,W+2,8) bf16 tensor of dff_to_pair_packed and `weight` the (Cout,3,1,9,9)
+ * layer), a second output `aux_out = out + aux_add` (the `x + out` of train_codes/Depth_Estimation_Network.py:104,110) and a fused
+ * 1x1x1 classifier `proj_out[pixel] = sum_c proj_w[c] * bf16(v[c])` (reference :53-57,105,111,116) on the stored value
+ * (proj_on_aux 0) or on the second output (1); skip_out: `out` itself is not written.  aux / proj / pair_input need plan 4. */
+int dff_conv3d_ex(const void *in0, int C0, const void *in1, int C1, int B, int S, int IH, int IW, const float *weight, int Cout,
+                  int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, const float *scale, const float *shift,
+                  const void *res_pre, const void *res_post, int relu, void *out, int elem, int plan, int pair_input,
+                  const void *aux_add, void *aux_out, const float *proj_w, float *proj_out, int proj_on_aux, int skip_out,
+                  void *scratch, int device, void *stream);
+/* FS (B,3,S,H,W) fp32 -> the first layer's tensor-core input (B,S,H,W+2,8) bf16: column c = [RGB(c-2) | RGB(c) | 0 0] */
+int dff_to_pair_packed(const float *FS, int B, int S, int H, int W, void *dst, int device, void *stream);
+
 /* SRD / Feature_Extraction channel-attention branch (reference train_codes/Depth_Estimation_Network.py:399-407), one pass:
  *   out = F + relu( conv1x1x1( relu( conv3x1x1(F; w_a) ); w_b ) )      (no BatchNorm, no bias)
  * F, out: channels-last (B,S,H,W,C) bf16, C in {8,16,32}, H*W % 16 == 0; w_a (C,C,3,1,1), w_b (C,C,1,1,1) fp32 in the
@@ -158,6 +173,11 @@ int dff_srd_attention(const void *F, int B, int S, int H, int W, int C, const fl
 /* cost (B,S,h,w) fp32 with H % h == 0 -> depth (B,H,W) fp32 */
 int dff_depth_head(const float *cost, int h, int w, const float *fd, const int64_t fd_strides[4], int B, int S, int H,
                    int W, float *depth, int device, void *stream);
+
+/* The four heads of DFF_net in one launch (what dff_forward runs last): cost4 = pre-softplus costs at 1/8, 1/4, 1/2, 1/1 resolution,
+ * each (B,S,h,w) fp32; depth4 = mid_out, pred1, pred2, pred3, each (B,H,W).  fast != 0: the bf16 mode's kernel (SFU exp/log). */
+int dff_depth_heads4(const float *const cost4[4], const float *fd, const int64_t fd_strides[4], int B, int S, int H, int W,
+                     float *const depth4[4], int fast, int device, void *stream);
 
 /* x (B,C,S,H,W) fp32 reference layout; alpha (B,3,S) [a0,a1,a2 per slice] or NULL (zeros); fov (B,S);
  * out (B,C,S,H,W); flow (B,2,S,H,W) or NULL.  Bug-compatible with the reference only for B == 1 (B > 1 uses
@@ -211,6 +231,18 @@ int dff_bn_eval_backward(const void *dy, const void *y_relu, const void *x, cons
                          const float *gamma, int64_t npix, int C, int elem, void *dx, void *dres, float *dgamma, float *dbeta,
                          void *scratch, int device, void *stream);
 int dff_add(const void *a, const void *b, int64_t n, int elem, void *out, int device, void *stream);
+
+/* ---- loss and optimizer of the reference's training loop (train_codes/train_code_Defocus.py:17-19,67,160-168) -----
+ * Total = sum_k weights[k] * mean over valid pixels of (pred4[k] - gt)^2 for the four heads (n elements each; mask: 1 byte per pixel).
+ * grad4[k] receives d Total / d pred4[k].  stats (8 floats): [0] valid count, [1] Total, [2..5] per-head masked MSE, [6] 1/count.
+ * scratch: 8192 doubles.  Replaces four boolean-mask gathers (`pred[mask]`, `gt[mask]`) + nn.MSELoss and their backward. */
+int dff_masked_mse(const float *const pred4[4], const float *gt, const uint8_t *mask, int64_t n, const float weights[4],
+                   float *const grad4[4], float *stats, void *scratch, int device, void *stream);
+/* One Adam step (no weight decay, no amsgrad) over flat fp32 buffers of n elements; `step` counts from 1; grad_scale (optional,
+ * device scalar) multiplies the gradients first.  Element-wise arithmetic, order and rounding of torch.optim.Adam's CUDA
+ * default, so states and checkpoints stay interchangeable with the reference's optimizer (train_code_Defocus.py:67,168). */
+int dff_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int step, const float *grad_scale, int device, void *stream);
 /* (1,k,k) pooling of (BS,H,W,C) channels-last volumes, forward and backward (max: first maximum in row-major order). */
 int dff_pool3d(const void *x, int BS, int H, int W, int C, int k, int is_max, int elem, void *out, int device, void *stream);
 int dff_pool3d_backward(const void *x, const void *dy, int BS, int H, int W, int C, int k, int is_max, int elem, void *dx,

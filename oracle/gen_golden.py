@@ -35,11 +35,85 @@ def same(a, b, what):
         what, (a - b).abs().max().item())
 
 
+def new_cases(tden):
+    """Round-2 additions (kept separate so the round-1 fixtures are not rewritten): G6 = train step at the C3 shape, G7 = three
+    optimizer steps of the reference's training loop."""
+    torch.manual_seed(0)
+    ref = tden.Network()
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    sd1 = synth.synthetic_state(sd0, seed=1)
+    crit = torch.nn.MSELoss()
+
+    def defocus_loss(r, gt, mask):    # train_code_Defocus.py:160-165
+        return 0.5 * crit(r[1][mask], gt[mask]) + 0.7 * crit(r[2][mask], gt[mask]) + 1.0 * crit(r[3][mask], gt[mask]) \
+            + 0.3 * crit(r[0][mask], gt[mask])
+
+    # ---- G6: train-mode forward + loss + gradients at BASELINE configs[2]'s stack shape: 2 x (5 slices, 256x256) -------------
+    ref.load_state_dict(sd1, strict=True)
+    ref.train()
+    FS, fd = synth.focal_stack(2, 5, 256, 256, seed=16), synth.focus_dists(2, 5, 256, 256, "defocus")
+    gt, mask = synth.gt_and_mask(2, 256, 256, seed=16)
+    r = ref(FS, fd)
+    loss = defocus_loss(r, gt, mask)
+    loss.backward()
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd1.items()}
+    o = O.dff_forward(sdo, FS, fd, train=True)
+    lo = O.defocus_loss(o, gt, mask)
+    lo.backward()
+    for a, b, n in zip(r, o, ("mid", "p1", "p2", "p3")):
+        same(a.detach(), b.detach(), "G6." + n)
+    same(loss.detach(), lo.detach(), "G6.loss")
+    gnames, gsum, gabs, gl2, small = [], [], [], [], {}
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            assert sdo[k].grad is None, k
+            continue
+        same(p.grad, sdo[k].grad, "G6.grad." + k)
+        gnames.append(k); gsum.append(float(p.grad.double().sum())); gabs.append(float(p.grad.double().abs().sum()))
+        gl2.append(float(p.grad.double().norm()))
+        if p.numel() <= 2400:
+            small["grad:" + k] = p.grad.numpy().copy()
+    new_sd = ref.state_dict()
+    bn = {("bn:" + k): v.numpy().copy() for k, v in new_sd.items() if "running" in k and ("dres4" in k or "FM_measure" in k)}
+    sub = lambda t: t.detach()[:, ::8, ::8].numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "g6_train_c3.npz"), mid=sub(r[0]), p1=sub(r[1]), p2=sub(r[2]), p3=sub(r[3]),
+                        out_sum=np.array([float(t.detach().double().sum()) for t in r]), loss=loss.detach(),
+                        grad_names=np.array(gnames), grad_sum=np.array(gsum), grad_abs=np.array(gabs), grad_l2=np.array(gl2),
+                        **small, **bn)
+
+    # ---- G7: three steps of the reference's training loop (train_code_Defocus.py:67,158-168), 2 x (4 slices, 32x32) --------
+    ref.load_state_dict(sd1, strict=True)
+    ref.train()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3, betas=(0.9, 0.99))
+    losses = []
+    for step in range(3):
+        FS, fd = synth.focal_stack(2, 4, 32, 32, seed=20 + step), synth.focus_dists(2, 4, 32, 32, "defocus")
+        gt, mask = synth.gt_and_mask(2, 32, 32, seed=20 + step)
+        r = ref(FS, fd)
+        opt.zero_grad()
+        loss = defocus_loss(r, gt, mask)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    fin = ref.state_dict()
+    keys = [k for k in fin if fin[k].is_floating_point()]
+    np.savez_compressed(os.path.join(OUT, "g7_train_3steps.npz"), losses=np.array(losses), keys=np.array(keys),
+                        p_sum=np.array([float(fin[k].double().sum()) for k in keys]),
+                        p_abs=np.array([float(fin[k].double().abs().sum()) for k in keys]),
+                        **{("w:" + k): fin[k].numpy().copy() for k in ("DFF_net.classif3.0.weight", "DFF_net.dres4.conv6.1.weight",
+                                                                       "DFF_net.dres4.conv6.1.running_var",
+                                                                       "DFF_net.FM_measure.Focus_extraction.0.1.bias")})
+    print("G6 loss", float(lo), "G7 losses", losses)
+
+
 def main():
     torch.set_num_threads(8)
     torch.use_deterministic_algorithms(True)
     os.makedirs(OUT, exist_ok=True)
     tden = load("train_codes/Depth_Estimation_Network.py", "ref_tden")
+    if "--new" in sys.argv:
+        new_cases(tden)
+        return
     eden = load("Depth_Estimation_Test/Depth_Estimation_Network.py", "ref_eden")
     e2e = load("End_to_End/End_to_End.py", "ref_e2e")
 

@@ -296,3 +296,35 @@ def test_layout_round_trip(rt):
     assert cl.shape == (2, 4, 8, 12, 4) and float(cl[..., 3].abs().max()) == 0.0
     assert torch.equal(rt.from_channels_last(cl, 3), x)
     assert torch.equal(cl[..., :3].permute(0, 4, 1, 2, 3), x)
+
+
+@pytest.mark.parametrize("fd_kind", ["scalars", "tiled", "strided"])
+@pytest.mark.parametrize("B,S,H,W", [(2, 5, 32, 32), (1, 10, 64, 96), (1, 3, 16, 16)])
+def test_depth_heads4_quad_kernel(rt, fd_kind, B, S, H, W):
+    """All four heads in one launch (C-ABI dff_depth_heads4): the bf16 mode's four-pixels-per-thread kernel (fixed 1/8, 1/4, 1/2, 1/1
+    pyramid, replicate-edge column loads) and the fp32 mode's kernel against the oracle's depth head (reference :92-98, 118-136)."""
+    import ctypes
+    from oracle import dff_oracle as O
+    costs = [_rand(B, S, H // r, W // r, seed=70 + r, scale=14.0) for r in (8, 4, 2, 1)]
+    costs[3][0, 0, 0, 0] = 31.0    # softplus threshold branch
+    if fd_kind == "scalars":
+        fd = torch.linspace(0.1, 1.5, S).view(1, S, 1, 1).expand(B, S, 1, 1).contiguous().cuda().expand(B, S, H, W)
+    elif fd_kind == "tiled":
+        fd = (_rand(B, S, H, W, seed=75).abs() + 0.1).cuda()
+    else:
+        fd = (_rand(B, S, H, W + 3, seed=76).abs() + 0.1).cuda()[..., 1:W + 1]     # unaligned rows: the generic-stride variant
+    f = rt.lib().dff_depth_heads4
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)] + [ctypes.c_int] * 4 + \
+                 [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    dc = [c.cuda() for c in costs]
+    cp = (ctypes.c_void_p * 4)(*[c.data_ptr() for c in dc])
+    strides = (ctypes.c_int64 * 4)(*fd.stride())
+    refs = [O.depth_head(c.double(), fd.cpu().double(), (H, W)) for c in costs]
+    for fast, tol in ((1, 3e-5), (0, 2e-6)):
+        outs = [torch.full((B, H, W), float("nan"), device="cuda") for _ in range(4)]
+        op = (ctypes.c_void_p * 4)(*[o.data_ptr() for o in outs])
+        rt.check(f(cp, fd.data_ptr(), strides, B, S, H, W, op, fast, 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        for o, r, k in zip(outs, refs, range(4)):
+            err = ((o.cpu().double() - r).abs() / r.abs()).max().item()
+            assert err <= tol, (fast, k, err)

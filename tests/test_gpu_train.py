@@ -162,3 +162,113 @@ def test_bf16_train_step_tensor_cores(built_lib):
         loss.backward()
         opt.step()
         assert np.isfinite(loss.item())
+
+
+def test_golden_g6_train_step_c3_shape(built_lib):
+    """Train-mode forward + loss + gradients at BASELINE configs[2]'s stack shape (2 x 5x3x256x256) against the reference's
+    committed golden (tests/golden/g6_train_c3.npz): the shapes the training benchmark runs, not only 32x32 toys."""
+    from dffinthewild_b200 import synth
+    g = golden("g6_train_c3.npz")
+    net = _net(_state())
+    FS, fd = synth.focal_stack(2, 5, 256, 256, seed=16), synth.focus_dists(2, 5, 256, 256, "defocus")
+    gt, mask = synth.gt_and_mask(2, 256, 256, seed=16)
+    outs = net(FS.cuda(), fd.cuda())
+    for o, n, s in zip(outs, NAMES, g["out_sum"]):
+        ref = g[n]
+        got = o.detach()[:, ::8, ::8].cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max(), n
+        assert abs(float(o.detach().double().sum()) - s) <= 1e-5 * abs(s), n
+    loss = _loss(outs, gt.cuda(), mask.cuda())
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    loss.backward()
+    params = dict(net.named_parameters())
+    for k, a, l2 in zip(g["grad_names"], g["grad_abs"], g["grad_l2"]):
+        gr = params[str(k)].grad.double()
+        assert abs(float(gr.abs().sum()) - a) <= 3e-3 * a + 1e-12, k
+        assert abs(float(gr.norm()) - l2) <= 3e-3 * l2 + 1e-12, k
+    for key in g.files:
+        if key.startswith("grad:"):
+            ref = torch.from_numpy(g[key]).double().flatten()
+            got = params[key[5:]].grad.double().cpu().flatten()
+            cos = float(torch.dot(ref, got) / (ref.norm() * got.norm() + 1e-300))
+            assert cos >= 0.9999, (key, cos)
+    new_sd = net.state_dict()
+    for key in g.files:
+        if key.startswith("bn:"):
+            ref = g[key]
+            assert np.abs(new_sd[key[3:]].cpu().numpy() - ref).max() <= 1e-4 * max(1e-6, np.abs(ref).max()), key
+
+
+def test_masked_mse_matches_reference_recipe(built_lib):
+    """dff_masked_mse = 0.5*MSE(pred1[mask], gt[mask]) + ... (train_code_Defocus.py:160-165), value and gradients."""
+    from dffinthewild_b200 import synth
+    from dffinthewild_b200 import train_step as TS
+    gt, mask = synth.gt_and_mask(3, 40, 56, seed=51)
+    gen = torch.Generator().manual_seed(52)
+    preds = [(gt + 0.3 * torch.randn(gt.shape, generator=gen)).cuda().requires_grad_(True) for _ in range(4)]
+    ref_preds = [p.detach().clone().double().requires_grad_(True) for p in preds]
+    w = (0.3, 0.5, 0.7, 1.0)
+    loss = TS.masked_mse_loss(preds, gt.cuda(), mask.cuda(), w)
+    (loss * 1.7).backward()
+    crit = torch.nn.MSELoss()
+    ref = sum(wk * crit(p[mask.cuda()], gt.cuda().double()[mask.cuda()]) for wk, p in zip(w, ref_preds))
+    (ref * 1.7).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
+    for p, r in zip(preds, ref_preds):
+        assert (p.grad.double() - r.grad).abs().max().item() <= 1e-6 * r.grad.abs().max().item()
+    # no valid pixel: zero loss and zero gradients instead of 0/0
+    z = TS.masked_mse_loss([p.detach() for p in preds], gt.cuda(), torch.zeros_like(mask).cuda(), w)
+    assert z.item() == 0.0
+
+
+def test_adam_flat_is_bit_compatible_with_torch(built_lib):
+    """dff_adam_flat against torch.optim.Adam (the CUDA default, foreach implementation) with the reference's hyper-parameters
+    (train_code_Defocus.py:67): parameters and both moments bit-identical after 3 steps."""
+    import ctypes
+    from dffinthewild_b200 import runtime as rt
+    from dffinthewild_b200 import train_step as TS
+    l = rt.lib()
+    TS._declare(l)
+    gen = torch.Generator().manual_seed(61)
+    n = 100003
+    p0 = torch.randn(n, generator=gen).cuda()
+    grads = [(torch.randn(n, generator=gen) * (10.0 ** torch.randint(-6, 2, (n,), generator=gen).float())).cuda() for _ in range(3)]
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.99), foreach=True)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for t, g in enumerate(grads, 1):
+        ref.grad = g.clone()
+        opt.step()
+        rt.check(l.dff_adam_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.99, 1e-8, t, None, 0,
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    st = opt.state[ref]
+    assert torch.equal(m, st["exp_avg"]) and torch.equal(v, st["exp_avg_sq"])
+    assert torch.equal(p, ref.detach())
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_golden_g7_training_loop_trajectory(built_lib, precision, rtol):
+    """Three optimizer steps through TrainStep (fused masked-MSE, flat Adam) against the reference's own loop
+    (tests/golden/g7_train_3steps.npz): the loss trajectory — SURVEY.md §8(d)'s bf16 training gate — and, in fp32, the
+    parameters and running statistics after the third step."""
+    from dffinthewild_b200 import synth
+    from dffinthewild_b200 import train_step as TS
+    g = golden("g7_train_3steps.npz")
+    net = _net(_state())
+    net.DFF_net.precision = precision
+    stepper = TS.TrainStep(net, lr=1e-3, betas=(0.9, 0.99), weights=(0.3, 0.5, 0.7, 1.0))
+    for step in range(3):
+        FS, fd = synth.focal_stack(2, 4, 32, 32, seed=20 + step), synth.focus_dists(2, 4, 32, 32, "defocus")
+        gt, mask = synth.gt_and_mask(2, 32, 32, seed=20 + step)
+        info = stepper.step(FS.cuda(), fd.cuda(), gt.cuda(), mask.cuda())
+        assert abs(float(info["loss"]) - g["losses"][step]) <= rtol * g["losses"][step], (step, float(info["loss"]), g["losses"][step])
+    if precision == "fp32":
+        sd = net.state_dict()
+        for k in ("DFF_net.classif3.0.weight", "DFF_net.dres4.conv6.1.weight", "DFF_net.dres4.conv6.1.running_var"):
+            ref = g["w:" + k]
+            assert np.abs(sd[k].cpu().numpy() - ref).max() <= 2e-3 * np.abs(ref).max(), k
+        # the module still answers in eval mode with the stepped weights (flat-buffer views + invalidated weight pack)
+        net.eval()
+        with torch.no_grad():
+            o = net(FS.cuda(), fd.cuda())
+        assert all(torch.isfinite(t).all() for t in o)

@@ -98,3 +98,23 @@ def test_metrics_restatement():
     assert O.mask_abs_rel(est, gt, m) > 0
     assert 0 < O.bumpiness(gt, est, m) <= 5.0
     assert O.bumpiness(gt, gt, m) == 0.0
+
+
+def test_g7_three_training_steps():
+    """Three steps of the reference's training loop (train_code_Defocus.py:67,158-168): oracle forward + torch.optim.Adam on the
+    state_dict tensors reproduces the reference module's loss trajectory and final parameters."""
+    g = golden("g7_train_3steps.npz")
+    sd = synth.synthetic_state(_template(), seed=1)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-3, betas=(0.9, 0.99))
+    for step in range(3):
+        FS, fd = synth.focal_stack(2, 4, 32, 32, seed=20 + step), synth.focus_dists(2, 4, 32, 32, "defocus")
+        gt, mask = synth.gt_and_mask(2, 32, 32, seed=20 + step)
+        o = O.dff_forward(sd, FS, fd, train=True, update_stats=True)
+        opt.zero_grad()
+        loss = O.defocus_loss(o, gt, mask)
+        loss.backward()
+        opt.step()
+        _close(loss.detach(), g["losses"][step], 1e-4)
+    for k in ("DFF_net.classif3.0.weight", "DFF_net.dres4.conv6.1.weight", "DFF_net.dres4.conv6.1.running_var"):
+        _close(sd[k].detach(), g["w:" + k], 2e-3)
