@@ -425,47 +425,87 @@ template <int R> struct QuadTaps {
   }
 };
 
+// p = softplus(v) + 1e-6 with two SFU operations and fp32-grade accuracy everywhere: max(v,0) + log1p(exp(-|v|)), where log1p of a
+// small argument is its series (the plain log(1 + e) loses e's low bits below ~1e-3 — visible when every slice of a pixel is
+// strongly negative and the normalisation divides two sums of such terms).
+__device__ __forceinline__ float softplus_sfu(float v) {
+  const float e = __expf(-fabsf(v));
+  const float l = e < 3.9e-3f ? e * fmaf(e, fmaf(e, 0.33333334f, -0.5f), 1.f) : __logf(1.f + e);
+  return fmaxf(v, 0.f) + l + 1e-6f;
+}
+__device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+constexpr int kHeadRing = 8;   // slices of full-resolution operands in flight per thread (cp.async ring in shared memory)
+
+// The full-resolution operands (cost3 and, when it is tiled, focus_dists: 4 + 4 of the ~9.3 bytes per pixel and slice) are what has
+// to come from DRAM; with plain loads a thread has one slice in flight and 512 threads per SM cover a fifth of the latency-bandwidth
+// product.  Each thread therefore runs an 8-deep cp.async ring of its own 16-byte pieces (no barrier: a thread only reads what it
+// copied itself); the low-resolution heads' taps are L1/L2 hits.
 template <int FDMODE>   // 0: generic strides, 1: contiguous in x (float4), 2: one scalar per slice
-__global__ void __launch_bounds__(128) depth_head4_quad_kernel(const __grid_constant__ Head4 a, const float* __restrict__ fd, long long sb,
-                                                               long long ss, long long sy, long long sx, int B, int S, int H, int W) {
+__global__ void __launch_bounds__(128, 4) depth_head4_quad_kernel(const __grid_constant__ Head4 a, const float* __restrict__ fd, long long sb,
+                                                                  long long ss, long long sy, long long sx, int B, int S, int H, int W) {
+  __shared__ float4 ring_c[kHeadRing][128];
+  __shared__ float4 ring_f[FDMODE == 1 ? kHeadRing : 1][128];
   const int W4 = W >> 2;
-  const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (q >= (size_t)B * H * W4) return;
+  size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const bool live = q < (size_t)B * H * W4;
+  if (!live) q = 0;   // (keeps the thread's loads in range; it stores nothing)
   const int t = (int)(q % W4), y = (int)((q / W4) % H), b = (int)(q / ((size_t)W4 * H));
-  QuadTaps<8> t0; QuadTaps<4> t1; QuadTaps<2> t2; QuadTaps<1> t3;
-  t0.init(t, y, a.h[0], a.w[0], H); t1.init(t, y, a.h[1], a.w[1], H); t2.init(t, y, a.h[2], a.w[2], H); t3.init(t, y, a.h[3], a.w[3], H);
-  const int sl0 = a.h[0] * a.w[0], sl1 = a.h[1] * a.w[1], sl2 = a.h[2] * a.w[2], sl3 = a.h[3] * a.w[3];
+  QuadTaps<8> t0; QuadTaps<4> t1; QuadTaps<2> t2;
+  t0.init(t, y, a.h[0], a.w[0], H); t1.init(t, y, a.h[1], a.w[1], H); t2.init(t, y, a.h[2], a.w[2], H);
+  const int sl0 = a.h[0] * a.w[0], sl1 = a.h[1] * a.w[1], sl2 = a.h[2] * a.w[2];
+  const size_t sl3 = (size_t)H * W;
   const float* c0 = a.cost[0] + (size_t)b * S * sl0;
   const float* c1 = a.cost[1] + (size_t)b * S * sl1;
   const float* c2 = a.cost[2] + (size_t)b * S * sl2;
-  const float* c3 = a.cost[3] + (size_t)b * S * sl3;
+  const float* c3 = a.cost[3] + (size_t)b * S * sl3 + (size_t)y * W + 4 * t;
   const float* fp = fd + b * sb + y * sy + (long long)(4 * t) * sx;
+#pragma unroll
+  for (int d = 0; d < kHeadRing; ++d) {
+    if (d < S) {
+      cp_async16_ca(&ring_c[d][threadIdx.x], c3 + (size_t)d * sl3);
+      if (FDMODE == 1) cp_async16_ca(&ring_f[d][threadIdx.x], fp + d * ss);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   float num[4][4], den[4][4];
 #pragma unroll
   for (int hd = 0; hd < 4; ++hd)
 #pragma unroll
     for (int k = 0; k < 4; ++k) num[hd][k] = den[hd][k] = 0.f;
   for (int s = 0; s < S; ++s) {
-    float f[4];
-    if (FDMODE == 2) { f[0] = f[1] = f[2] = f[3] = __ldg(fp); }
-    else if (FDMODE == 1) { const float4 v = __ldg(reinterpret_cast<const float4*>(fp)); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
-    else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) f[k] = __ldg(fp + k * sx);
-    }
-    fp += ss;
     float v[4][4];
-    t0.eval(c0, v[0]); t1.eval(c1, v[1]); t2.eval(c2, v[2]); t3.eval(c3, v[3]);
-    c0 += sl0; c1 += sl1; c2 += sl2; c3 += sl3;
+    t0.eval(c0, v[0]); t1.eval(c1, v[1]); t2.eval(c2, v[2]);
+    c0 += sl0; c1 += sl1; c2 += sl2;
+    float f[4];
+    if (FDMODE == 2) { f[0] = f[1] = f[2] = f[3] = __ldg(fp + s * ss); }
+    else if (FDMODE == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) f[k] = __ldg(fp + s * ss + k * sx);
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(kHeadRing - 1) : "memory");
+    const int slot = s % kHeadRing;
+    {
+      const float4 c = ring_c[slot][threadIdx.x];
+      v[3][0] = c.x; v[3][1] = c.y; v[3][2] = c.z; v[3][3] = c.w;
+      if (FDMODE == 1) { const float4 g = ring_f[slot][threadIdx.x]; f[0] = g.x; f[1] = g.y; f[2] = g.z; f[3] = g.w; }
+    }
+    if (s + kHeadRing < S) {
+      cp_async16_ca(&ring_c[slot][threadIdx.x], c3 + (size_t)(s + kHeadRing) * sl3);
+      if (FDMODE == 1) cp_async16_ca(&ring_f[slot][threadIdx.x], fp + (long long)(s + kHeadRing) * ss);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
     for (int hd = 0; hd < 4; ++hd)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float pr = softplus_p<true>(v[hd][k]);
+        const float pr = softplus_sfu(v[hd][k]);
         den[hd][k] += pr;
         num[hd][k] = fmaf(f[k], pr, num[hd][k]);
       }
   }
+  if (!live) return;
   const size_t o = ((size_t)b * H + y) * W + 4 * t;
 #pragma unroll
   for (int hd = 0; hd < 4; ++hd)
@@ -565,8 +605,85 @@ __global__ void fov_warp_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
+// Four horizontally adjacent output pixels per thread: the row geometry is computed once, the four column geometries are
+// independent instruction streams, every channel contributes 16 tap loads in flight per thread and the results leave as one
+// 16-byte store per channel (the one-pixel kernel above is latency-bound at a fifth of the HBM bandwidth).  Same arithmetic, same
+// order, same rounding as fov_warp_kernel.
+__device__ __forceinline__ float fov_lin(int i, int n) {   // torch.linspace(-1, 1, n)[i]
+  if (n == 1) return -1.f;
+  const float step = 2.f / (float)(n - 1);
+  return i < n / 2 ? -1.f + step * (float)i : 1.f - step * (float)(n - 1 - i);
+}
+template <bool FLOW>
+__global__ void __launch_bounds__(128) fov_warp_quad_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+                                                            const float* __restrict__ fov, int B, int C, int S, int H, int W,
+                                                            float* __restrict__ out, float* __restrict__ flow) {
+  const int px0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int py = blockIdx.y;
+  const int bs = blockIdx.z, b = bs / S, s = bs % S;
+  if (px0 >= W) return;
+  const float a0 = alpha ? __ldg(alpha + (0 * 3 + 0) * S + s) : 0.f;  // sample 0 on purpose (reference broadcast quirk)
+  const float a1 = alpha ? __ldg(alpha + ((size_t)b * 3 + 1) * S + s) : 0.f;
+  const float a2 = alpha ? __ldg(alpha + ((size_t)b * 3 + 2) * S + s) : 0.f;
+  const float f = a0 + __ldg(fov + (size_t)b * S + s);
+  const float fly = (float)(H / 2) * (f - 1.f) * fov_lin(py, H) + a2;
+  const float gy = 2.0f * ((float)py - fly) / (float)max(H - 1, 1) - 1.0f;
+  const float iy = (gy + 1.f) * 0.5f * (float)(H - 1);
+  const float fy0 = floorf(iy);
+  const int y0 = (int)fy0, y1 = y0 + 1;
+  const float ty = iy - fy0;
+  const bool vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+  int x0[4];
+  float w00[4], w01[4], w10[4], w11[4], flx[4];
+  bool vx0[4], vx1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int px = px0 + k;
+    flx[k] = (float)(W / 2) * (f - 1.f) * fov_lin(px, W) + a1;
+    const float gx = 2.0f * ((float)px - flx[k]) / (float)max(W - 1, 1) - 1.0f;
+    const float ix = (gx + 1.f) * 0.5f * (float)(W - 1);
+    const float fx0 = floorf(ix);
+    x0[k] = (int)fx0;
+    const float tx = ix - fx0;
+    w00[k] = (1.f - tx) * (1.f - ty); w01[k] = tx * (1.f - ty); w10[k] = (1.f - tx) * ty; w11[k] = tx * ty;
+    vx0[k] = x0[k] >= 0 && x0[k] < W; vx1[k] = x0[k] + 1 >= 0 && x0[k] + 1 < W;
+  }
+  const size_t plane = (size_t)H * W;
+  if (FLOW) {
+    const size_t fo = (((size_t)b * 2 * S + s) * H + py) * W + px0;
+    *reinterpret_cast<float4*>(flow + fo) = make_float4(flx[0], flx[1], flx[2], flx[3]);
+    *reinterpret_cast<float4*>(flow + fo + (size_t)S * plane) = make_float4(fly, fly, fly, fly);
+  }
+  const float* p = x + ((size_t)b * C * S + s) * plane;
+  float* o = out + (((size_t)b * C * S + s) * H + py) * W + px0;
+  for (int c = 0; c < C; ++c, p += (size_t)S * plane, o += (size_t)S * plane) {
+    const float* r0 = p + (size_t)y0 * W;
+    const float* r1 = r0 + W;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float acc = 0.f;
+      if (vy0 && vx0[k]) acc += __ldg(r0 + x0[k]) * w00[k];
+      if (vy0 && vx1[k]) acc += __ldg(r0 + x0[k] + 1) * w01[k];
+      if (vy1 && vx0[k]) acc += __ldg(r1 + x0[k]) * w10[k];
+      if (vy1 && vx1[k]) acc += __ldg(r1 + x0[k] + 1) * w11[k];
+      v[k] = acc;
+    }
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
                     float* flow, cudaStream_t st) {
+  const bool vec = W % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && (!flow || reinterpret_cast<uintptr_t>(flow) % 16 == 0);
+  static const bool no_quad = getenv("DFF_FOV_NO_QUAD") != nullptr;
+  if (vec && !no_quad) {
+    dim3 grid(cdiv(W / 4, 128), H, B * S);
+    if (flow) fov_warp_quad_kernel<true><<<grid, 128, 0, st>>>(x, alpha, fov, B, C, S, H, W, out, flow);
+    else fov_warp_quad_kernel<false><<<grid, 128, 0, st>>>(x, alpha, fov, B, C, S, H, W, out, flow);
+    DFF_LAUNCH_CHECK("fov_warp_quad");
+    return 0;
+  }
   dim3 grid(cdiv(W, 128), H, B * S);
   fov_warp_kernel<<<grid, 128, 0, st>>>(x, alpha, fov, B, C, S, H, W, out, flow);
   DFF_LAUNCH_CHECK("fov_warp");
@@ -781,9 +898,52 @@ __global__ void spatial_mean_accum_kernel(const float* __restrict__ x, int Cs, i
   }
 }
 
+// bf16 channels-last volumes, one 16-byte piece (8 channels) per thread: consecutive lanes take consecutive pieces of a pixel, so a
+// warp's tap load is one contiguous run per pixel; packed bf16x2 blends in fp32.
+__global__ void __launch_bounds__(256) fov_warp_cl8_kernel(const uint4* __restrict__ x, const float* __restrict__ alpha,
+                                                           const float* __restrict__ fov, int B, int C8, int S, int H, int W,
+                                                           uint4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (pixel of the row, chunk)
+  if (i >= W * C8) return;
+  const int px = i / C8, c8 = i - px * C8, py = blockIdx.y;
+  const int bs = blockIdx.z, b = bs / S, s = bs % S;
+  const WarpGeom g = warp_geom(alpha, fov, b, s, S, H, W, px, py);
+  const uint4* base = x + (size_t)bs * H * W * C8 + c8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  auto tap = [&](int yy, int xx, float w) {
+    const uint4 r = __ldg(base + ((size_t)yy * W + xx) * C8);
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] = fmaf(__uint_as_float(u[j] << 16), w, acc[2 * j]);
+      acc[2 * j + 1] = fmaf(__uint_as_float(u[j] & 0xffff0000u), w, acc[2 * j + 1]);
+    }
+  };
+  if (g.vy0 && g.vx0) tap(g.y0, g.x0, g.w00);
+  if (g.vy0 && g.vx1) tap(g.y0, g.x0 + 1, g.w01);
+  if (g.vy1 && g.vx0) tap(g.y0 + 1, g.x0, g.w10);
+  if (g.vy1 && g.vx1) tap(g.y0 + 1, g.x0 + 1, g.w11);
+  uint4 o;
+  uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+    ou[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  out[(((size_t)bs * H + py) * W + px) * C8 + c8] = o;
+}
+
 int launch_fov_warp_cl(const void* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
                        cudaStream_t st) {
   if (C % 4) return fail(-1, "fov_warp_cl: C must be a multiple of 4");
+  if (bf16 && C % 8 == 0) {
+    dim3 grid(cdiv(W * (C / 8), 256), H, B * S);
+    fov_warp_cl8_kernel<<<grid, 256, 0, st>>>((const uint4*)x, alpha, fov, B, C / 8, S, H, W, (uint4*)out);
+    DFF_LAUNCH_CHECK("fov_warp_cl8");
+    return 0;
+  }
   dim3 grid(cdiv(W, 128), H, B * S);
   if (bf16) fov_warp_cl_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)x, alpha, fov, B, C, S, H, W, (__nv_bfloat16*)out);
   else fov_warp_cl_kernel<<<grid, 128, 0, st>>>((const float*)x, alpha, fov, B, C, S, H, W, (float*)out);

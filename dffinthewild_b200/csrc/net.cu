@@ -1076,11 +1076,24 @@ int forward_host_impl(const void* packed, const void* in_host, bool u8, int H0, 
   const size_t fd_elems = u8 ? fd_span(fd_strides, mb, S, H, W) : (size_t)mb * S * H * W;
   const size_t stage = host_stage_bytes(mb, in_stack, fd_elems, H, W);
   int rc = 0, nchunk = 0;
-  // chunk sizes: mb/4, mb/4, then mb/2 throughout.  The first host->device copy cannot overlap anything, so it is short; after that
-  // whichever side is slower (fp32 stacks: the copies, 0.64 ms per DDFF stack; uint8 stacks: the kernels) leaves the LAST chunk's
-  // kernels exposed — half-size chunks halve that, and their launch overhead hides under the other side.
+  // Chunk schedule.  Every chunk costs a fixed ~1.3 ms of launch prologues / pipeline drains on top of its per-stack time, the first
+  // chunk's host->device copy and the last chunk's device->host reads cannot overlap anything.  fp32 stacks (35 MB each) are
+  // copy-bound: mb/4, mb/4, then mb/2 throughout keeps the copy stream busy.  uint8 stacks (6 MB each) are kernel-bound: a short
+  // head and tail (mb/8) bracket chunks as large as the workspace allows, so the fixed cost is paid 3-4 times per call, not 8.
+  const int head = mb >= 8 ? mb / 8 : 1;
   for (int i0 = 0, n = 0; i0 < B && !rc; i0 += n, ++nchunk) {
-    n = nchunk < 2 ? (mb >= 4 ? mb / 4 : mb) : (mb >= 2 ? mb / 2 : mb);
+    if (!u8) n = nchunk < 2 ? (mb >= 4 ? mb / 4 : mb) : (mb >= 2 ? mb / 2 : mb);
+    else if (B <= 2 * head + 1) n = B;
+    else if (nchunk == 0) n = head;
+    else {
+      const int left = B - i0;
+      if (left <= head) n = left;
+      else {   // the middle, in equal parts no larger than mb
+        const int mid = left - head, parts = (mid + mb - 1) / mb;
+        n = (mid + parts - 1) / parts;
+      }
+    }
+    if (n > mb) n = mb;
     if (n > B - i0) n = B - i0;
     const int k = nchunk % kHostStages;
     char* io = (char*)dev_io + k * stage;

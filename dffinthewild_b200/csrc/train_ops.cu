@@ -448,7 +448,7 @@ int launch_masked_mse(const float* const pred[4], const float* gt, const unsigne
 
 // Adam over ONE flat fp32 buffer (parameters, gradients, exp_avg, exp_avg_sq all flat and aligned): the element-wise arithmetic of
 // torch.optim.Adam's default CUDA (foreach) implementation in the same order and rounding —
-//   m = lerp(m, g, 1-b1) ; v = v*b2 + (1-b2)*g*g ; denom = sqrt(v)/sqrt(1-b2^t) + eps ; p = p + (-lr/(1-b1^t)) * (m/denom)
+//   m = lerp(m, g, 1-b1) ; v = v*b2 + (1-b2)*(g*g) ; denom = sqrt(v)/sqrt(1-b2^t) + eps ; p = p + (-lr/(1-b1^t)) * (m/denom)
 // — so optimizer states stay interchangeable with the reference's `torch.optim.Adam(model.parameters(), betas=(0.9, 0.99))`.
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, size_t n, float one_minus_b1, float b2, float one_minus_b2,
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
     float mi = m[i], vi = v[i];
     mi = mi + one_minus_b1 * (gr - mi);                 // lerp, weight < 0.5
     vi = __fmul_rn(vi, b2);
-    vi = vi + __fmul_rn(one_minus_b2, gr) * gr;         // addcmul: self + (value * t1) * t2
+    vi = fmaf(one_minus_b2, __fmul_rn(gr, gr), vi);     // _foreach_addcmul_: self + value * (t1 * t2)
     const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
     p[i] = p[i] + neg_step * __fdiv_rn(mi, denom);      // addcdiv: self + value * (t1 / t2)
     m[i] = mi;

@@ -169,6 +169,19 @@ class ConvFn(torch.autograd.Function):
         return dx0, dx1, dw, None, None, None, None
 
 
+class ToChannelsLastFn(torch.autograd.Function):
+    """FS (B,3,S,H,W) fp32 -> channels-last (B,S,H,W,Cp): only on the tape when the caller wants d loss / d FS."""
+
+    @staticmethod
+    def forward(ctx, FS, Cp, bf16):
+        ctx.C = FS.shape[1]
+        return rt.to_channels_last(FS, Cp, bf16)
+
+    @staticmethod
+    def backward(ctx, dx):
+        return rt.from_channels_last(dx.contiguous(), ctx.C), None, None
+
+
 class BnActFn(torch.autograd.Function):
     """out = [relu](BN_batchstats(x) + res_pre) + res_post.  bn = the module's nn.BatchNorm3d (None: no normalisation)."""
 
@@ -391,7 +404,8 @@ def dff_net_train_forward(net, FS, focus_dists):
     while fd.dim() < 4:
         fd = fd.unsqueeze(0)
     fd = fd.expand(B, S, H, W)
-    x0 = rt.to_channels_last(FS, 8 if bf16 else 4, bf16)      # (B,S,H,W,4|8): image channels + zero padding
+    # (B,S,H,W,4|8): image channels + zero padding
+    x0 = ToChannelsLastFn.apply(FS, 8 if bf16 else 4, bf16) if FS.requires_grad else rt.to_channels_last(FS, 8 if bf16 else 4, bf16)
     fm = net.FM_measure.Focus_extraction
     v1 = _srd(fm[2], _cbn(x0, fm[0], relu=True, cin_pad=5 if bf16 else 1))
     v2 = _srd(net.FM_conv1[1], _efd(net.FM_conv1[0], v1))
