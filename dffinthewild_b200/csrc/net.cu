@@ -66,6 +66,11 @@ int launch_bn_backward(const void* dy, const void* y, const void* x, const float
 int launch_bn_eval_stats(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C, float* scale,
                          float* shift, float* mean, float* invstd, cudaStream_t st);
 int launch_add(const void* a, const void* b, size_t n, bool bf16, void* out, cudaStream_t st);
+size_t depth_metrics_scratch_bytes(int B);
+int launch_depth_metrics(const float* est, const float* gt, const unsigned char* mask, const float* conf, int B, int H, int W, int Hc,
+                         int Wc, float* out, double* scratch, cudaStream_t st);
+int launch_depth_to_jet(const float* est, int B, int H, int W, int Hc, int Wc, float lo, float hi, unsigned char* lut768,
+                        unsigned char* out, cudaStream_t st);
 int launch_masked_mse(const float* const pred[4], const float* gt, const unsigned char* mask, size_t n, const float w[4],
                       float* const grad[4], float* stats, double* scratch, cudaStream_t st);
 int launch_adam_flat(float* p, const float* g, float* m, float* v, size_t n, double lr, double b1, double b2, double eps, int step,
@@ -1298,6 +1303,26 @@ int dff_depth_heads4(const float* const cost4[4], const float* fd, const int64_t
   if (g.rc) return g.rc;
   const int h[4] = {H / 8, H / 4, H / 2, H}, w[4] = {W / 8, W / 4, W / 2, W};
   return launch_depth_head4(cost4, h, w, fd, fd_strides, B, S, H, W, depth4, fast != 0, (cudaStream_t)stream);
+}
+
+size_t dff_depth_metrics_scratch_bytes(int B) { return depth_metrics_scratch_bytes(B) + 1024; }
+
+int dff_depth_metrics(const float* est, const float* gt, const uint8_t* mask, const float* conf, int B, int H, int W, int Hc, int Wc,
+                      float* out12, void* scratch, int device, void* stream) {
+  if (!est || !gt || !out12 || !scratch) return fail(DFF_E_ARG, "dff_depth_metrics: null pointer");
+  if (B < 1 || Hc < 1 || Wc < 1 || Hc > H || Wc > W) return fail(DFF_E_ARG, "dff_depth_metrics: need 1 <= Hc <= H, 1 <= Wc <= W");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_depth_metrics(est, gt, mask, conf, B, H, W, Hc, Wc, out12, (double*)scratch, (cudaStream_t)stream);
+}
+
+int dff_depth_to_jet(const float* est, int B, int H, int W, int Hc, int Wc, float lo, float hi, uint8_t* rgb, void* scratch, int device,
+                     void* stream) {
+  if (!est || !rgb || !scratch) return fail(DFF_E_ARG, "dff_depth_to_jet: null pointer");
+  if (B < 1 || Hc < 1 || Wc < 1 || Hc > H || Wc > W || !(hi > lo)) return fail(DFF_E_ARG, "dff_depth_to_jet: bad crop or range");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_depth_to_jet(est, B, H, W, Hc, Wc, lo, hi, (unsigned char*)scratch, rgb, (cudaStream_t)stream);
 }
 
 int dff_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,

@@ -179,6 +179,19 @@ int dff_depth_head(const float *cost, int h, int w, const float *fd, const int64
 int dff_depth_heads4(const float *const cost4[4], const float *fd, const int64_t fd_strides[4], int B, int S, int H, int W,
                      float *const depth4[4], int fast, int device, void *stream);
 
+/* ---- evaluation tail on the device ------------------------------------------------------------------------------
+ * The masked depth metrics of metrics.py:90-133 for B maps at once: est (B,H,W) as the forward returns it (padded), metrics over the
+ * [:Hc,:Wc] crop (test.py:125) against gt (B,Hc,Wc), mask (B,Hc,Wc) bytes or NULL (all valid), conf (B,Hc,Wc) or NULL.
+ * out12 (B,12) fp32: abs_rel, sq_rel, mse, mae, rmse, rmse_log, accuracy_1, accuracy_2, accuracy_3, mse_w_conf, mae_w_conf, valid count.
+ * fp64 accumulation, fixed reduction order.  scratch >= dff_depth_metrics_scratch_bytes(B). */
+size_t dff_depth_metrics_scratch_bytes(int B);
+int dff_depth_metrics(const float *est, const float *gt, const uint8_t *mask, const float *conf, int B, int H, int W, int Hc, int Wc,
+                      float *out12, void *scratch, int device, void *stream);
+/* test.py:133-140: est[:Hc,:Wc] -> (est - lo)/(hi - lo) -> matplotlib 'jet' (256-entry table) -> rgb (B,Hc,Wc,3) uint8.
+ * scratch >= 768 bytes. */
+int dff_depth_to_jet(const float *est, int B, int H, int W, int Hc, int Wc, float lo, float hi, uint8_t *rgb, void *scratch, int device,
+                     void *stream);
+
 /* x (B,C,S,H,W) fp32 reference layout; alpha (B,3,S) [a0,a1,a2 per slice] or NULL (zeros); fov (B,S);
  * out (B,C,S,H,W); flow (B,2,S,H,W) or NULL.  Bug-compatible with the reference only for B == 1 (B > 1 uses
  * sample 0's scale correction exactly as End_to_End.py:112-118 does). */

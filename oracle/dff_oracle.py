@@ -270,6 +270,24 @@ def mask_abs_rel(est, gt, mask):
     return float(np.mean(np.abs(est[mask] - gt[mask]) / gt[mask]))
 
 
+def depth_metrics(est, gt, mask, conf=None):
+    """Every masked figure of metrics.py:90-133 (abs_rel :90-91, sq_rel :93-94, mse :96-97, mae :99-100, rmse :102-103,
+    rmse_log :105-109, accuracy_k :112-121, *_w_conf :123-127) in the reference's own numpy arithmetic."""
+    import numpy as np
+    e, g = est[mask], gt[mask]
+    out = {"abs_rel": np.mean(np.abs(g - e) / g), "sq_rel": np.mean(np.power(g - e, 2) / g), "mse": np.mean(np.power(g - e, 2)),
+           "mae": np.mean(np.abs(g - e)), "rmse": np.sqrt(np.mean(np.power(e - g, 2))),
+           "rmse_log": np.sqrt(np.mean(np.power(np.log(g) - np.log(e), 2)))}
+    th = np.maximum(e / g, g / e)
+    for k in (1, 2, 3):
+        out["accuracy_%d" % k] = np.sum(np.where(th < (1.25 ** k), 1, 0)) / np.sum(mask)
+    if conf is not None:
+        c = conf[mask]
+        out["mse_w_conf"] = np.sum(c * np.power(g - e, 2)) / np.sum(c)
+        out["mae_w_conf"] = np.sum(c * np.abs(g - e)) / np.sum(c)
+    return {k: float(v) for k, v in out.items()}
+
+
 def bumpiness(gt, est, mask, clip=0.05, factor=100):
     """get_bumpiness (metrics.py:41-61) with scikit-image's Scharr filters restated via scipy.ndimage
     (skimage 0.19.2 is not installed and not vendored: bumpiness parity is unpinned)."""

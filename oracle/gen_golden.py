@@ -35,9 +35,15 @@ def same(a, b, what):
         what, (a - b).abs().max().item())
 
 
-def new_cases(tden):
+def new_cases(tden, only_g8=False):
     """Round-2 additions (kept separate so the round-1 fixtures are not rewritten): G6 = train step at the C3 shape, G7 = three
     optimizer steps of the reference's training loop."""
+    if not only_g8:
+        _train_cases(tden)
+    _metric_cases()
+
+
+def _train_cases(tden):
     torch.manual_seed(0)
     ref = tden.Network()
     sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
@@ -106,13 +112,43 @@ def new_cases(tden):
     print("G6 loss", float(lo), "G7 losses", losses)
 
 
+def _metric_cases():
+    # ---- G8: the reference's metrics.py (imported unmodified behind a stub for the absent scikit-image, which only get_bumpiness uses)
+    import types
+    sk, skf = types.ModuleType("skimage"), types.ModuleType("skimage.filters")
+    sk.filters = skf
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.filters", skf)
+    met = load("Depth_Estimation_Test/metrics.py", "ref_metrics")
+    rng = np.random.Generator(np.random.PCG64(88))
+    gt = rng.uniform(0.05, 1.5, (2, 61, 90)).astype(np.float32)
+    est = (gt * rng.uniform(0.7, 1.4, gt.shape)).astype(np.float32)
+    mask = rng.uniform(0, 1, gt.shape) > 0.15
+    conf = rng.uniform(0, 1, gt.shape).astype(np.float32)
+    vals = {}
+    for b in range(2):
+        e, g, m, c = est[b], gt[b], mask[b], conf[b]
+        r = {"abs_rel": met.mask_abs_rel(e, g, m), "sq_rel": met.mask_sq_rel(e, g, m), "mse": met.mask_mse(e, g, m),
+             "mae": met.mask_mae(e, g, m), "rmse": met.mask_rmse(e, g, m), "rmse_log": met.mask_rmse_log(e, g, m),
+             "accuracy_1": met.mask_accuracy_k(e, g, 1, m), "accuracy_2": met.mask_accuracy_k(e, g, 2, m),
+             "accuracy_3": met.mask_accuracy_k(e, g, 3, m), "mse_w_conf": met.mask_mse_w_conf(e, g, c, m),
+             "mae_w_conf": met.mask_mae_w_conf(e, g, c, m)}
+        o = O.depth_metrics(e, g, m, c)
+        for k, v in r.items():
+            assert float(v) == o[k], ("G8", k, float(v), o[k])
+            vals.setdefault(k, []).append(float(v))
+    np.savez_compressed(os.path.join(OUT, "g8_metrics.npz"), est=est, gt=gt, mask=mask, conf=conf,
+                        **{k: np.array(v, dtype=np.float64) for k, v in vals.items()})
+    print("G8", {k: v[0] for k, v in vals.items()})
+
+
 def main():
     torch.set_num_threads(8)
     torch.use_deterministic_algorithms(True)
     os.makedirs(OUT, exist_ok=True)
     tden = load("train_codes/Depth_Estimation_Network.py", "ref_tden")
     if "--new" in sys.argv:
-        new_cases(tden)
+        new_cases(tden, only_g8="--g8" in sys.argv)
         return
     eden = load("Depth_Estimation_Test/Depth_Estimation_Network.py", "ref_eden")
     e2e = load("End_to_End/End_to_End.py", "ref_e2e")

@@ -118,3 +118,12 @@ def test_g7_three_training_steps():
         _close(loss.detach(), g["losses"][step], 1e-4)
     for k in ("DFF_net.classif3.0.weight", "DFF_net.dres4.conv6.1.weight", "DFF_net.dres4.conv6.1.running_var"):
         _close(sd[k].detach(), g["w:" + k], 2e-3)
+
+
+def test_g8_metrics_restatement_matches_reference_metrics_py():
+    """oracle.depth_metrics against the values the reference's own metrics.py (:90-133) produced (tests/golden/g8_metrics.npz)."""
+    g = golden("g8_metrics.npz")
+    for b in range(2):
+        o = O.depth_metrics(g["est"][b], g["gt"][b], g["mask"][b], g["conf"][b])
+        for k, v in o.items():
+            assert abs(v - g[k][b]) <= 1e-6 * abs(g[k][b]), (k, v, g[k][b])
