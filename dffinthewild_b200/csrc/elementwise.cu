@@ -609,15 +609,15 @@ __global__ void fov_warp_kernel(const float* __restrict__ x, const float* __rest
 // independent instruction streams, every channel contributes 16 tap loads in flight per thread and the results leave as one
 // 16-byte store per channel (the one-pixel kernel above is latency-bound at a fifth of the HBM bandwidth).  Same arithmetic, same
 // order, same rounding as fov_warp_kernel.
-__device__ __forceinline__ float fov_lin(int i, int n) {   // torch.linspace(-1, 1, n)[i]
+__device__ __forceinline__ float fov_lin(int i, int n, float step) {   // torch.linspace(-1, 1, n)[i], step = 2/(n-1) in fp32
   if (n == 1) return -1.f;
-  const float step = 2.f / (float)(n - 1);
   return i < n / 2 ? -1.f + step * (float)i : 1.f - step * (float)(n - 1 - i);
 }
 template <bool FLOW>
 __global__ void __launch_bounds__(128) fov_warp_quad_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
                                                             const float* __restrict__ fov, int B, int C, int S, int H, int W,
-                                                            float* __restrict__ out, float* __restrict__ flow) {
+                                                            float stepW, float stepH, float* __restrict__ out,
+                                                            float* __restrict__ flow) {
   const int px0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int py = blockIdx.y;
   const int bs = blockIdx.z, b = bs / S, s = bs % S;
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(128) fov_warp_quad_kernel(const float* __restr
   const float a1 = alpha ? __ldg(alpha + ((size_t)b * 3 + 1) * S + s) : 0.f;
   const float a2 = alpha ? __ldg(alpha + ((size_t)b * 3 + 2) * S + s) : 0.f;
   const float f = a0 + __ldg(fov + (size_t)b * S + s);
-  const float fly = (float)(H / 2) * (f - 1.f) * fov_lin(py, H) + a2;
+  const float fly = (float)(H / 2) * (f - 1.f) * fov_lin(py, H, stepH) + a2;
   const float gy = 2.0f * ((float)py - fly) / (float)max(H - 1, 1) - 1.0f;
   const float iy = (gy + 1.f) * 0.5f * (float)(H - 1);
   const float fy0 = floorf(iy);
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(128) fov_warp_quad_kernel(const float* __restr
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int px = px0 + k;
-    flx[k] = (float)(W / 2) * (f - 1.f) * fov_lin(px, W) + a1;
+    flx[k] = (float)(W / 2) * (f - 1.f) * fov_lin(px, W, stepW) + a1;
     const float gx = 2.0f * ((float)px - flx[k]) / (float)max(W - 1, 1) - 1.0f;
     const float ix = (gx + 1.f) * 0.5f * (float)(W - 1);
     const float fx0 = floorf(ix);
@@ -678,9 +678,12 @@ int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B,
   const bool vec = W % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && (!flow || reinterpret_cast<uintptr_t>(flow) % 16 == 0);
   static const bool no_quad = getenv("DFF_FOV_NO_QUAD") != nullptr;
   if (vec && !no_quad) {
-    dim3 grid(cdiv(W / 4, 128), H, B * S);
-    if (flow) fov_warp_quad_kernel<true><<<grid, 128, 0, st>>>(x, alpha, fov, B, C, S, H, W, out, flow);
-    else fov_warp_quad_kernel<false><<<grid, 128, 0, st>>>(x, alpha, fov, B, C, S, H, W, out, flow);
+    // (the linspace steps are per-call constants: computed here in fp32 exactly as the device would, 2.f / (float)(n - 1))
+    const float stepW = W > 1 ? 2.f / (float)(W - 1) : 0.f, stepH = H > 1 ? 2.f / (float)(H - 1) : 0.f;
+    const int bt = (W / 4) % 128 == 0 ? 128 : ((W / 4) % 64 == 0 ? 64 : ((W / 4) % 96 == 0 ? 96 : ((W / 4) <= 64 ? 64 : 128)));
+    dim3 grid(cdiv(W / 4, bt), H, B * S);
+    if (flow) fov_warp_quad_kernel<true><<<grid, bt, 0, st>>>(x, alpha, fov, B, C, S, H, W, stepW, stepH, out, flow);
+    else fov_warp_quad_kernel<false><<<grid, bt, 0, st>>>(x, alpha, fov, B, C, S, H, W, stepW, stepH, out, flow);
     DFF_LAUNCH_CHECK("fov_warp_quad");
     return 0;
   }
@@ -851,10 +854,11 @@ __global__ void fov_warp_cl_kernel(const T* __restrict__ x, const float* __restr
   }
 }
 
-// The alignment head's input (reference :71-76, 81-86, 92-97):  out (B,S,H,W,2C+8) = [ feat[b, S-1] | feat[b, s] | flow_x, flow_y, 0 x 6 ]
+// The alignment head's input (reference :71-76, 81-86, 92-97):  out (B,S,H,W,Cs) = [ feat[b, S-1] | feat[b, s] | flow_x, flow_y, 0 ... ]
+// with Cs >= 2C+8 stored channels (Cs = 2C+16 keeps the 8-channel chunk count even for the tensor-core kernels)
 template <typename T>
 __global__ void pair_volume_kernel(const T* __restrict__ feat, const float* __restrict__ alpha, const float* __restrict__ fov, int B,
-                                   int C, int S, int H, int W, T* __restrict__ out) {
+                                   int C, int S, int H, int W, T* __restrict__ out, int Cs) {
   const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
   const int bs = blockIdx.z, b = bs / S, s = bs % S;
   if (px >= W) return;
@@ -862,13 +866,13 @@ __global__ void pair_volume_kernel(const T* __restrict__ feat, const float* __re
   const size_t pin = ((size_t)py * W + px) * C;
   const T* cur = feat + (size_t)bs * H * W * C + pin;
   const T* last = feat + ((size_t)b * S + (S - 1)) * H * W * C + pin;
-  T* o = out + (((size_t)bs * H + py) * W + px) * (2 * C + 8);
+  T* o = out + (((size_t)bs * H + py) * W + px) * Cs;
   for (int c = 0; c < C; c += 4) {
     Elem<T>::store4(o + c, Elem<T>::load4(last + c));
     Elem<T>::store4(o + C + c, Elem<T>::load4(cur + c));
   }
   Elem<T>::store4(o + 2 * C, make_float4(g.flx, g.fly, 0.f, 0.f));
-  Elem<T>::store4(o + 2 * C + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+  for (int c = 2 * C + 4; c < Cs; c += 4) Elem<T>::store4(o + c, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
 // alpha_out[b][c][s] = (alpha_in ? alpha_in[b][c][s] : 0) + scale[c] * mean over (y, x) of x[b,s,y,x,c]     (c < 3; x fp32, Cs stored)
@@ -951,11 +955,13 @@ int launch_fov_warp_cl(const void* x, const float* alpha, const float* fov, int 
   return 0;
 }
 int launch_pair_volume(const void* feat, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
-                       cudaStream_t st) {
+                       cudaStream_t st, int Cs) {
   if (C % 4) return fail(-1, "pair_volume: C must be a multiple of 4");
+  if (Cs == 0) Cs = 2 * C + 8;
+  if (Cs % 4 || Cs < 2 * C + 4) return fail(-1, "pair_volume: stored channels must be a multiple of 4 and >= 2C+4");
   dim3 grid(cdiv(W, 128), H, B * S);
-  if (bf16) pair_volume_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)feat, alpha, fov, B, C, S, H, W, (__nv_bfloat16*)out);
-  else pair_volume_kernel<<<grid, 128, 0, st>>>((const float*)feat, alpha, fov, B, C, S, H, W, (float*)out);
+  if (bf16) pair_volume_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)feat, alpha, fov, B, C, S, H, W, (__nv_bfloat16*)out, Cs);
+  else pair_volume_kernel<<<grid, 128, 0, st>>>((const float*)feat, alpha, fov, B, C, S, H, W, (float*)out, Cs);
   DFF_LAUNCH_CHECK("pair_volume");
   return 0;
 }

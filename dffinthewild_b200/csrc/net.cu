@@ -33,7 +33,7 @@ int launch_srd_attention_mma(const void* F, const float* w0, const float* w1, vo
 int launch_fov_warp_cl(const void* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
                        cudaStream_t st);
 int launch_pair_volume(const void* feat, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
-                       cudaStream_t st);
+                       cudaStream_t st, int Cs = 0);
 int launch_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, const float* alpha_in, float s0, float s1, float s2,
                               float* alpha_out, cudaStream_t st);
 int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
@@ -179,13 +179,14 @@ struct Net {
   int64_t raw_numel = 0;
   size_t packed_bytes = 0;
 
+  // cin_store > 0: the input tensor stores that many channels in both precisions (zero weights beyond cin)
   void add(const std::string& name, const std::string& bn, int cin, int cout, int kd, int kh, int kw, int stride, int dil,
-           bool transposed = false, bool bias = false) {
+           bool transposed = false, bool bias = false, int cin_store = 0) {
     Layer l{name, bn, cin, cout, kd, kh, kw, stride, dil, transposed, bias};
-    l.CinP = (int)align_up(cin, 4);
+    l.CinP = cin_store ? cin_store : (int)align_up(cin, 4);
     l.CoutP = (int)align_up(cout, 8);
     l.ntaps = kd * kh * kw;
-    l.CinT = (int)align_up(cin, 8);
+    l.CinT = cin_store ? cin_store : (int)align_up(cin, 8);
     l.Ntc = (int)align_up(cout, 16);
     auto reg = [&](const std::string& n, int64_t numel) {
       params.push_back({n, numel, raw_numel});
@@ -278,10 +279,37 @@ static Net build_dff() {
   return n;
 }
 
+// FlowNetwork(8), the End-to-End alignment network (reference End_to_End/End_to_End.py:18-61); keys relative to
+// `optical_flow_aggregation.`.  Every layer is per-slice 2-D: 1x3x3 or 1x1x1.
+static Net build_flow() {
+  Net n;
+  auto block = [&](const std::string& p, int cin, int cout, int stride) {   // resnet_block_2d_OF (reference :135-145)
+    n.cbn(p + ".conv.0", cin, cout, 1, 3, 3, stride);
+    n.cbn(p + ".conv.2", cout, cout, 1, 3, 3);
+    n.add(p + ".feature", "", cin, cout, 1, 1, 1, stride, 1);
+  };
+  block("OF_feature.0", 3, 8, 1);
+  block("OF_feature.1", 8, 8, 1);
+  block("OF_feature1.0", 8, 16, 2);
+  block("OF_feature1.1", 16, 16, 1);
+  block("OF_feature2.0", 16, 32, 2);
+  block("OF_feature2.1", 32, 32, 1);
+  auto head = [&](const std::string& p, int c) {   // reference :31-61: input = [last slice | slice | flow] = 2c+2 channels, stored as 2c+16
+    n.add(p + ".0.0", p + ".0.1", 2 * c + 2, 2 * c, 1, 3, 3, 1, 1, false, false, 2 * c + 16);
+    n.cbn(p + ".2", 2 * c, 2 * c, 1, 3, 3);
+    n.cbn(p + ".4", 2 * c, 2 * c, 1, 3, 3);
+    n.add(p + ".6", "", 2 * c, 3, 1, 3, 3, 1, 1, false, true);
+  };
+  head("conv1", 32);
+  head("conv2", 16);
+  head("conv3", 8);
+  return n;
+}
+
 static const Net& net_of(int which) {
   static const Net dffnet = build_dff();
-  (void)which;
-  return dffnet;
+  static const Net flownet = build_flow();
+  return which == DFF_NET_FLOW ? flownet : dffnet;
 }
 
 // ---- tap tables --------------------------------------------------------------------------------------------
@@ -622,6 +650,19 @@ struct Runner {
     return out;
   }
   Ten aux_last, proj_last;
+  void* alloc_bytes(size_t bytes) {
+    bytes = align_up(bytes, 256);
+    void* p = nullptr;
+    if (!dry) {
+      if (off + bytes > ws_bytes) {
+        if (!rc) rc = fail(DFF_E_WORKSPACE, "workspace too small");
+      } else {
+        p = ws + off;
+      }
+    }
+    off += bytes;
+    return p;
+  }
   Ten pool(const Ten& in, int k, bool is_max) {
     Ten out = alloc(in.B, in.S, in.H / k, in.W / k, in.C);
     const double ivox = (double)in.B * in.S * in.H * in.W;
@@ -826,6 +867,58 @@ static int forward_impl(const void* packed, const FwdIn& fin, const float* fd, c
   return 0;
 }
 
+// FlowNetwork.forward (reference End_to_End/End_to_End.py:63-104): three feature scales, coarse-to-fine estimation of the per-slice
+// similarity warp (alpha: scale correction x 0.001, x shift, y shift), final warp of the focal stack.  FS_out (B,3,S,H,W) fp32.
+static int flow_forward_impl(const void* packed, const float* FS, const float* fov, int B, int S, int H, int W, float* FS_out,
+                             float* alpha_out, void* ws, size_t ws_bytes, int mode, cudaStream_t st, bool dry, size_t* need) {
+  if (B < 1 || S < 1 || H < 4 || W < 4 || H % 4 || W % 4)
+    return fail(DFF_E_ARG, "dff_flow_forward: need B,S >= 1 and H,W positive multiples of 4");
+  g_pdl_call = (double)B * S * H * W <= 8.0 * 10 * 384 * 576;
+  Runner r{net_of(DFF_NET_FLOW), (const char*)packed, (char*)ws, ws_bytes, 0, dry, (mode & DFF_BF16) != 0, st};
+  r.use_tc = r.bf16 && !(mode & DFF_NO_TC);
+  r.use_slab = !(mode & DFF_NO_SLAB);
+  const int c_in = r.use_tc ? 8 : 4;
+  Ten x0 = r.alloc(B, S, H, W, c_in);
+  if (!dry && !r.rc) r.rc = launch_to_cl(FS, B, 3, S, H, W, x0.p, c_in, r.bf16, st);
+  auto block = [&](const std::string& p, const Ten& x) {
+    Ten t = r.conv(p + ".conv.0.0", x, Runner::relu());
+    Ten f = r.conv(p + ".feature", x);
+    EpiOpt e = Runner::relu();
+    e.res_pre = &f;
+    return r.conv(p + ".conv.2.0", t, e);
+  };
+  Ten fe1 = block("OF_feature.1", block("OF_feature.0", x0));
+  Ten fe2 = block("OF_feature1.1", block("OF_feature1.0", fe1));
+  Ten fe3 = block("OF_feature2.1", block("OF_feature2.0", fe2));
+  const float* alpha = nullptr;
+  const char* heads[3] = {"conv1", "conv2", "conv3"};
+  const Ten* feats[3] = {&fe3, &fe2, &fe1};
+  for (int k = 0; k < 3; ++k) {
+    const Ten& f = *feats[k];
+    const std::string h = heads[k];
+    Ten warped = r.alloc(f.B, f.S, f.H, f.W, f.C);
+    Ten vol = r.alloc(f.B, f.S, f.H, f.W, 2 * f.C + 16);
+    if (!dry && !r.rc) r.rc = launch_fov_warp_cl(f.p, alpha, fov, B, f.C, S, f.H, f.W, warped.p, r.bf16, st);
+    if (!dry && !r.rc) r.rc = launch_pair_volume(warped.p, alpha, fov, B, f.C, S, f.H, f.W, vol.p, r.bf16, st, 2 * f.C + 16);
+    Ten t = r.conv(h + ".0.0", vol, Runner::relu());
+    t = r.conv(h + ".2.0", t, Runner::relu());
+    t = r.conv(h + ".4.0", t, Runner::relu());
+    EpiOpt eo;
+    eo.out_f32 = true;
+    Ten o = r.conv(h + ".6", t, eo);                     // (B,S,h,w,3) fp32, bias in the epilogue
+    float* na = (float*)r.alloc_bytes((size_t)B * 3 * S * sizeof(float));
+    // AdaptiveAvgPool3d((S,1,1)) + the 0.001 factor on the scale term + the running sum (reference :78-79, 88-90, 99-101)
+    if (!dry && !r.rc) r.rc = launch_spatial_mean_accum((const float*)o.p, 3, B, S, f.H, f.W, alpha, 0.001f, 1.f, 1.f, na, st);
+    alpha = na;
+  }
+  if (need) *need = r.off;
+  if (dry) return 0;
+  if (r.rc) return r.rc;
+  DFF_TRY(launch_fov_warp(FS, alpha, fov, B, 3, S, H, W, FS_out, nullptr, st));
+  if (alpha_out) DFF_CUDA(cudaMemcpyAsync(alpha_out, alpha, (size_t)B * 3 * S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 struct DeviceGuard {
   int prev = -1;
   int rc = 0;
@@ -935,6 +1028,21 @@ int dff_forward(const void* packed, const float* FS, const float* fd, const int6
   if (g.rc) return g.rc;
   return forward_impl(packed, FwdIn(FS), fd, fd_strides, B, S, H, W, out4, cost4, workspace, workspace_bytes, mode,
                       (cudaStream_t)stream, false, nullptr);
+}
+
+size_t dff_flow_workspace_bytes(int B, int S, int H, int W, int mode) {
+  size_t need = 0;
+  if (flow_forward_impl(nullptr, nullptr, nullptr, B, S, H, W, nullptr, nullptr, nullptr, 0, mode, nullptr, true, &need)) return 0;
+  return need;
+}
+
+int dff_flow_forward(const void* packed_flow, const float* FS, const float* fov, int B, int S, int H, int W, float* FS_out,
+                     float* alpha_out, void* workspace, size_t workspace_bytes, int mode, int device, void* stream) {
+  if (!packed_flow || !FS || !fov || !FS_out || !workspace) return fail(DFF_E_ARG, "dff_flow_forward: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return flow_forward_impl(packed_flow, FS, fov, B, S, H, W, FS_out, alpha_out, workspace, workspace_bytes, mode,
+                           (cudaStream_t)stream, false, nullptr);
 }
 
 int dff_forward_u8(const void* packed, const uint8_t* FS_u8, int H0, int W0, const float* fd, const int64_t fd_strides[4], int B,
@@ -1556,7 +1664,7 @@ int dff_pair_volume(const void* feat, const float* alpha, const float* fov, int 
   if (!feat || !fov || !out) return fail(DFF_E_ARG, "dff_pair_volume: null pointer");
   DeviceGuard g(device);
   if (g.rc) return g.rc;
-  return launch_pair_volume(feat, alpha, fov, B, C, S, H, W, out, elem == DFF_BF16, (cudaStream_t)stream);
+  return launch_pair_volume(feat, alpha, fov, B, C, S, H, W, out, elem == DFF_BF16, (cudaStream_t)stream, 0);
 }
 int dff_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, const float* alpha_in, float s0, float s1, float s2,
                            float* alpha_out, int device, void* stream) {

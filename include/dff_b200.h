@@ -265,8 +265,15 @@ int dff_depth_head_backward(const float *cost, int h, int w, const float *fd, co
                             int W, const float *ddepth, float *dcost, int device, void *stream);
 
 /* ---- End-to-End alignment network (FlowNetwork.forward, End_to_End/End_to_End.py:63-104) --------------------------------------
- * dffinthewild_b200/End_to_End.py composes it from dff_conv3d (the six resnet_block_2d_OF blocks and the three alignment heads,
- * all 1x3x3 / 1x1x1 convolutions on channels-last volumes) and the three calls below. */
+ * dff_flow_forward runs the whole alignment network in one call: six resnet_block_2d_OF blocks, three alignment heads (BatchNorm
+ * folded once by dff_pack_weights(DFF_NET_FLOW)), the feature warps, the pairwise volumes, the per-slice spatial means and the final
+ * FOV_warp of the focal stack.  FS (B,3,S,H,W) fp32, fov (B,S) fp32 -> FS_out (B,3,S,H,W) fp32; alpha_out (B,3,S) optional: the
+ * estimated (scale correction, x shift, y shift) per slice.  mode: DFF_FP32 (FFMA parity path) or DFF_BF16 (tcgen05 kernels, bf16
+ * feature volumes; alpha, the final warp and the stack stay fp32).  H, W multiples of 4.  The three single operators below are its
+ * building blocks (unit-parity surface). */
+size_t dff_flow_workspace_bytes(int B, int S, int H, int W, int mode);
+int dff_flow_forward(const void *packed_flow, const float *FS, const float *fov, int B, int S, int H, int W, float *FS_out,
+                     float *alpha_out, void *workspace, size_t workspace_bytes, int mode, int device, void *stream);
 /* FOV_warp (End_to_End.py:106-134) of a channels-last volume (B,S,H,W,C), C % 4 == 0; alpha (B,3,S) or NULL, fov (B,S) */
 int dff_fov_warp_cl(const void *x, const float *alpha, const float *fov, int B, int C, int S, int H, int W, void *out, int elem,
                     int device, void *stream);

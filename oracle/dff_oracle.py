@@ -217,8 +217,8 @@ def _pair_volume(fe, flow):
     return torch.cat((last, fe, flow), 1).contiguous()
 
 
-def flow_forward(sd, FS, fovs, prefix="optical_flow_aggregation.", train=False):
-    """FlowNetwork.forward (E2E:63-104): returns the aligned focal stack."""
+def flow_forward(sd, FS, fovs, prefix="optical_flow_aggregation.", train=False, return_alpha=False):
+    """FlowNetwork.forward (E2E:63-104): returns the aligned focal stack [and the accumulated alpha (B,3,S,1,1)]."""
     c = Ctx(sd, train, prefix)
     fe1 = _res2d_of(c, _res2d_of(c, FS, "OF_feature.0", 1), "OF_feature.1", 1)
     fe2 = _res2d_of(c, _res2d_of(c, fe1, "OF_feature1.0", 2), "OF_feature1.1", 1)
@@ -234,7 +234,7 @@ def flow_forward(sd, FS, fovs, prefix="optical_flow_aggregation.", train=False):
     na = _align_head(c, _pair_volume(fe1, flow), "conv3")
     alpha = torch.cat((0.001 * na[:, :1], na[:, 1:]), 1) + alpha
     out, _ = fov_warp(FS, alpha, fovs)
-    return out
+    return (out, alpha) if return_alpha else out
 
 
 def e2e_forward(sd, FS, focus_dists, fovs):
