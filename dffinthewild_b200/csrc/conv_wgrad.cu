@@ -11,6 +11,8 @@
 // channels, sums over all positions of the tile in registers (one activation load feeds COB FMAs, the dy row is a shared-memory
 // broadcast), and adds its partial sums to the fp32 gradient in the reference's weight layout with red.global.add.f32.
 // fp32 accumulate; the order of the global adds is not fixed, which moves results by ~1e-7 relative (gate: gradient cosine).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dff {
@@ -124,6 +126,201 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_kernel(const __grid_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// bf16 weight gradient on the tensor cores (warp-level mma.sync m16n8k16, fp32 accumulate).
+//
+//   dW_t[ci][co] = sum over the tile's positions p of  X[p*is + d_t][ci] * dY[p][co]        = (X_t^T) (dY):  M = ci, N = co, K = positions
+//
+// Both operands are channels-last, i.e. K-rows of contiguous M / N elements — exactly what ldmatrix.trans turns into the A (row) and
+// B (col) fragments: a tap is a different base address of the same staged input region, a stride-2 layer a different row pitch, so
+// ordinary, strided and (per output-parity phase) transposed convolutions and the two-source concat share the kernel.  One CTA owns
+// 32 x TY output positions of one (batch, slice); it stages the halo'd input region for CK channels and the dy tile (all output
+// channels) in shared memory as bf16, its 8 warps split the (tap, 16-channel block, 8-output-channel block) accumulators — 8-channel
+// tensors pair two taps in one m16 block — and each accumulator runs over the tile's K = 32*TY positions in registers before it is
+// added to the fp32 gradient (reference weight layout) with red.global.add.f32.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4_t(unsigned addr, unsigned& r0, unsigned& r1, unsigned& r2, unsigned& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(unsigned addr, unsigned& r0, unsigned& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* d, unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct WgradMmaArgs {
+  WgradArgs w;
+  int CK, TY;      // channels staged per pass (8, 16, 32 or 64); tile rows
+};
+
+__global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __grid_constant__ WgradMmaArgs ga) {
+  extern __shared__ __align__(16) unsigned char smem_b[];
+  const WgradArgs& g = ga.w;
+  const ConvArgs& a = g.a;
+  const int CK = ga.CK, TY = ga.TY;
+  const int REGPOS = a.RZ * a.RY * a.RX;
+  const int NP = 32 * TY;
+  const int CoP = (g.Cout + 7) & ~7;
+  __nv_bfloat16* in_s = reinterpret_cast<__nv_bfloat16*>(smem_b);            // [REGPOS][CK]
+  __nv_bfloat16* dy_s = in_s + (size_t)REGPOS * CK;                           // [NP][CoP]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bs = blockIdx.z, b = bs / a.S, s = bs % a.S;
+  const int ty0 = blockIdx.y * TY, tx0 = blockIdx.x * 32;
+  const int gy0 = ty0 * a.isy + a.dymin, gx0 = tx0 * a.isx + a.dxmin, gz0 = s + a.dzmin;
+
+  // ---- dy tile, bf16, zero outside the phase grid ---------------------------------------------------------------------
+  {
+    const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(g.dy);
+    const int q8 = CoP / 8;
+    for (int i = tid; i < NP * q8; i += kWgThreads) {
+      const int q = i % q8, pos = i / q8;
+      const int ox = tx0 + (pos & 31), oy = ty0 + (pos >> 5);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (ox < a.OWt && oy < a.OHt && 8 * q < g.CoS) {
+        const size_t pix = (((size_t)b * a.S + s) * a.OH + (oy * a.osy + a.ooy)) * a.OW + (ox * a.osx + a.oox);
+        v = __ldg(reinterpret_cast<const uint4*>(dy + pix * g.CoS + 8 * q));
+      }
+      *reinterpret_cast<uint4*>(dy_s + (size_t)pos * CoP + 8 * q) = v;
+    }
+  }
+  const int Ctot = a.C0 + a.C1;
+  const int s8 = CK / 8;                         // 8-channel slots per tap
+  const int nslots = a.taps.n * s8;
+  const int nmt = (nslots + 1) / 2;              // m16 blocks: two consecutive slots each
+  const int nnt = CoP / 8;
+  const int ngrp = (nnt + 1) / 2;                // n8 blocks are taken two at a time
+  const int nitems = nmt * ngrp;
+  const unsigned in_u = (unsigned)__cvta_generic_to_shared(in_s), dy_u = (unsigned)__cvta_generic_to_shared(dy_s);
+  // ldmatrix row this lane supplies: matrix j = lane / 8 -> (m half j & 1, k half j >> 1), row r = lane % 8 -> position k = 8*(j>>1) + r
+  const int lj = lane >> 3, lr = lane & 7, lk = 8 * (lj >> 1) + lr;
+  const int gq = lane >> 2, t4 = lane & 3;
+
+  for (int c0 = 0; c0 < Ctot; c0 += CK) {
+    const bool second = c0 >= a.C0;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(second ? a.in1 : a.in0);
+    const int Csrc = second ? a.C1 : a.C0;
+    const int cb = second ? c0 - a.C0 : c0;
+    __syncthreads();
+    for (int i = tid; i < REGPOS * s8; i += kWgThreads) {
+      const int q = i % s8, pos = i / s8;
+      const int x = pos % a.RX, y = (pos / a.RX) % a.RY, z = pos / (a.RX * a.RY);
+      const int gz = gz0 + z, gy = gy0 + y, gx = gx0 + x;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (gz >= 0 && gz < a.S && gy >= 0 && gy < a.IH && gx >= 0 && gx < a.IW)
+        v = __ldg(reinterpret_cast<const uint4*>(src + ((((size_t)b * a.S + gz) * a.IH + gy) * a.IW + gx) * Csrc + cb + 8 * q));
+      *reinterpret_cast<uint4*>(in_s + (size_t)pos * CK + 8 * q) = v;
+    }
+    __syncthreads();
+    for (int it = warp; it < nitems; it += kWgThreads / 32) {
+      const int mt = it / ngrp, ng = it - mt * ngrp;
+      const int slot0 = 2 * mt, slot1 = min(2 * mt + 1, nslots - 1);
+      const int myslot = (lj & 1) ? slot1 : slot0;
+      const int tap = myslot / s8, c8 = myslot - tap * s8;
+      // element offset of this lane's row at k-step 0: tap origin + its position's pixel + its channel group
+      const int rowbase = ((((int)a.taps.dz[tap] - a.dzmin) * a.RY + ((int)a.taps.dy[tap] - a.dymin)) * a.RX + ((int)a.taps.dx[tap] - a.dxmin) +
+                           lk * a.isx) * CK + 8 * c8;
+      const int n0 = 2 * ng, n1 = min(2 * ng + 1, nnt - 1);
+      const unsigned brow = dy_u + 2u * (unsigned)((lane & 15) * CoP);
+      float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int ks = 0; ks < 2 * TY; ++ks) {
+        // 16 consecutive positions of one tile row: row ks / 2, columns 16 * (ks & 1) ...
+        const int koff = ((ks >> 1) * a.isy * a.RX + (ks & 1) * 16 * a.isx) * CK;
+        unsigned a0, a1, a2, a3, b0, b1;
+        ldsm_x4_t(in_u + 2u * (unsigned)(rowbase + koff), a0, a1, a2, a3);
+        const unsigned bk = brow + 2u * (unsigned)(ks * 16 * CoP);
+        ldsm_x2_t(bk + 16u * (unsigned)n0, b0, b1);
+        mma_bf16_16816(acc0, a0, a1, a2, a3, b0, b1);
+        if (n1 != n0) {
+          ldsm_x2_t(bk + 16u * (unsigned)n1, b0, b1);
+          mma_bf16_16816(acc1, a0, a1, a2, a3, b0, b1);
+        }
+      }
+      // d0,d1: (m = gq, n = 2*t4, 2*t4+1) ; d2,d3: (m = gq + 8, ...): m < 8 belongs to slot0, m >= 8 to slot1
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int slot = half ? 2 * mt + 1 : slot0;
+        if (slot >= nslots) continue;
+        const int tp = slot / s8, cc = slot - tp * s8;
+        const int cig = g.ci_base + c0 + 8 * cc + gq;
+        if (cig >= g.Cin) continue;
+        const int wi = a.taps.widx[tp];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          if (nb == 1 && n1 == n0) continue;
+          const float* acc = nb ? acc1 : acc0;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int co = 8 * (nb ? n1 : n0) + 2 * t4 + e;
+            if (co >= g.Cout) continue;
+            const size_t o = g.wt_transposed ? ((size_t)cig * g.Cout + co) * g.ntaps_total + wi
+                                             : ((size_t)co * g.Cin + cig) * g.ntaps_total + wi;
+            atomicAdd(g.dw + o, acc[2 * half + e]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// plan: input region extent for a tile of TY rows; returns the shared-memory bytes of the mma kernel for (CK, TY)
+static size_t wg_mma_plan(ConvArgs& a, int CK, int TY, int Cout) {
+  int dzmax = -100, dymax = -100, dxmax = -100;
+  a.dzmin = a.dymin = a.dxmin = 100;
+  for (int t = 0; t < a.taps.n; ++t) {
+    a.dzmin = a.taps.dz[t] < a.dzmin ? a.taps.dz[t] : a.dzmin;
+    a.dymin = a.taps.dy[t] < a.dymin ? a.taps.dy[t] : a.dymin;
+    a.dxmin = a.taps.dx[t] < a.dxmin ? a.taps.dx[t] : a.dxmin;
+    dzmax = a.taps.dz[t] > dzmax ? a.taps.dz[t] : dzmax;
+    dymax = a.taps.dy[t] > dymax ? a.taps.dy[t] : dymax;
+    dxmax = a.taps.dx[t] > dxmax ? a.taps.dx[t] : dxmax;
+  }
+  a.TY = TY;
+  a.RZ = dzmax - a.dzmin + 1;
+  a.RY = (TY - 1) * a.isy + (dymax - a.dymin) + 1;
+  a.RX = 31 * a.isx + (dxmax - a.dxmin) + 1;
+  a.RXP = a.RX;
+  const int CoP = (Cout + 7) & ~7;
+  return ((size_t)a.RZ * a.RY * a.RX * CK + (size_t)32 * TY * CoP) * 2;
+}
+
+static int launch_conv_wgrad_mma(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, int ci_base, float* dw, int ntaps_total,
+                                 int wt_transposed, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (a.C0 % 8 || a.C1 % 8 || CoS % 8 || a.C0 < 8) return 0;
+  // channels per pass: the largest of 64, 32, 16 that divides both sources (8-channel tensors: 8, two taps per m16 block)
+  int CK = 8;
+  for (int c = 64; c >= 16; c >>= 1)
+    if (a.C0 % c == 0 && a.C1 % c == 0) { CK = c; break; }
+  const size_t budget = 110 * 1024;   // two CTAs per SM
+  int TY = 0;
+  size_t smem = 0;
+  for (;; CK >>= 1) {
+    for (int ty = 16; ty >= 2; ty >>= 1) {
+      if (ty > 2 && (ty >> 1) >= a.OHt) continue;      // no taller than the phase grid needs
+      ConvArgs t = a;
+      const size_t sz = wg_mma_plan(t, CK, ty, Cout);
+      if (sz <= budget) { TY = ty; smem = sz; break; }
+    }
+    if (TY || CK == 8) break;
+  }
+  if (!TY) return 0;
+  WgradMmaArgs ga{};
+  wg_mma_plan(a, CK, TY, Cout);
+  ga.w.a = a; ga.w.dy = dy; ga.w.CoS = CoS; ga.w.Cout = Cout; ga.w.Cin = Cin; ga.w.dw = dw; ga.w.ntaps_total = ntaps_total;
+  ga.w.wt_transposed = wt_transposed; ga.w.ci_base = ci_base;
+  ga.CK = CK; ga.TY = TY;
+  dim3 grid(cdiv(a.OWt, 32), cdiv(a.OHt, TY), a.B * a.S);
+  DFF_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_wgrad_mma_kernel<<<grid, kWgThreads, smem, st>>>(ga);
+  DFF_LAUNCH_CHECK("conv_wgrad_mma");
+  *handled = true;
+  return 0;
+}
+
 static size_t wg_plan(ConvArgs& a, int CK, int Cout) {
   int dzmax = -100, dymax = -100, dxmax = -100;
   a.dzmin = a.dymin = a.dxmin = 100;
@@ -148,6 +345,12 @@ static size_t wg_plan(ConvArgs& a, int CK, int Cout) {
 int launch_conv_wgrad(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, int ci_base, float* dw, int ntaps_total,
                       int wt_transposed, bool bf16, cudaStream_t st) {
   if (a.C0 % 4 || a.C1 % 4) return fail(-1, "conv_wgrad: stored input channels must be multiples of 4");
+  static const bool no_mma = getenv("DFF_B200_WGRAD_FFMA") != nullptr;   // A/B switch: the fp32-FMA kernel also for bf16 tensors
+  if (bf16 && !no_mma) {
+    bool handled = false;
+    DFF_TRY(launch_conv_wgrad_mma(a, dy, CoS, Cout, Cin, ci_base, dw, ntaps_total, wt_transposed, st, &handled));
+    if (handled) return 0;
+  }
   WgradArgs g{};
   int CK = (a.C0 % 8 == 0 && a.C1 % 8 == 0) ? 8 : 4;
   size_t smem = wg_plan(a, CK, Cout);

@@ -386,19 +386,19 @@ template <int R> struct QuadTaps {
   int o0, o1;         // source row offsets (elements)
   float ly, lx[4];
   __device__ __forceinline__ void init(int t, int y, int h, int w, int H) {
-    // rows: ATen's upsample_bilinear2d (align_corners=False): src = scale*(dst+0.5)-0.5, clamped at 0
-    float fy = (float)h / (float)H * ((float)y + 0.5f) - 0.5f;
+    // rows: ATen's upsample_bilinear2d (align_corners=False): src = scale*(dst+0.5)-0.5, clamped at 0 (scale = 1/R exactly)
+    float fy = (1.f / (float)R) * ((float)y + 0.5f) - 0.5f;
     fy = fy < 0.f ? 0.f : fy;
     const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
     ly = fy - (float)y0;
     o0 = y0 * w; o1 = y1 * w;
     const int x = 4 * t;
-    const int c0 = R == 1 ? x : (int)floorf(((float)x + 0.5f) / (float)R - 0.5f);
+    const int c0 = R == 1 ? x : (int)floorf(((float)x + 0.5f) * (1.f / (float)R) - 0.5f);
 #pragma unroll
     for (int j = 0; j < NC; ++j) col[j] = min(max(c0 + j, 0), w - 1);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float fx = ((float)(x + k) + 0.5f) / (float)R - 0.5f;     // exact: R is a power of two
+      const float fx = ((float)(x + k) + 0.5f) * (1.f / (float)R) - 0.5f;     // exact: R is a power of two
       const float x0 = floorf(fx);
       lx[k] = (R == 1 || x0 < 0.f || x0 >= (float)(w - 1)) ? 0.f : fx - x0;
     }
@@ -428,10 +428,14 @@ template <int R> struct QuadTaps {
 // p = softplus(v) + 1e-6 with two SFU operations and fp32-grade accuracy everywhere: max(v,0) + log1p(exp(-|v|)), where log1p of a
 // small argument is its series (the plain log(1 + e) loses e's low bits below ~1e-3 — visible when every slice of a pixel is
 // strongly negative and the normalisation divides two sums of such terms).
+// (returns softplus(v) WITHOUT the +1e-6: the caller adds S*1e-6 to the denominator and 1e-6*sum(fd) to the numerator once per pixel)
 __device__ __forceinline__ float softplus_sfu(float v) {
-  const float e = __expf(-fabsf(v));
-  const float l = e < 3.9e-3f ? e * fmaf(e, fmaf(e, 0.33333334f, -0.5f), 1.f) : __logf(1.f + e);
-  return fmaxf(v, 0.f) + l + 1e-6f;
+  float e, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(v) * -1.4426950408889634f));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + e));
+  l *= 0.6931471805599453f;
+  const float ser = e * fmaf(e, -0.5f, 1.f);      // log1p(e) for small e (error e^3/3 < 2e-8)
+  return fmaxf(v, 0.f) + (e < 3.9e-3f ? ser : l);
 }
 __device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -447,11 +451,12 @@ __global__ void __launch_bounds__(128, 4) depth_head4_quad_kernel(const __grid_c
                                                                   long long ss, long long sy, long long sx, int B, int S, int H, int W) {
   __shared__ float4 ring_c[kHeadRing][128];
   __shared__ float4 ring_f[FDMODE == 1 ? kHeadRing : 1][128];
+  // block = 32 quads (128 pixels) x 4 rows; grid = (row segments, H / 4, B)
   const int W4 = W >> 2;
-  size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const bool live = q < (size_t)B * H * W4;
-  if (!live) q = 0;   // (keeps the thread's loads in range; it stores nothing)
-  const int t = (int)(q % W4), y = (int)((q / W4) % H), b = (int)(q / ((size_t)W4 * H));
+  int t = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 4 + (threadIdx.x >> 5), b = blockIdx.z;
+  const bool live = t < W4;
+  if (!live) t = 0;   // (keeps the thread's loads in range; it stores nothing)
   QuadTaps<8> t0; QuadTaps<4> t1; QuadTaps<2> t2;
   t0.init(t, y, a.h[0], a.w[0], H); t1.init(t, y, a.h[1], a.w[1], H); t2.init(t, y, a.h[2], a.w[2], H);
   const int sl0 = a.h[0] * a.w[0], sl1 = a.h[1] * a.w[1], sl2 = a.h[2] * a.w[2];
@@ -469,7 +474,7 @@ __global__ void __launch_bounds__(128, 4) depth_head4_quad_kernel(const __grid_c
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  float num[4][4], den[4][4];
+  float num[4][4], den[4][4], fsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int hd = 0; hd < 4; ++hd)
 #pragma unroll
@@ -497,6 +502,8 @@ __global__ void __launch_bounds__(128, 4) depth_head4_quad_kernel(const __grid_c
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
+    for (int k = 0; k < 4; ++k) fsum[k] += f[k];
+#pragma unroll
     for (int hd = 0; hd < 4; ++hd)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -506,11 +513,16 @@ __global__ void __launch_bounds__(128, 4) depth_head4_quad_kernel(const __grid_c
       }
   }
   if (!live) return;
+  // p = softplus + 1e-6 (reference :93): the constant enters the two sums once per pixel
+  const float eps_den = 1e-6f * (float)S;
   const size_t o = ((size_t)b * H + y) * W + 4 * t;
 #pragma unroll
-  for (int hd = 0; hd < 4; ++hd)
-    *reinterpret_cast<float4*>(a.depth[hd] + o) = make_float4(__fdividef(num[hd][0], den[hd][0]), __fdividef(num[hd][1], den[hd][1]),
-                                                              __fdividef(num[hd][2], den[hd][2]), __fdividef(num[hd][3], den[hd][3]));
+  for (int hd = 0; hd < 4; ++hd) {
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = __fdividef(fmaf(1e-6f, fsum[k], num[hd][k]), den[hd][k] + eps_den);
+    *reinterpret_cast<float4*>(a.depth[hd] + o) = make_float4(r[0], r[1], r[2], r[3]);
+  }
 }
 
 // cost[0..2]: upsampled heads (any resolution dividing H, W) ; cost[3]: the full-resolution head.  fast: SFU exp/log.
@@ -527,9 +539,8 @@ int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4
                        W == w[3] && w[0] >= 2 && h[0] >= 1;
   bool aligned = (reinterpret_cast<uintptr_t>(cost[3]) % 16 == 0);
   for (int k = 0; k < 4; ++k) aligned = aligned && (reinterpret_cast<uintptr_t>(depth[k]) % 16 == 0);
-  if (fast && pyramid && aligned && !no_quad) {
-    const size_t nq = (size_t)B * H * (W / 4);
-    const unsigned g = (unsigned)((nq + 127) / 128);
+  if (fast && pyramid && aligned && !no_quad && B <= 65535) {
+    const dim3 g(cdiv(W / 4, 32), H / 4, B);
     const bool fd_scalar = st4[2] == 0 && st4[3] == 0;
     const bool fd_vec = st4[3] == 1 && st4[2] % 4 == 0 && st4[1] % 4 == 0 && st4[0] % 4 == 0 && reinterpret_cast<uintptr_t>(fd) % 16 == 0;
     if (fd_scalar) depth_head4_quad_kernel<2><<<g, 128, 0, st>>>(a, fd, st4[0], st4[1], st4[2], st4[3], B, S, H, W);

@@ -279,3 +279,58 @@ def test_golden_g7_training_loop_trajectory(built_lib, precision, rtol):
         with torch.no_grad():
             o = net(FS.cuda(), fd.cuda())
         assert all(torch.isfinite(t).all() for t in o)
+
+
+WGRAD_CASES = [
+    # name, C0, C1, Cout, k, stride, dil, transposed, S, H, W
+    ("c3_16_8", 16, 0, 8, (3, 3, 3), 1, 1, False, 3, 40, 72),
+    ("c3_8+8_8_two_sources", 8, 8, 8, (3, 3, 3), 1, 1, False, 3, 32, 64),
+    ("srd_1x3x3_8_8_tap_pairs", 8, 0, 8, (1, 3, 3), 1, 1, False, 2, 32, 40),
+    ("fm_9x9_dil2_first_layer", 8, 0, 8, (1, 9, 9), 1, 2, False, 2, 32, 64),
+    ("s2_8_16", 8, 0, 16, (3, 3, 3), 2, 1, False, 3, 64, 96),
+    ("s2_32_64", 32, 0, 64, (3, 3, 3), 2, 1, False, 2, 24, 40),
+    ("c3_64_64", 64, 0, 64, (3, 3, 3), 1, 1, False, 3, 12, 20),
+    ("c3_128+64_128", 128, 64, 128, (3, 3, 3), 1, 1, False, 2, 6, 10),
+    ("up_32_16", 32, 0, 16, (3, 3, 3), 2, 1, True, 3, 16, 24),
+    ("up_16_8", 16, 0, 8, (3, 3, 3), 2, 1, True, 2, 32, 48),
+    ("att_3x1x1_16", 16, 0, 16, (3, 1, 1), 1, 1, False, 5, 16, 48),
+    ("cls_1x1x1_8_1", 8, 0, 1, (1, 1, 1), 1, 1, False, 2, 32, 64),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=[c[0] for c in WGRAD_CASES])
+def test_wgrad_tensor_core_kernel(built_lib, case):
+    """bf16 weight gradient (C-ABI dff_conv3d_wgrad, warp-level tensor-core kernel) against torch's fp64 convolution weight
+    gradient on the same bf16-rounded operands: exact products, fp32 accumulation -> 2e-5 of the largest entry (the only error is
+    fp32 summation order over B*S*OH*OW terms); every layer class of the network incl. strided, transposed, two-source, dilated."""
+    import ctypes
+    import torch.nn.functional as F
+    from dffinthewild_b200 import runtime as rt
+    from dffinthewild_b200 import train as tr
+    name, c0, c1, cout, k, stride, dil, transposed, S, H, W = case
+    l = tr._lib()
+    B = 2
+    g = torch.Generator().manual_seed(71)
+    cin = c0 + c1
+    x = (torch.rand(B, cin, S, H, W, generator=g) * 2 - 1).bfloat16().float()
+    OH, OW = (2 * H, 2 * W) if transposed else (H // stride, W // stride)
+    cos = max(8, (cout + 7) // 8 * 8)
+    dy = (torch.rand(B, cout, S, OH, OW, generator=g) * 2 - 1).bfloat16().float()
+    wshape = (cin, cout) + k if transposed else (cout, cin) + k
+    w = torch.zeros(wshape, dtype=torch.float64, requires_grad=True)
+    if transposed:
+        y = F.conv_transpose3d(x.double(), w, None, stride=(1, 2, 2), padding=1, output_padding=(0, 1, 1))
+    else:
+        pad = ((k[0] - 1) // 2, dil * (k[1] - 1) // 2, dil * (k[2] - 1) // 2)
+        y = F.conv3d(x.double(), w, None, (1, stride, stride), pad, (1, dil, dil))
+    (y * dy.double()).sum().backward()
+    ref = w.grad
+    x0 = rt.to_channels_last(x[:, :c0].cuda().contiguous(), c0, True)
+    x1 = rt.to_channels_last(x[:, c0:].cuda().contiguous(), c1, True) if c1 else None
+    dyc = rt.to_channels_last(dy.cuda(), cos, True)
+    dw = torch.full(wshape, float("nan"), dtype=torch.float32, device="cuda")
+    rt.check(l.dff_conv3d_wgrad(x0.data_ptr(), c0, x1.data_ptr() if c1 else None, c1, B, S, H, W, dyc.data_ptr(), cos, cin, cout, k[0], k[1],
+                                k[2], 2 if transposed else stride, dil, 1 if transposed else 0, dw.data_ptr(), rt.BF16, 0,
+                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    err = (dw.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item(), (name, err, ref.abs().max().item())
