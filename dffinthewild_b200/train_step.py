@@ -75,8 +75,13 @@ def masked_mse_loss(outs, gt, mask, weights):
 class TrainStep:
     """Flat parameter / gradient / Adam-state buffers + the step of the reference's training loop."""
 
-    def __init__(self, model, lr, betas=(0.9, 0.99), eps=1e-8, weights=(0.3, 0.5, 0.7, 1.0), group=None):
+    def __init__(self, model, lr, betas=(0.9, 0.99), eps=1e-8, weights=(0.3, 0.5, 0.7, 1.0), group=None, use_graph=True):
         self.model, self.lr, self.betas, self.eps, self.weights, self.group = model, lr, betas, eps, weights, group
+        # forward + loss + backward of a fixed-shape step are ~1500 kernel launches behind ~3000 Python-level operator calls: after two
+        # eager steps they are captured into ONE CUDA graph (static input buffers) and replayed, which takes the host out of the loop.
+        # The gradient all-reduce and the Adam kernel (whose bias corrections change every step) stay outside the graph.
+        self.use_graph = use_graph and not isinstance(model, torch.nn.DataParallel)
+        self._graph, self._static, self._eager_steps = None, None, 0
         net = model.module if isinstance(model, torch.nn.DataParallel) else model
         self.skip = D.unused_parameter_names(net)
         self.bucket = D.GradBucket(net, skip=self.skip)
@@ -118,12 +123,50 @@ class TrainStep:
         self._ar_events[-1][1].synchronize()
         return sum(a.elapsed_time(b) for a, b in self._ar_events) / len(self._ar_events)
 
-    def step(self, FS, fd, gt, mask, time_allreduce=False):
-        info = {}
+    def _fwd_bwd(self, FS, fd, gt, mask):
         outs = self.model(FS, fd)
         self.bucket.zero()
         loss = masked_mse_loss(outs, gt, mask, self.weights)
         loss.backward()
+        return loss.detach()
+
+    def _fwd_bwd_graphed(self, FS, fd, gt, mask):
+        sig = tuple((tuple(t.shape), t.dtype, tuple(t.stride())) for t in (FS, fd, gt, mask))
+        if self._graph is not None and self._static["sig"] == sig:
+            st = self._static
+            for dst, src in zip(st["in"], (FS, fd, gt, mask)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src)
+            self._graph.replay()
+            return st["loss"]
+        if self._eager_steps < 2 or self._graph is False:
+            self._eager_steps += 1
+            return self._fwd_bwd(FS, fd, gt, mask)
+        try:
+            self.bucket.rebind()
+            static_in = [t.clone() for t in (FS, fd, gt, mask)]
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                loss = self._fwd_bwd(*static_in)
+            self._graph, self._static = graph, {"sig": sig, "in": static_in, "loss": loss}
+            return loss        # (capture does not execute: the caller gets this step's numbers from the replay below)
+        except Exception as ex:   # capture is an optimisation: report once, keep training eagerly
+            import warnings
+            warnings.warn("dff_b200: CUDA-graph capture of the training step failed (%s: %s); running eagerly" % (type(ex).__name__, ex))
+            self._graph = False
+            torch.cuda.synchronize()
+            return self._fwd_bwd(FS, fd, gt, mask)
+
+    def step(self, FS, fd, gt, mask, time_allreduce=False):
+        info = {}
+        if self.use_graph:
+            captured_before = self._graph not in (None, False)
+            loss = self._fwd_bwd_graphed(FS, fd, gt, mask)
+            if not captured_before and self._graph not in (None, False):
+                self._graph.replay()      # the step that captured the graph has not run yet
+        else:
+            loss = self._fwd_bwd(FS, fd, gt, mask)
         world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
         if world > 1:
             n_r = mask.sum().float()
@@ -144,5 +187,6 @@ class TrainStep:
             if time_allreduce:
                 self._ar_events.append((a0, a1))     # read after the timed loop (no host sync inside a step)
         self._adam()
-        info["loss"] = loss.detach()
+        info["loss"] = loss
+        info["graphed"] = self._graph not in (None, False)
         return info
