@@ -11,6 +11,7 @@
 // channels, sums over all positions of the tile in registers (one activation load feeds COB FMAs, the dy row is a shared-memory
 // broadcast), and adds its partial sums to the fp32 gradient in the reference's weight layout with red.global.add.f32.
 // fp32 accumulate; the order of the global adds is not fixed, which moves results by ~1e-7 relative (gate: gradient cosine).
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -155,6 +156,8 @@ __device__ __forceinline__ void mma_bf16_16816(float* d, unsigned a0, unsigned a
 struct WgradMmaArgs {
   WgradArgs w;
   int CK, TY;      // channels staged per pass (8, 16, 32 or 64); tile rows
+  int nsplit;      // CTAs per tile: low-resolution layers have few tiles but thousands of accumulators — the accumulator list is dealt
+                   // round-robin to `nsplit` CTAs that stage the same (L2-resident) region (blockIdx.x = tile_x * nsplit + split)
 };
 
 __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __grid_constant__ WgradMmaArgs ga) {
@@ -169,7 +172,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
   __nv_bfloat16* dy_s = in_s + (size_t)REGPOS * CK;                           // [NP][CoP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bs = blockIdx.z, b = bs / a.S, s = bs % a.S;
-  const int ty0 = blockIdx.y * TY, tx0 = blockIdx.x * 32;
+  const int split = blockIdx.x % ga.nsplit;
+  const int ty0 = blockIdx.y * TY, tx0 = (blockIdx.x / ga.nsplit) * 32;
   const int gy0 = ty0 * a.isy + a.dymin, gx0 = tx0 * a.isx + a.dxmin, gz0 = s + a.dzmin;
 
   // ---- dy tile, bf16, zero outside the phase grid ---------------------------------------------------------------------
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
       *reinterpret_cast<uint4*>(in_s + (size_t)pos * CK + 8 * q) = v;
     }
     __syncthreads();
-    for (int it = warp; it < nitems; it += kWgThreads / 32) {
+    for (int it = split * (kWgThreads / 32) + warp; it < nitems; it += ga.nsplit * (kWgThreads / 32)) {
       const int mt = it / ngrp, ng = it - mt * ngrp;
       const int slot0 = 2 * mt, slot1 = min(2 * mt + 1, nslots - 1);
       const int myslot = (lj & 1) ? slot1 : slot0;
@@ -313,7 +317,15 @@ static int launch_conv_wgrad_mma(ConvArgs a, const void* dy, int CoS, int Cout, 
   ga.w.a = a; ga.w.dy = dy; ga.w.CoS = CoS; ga.w.Cout = Cout; ga.w.Cin = Cin; ga.w.dw = dw; ga.w.ntaps_total = ntaps_total;
   ga.w.wt_transposed = wt_transposed; ga.w.ci_base = ci_base;
   ga.CK = CK; ga.TY = TY;
-  dim3 grid(cdiv(a.OWt, 32), cdiv(a.OHt, TY), a.B * a.S);
+  // enough CTAs for ~3 per SM where the accumulator list allows it (>= 8 warp-items per CTA)
+  const int ntile = cdiv(a.OWt, 32) * cdiv(a.OHt, TY) * a.B * a.S;
+  const int s8 = CK / 8, nmt = (a.taps.n * s8 + 1) / 2, ngrp = (((Cout + 7) / 8) + 1) / 2;
+  const int nitems = nmt * ngrp;
+  int nsplit = 1;
+  if (ntile < 3 * 148) nsplit = std::min(cdiv(3 * 148, ntile), std::max(1, nitems / 8));
+  if (nsplit > 64) nsplit = 64;
+  ga.nsplit = nsplit;
+  dim3 grid(cdiv(a.OWt, 32) * nsplit, cdiv(a.OHt, TY), a.B * a.S);
   DFF_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   conv_wgrad_mma_kernel<<<grid, kWgThreads, smem, st>>>(ga);
   DFF_LAUNCH_CHECK("conv_wgrad_mma");

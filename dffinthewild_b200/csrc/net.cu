@@ -377,11 +377,25 @@ static int num_sms_of_current_device() {
   return n;
 }
 
+// Single-operator calls pack their weights on the fly: the per-tap TMA layout is only needed by the few shapes the slab kernel
+// rejects, so it is packed when (and only when) run_conv falls through to that kernel.
+struct LazyTcPack {
+  const float* w;
+  void* dst;
+  int Cout, Cin, CinT, ntaps, Ntc, transposed;
+  bool done;
+};
+static int ensure_tc_pack(LazyTcPack* z, cudaStream_t st) {
+  if (!z || z->done) return 0;
+  z->done = true;
+  return launch_pack_weight_tc(z->w, z->dst, z->Cout, z->Cin, z->CinT, z->ntaps, z->Ntc, z->transposed, st);
+}
+
 // `wtc` != null selects the tcgen05 path (bf16 only); otherwise the FFMA kernel runs.
 static int run_conv(const Layer& l, const float* w, const float* scale, const float* shift, const Ten& in, const EpiOpt& e,
                     Ten& out, bool bf16, cudaStream_t st, const void* wtc = nullptr, const void* wslab = nullptr,
                     int* nlaunch = nullptr, bool count_only = false, bool use_row = true, const char* packed_base = nullptr,
-                    bool use_fold = false) {
+                    bool use_fold = false, LazyTcPack* lazy = nullptr) {
   int dummy = 0;
   if (!nlaunch) nlaunch = &dummy;
   *nlaunch = 0;
@@ -486,6 +500,7 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     if (wtc) {
       if (wslab && use_row && conv_row_supported(a, l.Ntc)) return launch_conv_row(a, wslab, l.Ntc, nsm, st);
       if (wslab && conv_slab_supported(a, nullptr, 1, l.Ntc)) return launch_conv_slab(a, nullptr, 1, wslab, l.Ntc, nsm, st);
+      DFF_TRY(ensure_tc_pack(lazy, st));
       return launch_conv_tc(a, wtc, l.pair_x ? 45 : l.ntaps, l.Ntc, nsm, st);
     }
     return launch_conv_ffma(a, bf16, st);
@@ -543,7 +558,10 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
       a.OHt = in.H; a.OWt = in.W;
       if (wtc) {
         if (wslab && conv_slab_supported(a, nullptr, 1, l.Ntc)) DFF_TRY(launch_conv_slab(a, nullptr, 1, wslab, l.Ntc, nsm, st));
-        else DFF_TRY(launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st));
+        else {
+          DFF_TRY(ensure_tc_pack(lazy, st));
+          DFF_TRY(launch_conv_tc(a, wtc, l.ntaps, l.Ntc, nsm, st));
+        }
       } else {
         DFF_TRY(launch_conv_ffma(a, bf16, st));
       }
@@ -1322,8 +1340,8 @@ int dff_conv3d_ex(const void* in0, int C0, const void* in1, int C1, int B, int S
     }
     DFF_TRY(pack_layer_folded_ss(l, pk, st));
   } else if (tc) {
-    DFF_TRY(launch_pack_weight_tc(weight, pk + l.pk_wtc, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
-    DFF_TRY(launch_pack_weight_slab(weight, pk + l.pk_wslab, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
+    if (plan == 2) DFF_TRY(launch_pack_weight_tc(weight, pk + l.pk_wtc, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
+    else DFF_TRY(launch_pack_weight_slab(weight, pk + l.pk_wslab, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, st));
   } else {
     DFF_TRY(launch_pack_weight(weight, (float*)(pk + l.pk_w), Cout, Cin, l.ntaps, l.CinP, l.CoutP, transposed ? 1 : 0, st));
   }
@@ -1366,8 +1384,9 @@ int dff_conv3d_ex(const void* in0, int C0, const void* in1, int C1, int B, int S
     return run_conv(l, (const float*)(pk + l.pk_w), (const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), in, e, o, true, st,
                     pk + l.pk_wtc, pk + l.pk_wslab, nullptr, false, true, pk, !no_fold);
   }
+  LazyTcPack lazy{weight, pk + l.pk_wtc, Cout, Cin, Cin, l.ntaps, l.Ntc, transposed ? 1 : 0, plan == 2 || !tc};
   return run_conv(l, (const float*)(pk + l.pk_w), scale, shift, in, e, o, elem == DFF_BF16, st, tc ? pk + l.pk_wtc : nullptr,
-                  (tc && plan != 2) ? pk + l.pk_wslab : nullptr, nullptr, false, plan == 1);
+                  (tc && plan != 2) ? pk + l.pk_wslab : nullptr, nullptr, false, plan == 1, nullptr, false, &lazy);
 }
 
 int dff_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const float* weight, int Cout,
@@ -1516,9 +1535,9 @@ int dff_conv3d_dgrad(const void* dy, int CoS, int B, int S, int OH, int OW, cons
   return 0;
 }
 
-int dff_conv3d_wgrad(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const void* dy, int CoS,
-                     int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, float* dw, int elem,
-                     int device, void* stream) {
+static int conv3d_wgrad_impl(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const void* dy, int CoS,
+                             int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, float* dw, int elem,
+                             int device, void* stream, bool accumulate) {
   if (!in0 || !dy || !dw) return fail(DFF_E_ARG, "dff_conv3d_wgrad: null pointer");
   if (C0 % 4 || C1 % 4) return fail(DFF_E_ARG, "dff_conv3d_wgrad: stored channels must be multiples of 4");
   if (kd * kh * kw > kMaxTaps) return fail(DFF_E_ARG, "dff_conv3d_wgrad: too many taps");
@@ -1526,7 +1545,7 @@ int dff_conv3d_wgrad(const void* in0, int C0, const void* in1, int C1, int B, in
   if (g.rc) return g.rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int ntaps = kd * kh * kw;
-  DFF_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cin * Cout * ntaps * sizeof(float), st));
+  if (!accumulate) DFF_CUDA(cudaMemsetAsync(dw, 0, (size_t)Cin * Cout * ntaps * sizeof(float), st));
   ConvArgs a{};
   a.in0 = in0; a.C0 = C0; a.in1 = (in1 && C1) ? in1 : nullptr; a.C1 = a.in1 ? C1 : 0;
   a.B = B; a.S = S; a.IH = IH; a.IW = IW;
@@ -1546,6 +1565,19 @@ int dff_conv3d_wgrad(const void* in0, int C0, const void* in1, int C1, int B, in
       DFF_TRY(launch_conv_wgrad(a, dy, CoS, Cout, Cin, 0, dw, ntaps, 1, bf16, st));
     }
   return 0;
+}
+
+int dff_conv3d_wgrad(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const void* dy, int CoS,
+                     int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, float* dw, int elem,
+                     int device, void* stream) {
+  return conv3d_wgrad_impl(in0, C0, in1, C1, B, S, IH, IW, dy, CoS, Cin, Cout, kd, kh, kw, stride_hw, dil_hw, transposed, dw, elem, device,
+                           stream, false);
+}
+int dff_conv3d_wgrad_acc(const void* in0, int C0, const void* in1, int C1, int B, int S, int IH, int IW, const void* dy, int CoS,
+                         int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, float* dw, int elem,
+                         int device, void* stream) {
+  return conv3d_wgrad_impl(in0, C0, in1, C1, B, S, IH, IW, dy, CoS, Cin, Cout, kd, kh, kw, stride_hw, dil_hw, transposed, dw, elem, device,
+                           stream, true);
 }
 
 size_t dff_bn_scratch_bytes(int C) { return bn_partial_bytes(C); }

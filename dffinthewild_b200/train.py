@@ -37,6 +37,7 @@ def _declare_train(lib):
         "dff_conv3d_dgrad_scratch_bytes": (sz, [i, i, i, i, i]),
         "dff_conv3d_dgrad": (i, [vp, i, i, i, i, i, vp, i, i, i, i, i, i, i, i, i, i, vp, i, vp, i, vp]),
         "dff_conv3d_wgrad": (i, [vp, i, vp, i, i, i, i, i, vp, i, i, i, i, i, i, i, i, i, vp, i, i, vp]),
+        "dff_conv3d_wgrad_acc": (i, [vp, i, vp, i, i, i, i, i, vp, i, i, i, i, i, i, i, i, i, vp, i, i, vp]),
         "dff_bn_scratch_bytes": (sz, [i]),
         "dff_bn_train_forward": (i, [vp, i64, i, i, vp, vp, vp, vp, f, f, vp, vp, i, vp, vp, vp, vp, vp, i, vp]),
         "dff_bn_train_backward": (i, [vp, vp, vp, vp, vp, vp, i64, i, i, vp, vp, vp, vp, vp, i, vp]),
@@ -105,6 +106,9 @@ class ConvFn(torch.autograd.Function):
         _conv_call(l, x0, x1, w, Cout, 2 if transposed else stride, dil, transposed, out, elem, 1 if bf16 else 0)
         ctx.save_for_backward(x0, x1, w)
         ctx.cfg = (stride, dil, transposed, cin_pad, Cout, OH, OW)
+        # gradient sink (train_step.TrainStep): the weight gradient is accumulated straight into the parameter's slot of the flat,
+        # once-per-step-zeroed bucket — no temporary, no AccumulateGrad add
+        ctx.sink = weight if getattr(weight, "_dff_grad_sink", False) else None
         return out
 
     @staticmethod
@@ -160,7 +164,13 @@ class ConvFn(torch.autograd.Function):
             else:
                 dx1 = dx
         dw = None
-        if needs[2]:
+        sink = ctx.sink
+        if needs[2] and sink is not None and sink.grad is not None and sink.grad.is_contiguous() and sink.grad.dtype == torch.float32:
+            # (stored channels beyond the layer's Cin — the first layer's padding — are skipped by the kernel)
+            cin_true = sink.shape[0] if transposed else sink.shape[1]
+            rt.check(l.dff_conv3d_wgrad_acc(_p(x0), C0, _p(x1), C1, B, S, IH, IW, _p(dy), CoS, cin_true, Cout, kd, kh, kw, st, dil,
+                                            1 if transposed else 0, _p(sink.grad), elem, dev.index, _st(dev)))
+        elif needs[2]:
             dw = torch.empty_like(w)
             rt.check(l.dff_conv3d_wgrad(_p(x0), C0, _p(x1), C1, B, S, IH, IW, _p(dy), CoS, Cin, Cout, kd, kh, kw, st, dil,
                                         1 if transposed else 0, _p(dw), elem, dev.index, _st(dev)))
@@ -224,6 +234,8 @@ class BnActFn(torch.autograd.Function):
         # ReLU mask source: the output before res_post.  Without res_post that is `out` itself; with it, relu(x) > 0 <=> x > 0
         # (no-BN layers, reference :399-402) so the raw input serves as the mask.
         ctx.relu, ctx.has_post, ctx.batch_stats = relu, res_post is not None, batch_stats
+        sink = gamma is not None and getattr(gamma, "_dff_grad_sink", False) and getattr(beta, "_dff_grad_sink", False)
+        ctx.sinks = (gamma, beta) if sink else (None, None)
         ctx.save_for_backward(x, gamma, mean, invstd, out if (relu and res_post is None) else None)
         return out
 
@@ -244,9 +256,14 @@ class BnActFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if needs[3] else None
         dgamma = dbeta = None
+        sunk = False
         if gamma is not None:
-            dgamma = torch.empty(C, dtype=torch.float32, device=dev)
-            dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+            gs, bs_ = ctx.sinks
+            if gs is not None and gs.grad is not None and bs_.grad is not None and gs.grad.is_contiguous() and bs_.grad.is_contiguous():
+                dgamma, dbeta, sunk = gs.grad, bs_.grad, True      # every BatchNorm runs once per step: plain overwrite of its slot
+            else:
+                dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+                dbeta = torch.empty(C, dtype=torch.float32, device=dev)
             scratch = torch.empty(l.dff_bn_scratch_bytes(C), dtype=torch.uint8, device=dev)
             fn = l.dff_bn_train_backward if ctx.batch_stats else l.dff_bn_eval_backward
             rt.check(fn(_p(dy), _p(mask), _p(x), _p(mean), _p(invstd), _p(gamma), npix, C, _elem(x), _p(dx), _p(dres), _p(dgamma), _p(dbeta),
@@ -254,6 +271,8 @@ class BnActFn(torch.autograd.Function):
         else:
             rt.check(l.dff_bn_train_backward(_p(dy), _p(mask), None, None, None, None, npix, C, _elem(x), _p(dx), _p(dres), None, None,
                                              None, dev.index, _st(dev)))
+        if sunk:
+            dgamma = dbeta = None
         return dx, dgamma, dbeta, dres, (dy if ctx.has_post else None), None, None
 
 

@@ -95,6 +95,8 @@ class TrainStep:
             self.flat_p[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + n].view_as(p)
             o += n
+        for p in params:          # weight / BatchNorm gradients are written straight into their bucket slots (train.py)
+            p._dff_grad_sink = True
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.t = 0

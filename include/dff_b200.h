@@ -221,6 +221,11 @@ int dff_conv3d_dgrad(const void *dy, int CoS, int B, int S, int OH, int OW, cons
 int dff_conv3d_wgrad(const void *in0, int C0, const void *in1, int C1, int B, int S, int IH, int IW, const void *dy, int CoS,
                      int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, float *dw, int elem,
                      int device, void *stream);
+/* Same, ADDED to dw (no clearing): lets a training loop accumulate every layer's gradient straight into its slot of one flat,
+ * once-per-step-zeroed gradient bucket (dffinthewild_b200/train_step.py) instead of a temporary + an add per parameter. */
+int dff_conv3d_wgrad_acc(const void *in0, int C0, const void *in1, int C1, int B, int S, int IH, int IW, const void *dy, int CoS,
+                         int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, int transposed, float *dw, int elem,
+                         int device, void *stream);
 /* out = [relu]( BN_batchstats(x) + res_pre ) + res_post ; saves mean / invstd, updates running statistics in place
  * (momentum, unbiased variance) when given.  gamma == NULL: no BatchNorm (activation / adds only).
  * scale_shift: 2*C floats of scratch; scratch: dff_bn_scratch_bytes(C). */
