@@ -355,6 +355,9 @@ def run_ours(args):
         roof["bandwidth_kernels"] = bw
     except Exception as ex:   # (a reporting extra must never take the bench line down)
         roof["aggregation_convs"] = {"error": str(ex)}
+    roof["operators_top12"] = [{"name": n, "ms_per_call": a["ms"] / a["calls"], "share_of_step": a["ms"] / total_prof_ms,
+                                "tflops": a["flops"] / (a["ms"] / 1e3) / 1e12, "gbs": a["bytes"] / (a["ms"] / 1e3) / 1e9}
+                               for n, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]]
     tr = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")   # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
     if os.path.exists(tr):
         t = json.load(open(tr))

@@ -249,6 +249,72 @@ __global__ void __launch_bounds__(256) maxpool2_bf16x8_kernel(const uint4* __res
   }
 }
 
+// The three average pools of hourglassup (AvgPool3d (1,2,2), (1,4,4), (1,8,8) of the same volume, reference :183-187, 248-250) in ONE
+// pass over the bf16 channels-last input: a lane owns one 2x2 block x 8 channels (four 16-byte loads), 16 lanes cover an 8x8 block,
+// the 4x4 and 8x8 means come from the same fp32 sums through two rounds of lane shuffles.  Reads the volume once instead of three times.
+__global__ void __launch_bounds__(256) avgpool_pyramid_bf16_kernel(const uint4* __restrict__ src, uint4* __restrict__ d2, uint4* __restrict__ d4,
+                                                                   uint4* __restrict__ d8, int BS, int H, int W, int C8) {
+  const int H8 = H / 8, W8 = W / 8;
+  const size_t nblk = (size_t)BS * H8 * W8 * C8;               // (8x8 block, 8-channel chunk) pairs, 16 lanes each
+  const size_t gi = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 4;
+  if (gi >= nblk) return;                                      // (whole 16-lane groups leave together: nblk is counted in groups)
+  const int l = threadIdx.x & 15, bx = l & 3, by = l >> 2;     // 2x2 block inside the 8x8 block
+  const int c8 = (int)(gi % C8);
+  size_t r = gi / C8;
+  const int X8 = (int)(r % W8); r /= W8;
+  const int Y8 = (int)(r % H8);
+  const size_t bs = r / H8;
+  const int y = 8 * Y8 + 2 * by, x = 8 * X8 + 2 * bx;
+  const uint4* p = src + ((bs * H + y) * W + x) * C8 + c8;
+  const uint4 v[4] = {__ldg(p), __ldg(p + C8), __ldg(p + (size_t)W * C8), __ldg(p + (size_t)W * C8 + C8)};
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t u[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] += __uint_as_float(u[j] << 16);
+      acc[2 * j + 1] += __uint_as_float(u[j] & 0xffff0000u);
+    }
+  }
+  auto pack = [&](float sc) {
+    uint4 o;
+    uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * j] * sc, acc[2 * j + 1] * sc);
+      ou[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return o;
+  };
+  d2[((bs * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * C8 + c8] = pack(0.25f);
+  // 4x4: the four 2x2 blocks with equal (bx >> 1, by >> 1): lane bits 0 and 2
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+  }
+  if ((bx & 1) == 0 && (by & 1) == 0) d4[((bs * (H / 4) + (y >> 2)) * (W / 4) + (x >> 2)) * C8 + c8] = pack(1.f / 16.f);
+  // 8x8: lane bits 1 and 3
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+  }
+  if (l == 0) d8[((bs * H8 + Y8) * W8 + X8) * C8 + c8] = pack(1.f / 64.f);
+}
+
+int launch_avgpool_pyramid(const void* src, void* d2, void* d4, void* d8, int BS, int H, int W, int C, cudaStream_t st) {
+  if (C % 8 || H % 8 || W % 8) return fail(-1, "avgpool_pyramid: C, H, W must be multiples of 8");
+  const size_t nthreads = (size_t)BS * (H / 8) * (W / 8) * (C / 8) * 16;
+  avgpool_pyramid_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>((const uint4*)src, (uint4*)d2, (uint4*)d4, (uint4*)d8, BS, H, W,
+                                                                                 C / 8);
+  DFF_LAUNCH_CHECK("avgpool_pyramid");
+  return 0;
+}
+
 int launch_pool(const void* src, void* dst, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st) {
   if (C % 4 || H % k || W % k) return fail(-1, "pool: C % 4, H % k, W % k must be 0");
   if (bf16 && is_max && k == 2 && C % 8 == 0) {

@@ -23,6 +23,7 @@ int launch_u8_to_cl(const unsigned char* src, int B, int S, int H0, int W0, int 
 int launch_u8_to_planar(const unsigned char* src, int B, int S, int H0, int W0, int H, int W, float* dst, cudaStream_t st);
 int launch_from_cl(const void* src, int B, int C, int S, int H, int W, int Cp, bool bf16, float* dst, cudaStream_t st);
 int launch_pool(const void* src, void* dst, int BS, int H, int W, int C, int k, bool is_max, bool bf16, cudaStream_t st);
+int launch_avgpool_pyramid(const void* src, void* d2, void* d4, void* d8, int BS, int H, int W, int C, cudaStream_t st);
 int launch_depth_head(const float* cost, int h, int w, const float* fd, const int64_t* st4, int B, int S, int H, int W,
                       float* depth, cudaStream_t st);
 int launch_depth_head4(const float* const cost[4], const int h[4], const int w[4], const float* fd, const int64_t* st4, int B, int S,
@@ -66,6 +67,7 @@ int launch_bn_backward(const void* dy, const void* y, const void* x, const float
 int launch_bn_eval_stats(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C, float* scale,
                          float* shift, float* mean, float* invstd, cudaStream_t st);
 int launch_add(const void* a, const void* b, size_t n, bool bf16, void* out, cudaStream_t st);
+int launch_adjoint_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int ci0, int nci, int CoS, int mode, cudaStream_t st);
 size_t depth_metrics_scratch_bytes(int B);
 int launch_depth_metrics(const float* est, const float* gt, const unsigned char* mask, const float* conf, int B, int H, int W, int Hc,
                          int Wc, float* out, double* scratch, cudaStream_t st);
@@ -743,7 +745,19 @@ struct Runner {
   // hourglassup (reference :247-273)
   Ten pyramid(const Ten& v3) {
     const std::string sp = "SPP_module.";
-    Ten x8 = pool(v3, 2, false), x16 = pool(v3, 4, false), x32 = pool(v3, 8, false);
+    Ten x8, x16, x32;
+    static const bool no_pyr = getenv("DFF_B200_NO_PYRAMID_POOL") != nullptr;
+    if (bf16 && v3.C % 8 == 0 && !no_pyr) {   // the three pools in one pass over V3
+      x8 = alloc(v3.B, v3.S, v3.H / 2, v3.W / 2, v3.C);
+      x16 = alloc(v3.B, v3.S, v3.H / 4, v3.W / 4, v3.C);
+      x32 = alloc(v3.B, v3.S, v3.H / 8, v3.W / 8, v3.C);
+      const double ivox = (double)v3.B * v3.S * v3.H * v3.W;
+      op_begin("avgpool_pyramid", 0, ivox * v3.C * 2.0 * (1.0 + 1.0 / 4 + 1.0 / 16 + 1.0 / 64), 1);
+      if (!dry && !rc) rc = launch_avgpool_pyramid(v3.p, x8.p, x16.p, x32.p, v3.B * v3.S, v3.H, v3.W, v3.C, st);
+      op_end();
+    } else {
+      x8 = pool(v3, 2, false); x16 = pool(v3, 4, false); x32 = pool(v3, 8, false);
+    }
     x8 = tower(sp + "dres8_0", sp + "dres8_1", x8);
     x16 = tower(sp + "dres16_0", sp + "dres16_1", x16);
     x32 = tower(sp + "dres32_0", sp + "dres32_1", x32);
@@ -1489,7 +1503,9 @@ static void taps_of(int kd, int kh, int kw, int dil, TapTable& t, bool negate) {
 }
 
 size_t dff_conv3d_dgrad_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw) {
-  return align_up((size_t)kd * kh * kw * align_up(Cout, 4) * align_up(Cin, 8) * 4, 256);
+  // FFMA pack | tensor-core path: the adjoint weight (reference layout) + the forward operator's own scratch
+  const size_t adj = align_up((size_t)kd * kh * kw * align_up(Cout, 8) * align_up(Cin, 8) * 4, 256);
+  return adj + dff_conv3d_scratch_bytes((int)align_up(Cout, 8), (int)align_up(Cin, 8), kd, kh, kw);
 }
 
 int dff_conv3d_dgrad(const void* dy, int CoS, int B, int S, int OH, int OW, const float* weight, int Cin, int Cout, int kd, int kh,
@@ -1505,6 +1521,20 @@ int dff_conv3d_dgrad(const void* dy, int CoS, int B, int S, int OH, int OW, cons
   if (g.rc) return g.rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int ntaps = kd * kh * kw, CaP = CoS, CbP = (int)align_up(nci, 8);
+  static const bool dgrad_ffma = getenv("DFF_B200_NO_TC") && atoi(getenv("DFF_B200_NO_TC")) != 0;
+  if (elem == DFF_BF16 && !dgrad_ffma && CoS % 8 == 0 && nci % 8 == 0) {
+    // tensor-core data gradient: the adjoint convolution through the forward operator (tcgen05 kernels), its weight re-laid out by
+    // one small kernel (flipped taps for stride 1, a transposed convolution for stride 2 and vice versa)
+    const int mode = transposed ? 2 : (stride_hw == 2 ? 1 : 0);
+    float* wa = (float*)scratch;
+    char* rest = (char*)scratch + align_up((size_t)ntaps * CoS * nci * 4, 256);
+    DFF_TRY(launch_adjoint_weight(weight, wa, Cout, Cin, ntaps, ci0, nci, CoS, mode, st));
+    if (mode == 1)
+      return dff_conv3d_ex(dy, CoS, nullptr, 0, B, S, OH, OW, wa, nci, 3, 3, 3, 2, 1, 1, nullptr, nullptr, nullptr, nullptr, 0, dx, DFF_BF16, 1,
+                           0, nullptr, nullptr, nullptr, nullptr, 0, 0, rest, device, stream);
+    return dff_conv3d_ex(dy, CoS, nullptr, 0, B, S, OH, OW, wa, nci, kd, kh, kw, mode == 2 ? 2 : 1, dil_hw, 0, nullptr, nullptr, nullptr, nullptr,
+                         0, dx, DFF_BF16, 1, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, rest, device, stream);
+  }
   DFF_TRY(launch_pack_weight_dgrad(weight, (float*)scratch, Cout, Cin, ntaps, ci0, nci, CaP, CbP, transposed ? 1 : 0, st));
   ConvArgs a{};
   a.in0 = dy; a.C0 = CoS; a.in1 = nullptr; a.C1 = 0;
@@ -1664,6 +1694,13 @@ int dff_pool3d(const void* x, int BS, int H, int W, int C, int k, int is_max, in
   DeviceGuard g(device);
   if (g.rc) return g.rc;
   return launch_pool(x, out, BS, H, W, C, k, is_max != 0, elem == DFF_BF16, (cudaStream_t)stream);
+}
+
+int dff_avgpool_pyramid(const void* x, int BS, int H, int W, int C, void* out2, void* out4, void* out8, int device, void* stream) {
+  if (!x || !out2 || !out4 || !out8) return fail(DFF_E_ARG, "dff_avgpool_pyramid: null pointer");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  return launch_avgpool_pyramid(x, out2, out4, out8, BS, H, W, C, (cudaStream_t)stream);
 }
 
 int dff_pool3d_backward(const void* x, const void* dy, int BS, int H, int W, int C, int k, int is_max, int elem, void* dx,

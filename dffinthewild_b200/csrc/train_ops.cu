@@ -292,6 +292,37 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, float* __r
   }
 }
 
+// Weight of the ADJOINT convolution in the reference layout, so that a data gradient is one more call of the forward operator
+// (tensor-core path).  a = dx channel inside [ci0, ci0+nci), b = dy channel (zero beyond Cout, i.e. for the stored padding of dy):
+//   mode 0  layer = stride-1 conv     : adjoint = stride-1 conv,       weight (nci, CoS, k)  = W[b][ci0+a][flipped tap]
+//   mode 1  layer = stride-2 conv     : adjoint = transposed conv,     weight (CoS, nci, k)  = W[b][ci0+a][tap]
+//   mode 2  layer = transposed conv   : adjoint = stride-2 conv,       weight (nci, CoS, k)  = Wt[ci0+a][b][tap]
+__global__ void adjoint_weight_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin, int ntaps, int ci0, int nci,
+                                      int CoS, int mode) {
+  const int n = nci * CoS * ntaps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int t = i % ntaps;
+    int a, b;
+    if (mode == 1) { a = (i / ntaps) % nci; b = i / (ntaps * nci); }
+    else { b = (i / ntaps) % CoS; a = i / (ntaps * CoS); }
+    float v = 0.f;
+    if (b < Cout && ci0 + a < Cin) {
+      if (mode == 0) v = w[((size_t)b * Cin + ci0 + a) * ntaps + (ntaps - 1 - t)];
+      else if (mode == 1) v = w[((size_t)b * Cin + ci0 + a) * ntaps + t];
+      else v = w[((size_t)(ci0 + a) * Cout + b) * ntaps + t];
+    }
+    dst[i] = v;
+  }
+}
+int launch_adjoint_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int ci0, int nci, int CoS, int mode, cudaStream_t st) {
+  const int n = nci * CoS * ntaps;
+  int g = cdiv(n, 256);
+  if (g > 512) g = 512;
+  adjoint_weight_kernel<<<g, 256, 0, st>>>(w, dst, Cout, Cin, ntaps, ci0, nci, CoS, mode);
+  DFF_LAUNCH_CHECK("adjoint_weight");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------------

@@ -138,27 +138,11 @@ class ConvFn(torch.autograd.Function):
                 continue
             nci = x.shape[-1]
             dx = torch.empty_like(x)
-            if not bf16:
-                scratch = torch.empty(l.dff_conv3d_dgrad_scratch_bytes(Cin, max(Cout, CoS), kd, kh, kw), dtype=torch.uint8, device=dev)
-                rt.check(l.dff_conv3d_dgrad(_p(dy), CoS, B, S, OH, OW, _p(w), Cin, Cout, kd, kh, kw, st, dil, 1 if transposed else 0,
-                                            ci0, nci, _p(dx), rt.FP32, _p(scratch), dev.index, _st(dev)))
-            else:
-                # tensor-core data gradient: the adjoint convolution, weights re-laid out on the fly (tiny tensors)
-                if transposed:      # adjoint of the transposed conv = stride-2 conv of dy, weight (Cin_t, Cout_t, k) read as (Cout_c, Cin_c, k)
-                    wa = w[ci0:ci0 + nci]
-                    if CoS > Cout:
-                        wa = torch.cat([wa, wa.new_zeros(nci, CoS - Cout, kd, kh, kw)], 1)
-                    _conv_call(l, dy, None, wa.contiguous(), nci, 2, 1, False, dx, rt.BF16, 1)
-                elif st == 2:       # adjoint of the stride-2 conv = transposed conv of dy, weight (Cout, nci, k) read as (Cin_t, Cout_t, k)
-                    wa = w[:, ci0:ci0 + nci]
-                    if CoS > Cout:
-                        wa = torch.cat([wa, wa.new_zeros(CoS - Cout, nci, kd, kh, kw)], 0)
-                    _conv_call(l, dy, None, wa.contiguous(), nci, 2, 1, True, dx, rt.BF16, 1)
-                else:               # adjoint of the stride-1 conv = stride-1 conv with flipped taps and swapped channel roles
-                    wa = w[:, ci0:ci0 + nci].flip(2, 3, 4).transpose(0, 1)
-                    if CoS > Cout:
-                        wa = torch.cat([wa, wa.new_zeros(nci, CoS - Cout, kd, kh, kw)], 1)
-                    _conv_call(l, dy, None, wa.contiguous(), nci, 1, dil, False, dx, rt.BF16, 1)
+            # fp32: FFMA kernels with adjoint tap tables.  bf16: the library runs the adjoint convolution on the tcgen05 kernels (flipped
+            # taps for stride 1, a transposed convolution for stride 2 and vice versa), re-laying the weight out with one small kernel.
+            scratch = torch.empty(l.dff_conv3d_dgrad_scratch_bytes(Cin, max(Cout, CoS), kd, kh, kw), dtype=torch.uint8, device=dev)
+            rt.check(l.dff_conv3d_dgrad(_p(dy), CoS, B, S, OH, OW, _p(w), Cin, Cout, kd, kh, kw, st, dil, 1 if transposed else 0,
+                                        ci0, nci, _p(dx), elem, _p(scratch), dev.index, _st(dev)))
             if idx == 0:
                 dx0 = dx
             else:

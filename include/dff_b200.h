@@ -263,6 +263,9 @@ int dff_adam_flat(float *param, const float *grad, float *exp_avg, float *exp_av
                   double beta2, double eps, int step, const float *grad_scale, int device, void *stream);
 /* (1,k,k) pooling of (BS,H,W,C) channels-last volumes, forward and backward (max: first maximum in row-major order). */
 int dff_pool3d(const void *x, int BS, int H, int W, int C, int k, int is_max, int elem, void *out, int device, void *stream);
+/* hourglassup's three average pools (AvgPool3d (1,2,2), (1,4,4), (1,8,8) of the same volume, train_codes/Depth_Estimation_Network.py:
+ * 183-187, 248-250) in one pass: x (BS,H,W,C) bf16 channels-last, C, H, W multiples of 8 -> out2, out4, out8 (bf16). */
+int dff_avgpool_pyramid(const void *x, int BS, int H, int W, int C, void *out2, void *out4, void *out8, int device, void *stream);
 int dff_pool3d_backward(const void *x, const void *dy, int BS, int H, int W, int C, int k, int is_max, int elem, void *dx,
                         int device, void *stream);
 /* d cost (B,S,h,w) from d depth (B,H,W) */

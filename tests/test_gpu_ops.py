@@ -347,3 +347,19 @@ def test_fov_warp_channels_last_bf16(rt, C):
                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     got = rt.from_channels_last(out, C)
     assert (got - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("C,BS,H,W", [(32, 6, 16, 48), (8, 3, 8, 8), (16, 2, 24, 40)])
+def test_avgpool_pyramid_one_pass(rt, C, BS, H, W):
+    """The three average pools of hourglassup in one pass (reference :248-250): each level = one bf16 rounding of the fp32 mean."""
+    import ctypes
+    x = _rand(BS, H, W, C, seed=23, scale=3.0).to(torch.bfloat16).cuda()
+    outs = [torch.full((BS, H // k, W // k, C), float("nan"), dtype=torch.bfloat16, device="cuda") for k in (2, 4, 8)]
+    f = rt.lib().dff_avgpool_pyramid
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p]
+    rt.check(f(x.data_ptr(), BS, H, W, C, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), 0,
+               torch.cuda.current_stream().cuda_stream))
+    for k, o in zip((2, 4, 8), outs):
+        ref = x.float().view(BS, H // k, k, W // k, k, C).mean(dim=(2, 4))
+        assert (o.float() - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item(), k
