@@ -185,7 +185,7 @@ def train_record(args, dev, world, rank):
     gt, mask = synth.gt_and_mask(B, H3, W3, seed=300 + rank)
     gt, mask = gt.to(dev), mask.to(dev)
     stepper = TS.TrainStep(net, lr=1e-4, betas=(0.9, 0.99), weights=(0.3, 0.5, 0.7, 1.0))
-    steps, warm = max(2, min(args.train_steps, args.steps)), 2
+    steps, warm = max(2, min(args.train_steps, args.steps)), 4    # (2 eager steps, the CUDA-graph capture, 1 replay)
     for _ in range(warm):
         stepper.step(FS, fd, gt, mask)
     if world > 1:

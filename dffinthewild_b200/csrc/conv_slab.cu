@@ -46,6 +46,7 @@ constexpr int kSlabMaxWSlot = 40 * 1024;                 // largest slot of the 
 constexpr int kSlabMaxWSlots = 8;
 constexpr int kSlabMaxOps = 128;
 constexpr int kSlabMaxPlanes = 8;
+constexpr int kSlabMaxAcc = 8;    // accumulator buffers: 2 (double buffer) or up to 8 slots (focal-merged form)
 constexpr int kSlabTW = 8, kSlabTH = 16;
 constexpr int kSlabSmemBudget = 228 * 1024;   // per SM; every co-resident CTA also costs ~1 KB static + 1 KB reserved
 
@@ -78,6 +79,13 @@ struct alignas(64) SlabParams {
   // streamed weights (layers whose weights do not fit in shared memory next to the plane ring): the MMA table is cut into blocks of
   // consecutive MMAs whose weights are one contiguous range of `wslab`; warp 7 streams them through a ring of `nwslots` slots
   int wstream, nwslots, nblk, wslot_bytes;
+  // focal-merged form ("zmerge", 3-tap focal dimension, one output phase, resident weights): the kernel is INPUT-stationary over the
+  // focal axis.  Plane z is multiplied once per spatial tap into the accumulators of the three output slices it feeds (z-1, z, z+1) with
+  // ONE tcgen05.mma of N' = 3N columns — the accumulators of consecutive slices are adjacent column blocks of a ring of `nslot` TMEM
+  // slots, the weights of the three focal taps adjacent row blocks of the B operand.  An SS-form MMA costs 32 + N'/4 clocks (the
+  // A-operand fetch dominates), so three taps cost 32 + 3N/4 instead of 3 * (32 + N/4): 2.6x fewer tensor-pipe clocks at N = 16,
+  // 2.1x at N = 32, 1.8x at N = 64; every plane is needed exactly once, so the plane ring needs no focal halo.
+  int zmerge, nslot, lgslot, zT;    // on/off; accumulator slots (power of two) and its log2; spatial MMAs per plane
   int egroups;                      // epilogue warp groups (1 or 2)
   int tma;                          // planes staged by ONE tiled TMA load each (single-chunk, single-view layers: box 8 ch x RX x RY)
   int gb[12], gbe[12];              // block range per MMA group
@@ -136,7 +144,8 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
     const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
     const bool valid = oy < p.OHt && ox < p.OWt;
     for (int s = s_begin; s < s_end; ++s, ++sc) {
-      const int buf = sc & 1;
+      const int buf = p.zmerge ? (sc & (p.nslot - 1)) : (sc & 1);
+      const uint32_t par = p.zmerge ? ((uint32_t)(sc >> p.lgslot) & 1u) : ((uint32_t)(sc >> 1) & 1u);
       const size_t row0 = ((size_t)b * p.S + s) * p.OH;
       uint4 rv[4];
       {
@@ -151,13 +160,13 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
           }
         }
       }
-      mbar_wait(tfull0 + 8 * buf, (sc >> 1) & 1);
+      mbar_wait(tfull0 + 8 * buf, par);
       fence_after();
       if (q == 3 && eg == 0) DFF_TR(3, sc);
       for (int ph = eg; ph < p.nph; ph += neg) {
         const size_t pix = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
         if (p.exp & 2) continue;
-        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N;
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N;   // (zmerge: nph == 1, buf = slot)
         if (FAST) {
           if (ph != eg) tc_epilogue_preload<RES, AUX>(ep, valid, pix, 0, rv);
           tc_epilogue_fast<RELU, RES, AUX, PROJ>(ep, ss_s, tacc, valid, pix, rv);
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   constexpr int kThreads = slab_threads(WS, E2);
   constexpr int kEG = E2 ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kSlabMaxPlanes + 4 + (WS ? 2 * kSlabMaxWSlots : 0)];
+  __shared__ __align__(8) uint64_t bars[2 * kSlabMaxPlanes + 2 * kSlabMaxAcc + (WS ? 2 * kSlabMaxWSlots : 0)];
   __shared__ uint32_t tmem_base_s;
   const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
@@ -187,8 +196,8 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   float* const ss = reinterpret_cast<float*>(smem_gen + p.ss_off);  // scale[N], shift[N], classifier weights[N]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kSlabMaxPlanes]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * kSlabMaxPlanes]), tempty0 = smem_u32(&bars[2 * kSlabMaxPlanes + 2]);
-  const uint32_t wfull0 = smem_u32(&bars[2 * kSlabMaxPlanes + 4]), wempty0 = wfull0 + 8 * kSlabMaxWSlots;   // (WS only)
+  const uint32_t tfull0 = smem_u32(&bars[2 * kSlabMaxPlanes]), tempty0 = smem_u32(&bars[2 * kSlabMaxPlanes + kSlabMaxAcc]);
+  const uint32_t wfull0 = smem_u32(&bars[2 * kSlabMaxPlanes + 2 * kSlabMaxAcc]), wempty0 = wfull0 + 8 * kSlabMaxWSlots;   // (WS only)
 
   if (threadIdx.x == 0) {
     if (WS)
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
       mbar_init(full0 + 8 * i, p.tma ? 1 : kSlabProducers);
       mbar_init(empty0 + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlabMaxAcc; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
       mbar_init(tempty0 + 8 * i, 128 * kEG);
     }
@@ -212,7 +221,19 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // ---- one-time: MMA table, weights (MMA order), BatchNorm scale/shift and the staging table into shared memory --------
-  if (!WS) {
+  if (!WS && p.zmerge) {
+    // [spatial op][K half][focal block j = 0,1,2 (dz = +1, 0, -1 -> output slices z-1, z, z+1)][N][8]
+    const int N3 = 3 * p.N, total = 2 * p.zT * N3;
+    const uint4* wg = reinterpret_cast<const uint4*>(p.wslab);
+    for (int i = threadIdx.x; i < total; i += kThreads) {
+      const int op = i / (2 * N3), rem = i - op * 2 * N3;
+      const int h = rem / N3, jn = rem - h * N3, j = jn / p.N, r = jn - j * p.N;
+      const int src = p.wsrc[2 * (p.g[2 - j] + op) + h];
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (src >= 0) v = __ldg(wg + (size_t)src * p.N + r);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_s + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+  } else if (!WS) {
     const int total = 2 * p.nops * p.N;  // 16-byte rows
     const uint4* wg = reinterpret_cast<const uint4*>(p.wslab);
 #pragma unroll 4
@@ -357,6 +378,62 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
     uint32_t wsph = 0;
     uint64_t a_prev = 0, a_cur = 0, a_next = 0;   // descriptor bases of the planes of slices s-1, s, s+1
     uint32_t e_prev = 0, e_cur = 0, e_next = 0;   // their `empty` barriers
+    if (p.zmerge) {
+      // ---- focal-merged schedule: one pass over the planes of an item, every plane multiplied into the slices it feeds ----
+      const uint32_t N = (uint32_t)p.N, smask = (uint32_t)p.nslot - 1u;
+      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+      const uint64_t bdz = b_hi | (uint64_t)((w_s >> 4) | (((uint32_t)(3 * p.N * 16) >> 4) << 16));   // LBO = one K half of 3N rows
+      const uint64_t bz_step = (uint32_t)(3 * p.N * 32) >> 4, bz_blk = (uint32_t)(p.N * 16) >> 4;
+      int q0 = 0;          // running index of the first slice of the current item (slot = index & smask, use count = index >> lgslot)
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        if (item + (int)gridDim.x >= p.nitems) pdl_trigger();
+        const int isp = item % p.nsplit;
+        const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
+        const int zlo = max(0, s_begin - 1), zhi = min(p.S, s_end + 1);
+        for (int z = zlo; z < zhi; ++z) {
+          mbar_wait(full0 + 8 * wslot, wphase);
+          const uint64_t a_pl = a_hi | (uint64_t)(planes16 + (uint32_t)wslot * pb16);
+          const uint32_t e_pl = empty0 + 8 * wslot;
+          if (++wslot == NP) { wslot = 0; wphase ^= 1; }
+          fence_proxy_async();
+          const int lo = max(z - 1, s_begin), hi = min(z + 1, s_end - 1);        // output slices this plane feeds
+          const int nlo = (z == zlo) ? lo : (hi == z + 1 ? hi : hi + 1);          // first slice whose accumulator starts at this plane
+          for (int sn = nlo; sn <= hi; ++sn) {     // a fresh slot: the epilogue must have drained its previous slice
+            const uint32_t qi = (uint32_t)(q0 + sn - s_begin);
+            mbar_wait(tempty0 + 8 * (qi & smask), ((qi >> p.lgslot) & 1u) ^ 1u);
+          }
+          fence_after();
+          if (leader) {
+            // a run of slices [r0, r1] = focal blocks j = r0-(z-1) .. of the B operand, consecutive accumulator slots unless the ring wraps
+            auto run = [&](int i, int r0, int r1, uint32_t acc) {
+              while (r0 <= r1) {
+                const uint32_t qi = (uint32_t)(q0 + r0 - s_begin), slot = qi & smask;
+                int cnt = r1 - r0 + 1;
+                if ((int)(slot + cnt) > p.nslot) cnt = p.nslot - (int)slot;       // wrap: split the instruction
+                const uint32_t idesc = idesc_base | (((uint32_t)cnt * N >> 3) << 17);
+                const uint64_t bd = bdz + (uint64_t)i * bz_step + (uint64_t)(r0 - (z - 1)) * bz_blk;
+                umma(tmem_base + slot * N, a_pl + p.tab[p.g[1] + i], bd, idesc, acc);
+                r0 += cnt;
+              }
+            };
+#pragma unroll 1
+            for (int i = 0; i < p.zT; ++i) {
+              if (i == 0) {
+                run(0, lo, nlo - 1, 1u);
+                run(0, nlo, hi, 0u);
+              } else {
+                run(i, lo, hi, 1u);
+              }
+            }
+            umma_commit(e_pl);                                   // the plane is not needed again
+            if (z - 1 >= s_begin) umma_commit(tfull0 + 8 * ((uint32_t)(q0 + z - 1 - s_begin) & smask));        // slice z-1 is complete
+            if (z == zhi - 1 && z < s_end) umma_commit(tfull0 + 8 * ((uint32_t)(q0 + z - s_begin) & smask));   // last plane: slice z too
+          }
+          __syncwarp();
+        }
+        q0 += s_end - s_begin;
+      }
+    } else
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       if (item + (int)gridDim.x >= p.nitems) pdl_trigger();
       const int isp = item % p.nsplit;
@@ -656,8 +733,17 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   static const int tma_mode = getenv("DFF_B200_SLAB_TMA") ? atoi(getenv("DFF_B200_SLAB_TMA")) : 2;
   p.tma = (tma_mode > 0 && (a.row_step > 0 || tma_mode > 1) && p.RX <= 256 && p.RY <= 256 && a.IW % p.stx == 0 && a.IH % p.sty == 0) ? 1 : 0;
   p.nelem = p.tma ? 0 : p.nviews * p.RY * p.RX * nchunk;   // (staging table of the cp.async producers)
-  const int np_min = 2 * p.hz + 2;
-  const int cols = 2 * nph * Ntc;
+  // focal-merged form: the three focal groups must be the same spatial MMAs (true for every 3x3x3 / strided / x-folded layer)
+  static const bool no_zmerge = getenv("DFF_B200_NO_ZMERGE") != nullptr;
+  bool zm = !no_zmerge && nph == 1 && p.hz == 1 && 3 * Ntc <= 256;
+  if (zm) {
+    const int T = p.ge[1] - p.g[1];
+    zm = T > 0 && p.ge[0] - p.g[0] == T && p.ge[2] - p.g[2] == T;
+    for (int i = 0; zm && i < T; ++i) zm = p.tab[p.g[0] + i] == p.tab[p.g[1] + i] && p.tab[p.g[2] + i] == p.tab[p.g[1] + i];
+    p.zT = T;
+  }
+  const int np_min = zm ? 2 : 2 * p.hz + 2;
+  int cols = 2 * nph * Ntc;
   if (cols > 512) return_false;
   p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   int fixed = 0;
@@ -673,10 +759,20 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   int occ = 4, NP = 0;
   fixed = lay_out(p.w_bytes);
   for (; occ >= 1; --occ) {
-    if (occ * p.tmem_cols > 512) continue;
+    // (focal-merged: at least 4 accumulator slots per CTA)
+    if (occ * (zm ? std::max(32, 4 * Ntc) : p.tmem_cols) > 512) continue;
     const int budget = kSlabSmemBudget / occ - 2048 - 256;  // static shared memory, the per-CTA reservation, allocation granularity
     NP = (budget - fixed) / p.plane_bytes;
     if (NP >= np_min) break;
+  }
+  if (zm && occ >= 1) {
+    // as many slots as the CTA's share of tensor memory holds (8 at most): the ring wraps — and an MMA has to be split — once per
+    // `nslot` planes
+    int ns = 8;
+    while (ns > 4 && occ * std::max(32, ns * Ntc) > 512) ns >>= 1;
+    p.zmerge = 1; p.nslot = ns; p.lgslot = ns == 8 ? 3 : 2;
+    cols = ns * Ntc;
+    p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   }
   if (occ < 1) {
     // Resident weights do not fit next to the plane ring: stream them (one CTA per SM, warp 7 feeds a ring of 3-4 slots with bulk

@@ -160,6 +160,10 @@ struct WgradMmaArgs {
                    // round-robin to `nsplit` CTAs that stage the same (L2-resident) region (blockIdx.x = tile_x * nsplit + split)
 };
 
+// Persistent over tiles: CTA (split, c) owns the accumulators `split, split + nsplit, ...` of the layer's list and walks the tiles
+// c, c + ncta, ... keeping them in registers (at most kWgMaxAcc m16 x n16 accumulators per warp), so the fp32 atomics into the
+// gradient happen once per CTA instead of once per tile.
+constexpr int kWgMaxAcc = 4;
 __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __grid_constant__ WgradMmaArgs ga) {
   extern __shared__ __align__(16) unsigned char smem_b[];
   const WgradArgs& g = ga.w;
@@ -171,26 +175,9 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
   __nv_bfloat16* in_s = reinterpret_cast<__nv_bfloat16*>(smem_b);            // [REGPOS][CK]
   __nv_bfloat16* dy_s = in_s + (size_t)REGPOS * CK;                           // [NP][CoP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bs = blockIdx.z, b = bs / a.S, s = bs % a.S;
-  const int split = blockIdx.x % ga.nsplit;
-  const int ty0 = blockIdx.y * TY, tx0 = (blockIdx.x / ga.nsplit) * 32;
-  const int gy0 = ty0 * a.isy + a.dymin, gx0 = tx0 * a.isx + a.dxmin, gz0 = s + a.dzmin;
-
-  // ---- dy tile, bf16, zero outside the phase grid ---------------------------------------------------------------------
-  {
-    const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(g.dy);
-    const int q8 = CoP / 8;
-    for (int i = tid; i < NP * q8; i += kWgThreads) {
-      const int q = i % q8, pos = i / q8;
-      const int ox = tx0 + (pos & 31), oy = ty0 + (pos >> 5);
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (ox < a.OWt && oy < a.OHt && 8 * q < g.CoS) {
-        const size_t pix = (((size_t)b * a.S + s) * a.OH + (oy * a.osy + a.ooy)) * a.OW + (ox * a.osx + a.oox);
-        v = __ldg(reinterpret_cast<const uint4*>(dy + pix * g.CoS + 8 * q));
-      }
-      *reinterpret_cast<uint4*>(dy_s + (size_t)pos * CoP + 8 * q) = v;
-    }
-  }
+  const int split = blockIdx.x % ga.nsplit, cta = blockIdx.x / ga.nsplit, ncta = gridDim.x / ga.nsplit;
+  const int tilesX = (a.OWt + 31) / 32, tilesY = (a.OHt + TY - 1) / TY;
+  const int ntile = tilesX * tilesY * a.B * a.S;
   const int Ctot = a.C0 + a.C1;
   const int s8 = CK / 8;                         // 8-channel slots per tap
   const int nslots = a.taps.n * s8;
@@ -202,51 +189,95 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
   // ldmatrix row this lane supplies: matrix j = lane / 8 -> (m half j & 1, k half j >> 1), row r = lane % 8 -> position k = 8*(j>>1) + r
   const int lj = lane >> 3, lr = lane & 7, lk = 8 * (lj >> 1) + lr;
   const int gq = lane >> 2, t4 = lane & 3;
+  const int q8 = CoP / 8;
+  const int wstep = ga.nsplit * (kWgThreads / 32);   // stride of this warp's accumulator list
 
   for (int c0 = 0; c0 < Ctot; c0 += CK) {
     const bool second = c0 >= a.C0;
     const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(second ? a.in1 : a.in0);
     const int Csrc = second ? a.C1 : a.C0;
     const int cb = second ? c0 - a.C0 : c0;
-    __syncthreads();
-    for (int i = tid; i < REGPOS * s8; i += kWgThreads) {
-      const int q = i % s8, pos = i / s8;
-      const int x = pos % a.RX, y = (pos / a.RX) % a.RY, z = pos / (a.RX * a.RY);
-      const int gz = gz0 + z, gy = gy0 + y, gx = gx0 + x;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (gz >= 0 && gz < a.S && gy >= 0 && gy < a.IH && gx >= 0 && gx < a.IW)
-        v = __ldg(reinterpret_cast<const uint4*>(src + ((((size_t)b * a.S + gz) * a.IH + gy) * a.IW + gx) * Csrc + cb + 8 * q));
-      *reinterpret_cast<uint4*>(in_s + (size_t)pos * CK + 8 * q) = v;
-    }
-    __syncthreads();
-    for (int it = split * (kWgThreads / 32) + warp; it < nitems; it += ga.nsplit * (kWgThreads / 32)) {
-      const int mt = it / ngrp, ng = it - mt * ngrp;
-      const int slot0 = 2 * mt, slot1 = min(2 * mt + 1, nslots - 1);
-      const int myslot = (lj & 1) ? slot1 : slot0;
-      const int tap = myslot / s8, c8 = myslot - tap * s8;
-      // element offset of this lane's row at k-step 0: tap origin + its position's pixel + its channel group
-      const int rowbase = ((((int)a.taps.dz[tap] - a.dzmin) * a.RY + ((int)a.taps.dy[tap] - a.dymin)) * a.RX + ((int)a.taps.dx[tap] - a.dxmin) +
-                           lk * a.isx) * CK + 8 * c8;
-      const int n0 = 2 * ng, n1 = min(2 * ng + 1, nnt - 1);
-      const unsigned brow = dy_u + 2u * (unsigned)((lane & 15) * CoP);
-      float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int ks = 0; ks < 2 * TY; ++ks) {
-        // 16 consecutive positions of one tile row: row ks / 2, columns 16 * (ks & 1) ...
-        const int koff = ((ks >> 1) * a.isy * a.RX + (ks & 1) * 16 * a.isx) * CK;
-        unsigned a0, a1, a2, a3, b0, b1;
-        ldsm_x4_t(in_u + 2u * (unsigned)(rowbase + koff), a0, a1, a2, a3);
-        const unsigned bk = brow + 2u * (unsigned)(ks * 16 * CoP);
-        ldsm_x2_t(bk + 16u * (unsigned)n0, b0, b1);
-        mma_bf16_16816(acc0, a0, a1, a2, a3, b0, b1);
-        if (n1 != n0) {
-          ldsm_x2_t(bk + 16u * (unsigned)n1, b0, b1);
-          mma_bf16_16816(acc1, a0, a1, a2, a3, b0, b1);
+    float acc[kWgMaxAcc][8];
+#pragma unroll
+    for (int u = 0; u < kWgMaxAcc; ++u)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
+    for (int tile = cta; tile < ntile; tile += ncta) {
+      int r = tile;
+      const int tx0 = (r % tilesX) * 32; r /= tilesX;
+      const int ty0 = (r % tilesY) * TY; r /= tilesY;
+      const int s = r % a.S, b = r / a.S;
+      const int gy0 = ty0 * a.isy + a.dymin, gx0 = tx0 * a.isx + a.dxmin, gz0 = s + a.dzmin;
+      __syncthreads();   // the previous tile's MMAs have read the staging buffers
+      // ---- dy tile (once per tile: the channel passes of a multi-pass layer re-stage it, they are few) and the input region ----
+      {
+        const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(g.dy);
+        for (int row = warp; row < TY; row += kWgThreads / 32) {
+          const int oy = ty0 + row;
+          const size_t rowpix = (((size_t)b * a.S + s) * a.OH + ((size_t)oy * a.osy + a.ooy)) * a.OW + a.oox;
+          for (int e = lane; e < 32 * q8; e += 32) {
+            const int px = e / q8, q = e - px * q8;
+            const int ox = tx0 + px;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (ox < a.OWt && oy < a.OHt && 8 * q < g.CoS) v = __ldg(reinterpret_cast<const uint4*>(dy + (rowpix + (size_t)ox * a.osx) * g.CoS + 8 * q));
+            *reinterpret_cast<uint4*>(dy_s + (size_t)(row * 32 + px) * CoP + 8 * q) = v;
+          }
+        }
+        const int nrow = a.RZ * a.RY;
+        for (int row = warp; row < nrow; row += kWgThreads / 32) {
+          const int z = row / a.RY, y = row - z * a.RY;
+          const int gz = gz0 + z, gy = gy0 + y;
+          const bool rok = gz >= 0 && gz < a.S && gy >= 0 && gy < a.IH;
+          const __nv_bfloat16* rp = src + ((((size_t)b * a.S + (rok ? gz : 0)) * a.IH + (rok ? gy : 0)) * a.IW) * Csrc + cb;
+          __nv_bfloat16* dp = in_s + (size_t)row * a.RX * CK;
+          for (int e = lane; e < a.RX * s8; e += 32) {
+            const int x = e / s8, q = e - x * s8;
+            const int gx = gx0 + x;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (rok && gx >= 0 && gx < a.IW) v = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)gx * Csrc + 8 * q));
+            *reinterpret_cast<uint4*>(dp + (size_t)x * CK + 8 * q) = v;
+          }
         }
       }
-      // d0,d1: (m = gq, n = 2*t4, 2*t4+1) ; d2,d3: (m = gq + 8, ...): m < 8 belongs to slot0, m >= 8 to slot1
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < kWgMaxAcc; ++u) {
+        const int it = split * (kWgThreads / 32) + warp + u * wstep;
+        if (it >= nitems) break;
+        const int mt = it / ngrp, ng = it - mt * ngrp;
+        const int slot0 = 2 * mt, slot1 = min(2 * mt + 1, nslots - 1);
+        const int myslot = (lj & 1) ? slot1 : slot0;
+        const int tap = myslot / s8, c8 = myslot - tap * s8;
+        // element offset of this lane's row at k-step 0: tap origin + its position's pixel + its channel group
+        const int rowbase = ((((int)a.taps.dz[tap] - a.dzmin) * a.RY + ((int)a.taps.dy[tap] - a.dymin)) * a.RX + ((int)a.taps.dx[tap] - a.dxmin) +
+                             lk * a.isx) * CK + 8 * c8;
+        const int n0 = 2 * ng, n1 = min(2 * ng + 1, nnt - 1);
+        const unsigned brow = dy_u + 2u * (unsigned)((lane & 15) * CoP);
+        for (int ks = 0; ks < 2 * TY; ++ks) {
+          // 16 consecutive positions of one tile row: row ks / 2, columns 16 * (ks & 1) ...
+          const int koff = ((ks >> 1) * a.isy * a.RX + (ks & 1) * 16 * a.isx) * CK;
+          unsigned a0, a1, a2, a3, b0, b1;
+          ldsm_x4_t(in_u + 2u * (unsigned)(rowbase + koff), a0, a1, a2, a3);
+          const unsigned bk = brow + 2u * (unsigned)(ks * 16 * CoP);
+          ldsm_x2_t(bk + 16u * (unsigned)n0, b0, b1);
+          mma_bf16_16816(acc[u], a0, a1, a2, a3, b0, b1);
+          if (n1 != n0) {
+            ldsm_x2_t(bk + 16u * (unsigned)n1, b0, b1);
+            mma_bf16_16816(acc[u] + 4, a0, a1, a2, a3, b0, b1);
+          }
+        }
+      }
+    }
+    // ---- flush this pass's accumulators: d0,d1: (m = gq, n = 2*t4, 2*t4+1) ; d2,d3: (m = gq + 8, ...): m < 8 -> slot0, m >= 8 -> slot1 ----
+#pragma unroll
+    for (int u = 0; u < kWgMaxAcc; ++u) {
+      const int it = split * (kWgThreads / 32) + warp + u * wstep;
+      if (it >= nitems) break;
+      const int mt = it / ngrp, ng = it - mt * ngrp;
+      const int n0 = 2 * ng, n1 = min(2 * ng + 1, nnt - 1);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const int slot = half ? 2 * mt + 1 : slot0;
+        const int slot = 2 * mt + half;
         if (slot >= nslots) continue;
         const int tp = slot / s8, cc = slot - tp * s8;
         const int cig = g.ci_base + c0 + 8 * cc + gq;
@@ -255,14 +286,13 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
           if (nb == 1 && n1 == n0) continue;
-          const float* acc = nb ? acc1 : acc0;
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int co = 8 * (nb ? n1 : n0) + 2 * t4 + e;
             if (co >= g.Cout) continue;
             const size_t o = g.wt_transposed ? ((size_t)cig * g.Cout + co) * g.ntaps_total + wi
                                              : ((size_t)co * g.Cin + cig) * g.ntaps_total + wi;
-            atomicAdd(g.dw + o, acc[2 * half + e]);
+            atomicAdd(g.dw + o, acc[u][4 * nb + 2 * half + e]);
           }
         }
       }
@@ -317,15 +347,16 @@ static int launch_conv_wgrad_mma(ConvArgs a, const void* dy, int CoS, int Cout, 
   ga.w.a = a; ga.w.dy = dy; ga.w.CoS = CoS; ga.w.Cout = Cout; ga.w.Cin = Cin; ga.w.dw = dw; ga.w.ntaps_total = ntaps_total;
   ga.w.wt_transposed = wt_transposed; ga.w.ci_base = ci_base;
   ga.CK = CK; ga.TY = TY;
-  // enough CTAs for ~3 per SM where the accumulator list allows it (>= 8 warp-items per CTA)
+  // the accumulator list is dealt to `nsplit` CTA groups so that a warp holds at most kWgMaxAcc of them in registers; each group gets
+  // an equal share of ~2 CTAs per SM, and every CTA of a group walks the tiles with that stride
   const int ntile = cdiv(a.OWt, 32) * cdiv(a.OHt, TY) * a.B * a.S;
   const int s8 = CK / 8, nmt = (a.taps.n * s8 + 1) / 2, ngrp = (((Cout + 7) / 8) + 1) / 2;
   const int nitems = nmt * ngrp;
-  int nsplit = 1;
-  if (ntile < 3 * 148) nsplit = std::min(cdiv(3 * 148, ntile), std::max(1, nitems / 8));
-  if (nsplit > 64) nsplit = 64;
+  const int nsplit = cdiv(nitems, kWgMaxAcc * (kWgThreads / 32));
+  int ncta = std::max(1, std::min(ntile, (2 * 148) / nsplit));
+  if (nsplit * ncta < 148 && ntile > ncta) ncta = std::min(ntile, cdiv(148, nsplit));
   ga.nsplit = nsplit;
-  dim3 grid(cdiv(a.OWt, 32) * nsplit, cdiv(a.OHt, TY), a.B * a.S);
+  dim3 grid(nsplit * ncta, 1, 1);
   DFF_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   conv_wgrad_mma_kernel<<<grid, kWgThreads, smem, st>>>(ga);
   DFF_LAUNCH_CHECK("conv_wgrad_mma");
