@@ -786,6 +786,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     // Every block costs the issuing warp a barrier wait and a tcgen05.commit (~250 clk that the tensor pipe idles), so blocks are made
     // as large as the ring allows: a group of MMAs is cut into the fewest blocks whose slot (<= 40 KB) still leaves room for three
     // slots and the minimal plane ring.
+    const int np_min = 2 * p.hz + 2;   // (shadows the focal-merged minimum: streamed-weight layers run the per-slice schedule)
     const int opb = Ntc * 32;
     int gmax = 0;
     for (int gi = 0; gi < 3 * nph; ++gi) gmax = std::max(gmax, p.ge[gi] - p.g[gi]);
