@@ -403,26 +403,56 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
             mbar_wait(tempty0 + 8 * (qi & smask), ((qi >> p.lgslot) & 1u) ^ 1u);
           }
           fence_after();
+          // The plane's MMAs as at most two (accumulator, B sub-block, N') segments per spatial op — the slices it feeds are consecutive
+          // accumulator slots unless the ring wraps — computed once per plane (warp-uniform), so that the issue loop below is a
+          // descriptor add and one or two tcgen05.mma per op.  Spatial op 0 starts the accumulator of the newest slice(s) (accumulate = 0).
+          uint32_t sd[2], si[2];
+          uint64_t sb[2];
+          int nseg = 0;
+          {
+            int r0 = lo;
+            while (r0 <= hi) {
+              const uint32_t slot = (uint32_t)(q0 + r0 - s_begin) & smask;
+              int cnt = hi - r0 + 1;
+              if ((int)slot + cnt > p.nslot) cnt = p.nslot - (int)slot;
+              sd[nseg] = tmem_base + slot * N;
+              si[nseg] = idesc_base | ((((uint32_t)cnt * N) >> 3) << 17);
+              sb[nseg] = (uint64_t)(r0 - (z - 1)) * bz_blk;
+              ++nseg;
+              r0 += cnt;
+            }
+          }
           if (leader) {
-            // a run of slices [r0, r1] = focal blocks j = r0-(z-1) .. of the B operand, consecutive accumulator slots unless the ring wraps
-            auto run = [&](int i, int r0, int r1, uint32_t acc) {
-              while (r0 <= r1) {
-                const uint32_t qi = (uint32_t)(q0 + r0 - s_begin), slot = qi & smask;
-                int cnt = r1 - r0 + 1;
-                if ((int)(slot + cnt) > p.nslot) cnt = p.nslot - (int)slot;       // wrap: split the instruction
-                const uint32_t idesc = idesc_base | (((uint32_t)cnt * N >> 3) << 17);
-                const uint64_t bd = bdz + (uint64_t)i * bz_step + (uint64_t)(r0 - (z - 1)) * bz_blk;
-                umma(tmem_base + slot * N, a_pl + p.tab[p.g[1] + i], bd, idesc, acc);
-                r0 += cnt;
+            const int g1 = p.g[1];
+            {   // spatial op 0: runs [lo, nlo-1] (accumulating) and [nlo, hi] (fresh), each split where the ring wraps
+              const uint64_t ad = a_pl + p.tab[g1];
+              for (int part = 0; part < 2; ++part) {
+                int r0 = part ? nlo : lo;
+                const int r1 = part ? hi : nlo - 1;
+                while (r0 <= r1) {
+                  const uint32_t slot = (uint32_t)(q0 + r0 - s_begin) & smask;
+                  int cnt = r1 - r0 + 1;
+                  if ((int)slot + cnt > p.nslot) cnt = p.nslot - (int)slot;
+                  umma(tmem_base + slot * N, ad, bdz + (uint64_t)(r0 - (z - 1)) * bz_blk, idesc_base | ((((uint32_t)cnt * N) >> 3) << 17),
+                       part ? 0u : 1u);
+                  r0 += cnt;
+                }
               }
-            };
+            }
+            uint64_t bd = bdz + bz_step;
+            if (nseg == 1) {
+              const uint32_t d0 = sd[0], i0 = si[0];
+              const uint64_t b0 = sb[0];
 #pragma unroll 1
-            for (int i = 0; i < p.zT; ++i) {
-              if (i == 0) {
-                run(0, lo, nlo - 1, 1u);
-                run(0, nlo, hi, 0u);
-              } else {
-                run(i, lo, hi, 1u);
+              for (int i = 1; i < p.zT; ++i, bd += bz_step) umma_acc(d0, a_pl + p.tab[g1 + i], bd + b0, i0);
+            } else {
+              const uint32_t d0 = sd[0], i0 = si[0], d1 = sd[1], i1 = si[1];
+              const uint64_t b0 = sb[0], b1 = sb[1];
+#pragma unroll 1
+              for (int i = 1; i < p.zT; ++i, bd += bz_step) {
+                const uint64_t ad = a_pl + p.tab[g1 + i];
+                umma_acc(d0, ad, bd + b0, i0);
+                umma_acc(d1, ad, bd + b1, i1);
               }
             }
             umma_commit(e_pl);                                   // the plane is not needed again
