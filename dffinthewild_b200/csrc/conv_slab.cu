@@ -70,6 +70,8 @@ struct alignas(64) SlabParams {
   int N, nops, nph;          // MMA N; table entries; output phases (1 = convolution, 4 = fused transposed convolution, 2 = x-folded one)
   int phy[4], phx[4];        // output offset of each phase
   int g[12], ge[12];         // MMA groups by (phase, focal offset): table range [g[ph*3+k], ge[ph*3+k])
+  int gw[12], nwu;           // resident weights: first weight slot of each group / number of slots — groups with the same weight sequence
+                             // (the two row phases of the row-folded first layer) share their slots in shared memory
   int tilesX, tilesY, nsplit, slen, nitems;
   int OHt, OWt, OH, OW, osy, osx, ooy, oox;
   int w_bytes, tmem_cols, nelem, elem_off, ss_off, planes_off;
@@ -90,6 +92,7 @@ struct alignas(64) SlabParams {
   int tma;                          // planes staged by ONE tiled TMA load each (single-chunk, single-view layers: box 8 ch x RX x RY)
   int gb[12], gbe[12];              // block range per MMA group
   uint8_t bop[kSlabMaxOps], bn[kSlabMaxOps];   // first MMA / number of MMAs of each block
+  uint8_t wop[kSlabMaxOps];   // MMA table entry whose `wsrc` fills weight slot u
   alignas(16) uint64_t tab[kSlabMaxOps + 4];  // (+1 quad: the issuer prefetches one quad ahead) per MMA, zero-extended to 64 bits (added to the descriptor): (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
   int16_t wsrc[2 * kSlabMaxOps];  // per MMA and K half: 8-channel weight block (tap * nchunk + chunk) in `wslab`, -1 = zeros
 };
@@ -234,12 +237,12 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
       asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_s + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
   } else if (!WS) {
-    const int total = 2 * p.nops * p.N;  // 16-byte rows
+    const int total = 2 * p.nwu * p.N;  // 16-byte rows
     const uint4* wg = reinterpret_cast<const uint4*>(p.wslab);
 #pragma unroll 4
     for (int i = threadIdx.x; i < total; i += kThreads) {
       const int blk = i / p.N, r = i - blk * p.N;
-      const int src = p.wsrc[blk];
+      const int src = p.wsrc[2 * p.wop[blk >> 1] + (blk & 1)];
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (src >= 0) v = __ldg(wg + (size_t)src * p.N + r);
       asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_s + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -552,7 +555,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
             const int z = s + k - 1;
             if (n0 > 0 && z >= 0 && z < p.S && !(p.exp & 4)) {  // (focal-dimension zero padding: nothing to multiply)
               const uint64_t ad0 = k == 0 ? a_prev : (k == 1 ? a_cur : a_next);
-              uint64_t bd = bd_base + (uint32_t)i0 * b_step;
+              uint64_t bd = bd_base + (uint32_t)p.gw[gi] * b_step;
               const ulonglong2* tq = reinterpret_cast<const ulonglong2*>(p.tab + i0);  // groups start on quad boundaries
               ulonglong2 t01 = tq[0], t23 = tq[1];
               int n = n0;
@@ -756,7 +759,26 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.nops = nops;
   if (nops == 0) return_false;
   p.N = Ntc;
-  p.w_bytes = nops * Ntc * 32;
+  // weight slots: a group whose weight sequence repeats an earlier group's shares its slots
+  {
+    int nwu = 0;
+    for (int gi = 0; gi < 3 * nph; ++gi) {
+      const int n = p.ge[gi] - p.g[gi];
+      int same = -1;
+      for (int gj = 0; gj < gi && same < 0; ++gj) {
+        if (p.ge[gj] - p.g[gj] != n || n == 0) continue;
+        bool eq = true;
+        for (int i = 0; i < 2 * n && eq; ++i) eq = p.wsrc[2 * p.g[gi] + i] == p.wsrc[2 * p.g[gj] + i];
+        if (eq) same = gj;
+      }
+      if (same >= 0) { p.gw[gi] = p.gw[same]; continue; }
+      // (groups start on quad boundaries of the MMA table; their weight slots simply follow each other)
+      p.gw[gi] = nwu;
+      for (int i = 0; i < n; ++i) p.wop[nwu++] = (uint8_t)(p.g[gi] + i);
+    }
+    p.nwu = nwu;
+  }
+  p.w_bytes = p.nwu * Ntc * 32;
   // ---- shared memory: table + weights + scale/shift + staging table + ring; as many co-resident CTAs as fit -----------------
   // planes staged by TMA: one box (8 channels x RX x RY) per chunk and view (descriptors encoded at launch); DFF_B200_SLAB_TMA=0 keeps
   // the cp.async producers, =1 restricts TMA to the row-folded first layer
@@ -772,7 +794,8 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     for (int i = 0; zm && i < T; ++i) zm = p.tab[p.g[0] + i] == p.tab[p.g[1] + i] && p.tab[p.g[2] + i] == p.tab[p.g[1] + i];
     p.zT = T;
   }
-  const int np_min = zm ? 2 : 2 * p.hz + 2;
+  static const int zm_np = getenv("DFF_ZM_NPMIN") ? atoi(getenv("DFF_ZM_NPMIN")) : 2;   // (A/B knob: minimal plane-ring depth of the focal-merged form)
+  const int np_min = zm ? zm_np : 2 * p.hz + 2;
   int cols = 2 * nph * Ntc;
   if (cols > 512) return_false;
   p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
