@@ -153,6 +153,11 @@ __device__ __forceinline__ void mma_bf16_16816(float* d, unsigned a0, unsigned a
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// 16-byte global -> shared copy without a register round trip; ok == false writes zeros (the convolution's padding)
+__device__ __forceinline__ void wg_cp16(unsigned dst, const void* src, bool ok) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+}
+
 struct WgradMmaArgs {
   WgradArgs w;
   int CK, TY;      // channels staged per pass (8, 16, 32 or 64); tile rows
@@ -192,11 +197,11 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
   const int q8 = CoP / 8;
   const int wstep = ga.nsplit * (kWgThreads / 32);   // stride of this warp's accumulator list
 
+  const __nv_bfloat16* const src0 = reinterpret_cast<const __nv_bfloat16*>(a.in0);
+  const __nv_bfloat16* const src1 = reinterpret_cast<const __nv_bfloat16*>(a.in1);
+  const __nv_bfloat16* const dyg = reinterpret_cast<const __nv_bfloat16*>(g.dy);
+  const int rowlen = a.RX * s8, nin = a.RZ * a.RY * rowlen;      // 16-byte pieces of the staged input region
   for (int c0 = 0; c0 < Ctot; c0 += CK) {
-    const bool second = c0 >= a.C0;
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(second ? a.in1 : a.in0);
-    const int Csrc = second ? a.C1 : a.C0;
-    const int cb = second ? c0 - a.C0 : c0;
     float acc[kWgMaxAcc][8];
 #pragma unroll
     for (int u = 0; u < kWgMaxAcc; ++u)
@@ -209,36 +214,31 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
       const int s = r % a.S, b = r / a.S;
       const int gy0 = ty0 * a.isy + a.dymin, gx0 = tx0 * a.isx + a.dxmin, gz0 = s + a.dzmin;
       __syncthreads();   // the previous tile's MMAs have read the staging buffers
-      // ---- dy tile (once per tile: the channel passes of a multi-pass layer re-stage it, they are few) and the input region ----
-      {
-        const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(g.dy);
-        for (int row = warp; row < TY; row += kWgThreads / 32) {
-          const int oy = ty0 + row;
-          const size_t rowpix = (((size_t)b * a.S + s) * a.OH + ((size_t)oy * a.osy + a.ooy)) * a.OW + a.oox;
-          for (int e = lane; e < 32 * q8; e += 32) {
-            const int px = e / q8, q = e - px * q8;
-            const int ox = tx0 + px;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (ox < a.OWt && oy < a.OHt && 8 * q < g.CoS) v = __ldg(reinterpret_cast<const uint4*>(dy + (rowpix + (size_t)ox * a.osx) * g.CoS + 8 * q));
-            *reinterpret_cast<uint4*>(dy_s + (size_t)(row * 32 + px) * CoP + 8 * q) = v;
-          }
-        }
-        const int nrow = a.RZ * a.RY;
-        for (int row = warp; row < nrow; row += kWgThreads / 32) {
-          const int z = row / a.RY, y = row - z * a.RY;
-          const int gz = gz0 + z, gy = gy0 + y;
-          const bool rok = gz >= 0 && gz < a.S && gy >= 0 && gy < a.IH;
-          const __nv_bfloat16* rp = src + ((((size_t)b * a.S + (rok ? gz : 0)) * a.IH + (rok ? gy : 0)) * a.IW) * Csrc + cb;
-          __nv_bfloat16* dp = in_s + (size_t)row * a.RX * CK;
-          for (int e = lane; e < a.RX * s8; e += 32) {
-            const int x = e / s8, q = e - x * s8;
-            const int gx = gx0 + x;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (rok && gx >= 0 && gx < a.IW) v = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)gx * Csrc + 8 * q));
-            *reinterpret_cast<uint4*>(dp + (size_t)x * CK + 8 * q) = v;
-          }
-        }
+      // ---- stage the dy tile and the halo'd input region with fire-and-forget 16-byte cp.async copies (zero fill outside the
+      // tensors / the phase grid): every thread has all of its copies in flight before anyone waits — the first version loaded
+      // and stored piece by piece and spent its time in exposed global-memory latency ----
+      for (int e = tid; e < NP * q8; e += kWgThreads) {
+        const int q = e % q8, pos = e / q8;
+        const int ox = tx0 + (pos & 31), oy = ty0 + (pos >> 5);
+        const bool ok = ox < a.OWt && oy < a.OHt && 8 * q < g.CoS;
+        const size_t pix = (((size_t)b * a.S + s) * a.OH + ((size_t)oy * a.osy + a.ooy)) * a.OW + ((size_t)ox * a.osx + a.oox);
+        wg_cp16(dy_u + 2u * (unsigned)(pos * CoP + 8 * q), ok ? (const void*)(dyg + pix * g.CoS + 8 * q) : (const void*)dyg, ok);
       }
+      for (int e = tid; e < nin; e += kWgThreads) {
+        const int row = e / rowlen, rem = e - row * rowlen;
+        const int x = rem / s8, q = rem - x * s8;
+        const int z = row / a.RY, y = row - z * a.RY;
+        const int gz = gz0 + z, gy = gy0 + y, gx = gx0 + x;
+        const int cabs = c0 + 8 * q;                                   // stored channel of this piece: first or second source
+        const bool second = cabs >= a.C0;
+        const __nv_bfloat16* sp = second ? src1 : src0;
+        const int Csrc = second ? a.C1 : a.C0, cs = second ? cabs - a.C0 : cabs;
+        const bool ok = gz >= 0 && gz < a.S && gy >= 0 && gy < a.IH && gx >= 0 && gx < a.IW;
+        const size_t off = ((((size_t)b * a.S + gz) * a.IH + gy) * a.IW + gx) * Csrc + cs;
+        wg_cp16(in_u + 2u * (unsigned)((row * a.RX + x) * CK + 8 * q), ok ? (const void*)(sp + off) : (const void*)src0, ok);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
 #pragma unroll
       for (int u = 0; u < kWgMaxAcc; ++u) {
@@ -325,10 +325,11 @@ static int launch_conv_wgrad_mma(ConvArgs a, const void* dy, int CoS, int Cout, 
                                  int wt_transposed, cudaStream_t st, bool* handled) {
   *handled = false;
   if (a.C0 % 8 || a.C1 % 8 || CoS % 8 || a.C0 < 8) return 0;
-  // channels per pass: the largest of 64, 32, 16 that divides both sources (8-channel tensors: 8, two taps per m16 block)
+  // channels per pass: the largest of 64, 32, 16 that divides the (virtually concatenated) input; a pass may straddle the two sources
+  // (8-channel tensors: 8, two taps per m16 block)
   int CK = 8;
   for (int c = 64; c >= 16; c >>= 1)
-    if (a.C0 % c == 0 && a.C1 % c == 0) { CK = c; break; }
+    if ((a.C0 + a.C1) % c == 0) { CK = c; break; }
   const size_t budget = 110 * 1024;   // two CTAs per SM
   int TY = 0;
   size_t smem = 0;
