@@ -168,7 +168,7 @@ struct WgradMmaArgs {
 // Persistent over tiles: CTA (split, c) owns the accumulators `split, split + nsplit, ...` of the layer's list and walks the tiles
 // c, c + ncta, ... keeping them in registers (at most kWgMaxAcc m16 x n16 accumulators per warp), so the fp32 atomics into the
 // gradient happen once per CTA instead of once per tile.
-constexpr int kWgMaxAcc = 8;
+constexpr int kWgMaxAcc = 4;
 __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __grid_constant__ WgradMmaArgs ga) {
   extern __shared__ __align__(16) unsigned char smem_b[];
   const WgradArgs& g = ga.w;
@@ -325,30 +325,22 @@ static int launch_conv_wgrad_mma(ConvArgs a, const void* dy, int CoS, int Cout, 
                                  int wt_transposed, cudaStream_t st, bool* handled) {
   *handled = false;
   if (a.C0 % 8 || a.C1 % 8 || CoS % 8 || a.C0 < 8) return 0;
-  // Channels per pass (CK: 64, 32, 16 dividing the virtually concatenated input — a pass may straddle the two sources; 8-channel
-  // tensors: 8, two taps per m16 block) and tile rows (TY) by a traffic model: the accumulator list of a pass is dealt to
-  // nsplit = items / (8 warps x kWgMaxAcc) CTA groups and every group stages every tile, so a tile row costs
-  //   nsplit * (input region of all channels + passes * dy tile) / TY     bytes of L2 -> shared-memory traffic.
-  // Wide layers at low resolution want few channels per pass (few groups), narrow full-resolution layers everything at once.
+  // channels per pass: the largest of 64, 32, 16 that divides the (virtually concatenated) input; a pass may straddle the two sources
+  // (8-channel tensors: 8, two taps per m16 block)
+  int CK = 8;
+  for (int c = 64; c >= 16; c >>= 1)
+    if ((a.C0 + a.C1) % c == 0) { CK = c; break; }
   const size_t budget = 110 * 1024;   // two CTAs per SM
-  int CK = 0, TY = 0;
+  int TY = 0;
   size_t smem = 0;
-  double best = 1e300;
-  const int Ctot = a.C0 + a.C1, nnt = (Cout + 7) / 8, ngrp_n = (nnt + 1) / 2;
-  for (int ck = 64; ck >= 8; ck >>= 1) {
-    if (Ctot % ck || (ck == 8 && Ctot % 16 == 0 && CK)) continue;
+  for (;; CK >>= 1) {
     for (int ty = 16; ty >= 2; ty >>= 1) {
       if (ty > 2 && (ty >> 1) >= a.OHt) continue;      // no taller than the phase grid needs
       ConvArgs t = a;
-      const size_t sz = wg_mma_plan(t, ck, ty, Cout);
-      if (sz > budget) continue;
-      const int items = ((a.taps.n * (ck / 8) + 1) / 2) * ngrp_n;
-      const int nsp = cdiv(items, kWgMaxAcc * (kWgThreads / 32)), npass = Ctot / ck;
-      const double in_all = (double)t.RZ * t.RY * t.RX * Ctot * 2, dyb = 32.0 * ty * ((Cout + 7) & ~7) * 2;
-      const double cost = nsp * (in_all + npass * dyb) / ty + 4096.0 * npass / ty;   // (+ a fixed per-tile-pass overhead)
-      if (cost < best) { best = cost; CK = ck; TY = ty; smem = sz; }
-      break;   // (smaller tiles of the same CK only cost more)
+      const size_t sz = wg_mma_plan(t, CK, ty, Cout);
+      if (sz <= budget) { TY = ty; smem = sz; break; }
     }
+    if (TY || CK == 8) break;
   }
   if (!TY) return 0;
   WgradMmaArgs ga{};
