@@ -158,6 +158,12 @@ __device__ __forceinline__ void wg_cp16(unsigned dst, const void* src, bool ok) 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
 }
 
+struct WgPiece {          // one staged 16-byte piece
+  int rel;                // source element offset relative to the tile / region origin
+  unsigned dst;           // byte offset inside the staging buffer
+  unsigned char x, y, z, pad;   // tile-relative coordinates (z bit 7: second source)
+};
+
 struct WgradMmaArgs {
   WgradArgs w;
   int CK, TY;      // channels staged per pass (8, 16, 32 or 64); tile rows
@@ -179,6 +185,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
   const int CoP = (g.Cout + 7) & ~7;
   __nv_bfloat16* in_s = reinterpret_cast<__nv_bfloat16*>(smem_b);            // [REGPOS][CK]
   __nv_bfloat16* dy_s = in_s + (size_t)REGPOS * CK;                           // [NP][CoP]
+  WgPiece* in_tab = reinterpret_cast<WgPiece*>(dy_s + (size_t)NP * CoP);      // [REGPOS * CK/8]
+  WgPiece* dy_tab = in_tab + (size_t)REGPOS * (CK / 8);                       // [NP * CoP/8]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x % ga.nsplit, cta = blockIdx.x / ga.nsplit, ncta = gridDim.x / ga.nsplit;
   const int tilesX = (a.OWt + 31) / 32, tilesY = (a.OHt + TY - 1) / TY;
@@ -201,12 +209,41 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
   const __nv_bfloat16* const src1 = reinterpret_cast<const __nv_bfloat16*>(a.in1);
   const __nv_bfloat16* const dyg = reinterpret_cast<const __nv_bfloat16*>(g.dy);
   const int rowlen = a.RX * s8, nin = a.RZ * a.RY * rowlen;      // 16-byte pieces of the staged input region
+  const int ndy = NP * q8;
   for (int c0 = 0; c0 < Ctot; c0 += CK) {
     float acc[kWgMaxAcc][8];
 #pragma unroll
     for (int u = 0; u < kWgMaxAcc; ++u)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
+    // ---- tables of the 16-byte pieces a tile stages (the same for every tile of this channel pass): destination in shared memory,
+    // source offset relative to the tile origin, coordinates for the bounds check — so that the per-tile staging loops are a table
+    // read, a few compares and a cp.async instead of five integer divisions per piece ----
+    __syncthreads();
+    for (int e = tid; e < nin; e += kWgThreads) {
+      const int row = e / rowlen, rem = e - row * rowlen;
+      const int x = rem / s8, q = rem - x * s8;
+      const int z = row / a.RY, y = row - z * a.RY;
+      const int cabs = c0 + 8 * q;
+      const bool second = cabs >= a.C0;
+      const int Csrc = second ? a.C1 : a.C0, cs = second ? cabs - a.C0 : cabs;
+      WgPiece pc;
+      pc.rel = (int)((((long long)z * a.IH + y) * a.IW + x) * Csrc + cs);
+      pc.dst = 2u * (unsigned)((row * a.RX + x) * CK + 8 * q);
+      pc.x = (unsigned char)x; pc.y = (unsigned char)y; pc.z = (unsigned char)(z | (second ? 0x80 : 0)); pc.pad = 0;
+      in_tab[e] = pc;
+    }
+    if (c0 == 0)
+      for (int e = tid; e < ndy; e += kWgThreads) {
+        const int q = e % q8, pos = e / q8;
+        const int px = pos & 31, py = pos >> 5;
+        WgPiece pc;
+        pc.rel = (int)((((long long)py * a.osy) * a.OW + (long long)px * a.osx) * g.CoS + 8 * q);
+        pc.dst = 2u * (unsigned)(pos * CoP + 8 * q);
+        pc.x = (unsigned char)px; pc.y = (unsigned char)py; pc.z = (unsigned char)(8 * q < g.CoS ? 0 : 1); pc.pad = 0;
+        dy_tab[e] = pc;
+      }
+    __syncthreads();
     for (int tile = cta; tile < ntile; tile += ncta) {
       int r = tile;
       const int tx0 = (r % tilesX) * 32; r /= tilesX;
@@ -217,25 +254,26 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_mma_kernel(const __g
       // ---- stage the dy tile and the halo'd input region with fire-and-forget 16-byte cp.async copies (zero fill outside the
       // tensors / the phase grid): every thread has all of its copies in flight before anyone waits — the first version loaded
       // and stored piece by piece and spent its time in exposed global-memory latency ----
-      for (int e = tid; e < NP * q8; e += kWgThreads) {
-        const int q = e % q8, pos = e / q8;
-        const int ox = tx0 + (pos & 31), oy = ty0 + (pos >> 5);
-        const bool ok = ox < a.OWt && oy < a.OHt && 8 * q < g.CoS;
-        const size_t pix = (((size_t)b * a.S + s) * a.OH + ((size_t)oy * a.osy + a.ooy)) * a.OW + ((size_t)ox * a.osx + a.oox);
-        wg_cp16(dy_u + 2u * (unsigned)(pos * CoP + 8 * q), ok ? (const void*)(dyg + pix * g.CoS + 8 * q) : (const void*)dyg, ok);
-      }
-      for (int e = tid; e < nin; e += kWgThreads) {
-        const int row = e / rowlen, rem = e - row * rowlen;
-        const int x = rem / s8, q = rem - x * s8;
-        const int z = row / a.RY, y = row - z * a.RY;
-        const int gz = gz0 + z, gy = gy0 + y, gx = gx0 + x;
-        const int cabs = c0 + 8 * q;                                   // stored channel of this piece: first or second source
-        const bool second = cabs >= a.C0;
-        const __nv_bfloat16* sp = second ? src1 : src0;
-        const int Csrc = second ? a.C1 : a.C0, cs = second ? cabs - a.C0 : cabs;
-        const bool ok = gz >= 0 && gz < a.S && gy >= 0 && gy < a.IH && gx >= 0 && gx < a.IW;
-        const size_t off = ((((size_t)b * a.S + gz) * a.IH + gy) * a.IW + gx) * Csrc + cs;
-        wg_cp16(in_u + 2u * (unsigned)((row * a.RX + x) * CK + 8 * q), ok ? (const void*)(sp + off) : (const void*)src0, ok);
+      {
+        // dy: the tile-relative pixel offset of every piece comes from the table built once per CTA
+        const size_t dpix0 = (((size_t)b * a.S + s) * a.OH + ((size_t)ty0 * a.osy + a.ooy)) * a.OW + ((size_t)tx0 * a.osx + a.oox);
+        const __nv_bfloat16* dbase = dyg + dpix0 * g.CoS;
+        for (int e = tid; e < ndy; e += kWgThreads) {
+          const WgPiece pc = dy_tab[e];
+          const bool ok = tx0 + (int)pc.x < a.OWt && ty0 + (int)pc.y < a.OHt && pc.z == 0;
+          wg_cp16(dy_u + pc.dst, ok ? (const void*)(dbase + pc.rel) : (const void*)dyg, ok);
+        }
+        // input region: rel is relative to the region origin (gz0, gy0, gx0) in the piece's own source (channel stride Csrc)
+        const long long org = (((long long)b * a.S + gz0) * a.IH + gy0) * (long long)a.IW + gx0;
+        const __nv_bfloat16* b0 = src0 + org * a.C0;
+        const __nv_bfloat16* b1 = src1 ? src1 + org * a.C1 : src0;
+        for (int e = tid; e < nin; e += kWgThreads) {
+          const WgPiece pc = in_tab[e];
+          const int gz = gz0 + (int)(pc.z & 0x7f), gy = gy0 + (int)pc.y, gx = gx0 + (int)pc.x;
+          const bool ok = gz >= 0 && gz < a.S && gy >= 0 && gy < a.IH && gx >= 0 && gx < a.IW;
+          const __nv_bfloat16* sp = (pc.z & 0x80) ? b1 : b0;
+          wg_cp16(in_u + pc.dst, ok ? (const void*)(sp + pc.rel) : (const void*)src0, ok);
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -318,7 +356,8 @@ static size_t wg_mma_plan(ConvArgs& a, int CK, int TY, int Cout) {
   a.RX = 31 * a.isx + (dxmax - a.dxmin) + 1;
   a.RXP = a.RX;
   const int CoP = (Cout + 7) & ~7;
-  return ((size_t)a.RZ * a.RY * a.RX * CK + (size_t)32 * TY * CoP) * 2;
+  const size_t pieces = (size_t)a.RZ * a.RY * a.RX * (CK / 8) + (size_t)32 * TY * (CoP / 8);
+  return ((size_t)a.RZ * a.RY * a.RX * CK + (size_t)32 * TY * CoP) * 2 + pieces * sizeof(WgPiece);
 }
 
 static int launch_conv_wgrad_mma(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, int ci_base, float* dw, int ntaps_total,
