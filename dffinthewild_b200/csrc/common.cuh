@@ -119,6 +119,7 @@ struct ConvArgs {
                            // (no row-parity views): the row-folded first layer.  Output: 8-channel groups `grp_rows` rows apart.
   int grp_rows;
   int proj_c;              // channels per pixel of the projection when a GEMM row holds several pixels (x-folded layers), 0 = all
+  const void* wz;          // slab kernel, optional: the layer's weights in the focal-merged streaming layout (pack_weight_slab_zmerge)
   TapTable taps;
 };
 

@@ -425,39 +425,59 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
               r0 += cnt;
             }
           }
-          if (leader) {
-            const int g1 = p.g[1];
-            {   // spatial op 0: runs [lo, nlo-1] (accumulating) and [nlo, hi] (fresh), each split where the ring wraps
-              const uint64_t ad = a_pl + p.tab[g1];
-              for (int part = 0; part < 2; ++part) {
-                int r0 = part ? nlo : lo;
-                const int r1 = part ? hi : nlo - 1;
-                while (r0 <= r1) {
-                  const uint32_t slot = (uint32_t)(q0 + r0 - s_begin) & smask;
-                  int cnt = r1 - r0 + 1;
-                  if ((int)slot + cnt > p.nslot) cnt = p.nslot - (int)slot;
-                  umma(tmem_base + slot * N, ad, bdz + (uint64_t)(r0 - (z - 1)) * bz_blk, idesc_base | ((((uint32_t)cnt * N) >> 3) << 17),
-                       part ? 0u : 1u);
-                  r0 += cnt;
+          // the plane's spatial MMAs, block by block: ONE block when the weights are resident; with streamed weights the whole warp
+          // waits for a block's ring slot, the elected lane issues its MMAs and hands the slot back when they have read it
+          const int g1 = p.g[1];
+          const int nblk = WS ? p.nblk : 1;
+#pragma unroll 1
+          for (int bk = 0; bk < nblk; ++bk) {
+            const int i_lo = WS ? (int)p.bop[bk] : 0, i_hi = WS ? i_lo + (int)p.bn[bk] : p.zT;
+            uint64_t bd = bdz + (WS ? (uint64_t)((uint32_t)(wsl * p.wslot_bytes) >> 4) : (uint64_t)0);   // weights of op i_lo
+            if (WS) {
+              mbar_wait(wfull0 + 8 * wsl, wsph);
+              fence_after();
+            }
+            if (leader) {
+              int i = i_lo;
+              if (i == 0) {   // spatial op 0: runs [lo, nlo-1] (accumulating) and [nlo, hi] (fresh), each split where the ring wraps
+                const uint64_t ad = a_pl + p.tab[g1];
+                for (int part = 0; part < 2; ++part) {
+                  int r0 = part ? nlo : lo;
+                  const int r1 = part ? hi : nlo - 1;
+                  while (r0 <= r1) {
+                    const uint32_t slot = (uint32_t)(q0 + r0 - s_begin) & smask;
+                    int cnt = r1 - r0 + 1;
+                    if ((int)slot + cnt > p.nslot) cnt = p.nslot - (int)slot;
+                    umma(tmem_base + slot * N, ad, bd + (uint64_t)(r0 - (z - 1)) * bz_blk, idesc_base | ((((uint32_t)cnt * N) >> 3) << 17),
+                         part ? 0u : 1u);
+                    r0 += cnt;
+                  }
+                }
+                i = 1;
+                bd += bz_step;
+              }
+              if (nseg == 1) {
+                const uint32_t d0 = sd[0], i0 = si[0];
+                const uint64_t b0 = sb[0];
+#pragma unroll 1
+                for (; i < i_hi; ++i, bd += bz_step) umma_acc(d0, a_pl + p.tab[g1 + i], bd + b0, i0);
+              } else {
+                const uint32_t d0 = sd[0], i0 = si[0], d1 = sd[1], i1 = si[1];
+                const uint64_t b0 = sb[0], b1 = sb[1];
+#pragma unroll 1
+                for (; i < i_hi; ++i, bd += bz_step) {
+                  const uint64_t ad = a_pl + p.tab[g1 + i];
+                  umma_acc(d0, ad, bd + b0, i0);
+                  umma_acc(d1, ad, bd + b1, i1);
                 }
               }
+              if (WS) umma_commit(wempty0 + 8 * wsl);
             }
-            uint64_t bd = bdz + bz_step;
-            if (nseg == 1) {
-              const uint32_t d0 = sd[0], i0 = si[0];
-              const uint64_t b0 = sb[0];
-#pragma unroll 1
-              for (int i = 1; i < p.zT; ++i, bd += bz_step) umma_acc(d0, a_pl + p.tab[g1 + i], bd + b0, i0);
-            } else {
-              const uint32_t d0 = sd[0], i0 = si[0], d1 = sd[1], i1 = si[1];
-              const uint64_t b0 = sb[0], b1 = sb[1];
-#pragma unroll 1
-              for (int i = 1; i < p.zT; ++i, bd += bz_step) {
-                const uint64_t ad = a_pl + p.tab[g1 + i];
-                umma_acc(d0, ad, bd + b0, i0);
-                umma_acc(d1, ad, bd + b1, i1);
-              }
+            if (WS) {
+              if (++wsl == p.nwslots) { wsl = 0; wsph ^= 1; }
             }
+          }
+          if (leader) {
             umma_commit(e_pl);                                   // the plane is not needed again
             if (z - 1 >= s_begin) umma_commit(tfull0 + 8 * ((uint32_t)(q0 + z - 1 - s_begin) & smask));        // slice z-1 is complete
             if (z == zhi - 1 && z < s_end) umma_commit(tfull0 + 8 * ((uint32_t)(q0 + z - s_begin) & smask));   // last plane: slice z too
@@ -600,7 +620,27 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
     // =============================== weight producer (streaming variant) ===============================
     // walks exactly the issuer's schedule; one bulk copy (global -> shared, completion on the slot's `full` barrier) per block
     pdl_trigger();
-    if (lane == 0) {
+    if (lane == 0 && p.zmerge) {
+      const char* const wg = reinterpret_cast<const char*>(p.wslab);     // (the focal-merged layout: launch_conv_slab passes a.wz)
+      int wsl = 0;
+      uint32_t eph = 1;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        const int isp = item % p.nsplit;
+        const int s_begin = isp * p.slen, s_end = min(p.S, s_begin + p.slen);
+        const int zlo = max(0, s_begin - 1), zhi = min(p.S, s_end + 1);
+        for (int z = zlo; z < zhi; ++z)
+          for (int b = 0; b < p.nblk; ++b) {
+            mbar_wait(wempty0 + 8 * wsl, eph);
+            const uint32_t bytes = (uint32_t)p.bn[b] * (uint32_t)p.N * 96u;
+            mbar_expect_tx(wfull0 + 8 * wsl, bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             w_s + (uint32_t)(wsl * p.wslot_bytes)),
+                         "l"(wg + (size_t)p.bop[b] * p.N * 96), "r"(bytes), "r"(wfull0 + 8 * wsl)
+                         : "memory");
+            if (++wsl == p.nwslots) { wsl = 0; eph ^= 1; }
+          }
+      }
+    } else if (lane == 0) {
       const char* const wg = reinterpret_cast<const char*>(p.wslab);
       const int ngrp = 3 * p.nph;
       int wsl = 0;
@@ -839,6 +879,36 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     // Every block costs the issuing warp a barrier wait and a tcgen05.commit (~250 clk that the tensor pipe idles), so blocks are made
     // as large as the ring allows: a group of MMAs is cut into the fewest blocks whose slot (<= 40 KB) still leaves room for three
     // slots and the minimal plane ring.
+    static const bool no_zmws = getenv("DFF_B200_NO_ZMWS") != nullptr;   // (A/B knob)
+    if (zm && a.wz && !no_zmws && 8 * Ntc <= 512) {
+      // focal-merged AND streamed: the weights of one spatial MMA (three focal taps, 96*N bytes) are contiguous in `wz`, so the ring
+      // is fed block by block with one bulk copy each; every plane replays the same sequence of blocks
+      const int T = p.zT, opz = 96 * Ntc;
+      const int budget = kSlabSmemBudget - 2048 - 256 - 256;
+      int per_slot = 0, nw = 0;
+      for (int parts = 1; parts <= 32 && !per_slot; ++parts) {
+        const int ps = cdiv(T, parts);
+        if (ps * opz > kSlabMaxWSlot) continue;
+        for (nw = 4; nw >= 3; --nw) {
+          fixed = lay_out(nw * ps * opz);
+          NP = (budget - fixed) / p.plane_bytes;
+          if (NP >= 3) { per_slot = ps; break; }
+        }
+      }
+      if (per_slot) {
+        int nb = 0;
+        for (int o = 0; o < T; o += per_slot) { p.bop[nb] = (uint8_t)o; p.bn[nb] = (uint8_t)std::min(per_slot, T - o); ++nb; }
+        p.nblk = nb;
+        occ = 1;
+        p.wslot_bytes = per_slot * opz;
+        p.wstream = 1;
+        p.nwslots = nw;
+        p.w_bytes = nw * p.wslot_bytes;
+        p.zmerge = 1; p.nslot = 8; p.lgslot = 3;
+        p.tmem_cols = 8 * Ntc <= 32 ? 32 : 8 * Ntc <= 64 ? 64 : 8 * Ntc <= 128 ? 128 : 8 * Ntc <= 256 ? 256 : 512;
+      }
+    }
+    if (!p.wstream) {
     const int np_min = 2 * p.hz + 2;   // (shadows the focal-merged minimum: streamed-weight layers run the per-slice schedule)
     const int opb = Ntc * 32;
     int gmax = 0;
@@ -876,6 +946,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     p.wstream = 1;
     p.nwslots = nw;
     p.w_bytes = nw * p.wslot_bytes;
+    }
   }
   if (NP > kSlabMaxPlanes) NP = kSlabMaxPlanes;
   p.NP = NP;
@@ -923,7 +994,7 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
   int occ = 1;
   if (!slab_plan(a, ptaps ? ptaps : &a.taps, ptaps ? nph : 1, Ntc, num_sms, p, &smem, &occ))
     return fail(-5, "conv_slab: unsupported layer shape");
-  p.wslab = wslab;
+  p.wslab = (p.zmerge && p.wstream) ? a.wz : wslab;   // (focal-merged streaming reads its own layout)
   if (p.tma) {
     for (int src = 0; src < (a.C1 ? 2 : 1); ++src) {
       const unsigned long long C = src ? a.C1 : a.C0;
@@ -1046,6 +1117,35 @@ __global__ void pack_weight_slab_rowfold_kernel(const float* __restrict__ wp, __
 int launch_pack_weight_slab_rowfold(const float* wpair, void* dst, int Cout, cudaStream_t st) {
   pack_weight_slab_rowfold_kernel<<<cdiv(60 * 4 * Cout * 8, 256), 256, 0, st>>>(wpair, (__nv_bfloat16*)dst, Cout);
   DFF_LAUNCH_CHECK("pack_weight_slab_rowfold");
+  return 0;
+}
+
+// Focal-merged streaming layout of a 3x3x3 convolution: bf16 [spatial tap u = kh*3+kw][chunk pair][K half][focal block j][Ntc][8] with
+// focal block j = 0, 1, 2 <-> dz = +1, 0, -1 <-> kd = 2, 1, 0 — the B operand of one merged MMA (all three focal taps of a spatial tap
+// and 16 input channels) is 96*Ntc contiguous bytes, so a block of consecutive merged MMAs is one bulk copy.
+__global__ void pack_weight_slab_zmerge_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin, int CinP,
+                                               int Ntc) {
+  const int ncp = CinP / 16;
+  const int n = 9 * ncp * 2 * 3 * Ntc * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int r = i;
+    const int e = r & 7; r >>= 3;
+    const int co = r % Ntc; r /= Ntc;
+    const int j = r % 3; r /= 3;
+    const int h = r & 1; r >>= 1;
+    const int cp = r % ncp, u = r / ncp;
+    const int ci = (2 * cp + h) * 8 + e, t = (2 - j) * 9 + u;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * 27 + t];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+int launch_pack_weight_slab_zmerge(const float* w, void* dst, int Cout, int Cin, int CinP, int Ntc, cudaStream_t st) {
+  const int n = 27 * CinP * Ntc;
+  int g = cdiv(n, 256);
+  if (g > 512) g = 512;
+  pack_weight_slab_zmerge_kernel<<<g, 256, 0, st>>>(w, (__nv_bfloat16*)dst, Cout, Cin, CinP, Ntc);
+  DFF_LAUNCH_CHECK("pack_weight_slab_zmerge");
   return 0;
 }
 

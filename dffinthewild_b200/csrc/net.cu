@@ -50,6 +50,7 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
 int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int CinP, int ntaps, int Ntc, int transposed,
                             cudaStream_t st);
 int launch_pack_weight_slab_deconv_fold(const float* w, void* dst, int Cout, int Cin, int CinP, cudaStream_t st);
+int launch_pack_weight_slab_zmerge(const float* w, void* dst, int Cout, int Cin, int CinP, int Ntc, cudaStream_t st);
 int launch_replicate_ss(const float* scale, const float* shift, float* dst, int C, int G, cudaStream_t st);
 int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, int CinP, int kd, int kh, int kw, int G, cudaStream_t st);
 int launch_pack_weight_slab_rowfold(const float* wpair, void* dst, int Cout, cudaStream_t st);
@@ -121,6 +122,8 @@ struct Layer {
   int CinT, Ntc;  // tensor-core path: stored input channels (multiple of 8) and MMA N (multiple of 16, >= 16)
   int64_t raw_w, raw_gamma, raw_beta, raw_mean, raw_var, raw_bias;  // element offsets in the raw buffer (-1: none)
   size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab, pk_proj, pk_pair, pk_wfold, pk_ssfold;                  // byte offsets in the packed buffer
+  size_t pk_wz = 0;      // focal-merged streaming layout (3x3x3 layers with >= 64 stored input channels, whose weights are streamed)
+  bool has_wz = false;
 };
 // Where each kernel layout of one layer lives inside a packed buffer (byte offsets from its start); `packed_bytes` is advanced.
 // Shared by the network's layer table and the single-operator entry point (dff_conv3d with the forward's plan).
@@ -169,6 +172,11 @@ static void layout_layer(Layer& l, size_t& packed_bytes) {
   }
   l.pk_proj = packed_bytes;   // C -> 1 projections (classifiers): contiguous fp32 weights for the fused epilogue
   if (cout == 1 && l.ntaps == 1) packed_bytes += align_up((size_t)l.CinT * sizeof(float), 256);
+  l.pk_wz = packed_bytes;
+  if (!transposed && kd == 3 && kh == 3 && kw == 3 && dil == 1 && l.CinT % 16 == 0 && l.CinT * l.Ntc >= 32 * 64) {
+    l.has_wz = true;
+    packed_bytes += align_up((size_t)27 * l.CinT * l.Ntc * 2, 256);
+  }
 }
 struct Param {
   std::string name;
@@ -421,6 +429,7 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
   a.aux_add = e.aux_add ? e.aux_add->p : nullptr;
   a.Cout = out.C;
   a.out_f32 = e.out_f32 ? 1 : 0;
+  a.wz = (wtc && packed_base && l.has_wz) ? packed_base + l.pk_wz : nullptr;
   if (e.proj && wtc && packed_base) {
     a.proj_w = (const float*)(packed_base + e.proj->pk_proj);
     a.proj_out = (float*)e.proj_out->p;
@@ -981,6 +990,7 @@ static int pack_layer_weights(const Layer& l, const float* w, char* pk, cudaStre
     if (l.transposed) DFF_TRY(launch_pack_weight_slab_deconv_fold(w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, st));
     else DFF_TRY(launch_pack_weight_slab_fold(w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st));
   }
+  if (l.has_wz) DFF_TRY(launch_pack_weight_slab_zmerge(w, pk + l.pk_wz, l.cout, l.cin, l.CinT, l.Ntc, st));
   return 0;
 }
 // scale/shift of the folded forms (replicated per pixel of the GEMM row) from the layer's scale/shift in `pk`
