@@ -12,9 +12,10 @@
 // broadcast), and adds its partial sums to the fp32 gradient in the reference's weight layout with red.global.add.f32.
 // fp32 accumulate; the order of the global adds is not fixed, which moves results by ~1e-7 relative (gate: gradient cosine).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dff {
 
@@ -397,9 +398,310 @@ static int launch_conv_wgrad_mma(ConvArgs a, const void* dy, int CoS, int Cout, 
   if (nsplit * ncta < 148 && ntile > ncta) ncta = std::min(ntile, cdiv(148, nsplit));
   ga.nsplit = nsplit;
   dim3 grid(nsplit * ncta, 1, 1);
+  static const bool log = getenv("DFF_B200_WGRAD_LOG") != nullptr;   // (profiling aid: one line per launch, joins with an ncu launch list)
+  if (log)
+    fprintf(stderr, "wgrad_mma Cin=%d+%d Cout=%d taps=%d B=%d S=%d OHt=%d OWt=%d is=%d os=%d CK=%d TY=%d nsplit=%d ncta=%d ntile=%d smem=%zu\n",
+            a.C0, a.C1, Cout, a.taps.n, a.B, a.S, a.OHt, a.OWt, a.isx, a.osx, CK, TY, nsplit, ncta, ntile, smem);
   DFF_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   conv_wgrad_mma_kernel<<<grid, kWgThreads, smem, st>>>(ga);
   DFF_LAUNCH_CHECK("conv_wgrad_mma");
+  *handled = true;
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-staged, double-buffered form of the tensor-core weight gradient (the default for bf16 tensors).
+//
+// Same contraction as conv_wgrad_mma_kernel (M = (tap, input channel), N = output channel, K = output positions, mma.sync m16n8k16),
+// re-organised around what bounded that kernel (profiles/r2_train_wgrad.txt): per-thread staging with index arithmetic, 2..8-way
+// shared-memory bank conflicts of the [position][CK] layout, one ldmatrix pair per MMA, no overlap of staging and math.
+//  * A tile (TX x TY positions of one (batch, slice), TX = 8 / 16 / 32 by the layer's width) is staged by ONE thread with tiled TMA
+//    loads — a 5-D box (8 channels, RX, RY, RZ, 1) per 8-channel chunk of the input region (zero padding = out-of-bounds fill, the
+//    second tensor map = the concat source) and a 4-D box (8, TX, TY, 1) per 8 output channels of dy (a transposed convolution's
+//    output-parity phase = a strided tensor map) — into two stages: tile i+1 lands while the warps work on tile i.
+//  * Layout [8-channel chunk][position][8]: the 8 rows of every ldmatrix are 128 contiguous bytes (conflict-free), and a tap is
+//    still only a different base address.
+//  * A warp owns a block of up to MW m16-tiles x NW n8-tiles (64 fp32 accumulators at most): the dy fragments of a k-step are loaded
+//    once for the whole block, each input fragment feeds NW MMAs.  Blocks are dealt to the 8 warps of `nsub` CTA groups; the input
+//    channels are split into `npass` groups of CK so that a CTA stages only the channels it multiplies.
+//  * The four phases of a transposed convolution run in ONE launch: they read the same input region, every tap belongs to exactly
+//    one phase, so a phase is just the dy set (one of four staged sub-tiles) a tap's m16-tile multiplies with.
+// Accumulators stay in registers over all tiles a CTA walks; one red.global.add.f32 per element and CTA at the end.
+// ------------------------------------------------------------------------------------------------------------------
+struct Wg2Args {
+  CUtensorMap tx[2];
+  CUtensorMap tdy[4];
+  TapTable taps;                 // the taps of all dy sets, concatenated
+  uint8_t tap_set[kMaxTaps];     // dy set (phase) of every tap
+  int nset;
+  int C0, S;
+  int tilesX, tilesY, ntile;
+  int isx, isy, dzmin, dymin, dxmin, RX, RY, REGP;
+  int TX, TY, NP;
+  int CK, s8, nsub, ncta;
+  int MT, NT, NB, MB, mper, nslots;
+  int Cout, Cin, ci_base, ntaps_total, wt_transposed;
+  float* dw;
+  unsigned x_bytes, dy_bytes, tx_bytes;   // per stage: input part, one dy set; bytes the TMA loads of one tile deliver
+};
+
+__device__ __forceinline__ void wg2_issue(const Wg2Args& g, int tile, int c0, uint32_t dst, uint32_t bar) {
+  using namespace tc;
+  int r = tile;
+  const int tx0 = (r % g.tilesX) * g.TX; r /= g.tilesX;
+  const int ty0 = (r % g.tilesY) * g.TY; r /= g.tilesY;
+  const int s = r % g.S, b = r / g.S;
+  const int gx0 = tx0 * g.isx + g.dxmin, gy0 = ty0 * g.isy + g.dymin, gz0 = s + g.dzmin;
+  mbar_expect_tx(bar, g.tx_bytes);
+  for (int c = 0; c < g.s8; ++c) {
+    const int cabs = c0 + 8 * c;
+    const int src = cabs >= g.C0 ? 1 : 0;
+    tma_load_5d(dst + (uint32_t)(c * g.REGP) * 16u, &g.tx[src], bar, src ? cabs - g.C0 : cabs, gx0, gy0, gz0, b);
+  }
+  for (int set = 0; set < g.nset; ++set)
+    for (int nt = 0; nt < g.NT; ++nt)
+      tma_load_4d(dst + g.x_bytes + (uint32_t)set * g.dy_bytes + (uint32_t)(nt * g.NP) * 16u, &g.tdy[set], bar, nt * 8, tx0, ty0, b * g.S + s);
+}
+
+template <int MW, int NW>
+__global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_tma_kernel(const __grid_constant__ Wg2Args g) {
+  using namespace tc;
+  extern __shared__ __align__(128) unsigned char smem_w[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t s0 = smem_u32(smem_w);
+  const uint32_t stage_bytes = g.x_bytes + (uint32_t)g.nset * g.dy_bytes;
+  const uint32_t bar0 = s0 + 2 * stage_bytes;
+  int r = blockIdx.x;
+  const int cta = r % g.ncta; r /= g.ncta;
+  const int sub = r % g.nsub, pass = r / g.nsub;
+  const int c0 = pass * g.CK;
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&g.tx[0]);
+    prefetch_tmap(&g.tdy[0]);
+  }
+  __syncthreads();
+  if (tid == 0 && cta < g.ntile) wg2_issue(g, cta, c0, s0, bar0);
+
+  // ---- this warp's block of accumulators: m16-tiles [mt0, mt0 + mcount) x n8-tiles [nt0, nt0 + NW) ----
+  const int item = sub * (kWgThreads / 32) + warp;
+  const bool active = item < g.MB * g.NB;
+  const int mb = active ? item / g.NB : 0, nb = active ? item - mb * g.NB : 0;
+  const int mt0 = mb * g.mper;
+  const int mcount = active ? max(0, min(g.mper, g.MT - mt0)) : 0;
+  const int nt0 = nb * NW;
+  // ldmatrix row of this lane: matrix j = lane / 8 -> (m half j & 1, k half j >> 1), row r -> position k = 8 * (j >> 1) + r of the k-step
+  const int lj = lane >> 3, lr = lane & 7, lk = 8 * (lj >> 1) + lr;
+  const int gq = lane >> 2, t4 = lane & 3;
+  const int lanepos = g.TX == 8 ? ((lk >> 3) * g.isy * g.RX + (lk & 7) * g.isx) : lk * g.isx;
+  uint32_t abase[MW];
+  uint32_t sets = 0;
+#pragma unroll
+  for (int i = 0; i < MW; ++i) {
+    const int mt = min(mt0 + i, g.MT - 1);
+    const int slot = min(2 * mt + (lj & 1), g.nslots - 1);
+    const int tap = slot / g.s8, c8 = slot - tap * g.s8;
+    const int tapoff = (((int)g.taps.dz[tap] - g.dzmin) * g.RY + ((int)g.taps.dy[tap] - g.dymin)) * g.RX + ((int)g.taps.dx[tap] - g.dxmin);
+    abase[i] = 16u * (uint32_t)(c8 * g.REGP + tapoff + lanepos);
+    sets |= (uint32_t)g.tap_set[(2 * mt) / g.s8] << (2 * i);
+  }
+  const uint32_t boff = g.x_bytes + 16u * (uint32_t)(nt0 * g.NP + (lane & 15) + (NW >= 2 ? (lane >> 4) * g.NP : 0));
+  const int nh = g.TX == 32 ? 2 : 1;
+  const uint32_t halfstep = 256u * (uint32_t)g.isx;
+  const uint32_t rowstep = 16u * (uint32_t)((g.TX == 8 ? 2 : 1) * g.isy * g.RX);
+  const int nrow = g.NP / (16 * nh);
+  float acc[MW][NW][4];
+#pragma unroll
+  for (int i = 0; i < MW; ++i)
+#pragma unroll
+    for (int n = 0; n < NW; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.f;
+
+  int stage = 0;
+  uint32_t par = 0;   // bit s: parity the next wait on stage s uses
+  for (int tile = cta; tile < g.ntile; tile += g.ncta) {
+    const int nxt = tile + g.ncta;
+    if (tid == 0 && nxt < g.ntile) wg2_issue(g, nxt, c0, s0 + (uint32_t)(stage ^ 1) * stage_bytes, bar0 + 8u * (uint32_t)(stage ^ 1));
+    mbar_wait(bar0 + 8u * (uint32_t)stage, (par >> stage) & 1u);
+    par ^= 1u << stage;
+    const uint32_t sb = s0 + (uint32_t)stage * stage_bytes;
+    if (mcount > 0) {
+#pragma unroll 1
+      for (int rr = 0; rr < nrow; ++rr) {
+#pragma unroll 1
+        for (int h = 0; h < nh; ++h) {
+          const uint32_t ka = sb + (uint32_t)rr * rowstep + (uint32_t)h * halfstep;
+          const uint32_t kb = sb + boff + 256u * (uint32_t)(rr * nh + h);
+          int cur = -1;
+          unsigned b[NW][2];
+#pragma unroll
+          for (int i = 0; i < MW; ++i) {
+            if (i < mcount) {
+              const int set = (int)((sets >> (2 * i)) & 3u);
+              if (set != cur) {
+                cur = set;
+                const uint32_t kbs = kb + (uint32_t)set * g.dy_bytes;
+                if (NW == 1) ldsm_x2_t(kbs, b[0][0], b[0][1]);
+                else {
+#pragma unroll
+                  for (int n = 0; n < NW; n += 2) ldsm_x4_t(kbs + 16u * (uint32_t)(n * g.NP), b[n][0], b[n][1], b[n + 1 < NW ? n + 1 : n][0], b[n + 1 < NW ? n + 1 : n][1]);
+                }
+              }
+              unsigned a0, a1, a2, a3;
+              ldsm_x4_t(ka + abase[i], a0, a1, a2, a3);
+#pragma unroll
+              for (int n = 0; n < NW; ++n) mma_bf16_16816(acc[i][n], a0, a1, a2, a3, b[n][0], b[n][1]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();   // every warp is done with this stage: the next iteration's TMA may overwrite it
+    stage ^= 1;
+  }
+  // ---- flush: d0,d1 = (m = gq, n = 2*t4, 2*t4+1), d2,d3 = (m = gq + 8, ...): m < 8 -> slot 2*mt, m >= 8 -> slot 2*mt + 1 ----
+#pragma unroll
+  for (int i = 0; i < MW; ++i) {
+    if (i >= mcount) continue;
+    const int mt = mt0 + i;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int slot = 2 * mt + half;
+      if (slot >= g.nslots) continue;
+      const int tp = slot / g.s8, cc = slot - tp * g.s8;
+      const int cig = g.ci_base + c0 + 8 * cc + gq;
+      if (cig >= g.Cin) continue;
+      const int wi = g.taps.widx[tp];
+#pragma unroll
+      for (int n = 0; n < NW; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int co = 8 * (nt0 + n) + 2 * t4 + e;
+          if (co >= g.Cout) continue;
+          const size_t o = g.wt_transposed ? ((size_t)cig * g.Cout + co) * g.ntaps_total + wi
+                                           : ((size_t)co * g.Cin + cig) * g.ntaps_total + wi;
+          atomicAdd(g.dw + o, acc[i][n][2 * half + e]);
+        }
+    }
+  }
+}
+
+int encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                     const unsigned* box);
+
+// `a`: geometry / sources / strides as for the other kernels; `pt[nph]`: the tap tables of the phases (nph = 1: an ordinary launch
+// with a.ooy/a.oox; nph = 4: the four output-parity phases (py, px) = (ph >> 1, ph & 1) of a stride-2 transposed convolution).
+int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const void* dy, int CoS, int Cout, int Cin, int ci_base,
+                          float* dw, int ntaps_total, int wt_transposed, cudaStream_t st, bool* handled) {
+  *handled = false;
+  static const bool no_tma = getenv("DFF_B200_WGRAD_NO_TMA") != nullptr;   // A/B switch: the per-thread-staged mma kernel
+  if (no_tma) return 0;
+  const int Ctot = a.C0 + a.C1;
+  if (a.C0 % 8 || a.C1 % 8 || CoS % 8 || a.C0 < 8 || nph < 1 || nph > 4) return 0;
+  const int NT = CoS / 8;
+  const int NW = NT >= 4 ? 4 : NT;
+  if (NW == 3 || NT % NW) return 0;
+  const int MW = NW == 4 ? 4 : 8;
+  Wg2Args ga{};
+  ga.taps.n = 0;
+  int dzmax = -100, dymax = -100, dxmax = -100;
+  ga.dzmin = ga.dymin = ga.dxmin = 100;
+  for (int ph = 0; ph < nph; ++ph)
+    for (int t = 0; t < pt[ph].n; ++t) {
+      const int k = ga.taps.n++;
+      if (k >= kMaxTaps) return 0;
+      ga.taps.dz[k] = pt[ph].dz[t]; ga.taps.dy[k] = pt[ph].dy[t]; ga.taps.dx[k] = pt[ph].dx[t]; ga.taps.widx[k] = pt[ph].widx[t];
+      ga.tap_set[k] = (uint8_t)ph;
+      ga.dzmin = std::min(ga.dzmin, (int)pt[ph].dz[t]); dzmax = std::max(dzmax, (int)pt[ph].dz[t]);
+      ga.dymin = std::min(ga.dymin, (int)pt[ph].dy[t]); dymax = std::max(dymax, (int)pt[ph].dy[t]);
+      ga.dxmin = std::min(ga.dxmin, (int)pt[ph].dx[t]); dxmax = std::max(dxmax, (int)pt[ph].dx[t]);
+    }
+  const int ntap = ga.taps.n;
+  if (!ntap) return 0;
+  // channels per pass: the smallest group that still gives every warp of a CTA a block (a CTA then stages only what it multiplies);
+  // merged phases need both halves of an m16-tile in one tap (CK >= 16)
+  const int NB = NT / NW;
+  int CK = 0;
+  for (int c = (nph > 1 ? 16 : 8); c <= 64; c <<= 1) {
+    if (Ctot % c) continue;
+    CK = c;
+    const int MT = (ntap * (c / 8) + 1) / 2;
+    if (cdiv(MT, MW) * NB >= kWgThreads / 32) break;
+  }
+  if (!CK) return 0;
+  const int s8 = CK / 8, nslots = ntap * s8, MT = (nslots + 1) / 2;
+  int MB = cdiv(MT, MW);
+  if (MB * NB < kWgThreads / 32) MB = std::min(MT, std::max(1, (kWgThreads / 32) / NB));
+  const int mper = cdiv(MT, MB);
+  MB = cdiv(MT, mper);
+  const int nsub = cdiv(MB * NB, kWgThreads / 32);
+  // tile: TX by the layer's width, TY for ~256 positions, halved until two stages of two CTAs fit next to each other
+  const int TX = a.OWt > 16 ? 32 : (a.OWt > 8 ? 16 : 8);
+  int TY = 256 / TX;
+  while (TY / 2 >= a.OHt && TX * (TY / 2) >= 16 && (TX != 8 || (TY / 2) % 2 == 0)) TY /= 2;
+  int RX = 0, RY = 0, RZ = 0, REGP = 0;
+  unsigned xb = 0, db = 0;
+  for (;; TY /= 2) {
+    if (TX * TY < 16 || (TX == 8 && TY % 2)) return 0;
+    RZ = dzmax - ga.dzmin + 1;
+    RY = (TY - 1) * a.isy + (dymax - ga.dymin) + 1;
+    RX = (TX - 1) * a.isx + (dxmax - ga.dxmin) + 1;
+    REGP = (RZ * RY * RX + 7) & ~7;
+    xb = (unsigned)(s8 * REGP) * 16u;
+    db = (unsigned)(NT * TX * TY) * 16u;
+    if (RX <= 256 && RY <= 256 && RZ <= 256 && 2 * (size_t)(xb + nph * db) + 64 <= 110 * 1024) break;
+  }
+  ga.nset = nph;
+  ga.C0 = a.C0; ga.S = a.S;
+  ga.tilesX = cdiv(a.OWt, TX); ga.tilesY = cdiv(a.OHt, TY);
+  ga.ntile = ga.tilesX * ga.tilesY * a.B * a.S;
+  if (ga.ntile <= 0) { *handled = true; return 0; }
+  ga.isx = a.isx; ga.isy = a.isy; ga.RX = RX; ga.RY = RY; ga.REGP = REGP;
+  ga.TX = TX; ga.TY = TY; ga.NP = TX * TY;
+  ga.CK = CK; ga.s8 = s8; ga.nsub = nsub;
+  ga.MT = MT; ga.NT = NT; ga.NB = NB; ga.MB = MB; ga.mper = mper; ga.nslots = nslots;
+  ga.Cout = Cout; ga.Cin = Cin; ga.ci_base = ci_base; ga.ntaps_total = ntaps_total; ga.wt_transposed = wt_transposed;
+  ga.dw = dw;
+  ga.x_bytes = xb; ga.dy_bytes = db;
+  ga.tx_bytes = (unsigned)(s8 * RZ * RY * RX) * 16u + (unsigned)nph * db;
+  const int npass = Ctot / CK, G = npass * nsub;
+  ga.ncta = std::max(1, std::min(ga.ntile, (2 * 148) / G));
+  for (int src = 0; src < (a.C1 ? 2 : 1); ++src) {
+    const unsigned long long C = src ? a.C1 : a.C0;
+    const unsigned long long dims[5] = {C, (unsigned long long)a.IW, (unsigned long long)a.IH, (unsigned long long)a.S, (unsigned long long)a.B};
+    const unsigned long long strides[4] = {C * 2, (unsigned long long)a.IW * C * 2, (unsigned long long)a.IH * a.IW * C * 2,
+                                           (unsigned long long)a.S * a.IH * a.IW * C * 2};
+    const unsigned box[5] = {8u, (unsigned)RX, (unsigned)RY, (unsigned)RZ, 1u};
+    DFF_TRY(encode_tmap_bf16(&ga.tx[src], src ? a.in1 : a.in0, 5, dims, strides, box));
+  }
+  for (int ph = 0; ph < nph; ++ph) {
+    const int ooy = nph > 1 ? (ph >> 1) : a.ooy, oox = nph > 1 ? (ph & 1) : a.oox;
+    const unsigned long long dims[4] = {(unsigned long long)CoS, (unsigned long long)a.OWt, (unsigned long long)a.OHt, (unsigned long long)a.S * a.B};
+    const unsigned long long strides[3] = {(unsigned long long)CoS * 2 * a.osx, (unsigned long long)a.OW * CoS * 2 * a.osy,
+                                           (unsigned long long)a.OH * a.OW * CoS * 2};
+    const unsigned box[4] = {8u, (unsigned)TX, (unsigned)TY, 1u};
+    DFF_TRY(encode_tmap_bf16(&ga.tdy[ph], (const char*)dy + ((size_t)ooy * a.OW + oox) * CoS * 2, 4, dims, strides, box));
+  }
+  const size_t smem = 2 * (size_t)(xb + nph * db) + 64;
+  static const bool log = getenv("DFF_B200_WGRAD_LOG") != nullptr;   // (profiling aid: one line per launch, joins with an ncu launch list)
+  if (log)
+    fprintf(stderr, "wgrad_tma Cin=%d+%d Cout=%d taps=%d nph=%d B=%d S=%d OHt=%d OWt=%d is=%d os=%d CK=%d TX=%d TY=%d MW=%d NW=%d MB=%d NB=%d mper=%d nsub=%d npass=%d ncta=%d ntile=%d smem=%zu\n",
+            a.C0, a.C1, Cout, ntap, nph, a.B, a.S, a.OHt, a.OWt, a.isx, a.osx, CK, TX, TY, MW, NW, MB, NB, mper, nsub, npass, ga.ncta, ga.ntile, smem);
+  dim3 grid(G * ga.ncta, 1, 1);
+#define DFF_WG2(MW_, NW_)                                                                                                     \
+  do {                                                                                                                        \
+    DFF_CUDA(cudaFuncSetAttribute(conv_wgrad_tma_kernel<MW_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_wgrad_tma_kernel<MW_, NW_><<<grid, kWgThreads, smem, st>>>(ga);                                                       \
+  } while (0)
+  if (NW == 4) DFF_WG2(4, 4);
+  else if (NW == 2) DFF_WG2(8, 2);
+  else DFF_WG2(8, 1);
+#undef DFF_WG2
+  DFF_LAUNCH_CHECK("conv_wgrad_tma");
   *handled = true;
   return 0;
 }
@@ -429,6 +731,11 @@ int launch_conv_wgrad(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, in
                       int wt_transposed, bool bf16, cudaStream_t st) {
   if (a.C0 % 4 || a.C1 % 4) return fail(-1, "conv_wgrad: stored input channels must be multiples of 4");
   static const bool no_mma = getenv("DFF_B200_WGRAD_FFMA") != nullptr;   // A/B switch: the fp32-FMA kernel also for bf16 tensors
+  if (bf16 && !no_mma) {
+    bool handled = false;
+    DFF_TRY(launch_conv_wgrad_tma(a, &a.taps, 1, dy, CoS, Cout, Cin, ci_base, dw, ntaps_total, wt_transposed, st, &handled));
+    if (handled) return 0;
+  }
   if (bf16 && !no_mma) {
     bool handled = false;
     DFF_TRY(launch_conv_wgrad_mma(a, dy, CoS, Cout, Cin, ci_base, dw, ntaps_total, wt_transposed, st, &handled));

@@ -56,6 +56,8 @@ int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, i
 int launch_pack_weight_slab_rowfold(const float* wpair, void* dst, int Cout, cudaStream_t st);
 int launch_conv_wgrad(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, int ci_base, float* dw, int ntaps_total,
                       int wt_transposed, bool bf16, cudaStream_t st);
+int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const void* dy, int CoS, int Cout, int Cin, int ci_base,
+                          float* dw, int ntaps_total, int wt_transposed, cudaStream_t st, bool* handled);
 size_t bn_partial_bytes(int C);
 int launch_bn_stats(const void* x, size_t npix, int C, bool bf16, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
@@ -1598,6 +1600,14 @@ static int conv3d_wgrad_impl(const void* in0, int C0, const void* in1, int C1, i
     return launch_conv_wgrad(a, dy, CoS, Cout, Cin, 0, dw, ntaps, 0, bf16, st);
   }
   a.OH = IH * 2; a.OW = IW * 2; a.OHt = IH; a.OWt = IW;
+  if (bf16) {   // the four output-parity phases in one launch (they share the staged input region)
+    TapTable pt[4];
+    for (int ph = 0; ph < 4; ++ph) deconv_taps(ph >> 1, ph & 1, pt[ph]);
+    a.isy = a.isx = 1; a.osy = a.osx = 2; a.ooy = a.oox = 0;
+    bool handled = false;
+    DFF_TRY(launch_conv_wgrad_tma(a, pt, 4, dy, CoS, Cout, Cin, 0, dw, ntaps, 1, st, &handled));
+    if (handled) return 0;
+  }
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       deconv_taps(py, px, a.taps);
