@@ -429,6 +429,7 @@ static int launch_conv_wgrad_mma(ConvArgs a, const void* dy, int CoS, int Cout, 
 //    one phase, so a phase is just the dy set (one of four staged sub-tiles) a tap's m16-tile multiplies with.
 // Accumulators stay in registers over all tiles a CTA walks; one red.global.add.f32 per element and CTA at the end.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr size_t kWg2Smem = 110 * 1024;   // two CTAs per SM
 struct Wg2Args {
   CUtensorMap tx[2];
   CUtensorMap tdy[4];
@@ -440,6 +441,8 @@ struct Wg2Args {
   int isx, isy, dzmin, dymin, dxmin, RX, RY, REGP;
   int TX, TY, NP;
   int CK, s8, nsub, ncta;
+  int nst, cs;                  // pipeline stages (2..4); CTAs per cluster (1, 2, 4, 8: the accumulators of a cluster are summed
+                                 // through distributed shared memory before they go to the gradient)
   int MT, NT, NB, MB, mper, nslots;
   int Cout, Cin, ci_base, ntaps_total, wt_transposed;
   float* dw;
@@ -471,20 +474,23 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_tma_kernel(const __g
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t s0 = smem_u32(smem_w);
   const uint32_t stage_bytes = g.x_bytes + (uint32_t)g.nset * g.dy_bytes;
-  const uint32_t bar0 = s0 + 2 * stage_bytes;
+  const uint32_t bar0 = s0 + (uint32_t)g.nst * stage_bytes;
   int r = blockIdx.x;
   const int cta = r % g.ncta; r /= g.ncta;
   const int sub = r % g.nsub, pass = r / g.nsub;
   const int c0 = pass * g.CK;
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+    for (int i = 0; i < g.nst; ++i) mbar_init(bar0 + 8u * (uint32_t)i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&g.tx[0]);
     prefetch_tmap(&g.tdy[0]);
   }
   __syncthreads();
-  if (tid == 0 && cta < g.ntile) wg2_issue(g, cta, c0, s0, bar0);
+  if (tid == 0)   // prologue: the first nst - 1 tiles of this CTA are in flight before anyone waits
+    for (int i = 0; i < g.nst - 1; ++i) {
+      const int t = cta + i * g.ncta;
+      if (t < g.ntile) wg2_issue(g, t, c0, s0 + (uint32_t)i * stage_bytes, bar0 + 8u * (uint32_t)i);
+    }
 
   // ---- this warp's block of accumulators: m16-tiles [mt0, mt0 + mcount) x n8-tiles [nt0, nt0 + NW) ----
   const int item = sub * (kWgThreads / 32) + warp;
@@ -524,8 +530,11 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_tma_kernel(const __g
   int stage = 0;
   uint32_t par = 0;   // bit s: parity the next wait on stage s uses
   for (int tile = cta; tile < g.ntile; tile += g.ncta) {
-    const int nxt = tile + g.ncta;
-    if (tid == 0 && nxt < g.ntile) wg2_issue(g, nxt, c0, s0 + (uint32_t)(stage ^ 1) * stage_bytes, bar0 + 8u * (uint32_t)(stage ^ 1));
+    {   // the stage consumed in the previous iteration takes the tile nst - 1 ahead
+      const int nxt = tile + (g.nst - 1) * g.ncta;
+      const int ns = stage == 0 ? g.nst - 1 : stage - 1;
+      if (tid == 0 && nxt < g.ntile) wg2_issue(g, nxt, c0, s0 + (uint32_t)ns * stage_bytes, bar0 + 8u * (uint32_t)ns);
+    }
     mbar_wait(bar0 + 8u * (uint32_t)stage, (par >> stage) & 1u);
     par ^= 1u << stage;
     const uint32_t sb = s0 + (uint32_t)stage * stage_bytes;
@@ -561,9 +570,62 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_tma_kernel(const __g
       }
     }
     __syncthreads();   // every warp is done with this stage: the next iteration's TMA may overwrite it
-    stage ^= 1;
+    if (++stage == g.nst) stage = 0;
   }
-  // ---- flush: d0,d1 = (m = gq, n = 2*t4, 2*t4+1), d2,d3 = (m = gq + 8, ...): m < 8 -> slot 2*mt, m >= 8 -> slot 2*mt + 1 ----
+  // ---- flush.  Fragment: d0,d1 = (m = gq, n = 2*t4, 2*t4+1), d2,d3 = (m = gq + 8, ...): m < 8 -> slot 2*mt, m >= 8 -> slot 2*mt + 1.
+  // Every CTA of a (pass, sub) group holds the same accumulator blocks for different tiles; the gradient takes one fp32 atomic per
+  // element and *cluster*: the CTAs of a cluster park their fragments in their own shared memory, CTA `rank` sums warp-slots
+  // rank, rank + cs, ... of all of them through distributed shared memory and issues the atomics (the atomics — every CTA adding
+  // its whole block to a few KB of gradient — were what bounded the low-channel layers) ----
+  if (g.cs > 1) {
+    float* dump = reinterpret_cast<float*>(smem_w);
+#pragma unroll
+    for (int i = 0; i < MW; ++i)
+#pragma unroll
+      for (int n = 0; n < NW; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dump[((((warp * MW + i) * NW + n) * 4 + e) << 5) + lane] = acc[i][n][e];
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    for (int ws = (int)rank; ws < kWgThreads / 32; ws += g.cs) {
+      const int it2 = sub * (kWgThreads / 32) + ws;
+      if (it2 >= g.MB * g.NB) continue;
+      const int mb2 = it2 / g.NB, nb2 = it2 - mb2 * g.NB;
+      const int mt02 = mb2 * g.mper, mc2 = max(0, min(g.mper, g.MT - mt02)), nt02 = nb2 * NW;
+      for (int pi = warp; pi < mc2 * NW; pi += kWgThreads / 32) {
+        const int i = pi / NW, n = pi - i * NW;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t la = s0 + 4u * (uint32_t)(((((ws * MW + i) * NW + n) * 4) << 5) + lane);
+        for (int q = 0; q < g.cs; ++q) {
+          uint32_t ra;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(q));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x;
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x) : "r"(ra + 128u * (uint32_t)e));
+            v[e] += x;
+          }
+        }
+        const int mt = mt02 + i;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int slot = 2 * mt + (e >> 1);
+          if (slot >= g.nslots) continue;
+          const int tp = slot / g.s8, cc = slot - tp * g.s8;
+          const int cig = g.ci_base + c0 + 8 * cc + gq;
+          const int co = 8 * (nt02 + n) + 2 * t4 + (e & 1);
+          if (cig >= g.Cin || co >= g.Cout) continue;
+          const int wi = g.taps.widx[tp];
+          const size_t o = g.wt_transposed ? ((size_t)cig * g.Cout + co) * g.ntaps_total + wi
+                                           : ((size_t)co * g.Cin + cig) * g.ntaps_total + wi;
+          atomicAdd(g.dw + o, v[e]);
+        }
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers may still be reading this CTA's fragments
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < MW; ++i) {
     if (i >= mcount) continue;
@@ -653,7 +715,7 @@ int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const 
     REGP = (RZ * RY * RX + 7) & ~7;
     xb = (unsigned)(s8 * REGP) * 16u;
     db = (unsigned)(NT * TX * TY) * 16u;
-    if (RX <= 256 && RY <= 256 && RZ <= 256 && 2 * (size_t)(xb + nph * db) + 64 <= 110 * 1024) break;
+    if (RX <= 256 && RY <= 256 && RZ <= 256 && 2 * (size_t)(xb + nph * db) + 64 <= kWg2Smem) break;
   }
   ga.nset = nph;
   ga.C0 = a.C0; ga.S = a.S;
@@ -670,6 +732,17 @@ int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const 
   ga.tx_bytes = (unsigned)(s8 * RZ * RY * RX) * 16u + (unsigned)nph * db;
   const int npass = Ctot / CK, G = npass * nsub;
   ga.ncta = std::max(1, std::min(ga.ntile, (2 * 148) / G));
+  // clusters of up to 8 CTAs of one group reduce their accumulators on chip; a group's CTA count is rounded down to a multiple
+  static const int cs_max = getenv("DFF_B200_WGRAD_CLUSTER") ? atoi(getenv("DFF_B200_WGRAD_CLUSTER")) : 8;   // (A/B knob; 1 = off)
+  int cs = 1;
+  while (cs * 2 <= cs_max && cs * 2 <= ga.ncta && cs * 2 <= 8) cs *= 2;
+  ga.ncta = ga.ncta / cs * cs;
+  ga.cs = cs;
+  const size_t stage = (size_t)xb + (size_t)nph * db;
+  const size_t dump = cs > 1 ? (size_t)(kWgThreads / 32) * MW * NW * 4 * 32 * sizeof(float) : 0;
+  int nst = (int)std::min<size_t>(4, (kWg2Smem - 64) / stage);
+  nst = std::max(2, std::min(nst, cdiv(ga.ntile, ga.ncta) + 1));
+  ga.nst = nst;
   for (int src = 0; src < (a.C1 ? 2 : 1); ++src) {
     const unsigned long long C = src ? a.C1 : a.C0;
     const unsigned long long dims[5] = {C, (unsigned long long)a.IW, (unsigned long long)a.IH, (unsigned long long)a.S, (unsigned long long)a.B};
@@ -686,16 +759,22 @@ int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const 
     const unsigned box[4] = {8u, (unsigned)TX, (unsigned)TY, 1u};
     DFF_TRY(encode_tmap_bf16(&ga.tdy[ph], (const char*)dy + ((size_t)ooy * a.OW + oox) * CoS * 2, 4, dims, strides, box));
   }
-  const size_t smem = 2 * (size_t)(xb + nph * db) + 64;
+  const size_t smem = std::max((size_t)nst * stage + 64, dump);
   static const bool log = getenv("DFF_B200_WGRAD_LOG") != nullptr;   // (profiling aid: one line per launch, joins with an ncu launch list)
   if (log)
-    fprintf(stderr, "wgrad_tma Cin=%d+%d Cout=%d taps=%d nph=%d B=%d S=%d OHt=%d OWt=%d is=%d os=%d CK=%d TX=%d TY=%d MW=%d NW=%d MB=%d NB=%d mper=%d nsub=%d npass=%d ncta=%d ntile=%d smem=%zu\n",
-            a.C0, a.C1, Cout, ntap, nph, a.B, a.S, a.OHt, a.OWt, a.isx, a.osx, CK, TX, TY, MW, NW, MB, NB, mper, nsub, npass, ga.ncta, ga.ntile, smem);
+    fprintf(stderr, "wgrad_tma Cin=%d+%d Cout=%d taps=%d nph=%d B=%d S=%d OHt=%d OWt=%d is=%d os=%d CK=%d TX=%d TY=%d MW=%d NW=%d MB=%d NB=%d mper=%d nsub=%d npass=%d ncta=%d ntile=%d nst=%d cs=%d smem=%zu\n",
+            a.C0, a.C1, Cout, ntap, nph, a.B, a.S, a.OHt, a.OWt, a.isx, a.osx, CK, TX, TY, MW, NW, MB, NB, mper, nsub, npass, ga.ncta, ga.ntile, nst, cs, smem);
   dim3 grid(G * ga.ncta, 1, 1);
 #define DFF_WG2(MW_, NW_)                                                                                                     \
   do {                                                                                                                        \
     DFF_CUDA(cudaFuncSetAttribute(conv_wgrad_tma_kernel<MW_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_wgrad_tma_kernel<MW_, NW_><<<grid, kWgThreads, smem, st>>>(ga);                                                       \
+    cudaLaunchConfig_t cfg = {};                                                                                              \
+    cfg.gridDim = grid; cfg.blockDim = dim3(kWgThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;                        \
+    cudaLaunchAttribute at[1];                                                                                                \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                                           \
+    at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                            \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                                                         \
+    DFF_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_tma_kernel<MW_, NW_>, ga));                                                   \
   } while (0)
   if (NW == 4) DFF_WG2(4, 4);
   else if (NW == 2) DFF_WG2(8, 2);
