@@ -701,22 +701,25 @@ int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const 
   const int mper = cdiv(MT, MB);
   MB = cdiv(MT, mper);
   const int nsub = cdiv(MB * NB, kWgThreads / 32);
-  // tile: TX by the layer's width, TY for ~256 positions, halved until two stages of two CTAs fit next to each other
+  // tile: TX by the layer's width; TY as tall as three pipeline stages allow (up to 1024 positions: every tile costs a block-wide
+  // barrier round and a TMA round trip) but no taller than leaves every CTA a few tiles; at least two stages must fit
+  const int npass = Ctot / CK, G = npass * nsub;
   const int TX = a.OWt > 16 ? 32 : (a.OWt > 8 ? 16 : 8);
-  int TY = 256 / TX;
-  while (TY / 2 >= a.OHt && TX * (TY / 2) >= 16 && (TX != 8 || (TY / 2) % 2 == 0)) TY /= 2;
-  int RX = 0, RY = 0, RZ = 0, REGP = 0;
+  int RX = 0, RY = 0, RZ = 0, REGP = 0, TY = 0;
   unsigned xb = 0, db = 0;
-  for (;; TY /= 2) {
-    if (TX * TY < 16 || (TX == 8 && TY % 2)) return 0;
-    RZ = dzmax - ga.dzmin + 1;
-    RY = (TY - 1) * a.isy + (dymax - ga.dymin) + 1;
-    RX = (TX - 1) * a.isx + (dxmax - ga.dxmin) + 1;
-    REGP = (RZ * RY * RX + 7) & ~7;
-    xb = (unsigned)(s8 * REGP) * 16u;
-    db = (unsigned)(NT * TX * TY) * 16u;
-    if (RX <= 256 && RY <= 256 && RZ <= 256 && 2 * (size_t)(xb + nph * db) + 64 <= kWg2Smem) break;
-  }
+  for (int want = 3; want >= 2 && !TY; --want)
+    for (int ty = 1024 / TX; TX * ty >= 16 && (TX != 8 || ty % 2 == 0); ty /= 2) {
+      if (ty / 2 >= a.OHt && TX * (ty / 2) >= 16 && (TX != 8 || (ty / 2) % 2 == 0)) continue;   // no taller than the phase grid needs
+      if (TX * ty > 256 && (long long)cdiv(a.OWt, TX) * cdiv(a.OHt, ty) * a.B * a.S < 4LL * std::max(1, 296 / G)) continue;
+      RZ = dzmax - ga.dzmin + 1;
+      RY = (ty - 1) * a.isy + (dymax - ga.dymin) + 1;
+      RX = (TX - 1) * a.isx + (dxmax - ga.dxmin) + 1;
+      REGP = (RZ * RY * RX + 7) & ~7;
+      xb = (unsigned)(s8 * REGP) * 16u;
+      db = (unsigned)(NT * TX * ty) * 16u;
+      if (RX <= 256 && RY <= 256 && RZ <= 256 && want * (size_t)(xb + nph * db) + 64 <= kWg2Smem) { TY = ty; break; }
+    }
+  if (!TY) return 0;
   ga.nset = nph;
   ga.C0 = a.C0; ga.S = a.S;
   ga.tilesX = cdiv(a.OWt, TX); ga.tilesY = cdiv(a.OHt, TY);
@@ -730,18 +733,41 @@ int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const 
   ga.dw = dw;
   ga.x_bytes = xb; ga.dy_bytes = db;
   ga.tx_bytes = (unsigned)(s8 * RZ * RY * RX) * 16u + (unsigned)nph * db;
-  const int npass = Ctot / CK, G = npass * nsub;
-  ga.ncta = std::max(1, std::min(ga.ntile, (2 * 148) / G));
-  // clusters of up to 8 CTAs of one group reduce their accumulators on chip; a group's CTA count is rounded down to a multiple
+  // clusters of up to 8 CTAs of one group reduce their accumulators on chip.  The grid is sized to ONE wave of co-resident clusters
+  // (cudaOccupancyMaxActiveClusters: clusters are placed per GPC, 2 x 148 CTAs of 8-CTA clusters do not all fit at once — the
+  // left-over clusters ran as a second wave and doubled the time of the full-resolution layers)
   static const int cs_max = getenv("DFF_B200_WGRAD_CLUSTER") ? atoi(getenv("DFF_B200_WGRAD_CLUSTER")) : 8;   // (A/B knob; 1 = off)
-  int cs = 1;
-  while (cs * 2 <= cs_max && cs * 2 <= ga.ncta && cs * 2 <= 8) cs *= 2;
-  ga.ncta = ga.ncta / cs * cs;
-  ga.cs = cs;
   const size_t stage = (size_t)xb + (size_t)nph * db;
+  int want_cta = std::max(1, std::min(ga.ntile, (2 * 148) / G));
+  int cs = 1;
+  while (cs * 2 <= cs_max && cs * 2 <= want_cta && cs * 2 <= 8) cs *= 2;
   const size_t dump = cs > 1 ? (size_t)(kWgThreads / 32) * MW * NW * 4 * 32 * sizeof(float) : 0;
   int nst = (int)std::min<size_t>(4, (kWg2Smem - 64) / stage);
-  nst = std::max(2, std::min(nst, cdiv(ga.ntile, ga.ncta) + 1));
+  nst = std::max(2, std::min(nst, cdiv(ga.ntile, want_cta) + 1));
+  const size_t smem = std::max((size_t)nst * stage + 64, dump);
+  const void* kfn = NW == 4 ? (const void*)conv_wgrad_tma_kernel<4, 4> : NW == 2 ? (const void*)conv_wgrad_tma_kernel<8, 2> : (const void*)conv_wgrad_tma_kernel<8, 1>;
+  DFF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cs > 1) {
+    cudaLaunchConfig_t qc = {};
+    qc.gridDim = dim3(cs * 64); qc.blockDim = dim3(kWgThreads); qc.dynamicSmemBytes = smem;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = (unsigned)cs; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa; qc.numAttrs = 1;
+    static thread_local unsigned long long ckey[16];   // tiny per-thread cache of the driver query: (variant, smem, cluster) -> clusters
+    static thread_local int cval[16], cn = 0;
+    const unsigned long long key = ((unsigned long long)NW << 40) | ((unsigned long long)smem << 8) | (unsigned)cs;
+    int ncl = 0;
+    for (int i = 0; i < cn; ++i)
+      if (ckey[i] == key) ncl = cval[i];
+    if (!ncl) {
+      if (cudaOccupancyMaxActiveClusters(&ncl, kfn, &qc) != cudaSuccess) { (void)cudaGetLastError(); ncl = 0; }
+      if (ncl > 0 && cn < 16) { ckey[cn] = key; cval[cn] = ncl; ++cn; }
+    }
+    if (ncl > 0) want_cta = std::min(want_cta, std::max(cs, ncl * cs / G));
+  }
+  ga.ncta = std::max(cs, want_cta / cs * cs);
+  ga.cs = cs;
   ga.nst = nst;
   for (int src = 0; src < (a.C1 ? 2 : 1); ++src) {
     const unsigned long long C = src ? a.C1 : a.C0;
@@ -759,7 +785,6 @@ int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const 
     const unsigned box[4] = {8u, (unsigned)TX, (unsigned)TY, 1u};
     DFF_TRY(encode_tmap_bf16(&ga.tdy[ph], (const char*)dy + ((size_t)ooy * a.OW + oox) * CoS * 2, 4, dims, strides, box));
   }
-  const size_t smem = std::max((size_t)nst * stage + 64, dump);
   static const bool log = getenv("DFF_B200_WGRAD_LOG") != nullptr;   // (profiling aid: one line per launch, joins with an ncu launch list)
   if (log)
     fprintf(stderr, "wgrad_tma Cin=%d+%d Cout=%d taps=%d nph=%d B=%d S=%d OHt=%d OWt=%d is=%d os=%d CK=%d TX=%d TY=%d MW=%d NW=%d MB=%d NB=%d mper=%d nsub=%d npass=%d ncta=%d ntile=%d nst=%d cs=%d smem=%zu\n",
@@ -767,7 +792,6 @@ int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const 
   dim3 grid(G * ga.ncta, 1, 1);
 #define DFF_WG2(MW_, NW_)                                                                                                     \
   do {                                                                                                                        \
-    DFF_CUDA(cudaFuncSetAttribute(conv_wgrad_tma_kernel<MW_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     cudaLaunchConfig_t cfg = {};                                                                                              \
     cfg.gridDim = grid; cfg.blockDim = dim3(kWgThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;                        \
     cudaLaunchAttribute at[1];                                                                                                \

@@ -1,5 +1,5 @@
-timeout 600 python -m pytest tests/test_gpu_train.py -x -q > gpurun_out/r3d_pytest.log 2>&1; tail -15 gpurun_out/r3d_pytest.log
-DFF_B200_WGRAD_LOG=1 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r3d_train_launches.csv python tools/train_profile.py bf16 0 > gpurun_out/r3d_train.log 2> gpurun_out/r3d_train.err
-tail -3 gpurun_out/r3d_train.log
+timeout 600 python -m pytest tests/test_gpu_train.py -x -q > gpurun_out/r3e_pytest.log 2>&1; tail -15 gpurun_out/r3e_pytest.log
+DFF_B200_WGRAD_LOG=1 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r3e_train_launches.csv python tools/train_profile.py bf16 0 > gpurun_out/r3e_train.log 2> gpurun_out/r3e_train.err
+tail -3 gpurun_out/r3e_train.log
 timeout 300 python tools/train_profile.py bf16 1 2>&1 | tail -2
 DFF_B200_WGRAD_CLUSTER=1 timeout 300 python tools/train_profile.py bf16 1 2>&1 | tail -1
