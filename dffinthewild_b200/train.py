@@ -70,6 +70,59 @@ def _elem(t):
 
 OUT_F32 = 16   # DFF_OUT_F32
 
+_bn_scratch_cache = {}
+_pending_nbt = []     # num_batches_tracked buffers of the BatchNorm layers of the running forward: bumped with ONE foreach add
+
+
+def _bn_scratch(l, C, dev):
+    """Scratch of the BatchNorm reductions (per-block partial sums): one buffer per (device, stream, C) serves every call — calls
+    on a stream are ordered, and a buffer created outside a CUDA-graph capture may be used inside one."""
+    st = torch.cuda.current_stream(dev)
+    key = (dev.index, st.cuda_stream, C)
+    buf = _bn_scratch_cache.get(key)
+    if buf is None:
+        buf = torch.empty(l.dff_bn_scratch_bytes(C), dtype=torch.uint8, device=dev)
+        if torch.cuda.is_current_stream_capturing():
+            return buf      # private-pool memory of the capture: not reusable outside it
+        _bn_scratch_cache[key] = buf
+    return buf
+
+
+class WgradSideStream:
+    """Context of a training step that joins before it reads the gradients (train_step.TrainStep): inside it the weight-gradient
+    kernels — which nothing in the backward pass consumes — go to a side stream and fill the gaps of the data-gradient chain
+    (hundreds of 5-50 us kernels on the main stream).  Operands are kept alive until `join()`; without this context every kernel
+    stays on the caller's stream, so `loss.backward(); optimizer.step()` of the reference scripts needs no extra synchronisation."""
+    active = None
+
+    def __init__(self, dev):
+        self.dev, self.side, self.keep = dev, torch.cuda.Stream(device=dev), []
+
+    def __enter__(self):
+        WgradSideStream.active = self
+        return self
+
+    def __exit__(self, *a):
+        WgradSideStream.active = None
+        self.join()
+
+    def fork(self, *tensors):
+        self.side.wait_stream(torch.cuda.current_stream(self.dev))
+        self.keep.append(tensors)
+        return _P(self.side.cuda_stream)
+
+    def join(self):
+        if self.keep:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)
+            del self.keep[:]
+
+
+def flush_batch_counters():
+    """nn.BatchNorm3d.num_batches_tracked += 1 for every BatchNorm that ran since the last flush (one launch instead of 58)."""
+    if _pending_nbt:
+        torch._foreach_add_(_pending_nbt, 1)
+        del _pending_nbt[:]
+
 
 def _conv_call(l, x0, x1, w, Cout, stride, dil, transposed, out, elem, tc):
     """One dff_conv3d call on channels-last tensors (no epilogue operands)."""
@@ -152,8 +205,10 @@ class ConvFn(torch.autograd.Function):
         if needs[2] and sink is not None and sink.grad is not None and sink.grad.is_contiguous() and sink.grad.dtype == torch.float32:
             # (stored channels beyond the layer's Cin — the first layer's padding — are skipped by the kernel)
             cin_true = sink.shape[0] if transposed else sink.shape[1]
+            ws = WgradSideStream.active
+            stream = ws.fork(x0, x1, dy) if (ws is not None and ws.dev == dev) else _st(dev)
             rt.check(l.dff_conv3d_wgrad_acc(_p(x0), C0, _p(x1), C1, B, S, IH, IW, _p(dy), CoS, cin_true, Cout, kd, kh, kw, st, dil,
-                                            1 if transposed else 0, _p(sink.grad), elem, dev.index, _st(dev)))
+                                            1 if transposed else 0, _p(sink.grad), elem, dev.index, stream))
         elif needs[2]:
             dw = torch.empty_like(w)
             rt.check(l.dff_conv3d_wgrad(_p(x0), C0, _p(x1), C1, B, S, IH, IW, _p(dy), CoS, Cin, Cout, kd, kh, kw, st, dil,
@@ -193,7 +248,7 @@ class BnActFn(torch.autograd.Function):
             invstd = torch.empty(C, dtype=torch.float32, device=dev)
             ss = torch.empty(2 * C, dtype=torch.float32, device=dev)
             if batch_stats:
-                scratch = torch.empty(l.dff_bn_scratch_bytes(C), dtype=torch.uint8, device=dev)
+                scratch = _bn_scratch(l, C, dev)
                 track = bn is not None and bn.track_running_stats and bn.running_mean is not None
                 momentum = 0.1
                 if bn is not None and track:
@@ -204,7 +259,7 @@ class BnActFn(torch.autograd.Function):
                                                 bn.eps if bn is not None else 1e-5, _p(res_pre), _p(res_post), 1 if relu else 0,
                                                 _p(out), _p(mean), _p(invstd), _p(ss), _p(scratch), dev.index, _st(dev)))
                 if track:
-                    bn.num_batches_tracked += 1
+                    _pending_nbt.append(bn.num_batches_tracked)
                     # the library wrote the running statistics through raw pointers: make the update visible to version-keyed caches
                     torch.autograd.graph.increment_version(bn.running_mean)
                     torch.autograd.graph.increment_version(bn.running_var)
@@ -248,7 +303,7 @@ class BnActFn(torch.autograd.Function):
             else:
                 dgamma = torch.empty(C, dtype=torch.float32, device=dev)
                 dbeta = torch.empty(C, dtype=torch.float32, device=dev)
-            scratch = torch.empty(l.dff_bn_scratch_bytes(C), dtype=torch.uint8, device=dev)
+            scratch = _bn_scratch(l, C, dev)
             fn = l.dff_bn_train_backward if ctx.batch_stats else l.dff_bn_eval_backward
             rt.check(fn(_p(dy), _p(mask), _p(x), _p(mean), _p(invstd), _p(gamma), npix, C, _elem(x), _p(dx), _p(dres), _p(dgamma), _p(dbeta),
                         _p(scratch), dev.index, _st(dev)))
@@ -403,6 +458,7 @@ def dff_net_train_forward(net, FS, focus_dists):
         raise rt.DffError("dff_b200: H and W must be multiples of 32 (pad with -1 like the reference dataloaders)")
     dev = FS.device
     rt._check_device(dev.index)
+    del _pending_nbt[:]
     fd = focus_dists
     while fd.dim() < 4:
         fd = fd.unsqueeze(0)
@@ -431,4 +487,5 @@ def dff_net_train_forward(net, FS, focus_dists):
     o3 = _cbn(out_in2, net.deconv_3)
     outc, _ = _hourglass(net.dres4, o3, v1, pre2, outb)
     p3 = head(_conv(AddFn.apply(o3, outc), net.classif3[0]))
+    flush_batch_counters()
     return mid, p1, p2, p3

@@ -102,6 +102,9 @@ class TrainStep:
         self.t = 0
         self.allreduce_bytes = 4 * (self.bucket.numel + 1)
         self.side = torch.cuda.Stream(device=dev)
+        import os
+        from . import train as _tr
+        self.wgrad_side = _tr.WgradSideStream(dev) if os.environ.get("DFF_B200_WGRAD_STREAM", "1") != "0" else None
         self._ar_events = []
         rt.packed_cache(net.DFF_net if hasattr(net, "DFF_net") else net).invalidate()
 
@@ -129,7 +132,11 @@ class TrainStep:
         outs = self.model(FS, fd)
         self.bucket.zero()
         loss = masked_mse_loss(outs, gt, mask, self.weights)
-        loss.backward()
+        if self.wgrad_side is not None:
+            with self.wgrad_side:          # weight gradients on a side stream, joined before anything reads the bucket
+                loss.backward()
+        else:
+            loss.backward()
         return loss.detach()
 
     def _fwd_bwd_graphed(self, FS, fd, gt, mask):
