@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   const SlabElem* const elems = reinterpret_cast<const SlabElem*>(smem_gen + p.elem_off);
   float* const ss = reinterpret_cast<float*>(smem_gen + p.ss_off);  // scale[N], shift[N], classifier weights[N]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) DFF_TR(0, 63);   // (trace build: kernel entry; row 63 = entry, tables done, dependency wait over, all roles done)
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kSlabMaxPlanes]);
   const uint32_t tfull0 = smem_u32(&bars[2 * kSlabMaxPlanes]), tempty0 = smem_u32(&bars[2 * kSlabMaxPlanes + kSlabMaxAcc]);
   const uint32_t wfull0 = smem_u32(&bars[2 * kSlabMaxPlanes + 2 * kSlabMaxAcc]), wempty0 = wfull0 + 8 * kSlabMaxWSlots;   // (WS only)
@@ -276,7 +277,9 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   fence_before();
   __syncthreads();
   fence_after();
+  if (threadIdx.x == 0) DFF_TR(1, 63);
   pdl_wait();      // everything above touched only weights and tables; from here on the previous layer's output is read
+  if (threadIdx.x == 0) DFF_TR(2, 63);
   const uint32_t tmem_base = tmem_base_s;
   const int hz = p.hz;
 
@@ -686,6 +689,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   }
   fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DFF_TR(3, 63);
   if (warp == kSlabMmaWarp) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -1030,6 +1034,8 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
     printf("trace C0=%d C1=%d N=%d nops=%d NP=%d occ=%d grid=%d wstream=%d nwslots=%d nblk=%d (clk since first event): full-wait tempty-wait issued | tfull-wait epi-done | empty-wait loads-issued\n", p.C0, p.C1, p.N, p.nops, p.NP, occ, grid, p.wstream, p.nwslots, p.nblk);
     long long t0 = h[5] ? h[5] : h[0];
     for (int i = 0; i < 40; ++i) { for (int j = 0; j < 7; ++j) printf("%8lld", h[i * 8 + j] ? h[i * 8 + j] - t0 : -1); printf(" | w-wait %6lld\n", h[i * 8 + 7]); }
+    printf("CTA 0 (clk since kernel entry): tables done %lld, dependency wait over %lld, first plane ready %lld, all roles done %lld\n",
+           h[63 * 8 + 1] - h[63 * 8], h[63 * 8 + 2] - h[63 * 8], h[0] - h[63 * 8], h[63 * 8 + 3] - h[63 * 8]);
   }
 #endif
   return 0;
