@@ -352,6 +352,29 @@ def run_ours(args):
             if n in ("depth_heads", "maxpool", "avgpool", "avgpool_pyramid", "to_channels_last") or "N_ch_attention(fused)" in n:
                 gbs = a["bytes"] / (a["ms"] / 1000.0) / 1e9
                 bw[n] = {"gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm"], "ms_per_call": a["ms"] / a["calls"]}
+        # the FOV warp of the End-to-End variant (End_to_End/End_to_End.py:106-134) is not on the DDFF path: timed here on its own,
+        # outside the timed region, 8 stacks of the C4 shape (BASELINE.json configs[3]) so that the tensors exceed L2
+        if rank == 0:
+            fb, fc, fs, fh, fw = 8, 3, 10, 512, 768
+            fx = torch.rand(fb, fc, fs, fh, fw, device=dev) * 2 - 1
+            fo = torch.empty_like(fx)
+            falpha = (torch.rand(fb, 3, fs, device=dev) - 0.5) * torch.tensor([0.002, 4.0, 4.0], device=dev).view(1, 3, 1)
+            ffov = 1.0 + 0.01 * torch.arange(fs, device=dev, dtype=torch.float32).view(1, fs).repeat(fb, 1)
+            stp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            warp = lambda: rt.check(lib.dff_fov_warp(fx.data_ptr(), falpha.data_ptr(), ffov.data_ptr(), fb, fc, fs, fh, fw, fo.data_ptr(),
+                                                     None, dev.index, stp))
+            for _ in range(3):
+                warp()
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            for _ in range(10):
+                warp()
+            w1.record()
+            torch.cuda.synchronize()
+            wms = w0.elapsed_time(w1) / 10
+            wgbs = 2 * 4 * fx.numel() / (wms / 1000.0) / 1e9
+            bw["fov_warp (8 x 3x10x512x768 fp32, not in the step)"] = {"gbs": wgbs, "frac_of_hbm_peak": wgbs / pk["hbm"], "ms_per_call": wms}
+            del fx, fo
         roof["bandwidth_kernels"] = bw
     except Exception as ex:   # (a reporting extra must never take the bench line down)
         roof["aggregation_convs"] = {"error": str(ex)}
