@@ -1154,6 +1154,7 @@ int dff_forward_profiled(const void* packed, const float* FS, const float* fd, c
 // copies of a DDFF stack take 0.64 ms, its kernels 0.68 ms + 1.3 ms per launch sequence: with three stages the copy stream never
 // idles, so only the first chunk's copy is exposed.
 constexpr int kHostStages = 3;
+constexpr int kHostMaxStages = 8;   // (two-stream schedule of the uint8 path: the same device buffer cut into smaller stages)
 // focus-distance elements one chunk of n stacks addresses through the strides
 static size_t fd_span(const int64_t* fds, int n, int S, int H, int W) {
   const int dims[4] = {n, S, H, W};
@@ -1175,8 +1176,10 @@ size_t dff_host_io_bytes_u8(int micro_batch, int S, int H0, int W0, int H, int W
 
 namespace {
 struct HostPipe {
-  cudaStream_t h2d = nullptr, d2h = nullptr;
-  cudaEvent_t in_ready[kHostStages] = {}, computed[kHostStages] = {}, out_done[kHostStages] = {};
+  cudaStream_t h2d = nullptr, d2h = nullptr, c2 = nullptr;   // copy streams; second compute stream (uint8 path)
+  cudaEvent_t in_ready[kHostMaxStages] = {}, computed[kHostMaxStages] = {}, out_done[kHostMaxStages] = {};
+  cudaEvent_t entry = nullptr, c2_done = nullptr;
+  cudaEvent_t ticket_done[2] = {};   // asynchronous calls: everything of call `ticket` is in host memory
   bool ok = false;
   int device = -1;
   HostPipe() = default;
@@ -1188,13 +1191,18 @@ struct HostPipe {
     if (device < 0) return;
     int prev = -1;
     if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
-    for (int k = 0; k < kHostStages; ++k) {
+    for (int k = 0; k < kHostMaxStages; ++k) {
       if (in_ready[k]) cudaEventDestroy(in_ready[k]);
       if (computed[k]) cudaEventDestroy(computed[k]);
       if (out_done[k]) cudaEventDestroy(out_done[k]);
     }
+    if (entry) cudaEventDestroy(entry);
+    if (c2_done) cudaEventDestroy(c2_done);
+    for (int t = 0; t < 2; ++t)
+      if (ticket_done[t]) cudaEventDestroy(ticket_done[t]);
     if (h2d) cudaStreamDestroy(h2d);
     if (d2h) cudaStreamDestroy(d2h);
+    if (c2) cudaStreamDestroy(c2);
     if (prev >= 0) cudaSetDevice(prev);
     cudaGetLastError();
   }
@@ -1207,7 +1215,12 @@ HostPipe* host_pipe(int device) {
     hp.device = device;
     if (cudaStreamCreateWithFlags(&hp.h2d, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaStreamCreateWithFlags(&hp.d2h, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    for (int k = 0; k < kHostStages; ++k) {
+    if (cudaStreamCreateWithFlags(&hp.c2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&hp.entry, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&hp.c2_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int t = 0; t < 2; ++t)
+      if (cudaEventCreateWithFlags(&hp.ticket_done[t], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int k = 0; k < kHostMaxStages; ++k) {
       if (cudaEventCreateWithFlags(&hp.in_ready[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&hp.computed[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&hp.out_done[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -1220,7 +1233,7 @@ HostPipe* host_pipe(int device) {
 // `in_host`: fp32 (B,3,S,H,W) stacks (u8 == false) or uint8 (B,S,H0,W0,3) stacks
 int forward_host_impl(const void* packed, const void* in_host, bool u8, int H0, int W0, const float* fd_host, const int64_t* fd_strides,
                       int B, int micro_batch, int S, int H, int W, float* const* out4_host, void* dev_io, void* workspace,
-                      size_t workspace_bytes, int mode, int device, cudaStream_t st) {
+                      size_t workspace_bytes, int mode, int device, cudaStream_t st, int ticket = -1) {
   if (B < 1 || micro_batch < 1) return fail(DFF_E_ARG, "dff_forward_host: B and micro_batch must be >= 1");
   if (u8 && (H0 < 1 || W0 < 1 || H0 > H || W0 > W)) return fail(DFF_E_ARG, "dff_forward_host_u8: need 1 <= H0 <= H and 1 <= W0 <= W");
   DeviceGuard g(device);
@@ -1231,51 +1244,115 @@ int forward_host_impl(const void* packed, const void* in_host, bool u8, int H0, 
   const size_t in_stack = u8 ? (size_t)3 * S * H0 * W0 : (size_t)3 * S * H * W * 4, map_px = (size_t)H * W;
   if (fd_span(fd_strides, mb, S, H, W) > (size_t)mb * S * H * W) return fail(DFF_E_ARG, "dff_forward_host: focus_dists strides exceed (B,S,H,W)");
   const size_t fd_elems = u8 ? fd_span(fd_strides, mb, S, H, W) : (size_t)mb * S * H * W;
-  const size_t stage = host_stage_bytes(mb, in_stack, fd_elems, H, W);
-  int rc = 0, nchunk = 0;
-  // Chunk schedule.  Every chunk costs a fixed ~1.3 ms of launch prologues / pipeline drains on top of its per-stack time, the first
-  // chunk's host->device copy and the last chunk's device->host reads cannot overlap anything.  fp32 stacks (35 MB each) are
-  // copy-bound: mb/4, mb/4, then mb/2 throughout keeps the copy stream busy.  uint8 stacks (6 MB each) are kernel-bound: a short
-  // head and tail (mb/8) bracket chunks as large as the workspace allows, so the fixed cost is paid 3-4 times per call, not 8.
-  const int head = mb >= 8 ? mb / 8 : 1;
-  for (int i0 = 0, n = 0; i0 < B && !rc; i0 += n, ++nchunk) {
-    if (!u8) n = nchunk < 2 ? (mb >= 4 ? mb / 4 : mb) : (mb >= 2 ? mb / 2 : mb);
-    else if (B <= 2 * head + 1) n = B;
-    else if (nchunk == 0) n = head;
-    else {
-      const int left = B - i0;
-      if (left <= head) n = left;
-      else {   // the middle, in equal parts no larger than mb
-        const int mid = left - head, parts = (mid + mb - 1) / mb;
-        n = (mid + parts - 1) / parts;
+  const size_t io_bytes = kHostStages * host_stage_bytes(mb, in_stack, fd_elems, H, W);   // what the caller sized `dev_io` for
+  int rc = 0;
+  // ---- chunk schedule ----
+  // Every chunk costs a fixed ~1.3 ms of launch prologues / pipeline drains on top of its per-stack time; the first chunk's
+  // host->device copy and the last chunk's device->host reads cannot overlap anything.  fp32 stacks (35 MB each) are copy-bound:
+  // mb/4, mb/4, then mb/2 throughout keeps the copy stream busy (one compute stream).  uint8 stacks (6 MB each) are kernel-bound:
+  // consecutive chunks ALTERNATE BETWEEN TWO COMPUTE STREAMS (each with its own half of the workspace) — two forwards in flight fill
+  // each other's prologues and drains, so the fixed cost of a chunk is hidden (measured: 2 x 32 stacks on two streams take the time
+  // of 1 x 64) and the chunks at both ends can be tiny: sizes mb/32, mb/10, equal middle parts <= mb/2, mb/10, mb/32.
+  std::vector<int> sizes;
+  static const int host_streams = getenv("DFF_B200_HOST_STREAMS") ? atoi(getenv("DFF_B200_HOST_STREAMS")) : 2;   // (A/B knob)
+  bool two = false;
+  if (u8 && host_streams >= 2 && B >= 16 && mb >= 16) {
+    // (asynchronous calls overlap their ends with the neighbouring calls: no small head / tail chunks, just halves of mb)
+    const int e0 = ticket >= 0 ? 0 : std::max(1, mb / 32), e1 = ticket >= 0 ? 0 : std::max(1, mb / 10), cap = mb / 2;
+    const int mid = B - 2 * (e0 + e1);
+    if (mid >= 2) {
+      int parts = std::max(2, (mid + cap - 1) / cap);
+      parts += parts & 1;
+      if (e0) { sizes.push_back(e0); sizes.push_back(e1); }
+      for (int i = 0, left = mid; i < parts; ++i) { const int n = (left + (parts - i) - 1) / (parts - i); sizes.push_back(n); left -= n; }
+      if (e0) { sizes.push_back(e1); sizes.push_back(e0); }
+      if (const char* sch = getenv("DFF_B200_HOST_SCHED")) {   // (experiments: explicit chunk sizes "2,6,24,24,6,2"; must sum to B)
+        std::vector<int> v;
+        int sum = 0;
+        for (const char* q = sch; *q;) { const int n = atoi(q); if (n > 0) { v.push_back(n); sum += n; } while (*q && *q != ',') ++q; if (*q) ++q; }
+        if (sum == B) sizes = v;
       }
+      int maxn = 0;
+      for (int n : sizes) maxn = std::max(maxn, n);
+      // both compute streams need a workspace, and the stages of up to two computing + one arriving + one leaving chunk
+      two = 2 * align_up(dff_workspace_bytes(maxn, S, H, W, mode), 256) <= workspace_bytes &&
+            4 * host_stage_bytes(maxn, in_stack, fd_span(fd_strides, maxn, S, H, W), H, W) <= io_bytes;
     }
-    if (n > mb) n = mb;
-    if (n > B - i0) n = B - i0;
-    const int k = nchunk % kHostStages;
+  }
+  if (!two) {
+    sizes.clear();
+    const int head = mb >= 8 ? mb / 8 : 1;
+    for (int i0 = 0, nchunk = 0; i0 < B; ++nchunk) {
+      int n;
+      if (!u8) n = nchunk < 2 ? (mb >= 4 ? mb / 4 : mb) : (mb >= 2 ? mb / 2 : mb);
+      else if (B <= 2 * head + 1) n = B;
+      else if (nchunk == 0) n = head;
+      else {
+        const int left = B - i0;
+        if (left <= head) n = left;
+        else {   // the middle, in equal parts no larger than mb
+          const int mid = left - head, parts = (mid + mb - 1) / mb;
+          n = (mid + parts - 1) / parts;
+        }
+      }
+      if (n > mb) n = mb;
+      if (n > B - i0) n = B - i0;
+      sizes.push_back(n);
+      i0 += n;
+    }
+  }
+  int smax = 0;
+  for (int n : sizes) smax = std::max(smax, n);
+  const int sb = two ? smax : mb;                                   // stacks a stage holds
+  const size_t sfd = two ? fd_span(fd_strides, sb, S, H, W) : fd_elems;
+  const size_t stage = host_stage_bytes(sb, in_stack, sfd, H, W);
+  const int nstages = two ? (int)std::min<size_t>(kHostMaxStages, io_bytes / stage) : kHostStages;
+  const size_t ws_half = two ? (workspace_bytes / 2) & ~(size_t)255 : workspace_bytes;
+  if (two) {   // the second stream starts after whatever the caller queued on its stream before this call
+    DFF_CUDA(cudaEventRecord(hp->entry, st));
+    DFF_CUDA(cudaStreamWaitEvent(hp->c2, hp->entry, 0));
+  }
+  int nchunk = 0;
+  for (int i0 = 0; nchunk < (int)sizes.size() && !rc; i0 += sizes[nchunk], ++nchunk) {
+    const int n = sizes[nchunk];
+    const int k = nchunk % nstages;
+    cudaStream_t cs = (two && (nchunk & 1)) ? hp->c2 : st;
+    char* wsp = (char*)workspace + ((two && (nchunk & 1)) ? ws_half : 0);
     char* io = (char*)dev_io + k * stage;
-    float* dfd = (float*)(io + align_up((size_t)mb * in_stack, 256));
-    char* o = (char*)dfd + align_up(fd_elems * 4, 256);
+    float* dfd = (float*)(io + align_up((size_t)sb * in_stack, 256));
+    char* o = (char*)dfd + align_up(sfd * 4, 256);
     float* dout[4];
-    for (int j = 0; j < 4; ++j) dout[j] = (float*)(o + j * align_up((size_t)mb * map_px * 4, 256));
+    for (int j = 0; j < 4; ++j) dout[j] = (float*)(o + j * align_up((size_t)sb * map_px * 4, 256));
     // stage k is free again once the maps of the chunk that used it last have left it
-    if (nchunk >= kHostStages) DFF_CUDA(cudaStreamWaitEvent(hp->h2d, hp->out_done[k], 0));
+    if (nchunk >= nstages) DFF_CUDA(cudaStreamWaitEvent(hp->h2d, hp->out_done[k], 0));
     DFF_CUDA(cudaMemcpyAsync(io, (const char*)in_host + (size_t)i0 * in_stack, (size_t)n * in_stack, cudaMemcpyHostToDevice, hp->h2d));
     DFF_CUDA(cudaMemcpyAsync(dfd, fd_host + (size_t)i0 * fd_strides[0], fd_span(fd_strides, n, S, H, W) * 4, cudaMemcpyHostToDevice, hp->h2d));
     DFF_CUDA(cudaEventRecord(hp->in_ready[k], hp->h2d));
-    DFF_CUDA(cudaStreamWaitEvent(st, hp->in_ready[k], 0));
+    DFF_CUDA(cudaStreamWaitEvent(cs, hp->in_ready[k], 0));
     const FwdIn fin = u8 ? FwdIn((const unsigned char*)io, H0, W0) : FwdIn((const float*)io);
-    rc = forward_impl(packed, fin, dfd, fd_strides, n, S, H, W, dout, nullptr, workspace, workspace_bytes, mode, st, false, nullptr);
+    rc = forward_impl(packed, fin, dfd, fd_strides, n, S, H, W, dout, nullptr, wsp, ws_half, mode, cs, false, nullptr);
     if (rc) break;
-    DFF_CUDA(cudaEventRecord(hp->computed[k], st));
+    DFF_CUDA(cudaEventRecord(hp->computed[k], cs));
     DFF_CUDA(cudaStreamWaitEvent(hp->d2h, hp->computed[k], 0));
     for (int j = 0; j < 4; ++j)
       if (out4_host[j])
         DFF_CUDA(cudaMemcpyAsync(out4_host[j] + (size_t)i0 * map_px, dout[j], (size_t)n * map_px * 4, cudaMemcpyDeviceToHost, hp->d2h));
     DFF_CUDA(cudaEventRecord(hp->out_done[k], hp->d2h));
   }
+  if (two) {   // the caller's stream is "after" everything this call computed
+    cudaEventRecord(hp->c2_done, hp->c2);
+    cudaStreamWaitEvent(st, hp->c2_done, 0);
+  }
+  if (ticket >= 0 && !rc) {
+    // asynchronous call: everything is queued; the maps are complete when the device->host stream gets here (its reads wait for
+    // the kernels, the kernels for the uploads).  The next call queues behind this one on the same streams — its uploads run during
+    // this call's kernels, its first kernels fill this call's drain.
+    DFF_CUDA(cudaEventRecord(hp->ticket_done[ticket], hp->d2h));
+    return 0;
+  }
   // the call returns with every map in host memory (and nothing of it still queued on the private streams)
   cudaError_t e1 = cudaStreamSynchronize(hp->h2d), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(hp->d2h);
+  if (two && e2 == cudaSuccess) e2 = cudaStreamSynchronize(hp->c2);
   if (rc) return rc;
   DFF_CUDA(e1);
   DFF_CUDA(e2);
@@ -1301,6 +1378,27 @@ int dff_forward_host_u8(const void* packed, const uint8_t* FS_u8_host, int H0, i
   return forward_host_impl(packed, FS_u8_host, true, H0, W0, fd_host, fd_strides, B, micro_batch, S, H, W, out4_host, dev_io, workspace,
                            workspace_bytes, mode, device, (cudaStream_t)stream);
 }
+
+int dff_forward_host_u8_async(const void* packed, const uint8_t* FS_u8_host, int H0, int W0, const float* fd_host,
+                              const int64_t fd_strides[4], int B, int micro_batch, int S, int H, int W, float* const out4_host[4],
+                              void* dev_io, void* workspace, size_t workspace_bytes, int mode, int device, void* stream, int ticket) {
+  if (!packed || !FS_u8_host || !fd_host || !fd_strides || !out4_host || !dev_io || !workspace)
+    return fail(DFF_E_ARG, "dff_forward_host_u8_async: null pointer");
+  if (ticket != 0 && ticket != 1) return fail(DFF_E_ARG, "dff_forward_host_u8_async: ticket must be 0 or 1");
+  return forward_host_impl(packed, FS_u8_host, true, H0, W0, fd_host, fd_strides, B, micro_batch, S, H, W, out4_host, dev_io, workspace,
+                           workspace_bytes, mode, device, (cudaStream_t)stream, ticket);
+}
+
+int dff_forward_host_wait(int device, int ticket) {
+  if (ticket != 0 && ticket != 1) return fail(DFF_E_ARG, "dff_forward_host_wait: ticket must be 0 or 1");
+  DeviceGuard g(device);
+  if (g.rc) return g.rc;
+  HostPipe* hp = host_pipe(device);
+  if (!hp) return fail(DFF_E_CUDA, "dff_forward_host_wait: no pipeline on this thread and device");
+  DFF_CUDA(cudaEventSynchronize(hp->ticket_done[ticket]));
+  return 0;
+}
+
 
 static Layer adhoc_layer(int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int dil_hw, bool transposed, bool tc, size_t* bytes) {
   Layer l{"adhoc", "", Cin, Cout, kd, kh, kw, stride_hw, dil_hw, transposed, false};

@@ -47,6 +47,8 @@ def _declare(lib):
         "dff_forward_u8": (i, [vp, vp, i, i, fp, c.POINTER(i64), i, i, i, i, c.POINTER(vp), c.POINTER(vp), vp, sz, i, i, vp]),
         "dff_host_io_bytes_u8": (sz, [i, i, i, i, i, i, c.POINTER(i64)]),
         "dff_forward_host_u8": (i, [vp, vp, i, i, fp, c.POINTER(i64), i, i, i, i, i, c.POINTER(vp), vp, vp, sz, i, i, vp]),
+        "dff_forward_host_u8_async": (i, [vp, vp, i, i, fp, c.POINTER(i64), i, i, i, i, i, c.POINTER(vp), vp, vp, sz, i, i, vp, i]),
+        "dff_forward_host_wait": (i, [i, i]),
         "dff_stage_u8": (i, [vp, i, i, i, i, i, i, fp, i, vp]),
         "dff_conv3d_scratch_bytes": (sz, [i, i, i, i, i]),
         "dff_conv3d": (i, [vp, i, vp, i, i, i, i, i, fp, i, i, i, i, i, i, i, fp, fp, vp, vp, i, vp, i, i, vp, i, vp]),

@@ -133,6 +133,17 @@ size_t dff_host_io_bytes_u8(int micro_batch, int S, int H0, int W0, int H, int W
 int dff_forward_host_u8(const void *packed, const uint8_t *FS_u8_host, int H0, int W0, const float *fd_host,
                         const int64_t fd_strides[4], int B, int micro_batch, int S, int H, int W, float *const out4_host[4],
                         void *dev_io, void *workspace, size_t workspace_bytes, int mode, int device, void *stream);
+/* Double-buffered variant for a dataloader loop that prefetches: the call only QUEUES the uploads, kernels and reads of its B
+ * stacks and returns; dff_forward_host_wait(device, ticket) blocks until the maps of the call that used `ticket` (0 or 1) are in
+ * host memory.  Two calls may be in flight per calling thread and device when they use different tickets AND different `dev_io`,
+ * `workspace` and output buffers: call i+1's uploads then run during call i's kernels and its first kernels fill call i's drain
+ * (a synchronous call exposes its first chunk's upload and its last chunk's read: ~6 % of a 64-stack call).  Usage:
+ *   async(batch 0, ticket 0); for i = 1..: async(batch i, ticket i & 1); wait(ticket (i-1) & 1); consume batch i-1. */
+int dff_forward_host_u8_async(const void *packed, const uint8_t *FS_u8_host, int H0, int W0, const float *fd_host,
+                              const int64_t fd_strides[4], int B, int micro_batch, int S, int H, int W,
+                              float *const out4_host[4], void *dev_io, void *workspace, size_t workspace_bytes, int mode,
+                              int device, void *stream, int ticket);
+int dff_forward_host_wait(int device, int ticket);
 /* the dataloader tail alone: FS_u8 (B,S,H0,W0,3) -> FS (B,3,S,H,W) fp32, normalised and -1 padded (the tensor the reference feeds) */
 int dff_stage_u8(const uint8_t *FS_u8, int H0, int W0, int B, int S, int H, int W, float *FS, int device, void *stream);
 

@@ -202,6 +202,57 @@ def test_u8_staging_is_bit_identical(built_lib):
         assert host32[0] is None and torch.equal(host32[3], ref[3].cpu())
 
 
+def test_host_pipeline_two_streams_and_double_buffering(built_lib):
+    """The host-buffer entry at a batch where its uint8 schedule alternates chunks between two compute streams (B, micro_batch >= 16)
+    and the double-buffered form (dff_forward_host_u8_async / dff_forward_host_wait, two calls in flight on different tickets and
+    buffers): bit-identical to the device-resident forward of the same stacks."""
+    import ctypes
+    from dffinthewild_b200 import runtime as rt
+    g = np.random.Generator(np.random.PCG64(9))
+    B, S, H0, W0, H, W = 20, 3, 30, 60, 32, 64
+    sd = _state()
+    net = _net(sd, "bf16")
+    batches = [torch.from_numpy(g.integers(0, 256, (B, S, H0, W0, 3), dtype=np.uint8)) for _ in range(3)]
+    fd = torch.linspace(0.28, 0.02, S).view(1, S, 1, 1).expand(B, S, 1, 1).contiguous()
+    with torch.no_grad():
+        refs = [net(b.cuda(), fd.cuda()) for b in batches]
+    host = rt.forward_host(net.DFF_net, batches[0].pin_memory(), fd.pin_memory(), "cuda:0", micro_batch=16)
+    for r, h, n in zip(refs[0], host, NAMES):
+        assert torch.equal(r.cpu(), h), n
+    # three calls through the asynchronous entry, two in flight
+    l = rt.lib()
+    dev = torch.device("cuda", 0)
+    packed = rt.packed_weights(net.DFF_net, dev)
+    strides = (ctypes.c_int64 * 4)(S, 1, 0, 0)
+    mb = 16
+    nio, nws = l.dff_host_io_bytes_u8(mb, S, H0, W0, H, W, strides), l.dff_workspace_bytes(mb, S, H, W, rt.BF16)
+    slots = []
+    for t in range(2):
+        outs = [torch.empty((B, H, W), dtype=torch.float32).pin_memory() for _ in range(4)]
+        slots.append((outs, (ctypes.c_void_p * 4)(*[o.data_ptr() for o in outs]), torch.empty(nio, dtype=torch.uint8, device=dev),
+                      torch.empty(nws, dtype=torch.uint8, device=dev)))
+    pinned = [b.pin_memory() for b in batches]
+    hfd = fd.pin_memory()
+    sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def begin(i):
+        outs, hp, io, ws = slots[i & 1]
+        rt.check(l.dff_forward_host_u8_async(packed.data_ptr(), pinned[i].data_ptr(), H0, W0, hfd.data_ptr(), strides, B, mb, S, H, W, hp,
+                                             io.data_ptr(), ws.data_ptr(), ws.numel(), rt.BF16, 0, sp, i & 1))
+
+    got = []
+    begin(0)
+    for i in range(1, 3):
+        begin(i)
+        rt.check(l.dff_forward_host_wait(0, (i - 1) & 1))
+        got.append([o.clone() for o in slots[(i - 1) & 1][0]])
+    rt.check(l.dff_forward_host_wait(0, 0))
+    got.append([o.clone() for o in slots[0][0]])
+    for i in range(3):
+        for r, h, n in zip(refs[i], got[i], NAMES):
+            assert torch.equal(r.cpu(), h), (i, n)
+
+
 def test_eval_with_grad_uses_running_statistics(built_lib):
     """net.eval() with gradients enabled (frozen-BN fine-tuning, input gradients): outputs must equal the inference path — running
     statistics, no buffer updates — and be differentiable (this used to normalise with batch statistics)."""
