@@ -538,25 +538,26 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
                 if (leader) {
                   const int o0 = p.bop[b];
                   int n = p.bn[b];
-                  uint64_t bd = bd_base + (uint64_t)((uint32_t)(wsl * p.wslot_bytes) >> 4);
+                  const uint32_t al = (uint32_t)ad0, ah = (uint32_t)(ad0 >> 32), bh = (uint32_t)(bd_base >> 32), bs = (uint32_t)b_step;
+                  uint32_t bl = (uint32_t)bd_base + ((uint32_t)(wsl * p.wslot_bytes) >> 4);
                   const ulonglong2* tq = reinterpret_cast<const ulonglong2*>(p.tab + o0);  // blocks start on quad boundaries
                   ulonglong2 t01 = tq[0], t23 = tq[1];
 #pragma unroll 1
                   for (; n >= 4; n -= 4) {
                     tq += 2;
                     const ulonglong2 n01 = tq[0], n23 = tq[1];
-                    umma(dacc, ad0 + t01.x, bd, idesc, acc);
-                    umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
-                    umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
-                    umma_acc(dacc, ad0 + t23.y, bd + 3 * b_step, idesc);
+                    umma2(dacc, al + (uint32_t)t01.x, ah, bl, bh, idesc, acc);
+                    umma2_acc(dacc, al + (uint32_t)t01.y, ah, bl + bs, bh, idesc);
+                    umma2_acc(dacc, al + (uint32_t)t23.x, ah, bl + 2 * bs, bh, idesc);
+                    umma2_acc(dacc, al + (uint32_t)t23.y, ah, bl + 3 * bs, bh, idesc);
                     acc = 1;
-                    bd += 4 * b_step;
+                    bl += 4 * bs;
                     t01 = n01; t23 = n23;
                   }
                   if (n > 0) {
-                    umma(dacc, ad0 + t01.x, bd, idesc, acc);
-                    if (n > 1) umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
-                    if (n > 2) umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
+                    umma2(dacc, al + (uint32_t)t01.x, ah, bl, bh, idesc, acc);
+                    if (n > 1) umma2_acc(dacc, al + (uint32_t)t01.y, ah, bl + bs, bh, idesc);
+                    if (n > 2) umma2_acc(dacc, al + (uint32_t)t23.x, ah, bl + 2 * bs, bh, idesc);
                   }
                   umma_commit(wempty0 + 8 * wsl);
                 }
@@ -578,7 +579,9 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
             const int z = s + k - 1;
             if (n0 > 0 && z >= 0 && z < p.S && !(p.exp & 4)) {  // (focal-dimension zero padding: nothing to multiply)
               const uint64_t ad0 = k == 0 ? a_prev : (k == 1 ? a_cur : a_next);
-              uint64_t bd = bd_base + (uint32_t)p.gw[gi] * b_step;
+              // 32-bit descriptor arithmetic (umma2): table entries and weight steps only touch the low words
+              const uint32_t al = (uint32_t)ad0, ah = (uint32_t)(ad0 >> 32), bh = (uint32_t)(bd_base >> 32), bs = (uint32_t)b_step;
+              uint32_t bl = (uint32_t)bd_base + (uint32_t)p.gw[gi] * bs;
               const ulonglong2* tq = reinterpret_cast<const ulonglong2*>(p.tab + i0);  // groups start on quad boundaries
               ulonglong2 t01 = tq[0], t23 = tq[1];
               int n = n0;
@@ -586,19 +589,19 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
               for (; n >= 4; n -= 4) {
                 tq += 2;
                 const ulonglong2 n01 = tq[0], n23 = tq[1];  // next quad (the table has one spare quad at the end)
-                umma(dacc, ad0 + t01.x, bd, idesc, acc);
-                umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
-                umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
-                umma_acc(dacc, ad0 + t23.y, bd + 3 * b_step, idesc);
+                umma2(dacc, al + (uint32_t)t01.x, ah, bl, bh, idesc, acc);
+                umma2_acc(dacc, al + (uint32_t)t01.y, ah, bl + bs, bh, idesc);
+                umma2_acc(dacc, al + (uint32_t)t23.x, ah, bl + 2 * bs, bh, idesc);
+                umma2_acc(dacc, al + (uint32_t)t23.y, ah, bl + 3 * bs, bh, idesc);
                 acc = 1;
-                bd += 4 * b_step;
+                bl += 4 * bs;
                 t01 = n01; t23 = n23;
               }
               if (n > 0) {
-                umma(dacc, ad0 + t01.x, bd, idesc, acc);
+                umma2(dacc, al + (uint32_t)t01.x, ah, bl, bh, idesc, acc);
                 acc = 1;
-                if (n > 1) umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
-                if (n > 2) umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
+                if (n > 1) umma2_acc(dacc, al + (uint32_t)t01.y, ah, bl + bs, bh, idesc);
+                if (n > 2) umma2_acc(dacc, al + (uint32_t)t23.x, ah, bl + 2 * bs, bh, idesc);
               }
             }
             if (++k == 3) { k = 0; dacc += p.N; acc = 0; }  // next output phase: next accumulator

@@ -96,6 +96,36 @@ __device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint64_t adesc, uint64
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
+// The same instruction from 32-bit descriptor halves.  Both descriptors change only in their low word from one MMA to the next (the
+// matrix start address and, for A, the leading-dimension offset live in bits 0-29; stride, version and layout in the constant high
+// word), and a single issuing warp is bound by its instruction count on the uniform datapath (~11 uniform instructions per MMA with
+// 64-bit descriptor arithmetic: 57 clk per MMA where the tensor pipe needs 40): one 32-bit add per descriptor, the 64-bit operands
+// packed inside the asm block so that the constant high words can stay in the odd registers of the pairs.
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.eq.u32 p, 0, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
