@@ -88,6 +88,10 @@ struct alignas(64) SlabParams {
   // A-operand fetch dominates), so three taps cost 32 + 3N/4 instead of 3 * (32 + N/4): 2.6x fewer tensor-pipe clocks at N = 16,
   // 2.1x at N = 32, 1.8x at N = 64; every plane is needed exactly once, so the plane ring needs no focal halo.
   int zmerge, nslot, lgslot, zT;    // on/off; accumulator slots (power of two) and its log2; spatial MMAs per plane
+  // two-phase layers (x-folded transposed convolutions) in the focal-merged form: phase ph has its own spatial MMAs (zTp[ph], table
+  // group 3*ph + 1), its own weight block (zwo[ph], in 16-byte rows) and its own ring of accumulator slots — columns
+  // (ph * nslot + slot) * N, so that the slots of consecutive slices stay adjacent for the merged N' = cnt * N instruction
+  int zTp[2], zwo[2];
   int egroups;                      // epilogue warp groups (1 or 2)
   int tma;                          // planes staged by ONE tiled TMA load each (single-chunk, single-view layers: box 8 ch x RX x RY)
   int gb[12], gbe[12];              // block range per MMA group
@@ -169,7 +173,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
       for (int ph = eg; ph < p.nph; ph += neg) {
         const size_t pix = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
         if (p.exp & 2) continue;
-        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * p.nph + ph) * p.N;   // (zmerge: nph == 1, buf = slot)
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (p.zmerge ? ph * p.nslot + buf : buf * p.nph + ph) * p.N;   // (zmerge: buf = slot, phase-major rings)
         if (FAST) {
           if (ph != eg) tc_epilogue_preload<RES, AUX>(ep, valid, pix, 0, rv);
           tc_epilogue_fast<RELU, RES, AUX, PROJ>(ep, ss_s, tacc, valid, pix, rv);
@@ -227,15 +231,18 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
   // ---- one-time: MMA table, weights (MMA order), BatchNorm scale/shift and the staging table into shared memory --------
   if (!WS && p.zmerge) {
     // [spatial op][K half][focal block j = 0,1,2 (dz = +1, 0, -1 -> output slices z-1, z, z+1)][N][8]
-    const int N3 = 3 * p.N, total = 2 * p.zT * N3;
+    const int N3 = 3 * p.N;
     const uint4* wg = reinterpret_cast<const uint4*>(p.wslab);
-    for (int i = threadIdx.x; i < total; i += kThreads) {
-      const int op = i / (2 * N3), rem = i - op * 2 * N3;
-      const int h = rem / N3, jn = rem - h * N3, j = jn / p.N, r = jn - j * p.N;
-      const int src = p.wsrc[2 * (p.g[2 - j] + op) + h];
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (src >= 0) v = __ldg(wg + (size_t)src * p.N + r);
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_s + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    for (int ph = 0; ph < p.nph; ++ph) {
+      const int total = 2 * p.zTp[ph] * N3;
+      for (int i = threadIdx.x; i < total; i += kThreads) {
+        const int op = i / (2 * N3), rem = i - op * 2 * N3;
+        const int h = rem / N3, jn = rem - h * N3, j = jn / p.N, r = jn - j * p.N;
+        const int src = p.wsrc[2 * (p.g[3 * ph + 2 - j] + op) + h];
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (src >= 0) v = __ldg(wg + (size_t)src * p.N + r);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_s + 16 * (p.zwo[ph] + i)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
     }
   } else if (!WS) {
     const int total = 2 * p.nwu * p.N;  // 16-byte rows
@@ -412,6 +419,10 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
           // The plane's MMAs as at most two (accumulator, B sub-block, N') segments per spatial op — the slices it feeds are consecutive
           // accumulator slots unless the ring wraps — computed once per plane (warp-uniform), so that the issue loop below is a
           // descriptor add and one or two tcgen05.mma per op.  Spatial op 0 starts the accumulator of the newest slice(s) (accumulate = 0).
+          // Two-phase layers repeat this per phase on the phase's own ring of slots, MMAs and weight block.
+#pragma unroll 1
+          for (int zph = 0; zph < p.nph; ++zph) {
+          const uint32_t tb_ph = tmem_base + (uint32_t)(zph * p.nslot) * N;
           uint32_t sd[2], si[2];
           uint64_t sb[2];
           int nseg = 0;
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
               const uint32_t slot = (uint32_t)(q0 + r0 - s_begin) & smask;
               int cnt = hi - r0 + 1;
               if ((int)slot + cnt > p.nslot) cnt = p.nslot - (int)slot;
-              sd[nseg] = tmem_base + slot * N;
+              sd[nseg] = tb_ph + slot * N;
               si[nseg] = idesc_base | ((((uint32_t)cnt * N) >> 3) << 17);
               sb[nseg] = (uint64_t)(r0 - (z - 1)) * bz_blk;
               ++nseg;
@@ -430,12 +441,12 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
           }
           // the plane's spatial MMAs, block by block: ONE block when the weights are resident; with streamed weights the whole warp
           // waits for a block's ring slot, the elected lane issues its MMAs and hands the slot back when they have read it
-          const int g1 = p.g[1];
+          const int g1 = p.g[3 * zph + 1];
           const int nblk = WS ? p.nblk : 1;
 #pragma unroll 1
           for (int bk = 0; bk < nblk; ++bk) {
-            const int i_lo = WS ? (int)p.bop[bk] : 0, i_hi = WS ? i_lo + (int)p.bn[bk] : p.zT;
-            uint64_t bd = bdz + (WS ? (uint64_t)((uint32_t)(wsl * p.wslot_bytes) >> 4) : (uint64_t)0);   // weights of op i_lo
+            const int i_lo = WS ? (int)p.bop[bk] : 0, i_hi = WS ? i_lo + (int)p.bn[bk] : p.zTp[zph];
+            uint64_t bd = bdz + (WS ? (uint64_t)((uint32_t)(wsl * p.wslot_bytes) >> 4) : (uint64_t)(uint32_t)p.zwo[zph]);   // weights of op i_lo
             if (WS) {
               mbar_wait(wfull0 + 8 * wsl, wsph);
               fence_after();
@@ -451,7 +462,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
                     const uint32_t slot = (uint32_t)(q0 + r0 - s_begin) & smask;
                     int cnt = r1 - r0 + 1;
                     if ((int)slot + cnt > p.nslot) cnt = p.nslot - (int)slot;
-                    umma(tmem_base + slot * N, ad, bd + (uint64_t)(r0 - (z - 1)) * bz_blk, idesc_base | ((((uint32_t)cnt * N) >> 3) << 17),
+                    umma(tb_ph + slot * N, ad, bd + (uint64_t)(r0 - (z - 1)) * bz_blk, idesc_base | ((((uint32_t)cnt * N) >> 3) << 17),
                          part ? 0u : 1u);
                     r0 += cnt;
                   }
@@ -479,6 +490,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
             if (WS) {
               if (++wsl == p.nwslots) { wsl = 0; wsph ^= 1; }
             }
+          }
           }
           if (leader) {
             umma_commit(e_pl);                                   // the plane is not needed again
@@ -834,12 +846,20 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.nelem = p.tma ? 0 : p.nviews * p.RY * p.RX * nchunk;   // (staging table of the cp.async producers)
   // focal-merged form: the three focal groups must be the same spatial MMAs (true for every 3x3x3 / strided / x-folded layer)
   static const bool no_zmerge = getenv("DFF_B200_NO_ZMERGE") != nullptr;
-  bool zm = !no_zmerge && nph == 1 && p.hz == 1 && 3 * Ntc <= 256;
+  static const bool no_zm2 = getenv("DFF_B200_NO_ZM2") != nullptr;   // (A/B knob: two-phase layers keep the per-slice schedule)
+  bool zm = !no_zmerge && (nph == 1 || (nph == 2 && !no_zm2)) && p.hz == 1 && 3 * Ntc <= 256;
   if (zm) {
-    const int T = p.ge[1] - p.g[1];
-    zm = T > 0 && p.ge[0] - p.g[0] == T && p.ge[2] - p.g[2] == T;
-    for (int i = 0; zm && i < T; ++i) zm = p.tab[p.g[0] + i] == p.tab[p.g[1] + i] && p.tab[p.g[2] + i] == p.tab[p.g[1] + i];
-    p.zT = T;
+    for (int ph = 0; ph < nph && zm; ++ph) {
+      const int g0 = 3 * ph;
+      const int T = p.ge[g0 + 1] - p.g[g0 + 1];
+      zm = T > 0 && p.ge[g0] - p.g[g0] == T && p.ge[g0 + 2] - p.g[g0 + 2] == T;
+      for (int i = 0; zm && i < T; ++i) zm = p.tab[p.g[g0] + i] == p.tab[p.g[g0 + 1] + i] && p.tab[p.g[g0 + 2] + i] == p.tab[p.g[g0 + 1] + i];
+      p.zTp[ph] = T;
+    }
+    p.zT = p.zTp[0];
+    p.zwo[0] = 0;
+    p.zwo[1] = 2 * p.zTp[0] * 3 * Ntc;
+    if (zm) p.w_bytes = (p.zTp[0] + (nph == 2 ? p.zTp[1] : 0)) * 96 * Ntc;   // [op][K half][3 focal blocks][N][8] per phase
   }
   static const int zm_np = getenv("DFF_ZM_NPMIN") ? atoi(getenv("DFF_ZM_NPMIN")) : 2;   // (A/B knob: minimal plane-ring depth of the focal-merged form)
   const int np_min = zm ? zm_np : 2 * p.hz + 2;
@@ -860,7 +880,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   fixed = lay_out(p.w_bytes);
   for (; occ >= 1; --occ) {
     // (focal-merged: at least 4 accumulator slots per CTA)
-    if (occ * (zm ? std::max(32, 4 * Ntc) : p.tmem_cols) > 512) continue;
+    if (occ * (zm ? std::max(32, nph * 4 * Ntc) : p.tmem_cols) > 512) continue;
     const int budget = kSlabSmemBudget / occ - 2048 - 256;  // static shared memory, the per-CTA reservation, allocation granularity
     NP = (budget - fixed) / p.plane_bytes;
     if (NP >= np_min) break;
@@ -869,9 +889,9 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     // as many slots as the CTA's share of tensor memory holds (8 at most): the ring wraps — and an MMA has to be split — once per
     // `nslot` planes
     int ns = 8;
-    while (ns > 4 && occ * std::max(32, ns * Ntc) > 512) ns >>= 1;
+    while (ns > 4 && occ * std::max(32, nph * ns * Ntc) > 512) ns >>= 1;
     p.zmerge = 1; p.nslot = ns; p.lgslot = ns == 8 ? 3 : 2;
-    cols = ns * Ntc;
+    cols = nph * ns * Ntc;
     p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   }
   if (occ < 1) {
@@ -887,7 +907,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     // as large as the ring allows: a group of MMAs is cut into the fewest blocks whose slot (<= 40 KB) still leaves room for three
     // slots and the minimal plane ring.
     static const bool no_zmws = getenv("DFF_B200_NO_ZMWS") != nullptr;   // (A/B knob)
-    if (zm && a.wz && !no_zmws && 8 * Ntc <= 512) {
+    if (zm && nph == 1 && a.wz && !no_zmws && 8 * Ntc <= 512) {
       // focal-merged AND streamed: the weights of one spatial MMA (three focal taps, 96*N bytes) are contiguous in `wz`, so the ring
       // is fed block by block with one bulk copy each; every plane replays the same sequence of blocks
       const int T = p.zT, opz = 96 * Ntc;

@@ -1,2 +1,3 @@
-timeout 500 python -m pytest tests/test_gpu_forms.py tests/test_gpu_ops.py tests/test_gpu_forward.py -x -q 2>&1 | tail -2
-timeout 300 python bench.py --steps 20 --no-cpu-baseline --no-train > gpurun_out/r3q_bench.json 2> gpurun_out/r3q.err; tail -2 gpurun_out/r3q.err
+timeout 500 python -m pytest tests/test_gpu_forms.py tests/test_gpu_ops.py tests/test_gpu_forward.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -3
+timeout 300 python bench.py --steps 20 --no-cpu-baseline --no-train > gpurun_out/r3t_bench.json 2> gpurun_out/r3t.err; tail -2 gpurun_out/r3t.err
+DFF_B200_NO_ZM2=1 timeout 300 python bench.py --steps 20 --no-cpu-baseline --no-train > gpurun_out/r3t_bench_nozm2.json 2>> gpurun_out/r3t.err
