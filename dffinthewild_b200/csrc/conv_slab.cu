@@ -59,6 +59,10 @@ constexpr int kSlabSmemBudget = 228 * 1024;   // per SM; every co-resident CTA a
 
 struct alignas(64) SlabParams {
   CUtensorMap tmap[8];   // (tma) per source (x4) and view: the view's pixels as a (C, W/stx, H/sty, S*B) bf16 tensor
+  // An 8-channel source without x-stride views is described as (8*W, 1, H/sty, S*B) instead: a pixel IS the channel run, so a box row
+  // is RX * 16 contiguous bytes.  The TMA unit retires about one innermost box row per clock: with 16-byte rows a 55 KB plane of the
+  // first layer took ~4000 clk to land (13.7 B/clk per SM) and bounded that layer (profiles/r2_changes_measured.txt).
+  int tmerge[2];
   const void* in0;
   const void* in1;
   const void* wslab;  // bf16 [tap][chunk][N][8]
@@ -97,7 +101,7 @@ struct alignas(64) SlabParams {
   int gb[12], gbe[12];              // block range per MMA group
   uint8_t bop[kSlabMaxOps], bn[kSlabMaxOps];   // first MMA / number of MMAs of each block
   uint8_t wop[kSlabMaxOps];   // MMA table entry whose `wsrc` fills weight slot u
-  alignas(16) uint64_t tab[kSlabMaxOps + 4];  // (+1 quad: the issuer prefetches one quad ahead) per MMA, zero-extended to 64 bits (added to the descriptor): (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
+  alignas(16) uint64_t tab[kSlabMaxOps + 8];  // (+2 quads: the issuer prefetches two quads ahead) per MMA, zero-extended to 64 bits (added to the descriptor): (A byte offset inside a ring slot >> 4) | (LBO >> 4) << 16
   int16_t wsrc[2 * kSlabMaxOps];  // per MMA and K half: 8-channel weight block (tap * nchunk + chunk) in `wslab`, -1 = zeros
 };
 
@@ -318,7 +322,8 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
             for (int c = 0; c < p.nchunk; ++c) {
               const int src = c >= p.nch0 ? 1 : 0, cc = src ? c - p.nch0 : c;
               for (int v = 0; v < p.nviews; ++v)
-                tma_load_4d(dst0 + c * p.CPS + v * p.VB, &p.tmap[src * 4 + v], full0 + 8 * slot, cc * 8, x0, y0, bz);
+                if (p.tmerge[src]) tma_load_4d(dst0 + c * p.CPS + v * p.VB, &p.tmap[src * 4 + v], full0 + 8 * slot, x0 * 8, 0, y0, bz);
+                else tma_load_4d(dst0 + c * p.CPS + v * p.VB, &p.tmap[src * 4 + v], full0 + 8 * slot, cc * 8, x0, y0, bz);
             }
           } else {
             asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * slot), "r"(total) : "memory");
@@ -592,28 +597,29 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
             if (n0 > 0 && z >= 0 && z < p.S && !(p.exp & 4)) {  // (focal-dimension zero padding: nothing to multiply)
               const uint64_t ad0 = k == 0 ? a_prev : (k == 1 ? a_cur : a_next);
               // 32-bit descriptor arithmetic (umma2): table entries and weight steps only touch the low words
-              const uint32_t al = (uint32_t)ad0, ah = (uint32_t)(ad0 >> 32), bh = (uint32_t)(bd_base >> 32), bs = (uint32_t)b_step;
-              uint32_t bl = (uint32_t)bd_base + (uint32_t)p.gw[gi] * bs;
+              const uint32_t al = (uint32_t)ad0, ah = (uint32_t)(ad0 >> 32), bh = (uint32_t)(bd_base >> 32), bb = (uint32_t)bd_base;
               const ulonglong2* tq = reinterpret_cast<const ulonglong2*>(p.tab + i0);  // groups start on quad boundaries
               ulonglong2 t01 = tq[0], t23 = tq[1];
+              ulonglong2 u01 = tq[2], u23 = tq[3];   // the quad after (prefetch distance 2: a constant-bank load issued behind the MMAs
+                                                     // of one iteration is not needed before the iteration after next)
               int n = n0;
 #pragma unroll 1
               for (; n >= 4; n -= 4) {
                 tq += 2;
-                const ulonglong2 n01 = tq[0], n23 = tq[1];  // next quad (the table has one spare quad at the end)
-                umma2(dacc, al + (uint32_t)t01.x, ah, bl, bh, idesc, acc);
-                umma2_acc(dacc, al + (uint32_t)t01.y, ah, bl + bs, bh, idesc);
-                umma2_acc(dacc, al + (uint32_t)t23.x, ah, bl + 2 * bs, bh, idesc);
-                umma2_acc(dacc, al + (uint32_t)t23.y, ah, bl + 3 * bs, bh, idesc);
+                const ulonglong2 n01 = tq[2], n23 = tq[3];  // (the table has two spare quads at the end)
+                umma2(dacc, al + (uint32_t)t01.x, ah, bb + (uint32_t)(t01.x >> 32), bh, idesc, acc);
+                umma2_acc(dacc, al + (uint32_t)t01.y, ah, bb + (uint32_t)(t01.y >> 32), bh, idesc);
+                umma2_acc(dacc, al + (uint32_t)t23.x, ah, bb + (uint32_t)(t23.x >> 32), bh, idesc);
+                umma2_acc(dacc, al + (uint32_t)t23.y, ah, bb + (uint32_t)(t23.y >> 32), bh, idesc);
                 acc = 1;
-                bl += 4 * bs;
-                t01 = n01; t23 = n23;
+                t01 = u01; t23 = u23;
+                u01 = n01; u23 = n23;
               }
               if (n > 0) {
-                umma2(dacc, al + (uint32_t)t01.x, ah, bl, bh, idesc, acc);
+                umma2(dacc, al + (uint32_t)t01.x, ah, bb + (uint32_t)(t01.x >> 32), bh, idesc, acc);
                 acc = 1;
-                if (n > 1) umma2_acc(dacc, al + (uint32_t)t01.y, ah, bl + bs, bh, idesc);
-                if (n > 2) umma2_acc(dacc, al + (uint32_t)t23.x, ah, bl + 2 * bs, bh, idesc);
+                if (n > 1) umma2_acc(dacc, al + (uint32_t)t01.y, ah, bb + (uint32_t)(t01.y >> 32), bh, idesc);
+                if (n > 2) umma2_acc(dacc, al + (uint32_t)t23.x, ah, bb + (uint32_t)(t23.x >> 32), bh, idesc);
               }
             }
             if (++k == 3) { k = 0; dacc += p.N; acc = 0; }  // next output phase: next accumulator
@@ -977,6 +983,14 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   }
   if (NP > kSlabMaxPlanes) NP = kSlabMaxPlanes;
   p.NP = NP;
+  if (!p.zmerge && !p.wstream) {
+    // resident weights, per-slice schedule: the upper half of a table entry carries the MMA's weight-slot offset (B descriptor units),
+    // so the issue loop adds one table half to each descriptor and keeps no running weight pointer (the other schedules add the
+    // whole 64-bit entry to the A descriptor: their upper halves stay zero)
+    for (int gi = 0; gi < 3 * nph; ++gi)
+      for (int i = p.g[gi]; i < p.ge[gi]; ++i)
+        p.tab[i] |= (uint64_t)((uint32_t)(p.gw[gi] + (i - p.g[gi])) * ((uint32_t)(Ntc * 32) >> 4)) << 32;
+  }
   // multi-phase layers (transposed convolutions) at one or two CTAs per SM are bound by their four epilogue warps: give them eight
   static const bool no_e2 = getenv("DFF_B200_NO_EPI2") != nullptr;
   p.egroups = (nph >= 2 && occ <= 2 && !no_e2) ? 2 : 1;
@@ -1026,8 +1040,17 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
     for (int src = 0; src < (a.C1 ? 2 : 1); ++src) {
       const unsigned long long C = src ? a.C1 : a.C0;
       const char* base = (const char*)(src ? a.in1 : a.in0);
+      static const bool no_merge = getenv("DFF_B200_NO_TMERGE") != nullptr;   // (A/B knob)
+      p.tmerge[src] = (!no_merge && C == 8 && p.stx == 1 && 8 * p.RX <= 256) ? 1 : 0;
       for (int v = 0; v < p.nviews; ++v) {
         const int vy = v / p.stx, vx = v % p.stx;
+        if (p.tmerge[src]) {   // (8*W, 1, H/sty, S*B): box rows of RX * 16 contiguous bytes
+          const unsigned long long dims[4] = {8ull * a.IW, 1ull, (unsigned long long)(a.IH / p.sty), (unsigned long long)a.S * a.B};
+          const unsigned long long strides[3] = {(unsigned long long)a.IW * 16, (unsigned long long)a.IW * 16 * p.sty, (unsigned long long)a.IH * a.IW * 16};
+          const unsigned box[4] = {8u * (unsigned)p.RX, 1u, (unsigned)p.RY, 1u};
+          DFF_TRY(encode_tmap_bf16(&p.tmap[src * 4 + v], base + (size_t)vy * a.IW * 16, 4, dims, strides, box));
+          continue;
+        }
         const unsigned long long dims[4] = {C, (unsigned long long)(a.IW / p.stx), (unsigned long long)(a.IH / p.sty), (unsigned long long)a.S * a.B};
         const unsigned long long strides[3] = {C * 2 * p.stx, (unsigned long long)a.IW * C * 2 * p.sty, (unsigned long long)a.IH * a.IW * C * 2};
         const unsigned box[4] = {8u, (unsigned)p.RX, (unsigned)p.RY, 1u};
