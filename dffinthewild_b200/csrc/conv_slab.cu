@@ -1104,23 +1104,37 @@ __global__ void pack_weight_slab_kernel(const float* __restrict__ w, __nv_bfloat
 // G*Cout output channels of ONE implicit-GEMM row, fed by kw+G-1 taps along x.  dst: bf16 [kd*kh*(kw+G-1)][Cin/8][G*Cout][8] with
 // W_G[g*Cout + co][ci][kd][kh][q] = W[co][ci][kd][kh][q - g] for 0 <= q - g < kw, else 0.
 __global__ void pack_weight_slab_fold_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin, int CinP,
-                                             int kd, int kh, int kw, int G) {
-  const int nchunk = CinP / 8, N = G * Cout, kq = kw + G - 1;
-  const int n = kd * kh * kq * nchunk * N * 8;
+                                             int kd, int kh, int kw, int G, int foldy) {
+  // foldy: the same along y — G vertically adjacent output pixels per GEMM row, kh+G-1 taps along y:
+  //   dst [kd*(kh+G-1)*kw][Cin/8][G*Cout][8],  W_G[g*Cout + co][ci][kd][p][kx] = W[co][ci][kd][p - g][kx] for 0 <= p - g < kh
+  const int nchunk = CinP / 8, N = G * Cout, kq = (foldy ? kh : kw) + G - 1;
+  const int n = kd * (foldy ? kw : kh) * kq * nchunk * N * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int j = i & 7, nn = (i >> 3) % N, c = (i / (8 * N)) % nchunk, t = i / (8 * N * nchunk);
-    const int q = t % kq, b = (t / kq) % kh, a = t / (kq * kh);
-    const int g = nn / Cout, co = nn % Cout, ci = c * 8 + j, kx = q - g;
+    const int g = nn / Cout, co = nn % Cout, ci = c * 8 + j;
+    int a, b, kx;
+    if (foldy) {   // tap order (kd, p, kx)
+      kx = t % kw;
+      const int pq = (t / kw) % kq;
+      a = t / (kw * kq);
+      b = pq - g;
+    } else {       // tap order (kd, kh, q)
+      const int q = t % kq;
+      b = (t / kq) % kh;
+      a = t / (kq * kh);
+      kx = q - g;
+    }
     float v = 0.f;
-    if (ci < Cin && kx >= 0 && kx < kw) v = w[((((size_t)co * Cin + ci) * kd + a) * kh + b) * kw + kx];
+    if (ci < Cin && kx >= 0 && kx < kw && b >= 0 && b < kh) v = w[((((size_t)co * Cin + ci) * kd + a) * kh + b) * kw + kx];
     dst[i] = __float2bfloat16_rn(v);
   }
 }
-int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, int CinP, int kd, int kh, int kw, int G, cudaStream_t st) {
-  const int n = kd * kh * (kw + G - 1) * CinP * G * Cout;
+int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, int CinP, int kd, int kh, int kw, int G, cudaStream_t st,
+                                 int foldy) {
+  const int n = kd * (foldy ? kw * (kh + G - 1) : kh * (kw + G - 1)) * CinP * G * Cout;
   int g = cdiv(n, 256);
   if (g > 512) g = 512;
-  pack_weight_slab_fold_kernel<<<g, 256, 0, st>>>(w, (__nv_bfloat16*)dst, Cout, Cin, CinP, kd, kh, kw, G);
+  pack_weight_slab_fold_kernel<<<g, 256, 0, st>>>(w, (__nv_bfloat16*)dst, Cout, Cin, CinP, kd, kh, kw, G, foldy);
   DFF_LAUNCH_CHECK("pack_weight_slab_fold");
   return 0;
 }

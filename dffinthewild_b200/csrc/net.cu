@@ -52,7 +52,8 @@ int launch_pack_weight_slab(const float* w, void* dst, int Cout, int Cin, int Ci
 int launch_pack_weight_slab_deconv_fold(const float* w, void* dst, int Cout, int Cin, int CinP, cudaStream_t st);
 int launch_pack_weight_slab_zmerge(const float* w, void* dst, int Cout, int Cin, int CinP, int Ntc, cudaStream_t st);
 int launch_replicate_ss(const float* scale, const float* shift, float* dst, int C, int G, cudaStream_t st);
-int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, int CinP, int kd, int kh, int kw, int G, cudaStream_t st);
+int launch_pack_weight_slab_fold(const float* w, void* dst, int Cout, int Cin, int CinP, int kd, int kh, int kw, int G, cudaStream_t st,
+                                 int foldy = 0);
 int launch_pack_weight_slab_rowfold(const float* wpair, void* dst, int Cout, cudaStream_t st);
 int launch_conv_wgrad(ConvArgs a, const void* dy, int CoS, int Cout, int Cin, int ci_base, float* dw, int ntaps_total,
                       int wt_transposed, bool bf16, cudaStream_t st);
@@ -124,6 +125,8 @@ struct Layer {
   int CinT, Ntc;  // tensor-core path: stored input channels (multiple of 8) and MMA N (multiple of 16, >= 16)
   int64_t raw_w, raw_gamma, raw_beta, raw_mean, raw_var, raw_bias;  // element offsets in the raw buffer (-1: none)
   size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab, pk_proj, pk_pair, pk_wfold, pk_ssfold;                  // byte offsets in the packed buffer
+  size_t pk_wfoldy = 0;  // y-folded form of the 8-output-channel x-folded layers (8-channel sources: merged TMA rows, no x-stride views)
+  bool has_foldy = false;
   size_t pk_wz = 0;      // focal-merged streaming layout (3x3x3 layers with >= 64 stored input channels, whose weights are streamed)
   bool has_wz = false;
 };
@@ -153,6 +156,13 @@ static void layout_layer(Layer& l, size_t& packed_bytes) {
     packed_bytes += align_up((size_t)kd * kh * (kw + l.gfold - 1) * l.CinT * l.gfold * cout * 2, 256);
     l.pk_ssfold = packed_bytes;
     packed_bytes += align_up((size_t)2 * l.gfold * cout * sizeof(float), 256);
+    // (measured: 3x3x3 layers gain — dres4.conv0 2.11 -> 1.73 ms; the 1x3x3 G = 4 layers lose 6 %: their epilogue then writes four
+    // 16-byte pieces per thread to four rows instead of 64 contiguous bytes)
+    if (cout == 8 && kd == 3 && kh == 3 && (cin == 8 || cin == 16)) {   // (sources of 8 channels each: checked per call)
+      l.has_foldy = true;
+      l.pk_wfoldy = packed_bytes;
+      packed_bytes += align_up((size_t)kd * (kh + l.gfold - 1) * kw * l.CinT * l.gfold * cout * 2, 256);
+    }
   }
   if (transposed && cout <= 32 && cout % 8 == 0 && cin % 8 == 0) {   // x-folded transposed conv: the two column phases in one GEMM row
     l.gfold = 2;
@@ -487,6 +497,34 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     a.OHt = out.H; a.OWt = out.W;
     *nlaunch = 1;
     if (count_only) return 0;
+    static const bool no_yfold = getenv("DFF_B200_NO_YFOLD") != nullptr;   // (A/B knob)
+    if (wtc && use_fold && packed_base && l.has_foldy && !no_yfold && !a.proj_w && !a.aux_add && !a.out_f32 && a.Cout == l.cout &&
+        a.C0 == 8 && (a.C1 == 0 || a.C1 == 8) && out.H % l.gfold == 0) {
+      // y-folded form: G vertically adjacent output pixels are the G*Cout channels of one GEMM row — tile rows G input rows apart through
+      // the descriptor's row-group stride (as in the row-folded first layer), 8-channel output groups one row apart.  Unlike the
+      // x-fold it needs no x-stride views, so the 8-channel sources are staged as merged rows (RX * 16 contiguous bytes per TMA row
+      // instead of 16: the TMA unit retires ~1 row per clock, which bounded these layers).
+      const int G = l.gfold, kp = l.kh + G - 1;
+      ConvArgs f = a;
+      f.taps.n = 0;
+      for (int ka = 0; ka < l.kd; ++ka)
+        for (int pq = 0; pq < kp; ++pq)
+          for (int kc = 0; kc < l.kw; ++kc) {
+            f.taps.dz[f.taps.n] = (int8_t)(ka - (l.kd - 1) / 2);
+            f.taps.dy[f.taps.n] = (int8_t)(pq - 1);
+            f.taps.dx[f.taps.n] = (int8_t)(kc - 1);
+            f.taps.widx[f.taps.n] = (uint8_t)((ka * kp + pq) * l.kw + kc);
+            ++f.taps.n;
+          }
+      f.isy = f.isx = 1; f.row_step = G; f.grp_rows = 1;
+      f.osy = G; f.osx = 1; f.ooy = f.oox = 0;
+      f.OHt = out.H / G; f.OWt = out.W;
+      f.Cout = G * l.cout;
+      f.scale = (const float*)(packed_base + l.pk_ssfold);
+      f.shift = f.scale + G * l.cout;
+      if (conv_slab_supported(f, nullptr, 1, G * l.cout))
+        return launch_conv_slab(f, nullptr, 1, packed_base + l.pk_wfoldy, G * l.cout, nsm, st);
+    }
     if (wtc && use_fold && packed_base && l.gfold > 1 && !a.proj_w && a.Cout == l.cout && a.OW % (8 * l.gfold) == 0) {
       // x-folded form: G adjacent output pixels are the G*Cout channels of one GEMM row; the input is read with x-stride G
       // (one staged view per residue), the output is the same memory viewed as (.., W/G, G*Cout)
@@ -991,6 +1029,7 @@ static int pack_layer_weights(const Layer& l, const float* w, char* pk, cudaStre
   if (l.gfold > 1) {
     if (l.transposed) DFF_TRY(launch_pack_weight_slab_deconv_fold(w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, st));
     else DFF_TRY(launch_pack_weight_slab_fold(w, pk + l.pk_wfold, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st));
+    if (l.has_foldy) DFF_TRY(launch_pack_weight_slab_fold(w, pk + l.pk_wfoldy, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st, 1));
   }
   if (l.has_wz) DFF_TRY(launch_pack_weight_slab_zmerge(w, pk + l.pk_wz, l.cout, l.cin, l.CinT, l.Ntc, st));
   return 0;

@@ -318,6 +318,12 @@ __device__ __forceinline__ void tc_epilogue_preload(const EpiArgs& p, bool valid
   if (!(RES || AUX) || !valid) return;
   const __nv_bfloat16* const src =
       reinterpret_cast<const __nv_bfloat16*>(AUX ? p.aux_add : (RES == 1 ? p.res_pre : p.res_post)) + (p.grp_stride ? pix * p.pix_c : pix * p.cstore);
+  if (p.grp_stride) {   // row-/y-folded forms: 8-channel group g of the GEMM row is the pixel g * grp_stride elements further
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+      if (c32 + 8 * h < p.cstore) rv[h] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)((c32 >> 3) + h) * p.grp_stride));
+    return;
+  }
 #pragma unroll
   for (int h = 0; h < 4; h += 2) {
     if (c32 + 8 * h + 16 <= p.cstore) ldg_nc_v8(src + c32 + 8 * h, rv[h], rv[h + 1]);   // (rows of >= 16 channels are 32-byte aligned)
@@ -379,7 +385,7 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiArgs& p, uint32_t ss_s
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
       po[h] = pack8(f);
-      if (p.grp_stride) *reinterpret_cast<uint4*>(out + (size_t)(c >> 3) * p.grp_stride) = po[h];   // (no residual operands in this form)
+      if (p.grp_stride) *reinterpret_cast<uint4*>(out + (size_t)(c >> 3) * p.grp_stride) = po[h];   // (second output / classifier do not exist in this form)
       if (AUX) {
         float a[8];
         unpack8(rvec, a);
