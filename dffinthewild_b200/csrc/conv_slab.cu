@@ -190,11 +190,15 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
   }
 }
 
-template <bool WS, bool E2>
+// I2 (with E2, without WS; one CTA per SM): a SECOND issuing warp (the last warp).  A two-phase layer whose planes leave room for one CTA
+// per SM — the row-folded first layer — is bound by its single issuing warp (3.4 k clk per slice for 60 MMAs the tensor pipe does in
+// 2.4 k); the phases have separate accumulators, so each issuer takes one phase and both commit to the (two-arrival) barriers.
+template <bool WS, bool E2, bool I2 = false>
 // (192 threads x 4 CTAs per SM: 85 registers per thread)
-__global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) conv_slab_kernel(const __grid_constant__ SlabParams p) {
+__global__ void __launch_bounds__(slab_threads(WS, E2) + (I2 ? 32 : 0), (WS || I2) ? 1 : (E2 ? 2 : 4)) conv_slab_kernel(const __grid_constant__ SlabParams p) {
   using namespace tc;
-  constexpr int kThreads = slab_threads(WS, E2);
+  static_assert(!(WS && I2), "the second issuer and the weight producer share the last warp");
+  constexpr int kThreads = slab_threads(WS, E2) + (I2 ? 32 : 0);
   constexpr int kEG = E2 ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kSlabMaxPlanes + 2 * kSlabMaxAcc + (WS ? 2 * kSlabMaxWSlots : 0)];
@@ -219,10 +223,10 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
       }
     for (int i = 0; i < p.NP; ++i) {
       mbar_init(full0 + 8 * i, p.tma ? 1 : kSlabProducers);
-      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, I2 ? 2 : 1);
     }
     for (int i = 0; i < kSlabMaxAcc; ++i) {
-      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tfull0 + 8 * i, I2 ? 2 : 1);
       mbar_init(tempty0 + 8 * i, 128 * kEG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -374,7 +378,8 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
         ++np;
       }
     }
-  } else if (warp == kSlabMmaWarp) {
+  } else if (warp == kSlabMmaWarp || (I2 && warp == kThreads / 32 - 1)) {
+    const int issuer = (I2 && warp != kSlabMmaWarp) ? 1 : 0;   // (I2: this warp issues the MMAs of output phase `issuer` only)
     // =============================== MMA issuer ===============================
     // The whole warp walks the schedule with warp-uniform values (everything derives from blockIdx and kernel parameters, the
     // MMA table is read from the parameter bank with a uniform index), so descriptors live in uniform registers and the
@@ -594,7 +599,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2), WS ? 1 : (E2 ? 2 : 4)) c
           for (int gi = 0; gi < ngrp; ++gi) {
             const int i0 = p.g[gi], n0 = p.ge[gi] - i0;
             const int z = s + k - 1;
-            if (n0 > 0 && z >= 0 && z < p.S && !(p.exp & 4)) {  // (focal-dimension zero padding: nothing to multiply)
+            if (n0 > 0 && z >= 0 && z < p.S && !(p.exp & 4) && (!I2 || gi / 3 == issuer)) {  // (focal-dimension zero padding: nothing to multiply)
               const uint64_t ad0 = k == 0 ? a_prev : (k == 1 ? a_cur : a_next);
               // 32-bit descriptor arithmetic (umma2): table entries and weight steps only touch the low words
               const uint32_t al = (uint32_t)ad0, ah = (uint32_t)(ad0 >> 32), bh = (uint32_t)(bd_base >> 32), bb = (uint32_t)bd_base;
@@ -1067,6 +1072,11 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
     DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<WS_, E2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
     DFF_CUDA(launch_pdl(conv_slab_kernel<WS_, E2_>, dim3(grid), dim3(slab_threads(WS_, E2_)), smem, st, p));                        \
   } while (0)
+  static const bool no_i2 = getenv("DFF_B200_NO_I2") != nullptr;   // (A/B knob: one issuing warp everywhere)
+  if (!no_i2 && !p.wstream && p.egroups == 2 && !p.zmerge && p.nph == 2 && p.hz == 0 && occ == 1) {
+    DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFF_CUDA(launch_pdl(conv_slab_kernel<false, true, true>, dim3(grid), dim3(slab_threads(false, true) + 32), smem, st, p));
+  } else
   if (p.wstream) { if (p.egroups == 2) DFF_SLAB_LAUNCH(true, true); else DFF_SLAB_LAUNCH(true, false); }
   else { if (p.egroups == 2) DFF_SLAB_LAUNCH(false, true); else DFF_SLAB_LAUNCH(false, false); }
 #undef DFF_SLAB_LAUNCH
