@@ -384,9 +384,10 @@ def run_ours(args):
     tr = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")   # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
     if os.path.exists(tr):
         t = json.load(open(tr))
-        if t.get("kernel") == top_name and t.get("micro_batch") == mb and t.get("precision") == args.precision:
-            roof["traffic"] = t["dram_bytes_per_launch"]
-            roof["traffic_source"] = t.get("source")
+        k = t.get("kernels", {}).get(top_name)
+        if k and t.get("micro_batch") == mb and t.get("precision") == args.precision:
+            roof["traffic"] = k["dram_bytes_per_launch"]
+            roof["traffic_source"] = k.get("source")
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
