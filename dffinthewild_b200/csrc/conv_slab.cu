@@ -144,6 +144,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
   ep.shift = ss + p.N;
   const int esz = ep.out_f32 ? 4 : 2;
   const void* const rsrc = ep.res_pre ? ep.res_pre : (ep.res_post ? ep.res_post : ep.aux_add);   // (a layer has at most one residual operand)
+  const bool z2 = p.zmerge && p.nph == 2;
   int sc = 0;
   for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
     if (item + (int)gridDim.x >= p.nitems) pdl_trigger();
@@ -177,7 +178,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
       for (int ph = eg; ph < p.nph; ph += neg) {
         const size_t pix = (row0 + (oy * p.osy + p.phy[ph])) * p.OW + (ox * p.osx + p.phx[ph]);
         if (p.exp & 2) continue;
-        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (p.zmerge ? ph * p.nslot + buf : buf * p.nph + ph) * p.N;   // (zmerge: buf = slot, phase-major rings)
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (z2 ? ph * p.nslot + buf : buf * p.nph + ph) * p.N;   // (two-phase focal-merged: buf = slot, phase-major rings)
         if (FAST) {
           if (ph != eg) tc_epilogue_preload<RES, AUX>(ep, valid, pix, 0, rv);
           tc_epilogue_fast<RELU, RES, AUX, PROJ>(ep, ss_s, tacc, valid, pix, rv);
@@ -193,7 +194,9 @@ __device__ __forceinline__ void slab_epilogue(const SlabParams& p, uint32_t tmem
 // I2 (with E2, without WS; one CTA per SM): a SECOND issuing warp (the last warp).  A two-phase layer whose planes leave room for one CTA
 // per SM — the row-folded first layer — is bound by its single issuing warp (3.4 k clk per slice for 60 MMAs the tensor pipe does in
 // 2.4 k); the phases have separate accumulators, so each issuer takes one phase and both commit to the (two-arrival) barriers.
-template <bool WS, bool E2, bool I2 = false>
+// Z2: the focal-merged schedule of a TWO-phase layer (its own instantiation: with the phase loop in the common code every
+// single-phase focal-merged layer ran 4 % slower — 17 % at the training batch — measured).
+template <bool WS, bool E2, bool I2 = false, bool Z2 = false>
 // (192 threads x 4 CTAs per SM: 85 registers per thread)
 __global__ void __launch_bounds__(slab_threads(WS, E2) + (I2 ? 32 : 0), (WS || I2) ? 1 : (E2 ? 2 : 4)) conv_slab_kernel(const __grid_constant__ SlabParams p) {
   using namespace tc;
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2) + (I2 ? 32 : 0), (WS || I
     // [spatial op][K half][focal block j = 0,1,2 (dz = +1, 0, -1 -> output slices z-1, z, z+1)][N][8]
     const int N3 = 3 * p.N;
     const uint4* wg = reinterpret_cast<const uint4*>(p.wslab);
-    for (int ph = 0; ph < p.nph; ++ph) {
+    for (int ph = 0; ph < (Z2 ? 2 : 1); ++ph) {
       const int total = 2 * p.zTp[ph] * N3;
       for (int i = threadIdx.x; i < total; i += kThreads) {
         const int op = i / (2 * N3), rem = i - op * 2 * N3;
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(slab_threads(WS, E2) + (I2 ? 32 : 0), (WS || I
           // descriptor add and one or two tcgen05.mma per op.  Spatial op 0 starts the accumulator of the newest slice(s) (accumulate = 0).
           // Two-phase layers repeat this per phase on the phase's own ring of slots, MMAs and weight block.
 #pragma unroll 1
-          for (int zph = 0; zph < p.nph; ++zph) {
+          for (int zph = 0; zph < (Z2 ? 2 : 1); ++zph) {
           const uint32_t tb_ph = tmem_base + (uint32_t)(zph * p.nslot) * N;
           uint32_t sd[2], si[2];
           uint64_t sb[2];
@@ -560,26 +563,25 @@ __global__ void __launch_bounds__(slab_threads(WS, E2) + (I2 ? 32 : 0), (WS || I
                 if (leader) {
                   const int o0 = p.bop[b];
                   int n = p.bn[b];
-                  const uint32_t al = (uint32_t)ad0, ah = (uint32_t)(ad0 >> 32), bh = (uint32_t)(bd_base >> 32), bs = (uint32_t)b_step;
-                  uint32_t bl = (uint32_t)bd_base + ((uint32_t)(wsl * p.wslot_bytes) >> 4);
+                  uint64_t bd = bd_base + (uint64_t)((uint32_t)(wsl * p.wslot_bytes) >> 4);
                   const ulonglong2* tq = reinterpret_cast<const ulonglong2*>(p.tab + o0);  // blocks start on quad boundaries
                   ulonglong2 t01 = tq[0], t23 = tq[1];
 #pragma unroll 1
                   for (; n >= 4; n -= 4) {
                     tq += 2;
                     const ulonglong2 n01 = tq[0], n23 = tq[1];
-                    umma2(dacc, al + (uint32_t)t01.x, ah, bl, bh, idesc, acc);
-                    umma2_acc(dacc, al + (uint32_t)t01.y, ah, bl + bs, bh, idesc);
-                    umma2_acc(dacc, al + (uint32_t)t23.x, ah, bl + 2 * bs, bh, idesc);
-                    umma2_acc(dacc, al + (uint32_t)t23.y, ah, bl + 3 * bs, bh, idesc);
+                    umma(dacc, ad0 + t01.x, bd, idesc, acc);
+                    umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
+                    umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
+                    umma_acc(dacc, ad0 + t23.y, bd + 3 * b_step, idesc);
                     acc = 1;
-                    bl += 4 * bs;
+                    bd += 4 * b_step;
                     t01 = n01; t23 = n23;
                   }
                   if (n > 0) {
-                    umma2(dacc, al + (uint32_t)t01.x, ah, bl, bh, idesc, acc);
-                    if (n > 1) umma2_acc(dacc, al + (uint32_t)t01.y, ah, bl + bs, bh, idesc);
-                    if (n > 2) umma2_acc(dacc, al + (uint32_t)t23.x, ah, bl + 2 * bs, bh, idesc);
+                    umma(dacc, ad0 + t01.x, bd, idesc, acc);
+                    if (n > 1) umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
+                    if (n > 2) umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
                   }
                   umma_commit(wempty0 + 8 * wsl);
                 }
@@ -601,30 +603,27 @@ __global__ void __launch_bounds__(slab_threads(WS, E2) + (I2 ? 32 : 0), (WS || I
             const int z = s + k - 1;
             if (n0 > 0 && z >= 0 && z < p.S && !(p.exp & 4) && (!I2 || gi / 3 == issuer)) {  // (focal-dimension zero padding: nothing to multiply)
               const uint64_t ad0 = k == 0 ? a_prev : (k == 1 ? a_cur : a_next);
-              // 32-bit descriptor arithmetic (umma2): table entries and weight steps only touch the low words
-              const uint32_t al = (uint32_t)ad0, ah = (uint32_t)(ad0 >> 32), bh = (uint32_t)(bd_base >> 32), bb = (uint32_t)bd_base;
+              uint64_t bd = bd_base + (uint32_t)p.gw[gi] * b_step;
               const ulonglong2* tq = reinterpret_cast<const ulonglong2*>(p.tab + i0);  // groups start on quad boundaries
               ulonglong2 t01 = tq[0], t23 = tq[1];
-              ulonglong2 u01 = tq[2], u23 = tq[3];   // the quad after (prefetch distance 2: a constant-bank load issued behind the MMAs
-                                                     // of one iteration is not needed before the iteration after next)
               int n = n0;
 #pragma unroll 1
               for (; n >= 4; n -= 4) {
                 tq += 2;
-                const ulonglong2 n01 = tq[2], n23 = tq[3];  // (the table has two spare quads at the end)
-                umma2(dacc, al + (uint32_t)t01.x, ah, bb + (uint32_t)(t01.x >> 32), bh, idesc, acc);
-                umma2_acc(dacc, al + (uint32_t)t01.y, ah, bb + (uint32_t)(t01.y >> 32), bh, idesc);
-                umma2_acc(dacc, al + (uint32_t)t23.x, ah, bb + (uint32_t)(t23.x >> 32), bh, idesc);
-                umma2_acc(dacc, al + (uint32_t)t23.y, ah, bb + (uint32_t)(t23.y >> 32), bh, idesc);
+                const ulonglong2 n01 = tq[0], n23 = tq[1];  // next quad (the table has spare quads at the end)
+                umma(dacc, ad0 + t01.x, bd, idesc, acc);
+                umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
+                umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
+                umma_acc(dacc, ad0 + t23.y, bd + 3 * b_step, idesc);
                 acc = 1;
-                t01 = u01; t23 = u23;
-                u01 = n01; u23 = n23;
+                bd += 4 * b_step;
+                t01 = n01; t23 = n23;
               }
               if (n > 0) {
-                umma2(dacc, al + (uint32_t)t01.x, ah, bb + (uint32_t)(t01.x >> 32), bh, idesc, acc);
+                umma(dacc, ad0 + t01.x, bd, idesc, acc);
                 acc = 1;
-                if (n > 1) umma2_acc(dacc, al + (uint32_t)t01.y, ah, bb + (uint32_t)(t01.y >> 32), bh, idesc);
-                if (n > 2) umma2_acc(dacc, al + (uint32_t)t23.x, ah, bb + (uint32_t)(t23.x >> 32), bh, idesc);
+                if (n > 1) umma_acc(dacc, ad0 + t01.y, bd + b_step, idesc);
+                if (n > 2) umma_acc(dacc, ad0 + t23.x, bd + 2 * b_step, idesc);
               }
             }
             if (++k == 3) { k = 0; dacc += p.N; acc = 0; }  // next output phase: next accumulator
@@ -988,14 +987,6 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   }
   if (NP > kSlabMaxPlanes) NP = kSlabMaxPlanes;
   p.NP = NP;
-  if (!p.zmerge && !p.wstream) {
-    // resident weights, per-slice schedule: the upper half of a table entry carries the MMA's weight-slot offset (B descriptor units),
-    // so the issue loop adds one table half to each descriptor and keeps no running weight pointer (the other schedules add the
-    // whole 64-bit entry to the A descriptor: their upper halves stay zero)
-    for (int gi = 0; gi < 3 * nph; ++gi)
-      for (int i = p.g[gi]; i < p.ge[gi]; ++i)
-        p.tab[i] |= (uint64_t)((uint32_t)(p.gw[gi] + (i - p.g[gi])) * ((uint32_t)(Ntc * 32) >> 4)) << 32;
-  }
   // multi-phase layers (transposed convolutions) at one or two CTAs per SM are bound by their four epilogue warps: give them eight
   static const bool no_e2 = getenv("DFF_B200_NO_EPI2") != nullptr;
   p.egroups = (nph >= 2 && occ <= 2 && !no_e2) ? 2 : 1;
@@ -1073,6 +1064,15 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
     DFF_CUDA(launch_pdl(conv_slab_kernel<WS_, E2_>, dim3(grid), dim3(slab_threads(WS_, E2_)), smem, st, p));                        \
   } while (0)
   static const bool no_i2 = getenv("DFF_B200_NO_I2") != nullptr;   // (A/B knob: one issuing warp everywhere)
+  if (p.zmerge && p.nph == 2 && !p.wstream) {
+    if (p.egroups == 2) {
+      DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DFF_CUDA(launch_pdl(conv_slab_kernel<false, true, false, true>, dim3(grid), dim3(slab_threads(false, true)), smem, st, p));
+    } else {
+      DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DFF_CUDA(launch_pdl(conv_slab_kernel<false, false, false, true>, dim3(grid), dim3(slab_threads(false, false)), smem, st, p));
+    }
+  } else
   if (!no_i2 && !p.wstream && p.egroups == 2 && !p.zmerge && p.nph == 2 && p.hz == 0 && occ == 1) {
     DFF_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DFF_CUDA(launch_pdl(conv_slab_kernel<false, true, true>, dim3(grid), dim3(slab_threads(false, true) + 32), smem, st, p));

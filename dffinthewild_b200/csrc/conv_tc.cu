@@ -17,6 +17,7 @@
 // Persistent CTAs (one per SM) walk the tile list; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
 #include <cstring>
 
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace dff {
@@ -200,8 +201,12 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
   EncodeTiledFn fn = get_encode();
   if (!fn) return fail(-3, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  // (A/B knob DFF_B200_TMAP_L2 = 0 | 64 | 128 | 256: L2 promotion of the tensor maps; default 256)
+  static const int l2p = getenv("DFF_B200_TMAP_L2") ? atoi(getenv("DFF_B200_TMAP_L2")) : 256;
+  const CUtensorMapL2promotion prom = l2p == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2p == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                      : l2p == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return 0;
 }

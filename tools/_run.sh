@@ -1,7 +1,6 @@
-set -x
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r4a_pytest.log 2>&1; tail -3 gpurun_out/r4a_pytest.log
-timeout 900 python bench.py > gpurun_out/r4a_bench.json 2> gpurun_out/r4a_bench.err; tail -2 gpurun_out/r4a_bench.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r4a_launches_bf16.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train > /dev/null 2>&1
-timeout 120 python tools/launch_by_layer.py gpurun_out/r4a_launches_bf16.csv 64 10 384 576 1 > gpurun_out/r4a_by_layer.txt 2>&1
-timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_slab --launch-count 1 -o gpurun_out/r4a_fm0 python tools/one_forward.py 64 10 384 576 bf16 > gpurun_out/r4a_ncu1.log 2>&1
-timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_slab --launch-skip 50 --launch-count 4 -o gpurun_out/r4a_dres4 python tools/one_forward.py 64 10 384 576 bf16 > gpurun_out/r4a_ncu2.log 2>&1
+timeout 300 python tools/train_profile.py bf16 1 2>&1 | tail -1
+timeout 500 python -m pytest tests/test_gpu_forms.py tests/test_gpu_forward.py -x -q 2>&1 | tail -2
+timeout 300 python bench.py --steps 20 --e2e-steps 2 --no-cpu-baseline --no-train 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
+print(round(d['value']), r['kernel'], round(r['frac'],3), round(r['aggregation_convs']['frac_of_tensor_peak'],3), [(o['name'][:22], round(o['ms_per_call'],3)) for o in r['operators_top12'][:9]])"
