@@ -1,6 +1,5 @@
-timeout 300 python tools/train_profile.py bf16 1 2>&1 | tail -1
-timeout 500 python -m pytest tests/test_gpu_forms.py tests/test_gpu_forward.py -x -q 2>&1 | tail -2
-timeout 300 python bench.py --steps 20 --e2e-steps 2 --no-cpu-baseline --no-train 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
-print(round(d['value']), r['kernel'], round(r['frac'],3), round(r['aggregation_convs']['frac_of_tensor_peak'],3), [(o['name'][:22], round(o['ms_per_call'],3)) for o in r['operators_top12'][:9]])"
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r4c_pytest.log 2>&1; tail -2 gpurun_out/r4c_pytest.log
+timeout 900 python bench.py > gpurun_out/r4c_bench.json 2> gpurun_out/r4c_bench.err; tail -2 gpurun_out/r4c_bench.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r4c_launches_bf16.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train > /dev/null 2>&1
+timeout 120 python tools/launch_by_layer.py gpurun_out/r4c_launches_bf16.csv 64 10 384 576 1 > gpurun_out/r4c_by_layer.txt 2>&1
+DFF_B200_WGRAD_STREAM=0 DFF_B200_WGRAD_LOG=1 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r4c_train_launches.csv python tools/train_profile.py bf16 0 > gpurun_out/r4c_train.log 2> gpurun_out/r4c_train.err
