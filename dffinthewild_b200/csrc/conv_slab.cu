@@ -63,6 +63,12 @@ struct alignas(64) SlabParams {
   // is RX * 16 contiguous bytes.  The TMA unit retires about one innermost box row per clock: with 16-byte rows a 55 KB plane of the
   // first layer took ~4000 clk to land (13.7 B/clk per SM) and bounded that layer (profiles/r2_changes_measured.txt).
   int tmerge[2];
+  // Wide-row mode (sources of 16 / 32 / 64n channels): a plane block is PIXEL-major — [row][pixel][cb channels], rb = 2 * cb = 32 / 64 /
+  // 128 bytes per pixel — written by TMA boxes (cb, RX, RY) in the matching 32B / 64B / 128B swizzle and read through swizzled K-major
+  // descriptors: ONE TMA row per pixel instead of one per 8 channels (the TMA unit saturates at 0.6 sixteen-byte rows per clock and SM:
+  // 9.6 B/clk, tools/ubench/tma_row_bench.cu).  A tap is still a start-address offset (any pixel, any 32-byte K step: the swizzle is a
+  // function of the absolute shared-memory address for TMA and MMA alike — tools/ubench/swz_probe.cu, base offset 0 everywhere).
+  int wr, rb;
   const void* in0;
   const void* in1;
   const void* wslab;  // bf16 [tap][chunk][N][8]
@@ -326,6 +332,14 @@ __global__ void __launch_bounds__(slab_threads(WS, E2) + (I2 ? 32 : 0), (WS || I
           if (!(p.exp & 1)) {
             const uint32_t dst0 = planes_s + slot * p.plane_bytes;
             const int x0 = tx0 / p.stx + p.ox, y0 = ty0 / p.sty + p.oy, bz = b * p.S + z;   // view coordinates of the staged region
+            if (p.wr) {
+              const int cb = p.rb >> 1, nblk = (p.nchunk * 8) / cb;
+              for (int blk = 0; blk < nblk; ++blk) {
+                const int cabs = blk * cb, src = cabs >= p.C0 ? 1 : 0, cc = src ? cabs - p.C0 : cabs;
+                for (int v = 0; v < p.nviews; ++v)
+                  tma_load_4d(dst0 + blk * p.CPS + v * p.VB, &p.tmap[src * 4 + v], full0 + 8 * slot, cc, x0, y0, bz);
+              }
+            } else
             for (int c = 0; c < p.nchunk; ++c) {
               const int src = c >= p.nch0 ? 1 : 0, cc = src ? c - p.nch0 : c;
               for (int v = 0; v < p.nviews; ++v)
@@ -392,7 +406,8 @@ __global__ void __launch_bounds__(slab_threads(WS, E2) + (I2 ? 32 : 0), (WS || I
     const bool leader = elect_one();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
     // descriptor high words: SBO (8-row group stride) | version 1 | no swizzle
-    const uint64_t a_hi = (uint64_t)(((uint32_t)p.sbo >> 4) | (1u << 14)) << 32;
+    const uint64_t a_hi = ((uint64_t)(((uint32_t)p.sbo >> 4) | (1u << 14)) << 32) |
+                          ((uint64_t)(p.wr ? (p.rb == 32 ? 6u : (p.rb == 64 ? 4u : 2u)) : 0u) << 61);   // (wide rows: 32B / 64B / 128B swizzle)
     const uint64_t b_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
     const uint64_t b_step = (uint32_t)(p.N * 32) >> 4;
     const uint64_t bd_base = b_hi | (uint64_t)((w_s >> 4) | (((uint32_t)(p.N * 16) >> 4) << 16));
@@ -777,11 +792,23 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.VB = (p.RY * p.RX * 16 + 127) & ~127;   // (each (chunk, view) block is the destination of one TMA box: 128-byte aligned)
   p.CPS = p.nviews * p.VB;
   p.plane_bytes = nchunk * p.CPS;
+  {
+    static const bool no_wr = getenv("DFF_B200_NO_WR") != nullptr;            // (A/B knob)
+    static const int tma_mode_wr = getenv("DFF_B200_SLAB_TMA") ? atoi(getenv("DFF_B200_SLAB_TMA")) : 2;
+    const int cb = a.C0 >= 64 ? 64 : a.C0;
+    const bool tma_ok = tma_mode_wr > 1 && p.RX <= 256 && p.RY <= 256 && a.IW % p.stx == 0 && a.IH % p.sty == 0;
+    if (!no_wr && !exp_aligned && tma_ok && a.row_step == 0 && (cb == 16 || cb == 32 || cb == 64) && a.C0 % cb == 0 && a.C1 % cb == 0) {
+      p.wr = 1; p.rb = 2 * cb;
+      p.VB = (p.RY * p.RX * p.rb + 1023) & ~1023;
+      p.CPS = p.nviews * p.VB;
+      p.plane_bytes = ((a.C0 + a.C1) / cb) * p.CPS;
+    }
+  }
   if (p.sty * p.oy < -kSlabElemBias || p.stx * p.ox < -kSlabElemBias || p.sty * (p.oy + p.RY) > 255 - kSlabElemBias ||
       p.stx * (p.ox + p.RX) > 255 - kSlabElemBias)
     return_false;   // (staging-table coordinates are biased bytes)
   p.tile_sy = a.row_step > 0 ? kSlabTH * a.row_step : kSlabTH * p.sty;
-  p.sbo = (a.row_step > 0 ? a.row_step : 1) * p.RX * 16;
+  p.sbo = (a.row_step > 0 ? a.row_step : 1) * p.RX * (p.wr ? p.rb : 16);
   if ((p.CPS >> 4) >= (1 << 14) || p.sbo >= (1 << 18)) return_false;
   auto aoff = [&](const VT& x, int chunk) {
     int o = chunk * p.CPS + x.view * p.VB + ((x.vy - p.oy) * p.RX + (x.vx - p.ox)) * 16;
@@ -805,6 +832,11 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
       for (auto& x : grp)
         for (int j = 0; j < nchunk; j += 2) {
           if (nops >= kSlabMaxOps) return_false;
+          if (p.wr) {   // 16 channels = one 32-byte K step of the pixel's row in block (8 j) / cb
+            const int cb = p.rb >> 1, c = 8 * j, blk = c / cb;
+            const int o = blk * p.CPS + x.view * p.VB + ((x.vy - p.oy) * p.RX + (x.vx - p.ox)) * p.rb + (c - blk * cb) * 2;
+            p.tab[nops] = (uint32_t)(o >> 4) | (1u << 16);
+          } else
           p.tab[nops] = (uint32_t)(aoff(x, j) >> 4) | ((uint32_t)(p.CPS >> 4) << 16);
           p.wsrc[2 * nops] = (int16_t)(x.widx * nchunk + j);
           p.wsrc[2 * nops + 1] = (int16_t)(x.widx * nchunk + j + 1);
@@ -1038,8 +1070,16 @@ int launch_conv_slab(const ConvArgs& a, const TapTable* ptaps, int nph, const vo
       const char* base = (const char*)(src ? a.in1 : a.in0);
       static const bool no_merge = getenv("DFF_B200_NO_TMERGE") != nullptr;   // (A/B knob)
       p.tmerge[src] = (!no_merge && C == 8 && p.stx == 1 && 8 * p.RX <= 256) ? 1 : 0;
+      if (p.wr) p.tmerge[src] = 0;
       for (int v = 0; v < p.nviews; ++v) {
         const int vy = v / p.stx, vx = v % p.stx;
+        if (p.wr) {   // pixel-major rows of cb channels, swizzled
+          const unsigned long long dims[4] = {C, (unsigned long long)(a.IW / p.stx), (unsigned long long)(a.IH / p.sty), (unsigned long long)a.S * a.B};
+          const unsigned long long strides[3] = {C * 2 * p.stx, (unsigned long long)a.IW * C * 2 * p.sty, (unsigned long long)a.IH * a.IW * C * 2};
+          const unsigned box[4] = {(unsigned)(p.rb >> 1), (unsigned)p.RX, (unsigned)p.RY, 1u};
+          DFF_TRY(encode_tmap_bf16(&p.tmap[src * 4 + v], base + ((size_t)vy * a.IW + vx) * C * 2, 4, dims, strides, box, p.rb));
+          continue;
+        }
         if (p.tmerge[src]) {   // (8*W, 1, H/sty, S*B): box rows of RX * 16 contiguous bytes
           const unsigned long long dims[4] = {8ull * a.IW, 1ull, (unsigned long long)(a.IH / p.sty), (unsigned long long)a.S * a.B};
           const unsigned long long strides[3] = {(unsigned long long)a.IW * 16, (unsigned long long)a.IW * 16 * p.sty, (unsigned long long)a.IH * a.IW * 16};

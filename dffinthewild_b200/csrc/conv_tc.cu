@@ -211,13 +211,16 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
   return 0;
 }
 
+// swizzle_bytes: 0 (none), 32, 64 or 128 — the swizzle span, equal to the bytes of the box's innermost row
 int encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
-                     const unsigned* box) {
+                     const unsigned* box, int swizzle_bytes) {
   cuuint64_t d[5], sb[4];
   cuuint32_t bx[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) sb[i] = strides_bytes[i];
-  return encode(m, base, rank, d, sb, bx, CU_TENSOR_MAP_SWIZZLE_NONE);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  return encode(m, base, rank, d, sb, bx, sw);
 }
 
 bool conv_tc_supported(const ConvArgs& a, int Ntc) {

@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_tma_kernel(const __g
 }
 
 int encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
-                     const unsigned* box);
+                     const unsigned* box, int swizzle_bytes);
 
 // `a`: geometry / sources / strides as for the other kernels; `pt[nph]`: the tap tables of the phases (nph = 1: an ordinary launch
 // with a.ooy/a.oox; nph = 4: the four output-parity phases (py, px) = (ph >> 1, ph & 1) of a stride-2 transposed convolution).

@@ -161,7 +161,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 // host: bf16 tiled tensor map without swizzle (conv_tc.cu); out-of-bounds elements read as zero
 int encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
-                     const unsigned* box);
+                     const unsigned* box, int swizzle_bytes = 0);
 
 // ---- fused epilogue of one 128-pixel x N accumulator tile --------------------------------------------------------------
 // y = acc*scale[c] + shift[c] (BatchNorm eval / bias; scale and shift are both given or both null, 16-byte aligned) ; += res_pre ; ReLU ; += res_post ; store bf16 channels-last (or fp32

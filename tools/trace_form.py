@@ -22,6 +22,12 @@ elif case == "conv0":
 elif case == "conv5":
     x, w = r(B, 32, S, H // 4, W // 4), r(32, 16, 3, 3, 3) * 0.1
     f = lambda: rt.conv3d_forward_plan(x, w, 2, 1, True, scale=r(16) + 1.5, shift=r(16), res_pre=r(B, 16, S, H // 2, W // 2), relu=True)
+elif case == "srd0":   # FM_measure...Focus_Measure.conv.0: 8 -> 8, 1x3x3, BN + ReLU (x-folded G = 4)
+    x, w = r(B, 8, S, H, W), r(8, 8, 1, 3, 3) * 0.2
+    f = lambda: rt.conv3d_forward_plan(x, w, 1, 1, False, scale=r(8) + 1.5, shift=r(8), relu=True)
+elif case == "srd2":   # ...conv.2: + residual before the ReLU
+    x, w = r(B, 8, S, H, W), r(8, 8, 1, 3, 3) * 0.2
+    f = lambda: rt.conv3d_forward_plan(x, w, 1, 1, False, scale=r(8) + 1.5, shift=r(8), res_pre=r(B, 8, S, H, W), relu=True)
 elif case == "first":
     x, w = r(B, 3, S, H, W), r(8, 3, 1, 9, 9) * 0.1
     f = lambda: rt.conv3d_forward_plan(x, w, 1, 2, False, scale=r(8) + 1.5, shift=r(8), relu=True)
