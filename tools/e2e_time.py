@@ -12,6 +12,7 @@ torch.manual_seed(0)
 net = Network()
 net.load_state_dict(synth.synthetic_state(net.state_dict(), seed=2))
 net.DFF_net.precision = prec
+net.optical_flow_aggregation.precision = prec
 net = net.cuda().eval()
 FS, fd, fov = synth.focal_stack(1, 10, H, W).cuda(), synth.focus_dists(1, 10, H, W, "ddff", tiled=False).cuda(), synth.fovs(1, 10).cuda()
 with torch.no_grad():
@@ -26,5 +27,5 @@ with torch.no_grad():
         torch.cuda.synchronize()
         ta += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
 V = 10 * H * W
-print("E2E 1x10x3x%dx%d: alignment network (fp32) %.2f ms [%.1f TFLOP/s, 56,504 FLOP/voxel], depth network (%s) %.2f ms -> %.1f stacks/s" % (
+print("E2E 1x10x3x%dx%d: alignment network %.2f ms [%.1f TFLOP/s, 56,504 FLOP/voxel], depth network (%s) %.2f ms -> %.1f stacks/s" % (
     H, W, ta / n, 56504.0 * V / (ta / n) / 1e9, prec, tb / n, 1000 * n / (ta + tb)))

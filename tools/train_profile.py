@@ -9,7 +9,7 @@ from dffinthewild_b200.Depth_Estimation_Network import Network
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 graph = (sys.argv[2] != "0") if len(sys.argv) > 2 else True
-B, S, H, W = 4, 5, 256, 256
+B, S, H, W = (int(sys.argv[3]) if len(sys.argv) > 3 else 4), 5, 256, 256
 torch.manual_seed(0)
 net = Network()
 net.load_state_dict(synth.synthetic_state(net.state_dict(), seed=1))
@@ -28,7 +28,7 @@ for _ in range(5):
     st.step(FS, fd, gt, mask)
 e1.record()
 torch.cuda.synchronize()
-print("train step %s graph=%s: %.2f ms/step (graphed: %s)" % (prec, graph, e0.elapsed_time(e1) / 5, info["graphed"]))
+print("train step %s graph=%s B=%d: %.2f ms/step = %.0f stacks/s (graphed: %s)" % (prec, graph, B, e0.elapsed_time(e1) / 5, 5000.0 * B / e0.elapsed_time(e1), info["graphed"]))
 torch.cuda.profiler.start()
 st.step(FS, fd, gt, mask)
 torch.cuda.synchronize()
