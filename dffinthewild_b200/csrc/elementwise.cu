@@ -952,6 +952,27 @@ __global__ void pair_volume_kernel(const T* __restrict__ feat, const float* __re
   for (int c = 2 * C + 4; c < Cs; c += 4) Elem<T>::store4(o + c, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
+// bf16, C % 8 == 0: one 16-byte piece of the output per thread — consecutive lanes write consecutive pieces of a pixel (coalesced
+// 16-byte accesses instead of 8-byte stores 2*Cs bytes apart); only the flow piece evaluates the warp geometry.  Same values.
+__global__ void __launch_bounds__(256) pair_volume_cl8_kernel(const uint4* __restrict__ feat, const float* __restrict__ alpha,
+                                                              const float* __restrict__ fov, int B, int C8, int S, int H, int W,
+                                                              uint4* __restrict__ out, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (pixel of the row, piece)
+  if (i >= W * P) return;
+  const int px = i / P, j = i - px * P, py = blockIdx.y;
+  const int bs = blockIdx.z, b = bs / S, s = bs % S;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (j < 2 * C8) {
+    const int ss = j < C8 ? S - 1 : s, c8 = j < C8 ? j : j - C8;
+    o = __ldg(feat + ((((size_t)b * S + ss) * H + py) * W + px) * C8 + c8);
+  } else if (j == 2 * C8) {
+    const WarpGeom g = warp_geom(alpha, fov, b, s, S, H, W, px, py);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(g.flx, g.fly);
+    o.x = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  out[(((size_t)bs * H + py) * W + px) * P + j] = o;
+}
+
 // alpha_out[b][c][s] = (alpha_in ? alpha_in[b][c][s] : 0) + scale[c] * mean over (y, x) of x[b,s,y,x,c]     (c < 3; x fp32, Cs stored)
 // = AdaptiveAvgPool3d((S,1,1)) of the head's last conv + the 0.001 factor on the scale term + the running sum (reference :78-79, 88-90)
 __global__ void spatial_mean_accum_kernel(const float* __restrict__ x, int Cs, int S, int H, int W, const float* __restrict__ alpha_in,
@@ -976,6 +997,49 @@ __global__ void spatial_mean_accum_kernel(const float* __restrict__ x, int Cs, i
     const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
     const size_t o = ((size_t)b * 3 + c) * S + s;
     alpha_out[o] = (alpha_in ? alpha_in[o] : 0.f) + sc * (float)(sh[c][0] / (double)n);
+  }
+}
+
+// Two-stage and deterministic: a fixed split of every slice (fixed partition, fixed tree), then one small block per slice.
+// (One block per slice — 10 blocks for a 10-slice stack — took 767 us at 512x768: 38 % of the alignment network's time at the C4 shape.)
+__global__ void __launch_bounds__(256) spatial_mean_partial_kernel(const float* __restrict__ x, int Cs, size_t n, double* __restrict__ partial) {
+  const int bs = blockIdx.y, nb = gridDim.x;
+  const float* p = x + (size_t)bs * n * Cs;
+  const size_t per = (n + nb - 1) / nb, lo = (size_t)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+  float f0 = 0, f1 = 0, f2 = 0;      // (<= a few hundred addends per thread; the cross-thread tree is double)
+  if (Cs == 4) {
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+      f0 += v.x; f1 += v.y; f2 += v.z;
+    }
+  } else {
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      f0 += p[i * Cs]; f1 += p[i * Cs + 1]; f2 += p[i * Cs + 2];
+    }
+  }
+  __shared__ double sh[3][256];
+  sh[0][threadIdx.x] = f0; sh[1][threadIdx.x] = f1; sh[2][threadIdx.x] = f2;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if ((int)threadIdx.x < k)
+      for (int c = 0; c < 3; ++c) sh[c][threadIdx.x] += sh[c][threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) partial[((size_t)bs * nb + blockIdx.x) * 3 + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void __launch_bounds__(96) spatial_mean_finish_kernel(const double* __restrict__ partial, int nb, int S, double n,
+                                                                const float* __restrict__ alpha_in, float s0, float s1, float s2,
+                                                                float* __restrict__ alpha_out) {
+  const int bs = blockIdx.x, b = bs / S, s = bs % S;
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;   // one warp per channel
+  double a = 0;
+  for (int i = lane; i < nb; i += 32) a += partial[((size_t)bs * nb + i) * 3 + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if (lane == 0) {
+    const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const size_t o = ((size_t)b * 3 + c) * S + s;
+    alpha_out[o] = (alpha_in ? alpha_in[o] : 0.f) + sc * (float)(a / n);
   }
 }
 
@@ -1036,17 +1100,43 @@ int launch_pair_volume(const void* feat, const float* alpha, const float* fov, i
   if (C % 4) return fail(-1, "pair_volume: C must be a multiple of 4");
   if (Cs == 0) Cs = 2 * C + 8;
   if (Cs % 4 || Cs < 2 * C + 4) return fail(-1, "pair_volume: stored channels must be a multiple of 4 and >= 2C+4");
+  if (bf16 && C % 8 == 0 && Cs % 8 == 0 && Cs >= 2 * C + 8) {
+    dim3 g8(cdiv(W * (Cs / 8), 256), H, B * S);
+    pair_volume_cl8_kernel<<<g8, 256, 0, st>>>((const uint4*)feat, alpha, fov, B, C / 8, S, H, W, (uint4*)out, Cs / 8);
+    DFF_LAUNCH_CHECK("pair_volume_cl8");
+    return 0;
+  }
   dim3 grid(cdiv(W, 128), H, B * S);
   if (bf16) pair_volume_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)feat, alpha, fov, B, C, S, H, W, (__nv_bfloat16*)out, Cs);
   else pair_volume_kernel<<<grid, 128, 0, st>>>((const float*)feat, alpha, fov, B, C, S, H, W, (float*)out, Cs);
   DFF_LAUNCH_CHECK("pair_volume");
   return 0;
 }
+// blocks per slice of the first stage (a function of the shape only: the result does not depend on the device)
+int spatial_mean_blocks(int B, int S, int H, int W) {
+  const size_t n = (size_t)H * W;
+  int nb = (int)(n / 4096);                                  // >= 16 pixels per thread
+  const int cap = (2368 + B * S - 1) / (B * S);              // ~16 blocks per SM in total
+  if (nb > cap) nb = cap;
+  if (nb > 256) nb = 256;
+  return nb < 1 ? 1 : nb;
+}
+size_t spatial_mean_scratch_bytes(int B, int S, int H, int W) { return (size_t)B * S * spatial_mean_blocks(B, S, H, W) * 3 * sizeof(double); }
+
 int launch_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, const float* alpha_in, float s0, float s1, float s2,
-                              float* alpha_out, cudaStream_t st) {
+                              float* alpha_out, void* scratch, cudaStream_t st) {
   if (Cs < 3) return fail(-1, "spatial_mean_accum: needs at least 3 stored channels");
-  spatial_mean_accum_kernel<<<B * S, 256, 0, st>>>(x, Cs, S, H, W, alpha_in, s0, s1, s2, alpha_out);
-  DFF_LAUNCH_CHECK("spatial_mean_accum");
+  if (B * S > 65535) return fail(-1, "spatial_mean_accum: more than 65535 slices");
+  if (!scratch) {   // (single-operator entry point without scratch: one block per slice)
+    spatial_mean_accum_kernel<<<B * S, 256, 0, st>>>(x, Cs, S, H, W, alpha_in, s0, s1, s2, alpha_out);
+    DFF_LAUNCH_CHECK("spatial_mean_accum");
+    return 0;
+  }
+  const int nb = spatial_mean_blocks(B, S, H, W);
+  spatial_mean_partial_kernel<<<dim3(nb, B * S), 256, 0, st>>>(x, Cs, (size_t)H * W, (double*)scratch);
+  DFF_LAUNCH_CHECK("spatial_mean_partial");
+  spatial_mean_finish_kernel<<<B * S, 96, 0, st>>>((const double*)scratch, nb, S, (double)H * W, alpha_in, s0, s1, s2, alpha_out);
+  DFF_LAUNCH_CHECK("spatial_mean_finish");
   return 0;
 }
 

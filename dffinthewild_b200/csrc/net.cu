@@ -36,7 +36,8 @@ int launch_fov_warp_cl(const void* x, const float* alpha, const float* fov, int 
 int launch_pair_volume(const void* feat, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
                        cudaStream_t st, int Cs = 0);
 int launch_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, const float* alpha_in, float s0, float s1, float s2,
-                              float* alpha_out, cudaStream_t st);
+                              float* alpha_out, void* scratch, cudaStream_t st);
+size_t spatial_mean_scratch_bytes(int B, int S, int H, int W);
 int launch_fov_warp(const float* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, float* out,
                     float* flow, cudaStream_t st);
 int launch_pack_weight(const float* w, float* dst, int Cout, int Cin, int ntaps, int CinP, int CoutP, int transposed,
@@ -977,6 +978,8 @@ static int flow_forward_impl(const void* packed, const float* FS, const float* f
   for (int k = 0; k < 3; ++k) {
     const Ten& f = *feats[k];
     const std::string h = heads[k];
+    // (measured and rejected: warp + pair volume as ONE kernel with a 16-byte output piece per thread — 267 us against 59 + 133 us at
+    // 512x768: three warp geometries per pixel instead of two, and the warp is issue-bound; profiles/r2_changes_measured.txt)
     Ten warped = r.alloc(f.B, f.S, f.H, f.W, f.C);
     Ten vol = r.alloc(f.B, f.S, f.H, f.W, 2 * f.C + 16);
     if (!dry && !r.rc) r.rc = launch_fov_warp_cl(f.p, alpha, fov, B, f.C, S, f.H, f.W, warped.p, r.bf16, st);
@@ -989,7 +992,8 @@ static int flow_forward_impl(const void* packed, const float* FS, const float* f
     Ten o = r.conv(h + ".6", t, eo);                     // (B,S,h,w,3) fp32, bias in the epilogue
     float* na = (float*)r.alloc_bytes((size_t)B * 3 * S * sizeof(float));
     // AdaptiveAvgPool3d((S,1,1)) + the 0.001 factor on the scale term + the running sum (reference :78-79, 88-90, 99-101)
-    if (!dry && !r.rc) r.rc = launch_spatial_mean_accum((const float*)o.p, 3, B, S, f.H, f.W, alpha, 0.001f, 1.f, 1.f, na, st);
+    void* msc = r.alloc_bytes(spatial_mean_scratch_bytes(B, S, f.H, f.W));
+    if (!dry && !r.rc) r.rc = launch_spatial_mean_accum((const float*)o.p, 3, B, S, f.H, f.W, alpha, 0.001f, 1.f, 1.f, na, msc, st);
     alpha = na;
   }
   if (need) *need = r.off;
@@ -1897,7 +1901,7 @@ int dff_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, c
   if (!x || !alpha_out) return fail(DFF_E_ARG, "dff_spatial_mean_accum: null pointer");
   DeviceGuard g(device);
   if (g.rc) return g.rc;
-  return launch_spatial_mean_accum(x, Cs, B, S, H, W, alpha_in, s0, s1, s2, alpha_out, (cudaStream_t)stream);
+  return launch_spatial_mean_accum(x, Cs, B, S, H, W, alpha_in, s0, s1, s2, alpha_out, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

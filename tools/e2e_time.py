@@ -16,11 +16,11 @@ net.optical_flow_aggregation.precision = prec
 net = net.cuda().eval()
 FS, fd, fov = synth.focal_stack(1, 10, H, W).cuda(), synth.focus_dists(1, 10, H, W, "ddff", tiled=False).cuda(), synth.fovs(1, 10).cuda()
 with torch.no_grad():
-    for _ in range(2):
+    for _ in range(10):
         net(FS, fd, fov)
     torch.cuda.synchronize()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    n = 3
+    n = 20
     ta = tb = 0.0
     for _ in range(n):
         e[0].record(); w = net.optical_flow_aggregation(FS, fov); e[1].record(); net.DFF_net(w, fd); e[2].record()
