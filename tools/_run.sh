@@ -1,5 +1,4 @@
-timeout 600 python -m pytest tests/test_e2e.py -x -q 2>&1 | tail -3
-timeout 600 python -m pytest tests/test_gpu_ops.py -x -q -k "pair or warp or flow or mean" 2>&1 | tail -3
-timeout 200 python tools/e2e_time.py 512 768 bf16 2>&1 | tail -1
-timeout 200 python tools/e2e_time.py 512 768 bf16 2>&1 | tail -1
-timeout 200 python tools/e2e_time.py 512 768 fp32 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r5_pytest.log 2>&1; tail -3 gpurun_out/r5_pytest.log
+timeout 900 python bench.py > gpurun_out/r5_bench.json 2> gpurun_out/r5_bench.err; tail -2 gpurun_out/r5_bench.err; head -c 600 gpurun_out/r5_bench.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r5_launches_bf16.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train > /dev/null 2>&1
+timeout 120 python tools/launch_by_layer.py gpurun_out/r5_launches_bf16.csv 64 10 384 576 1 > gpurun_out/r5_by_layer.txt 2>&1; head -3 gpurun_out/r5_by_layer.txt
