@@ -1,4 +1,6 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r5_pytest.log 2>&1; tail -3 gpurun_out/r5_pytest.log
-timeout 900 python bench.py > gpurun_out/r5_bench.json 2> gpurun_out/r5_bench.err; tail -2 gpurun_out/r5_bench.err; head -c 600 gpurun_out/r5_bench.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r5_launches_bf16.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train > /dev/null 2>&1
-timeout 120 python tools/launch_by_layer.py gpurun_out/r5_launches_bf16.csv 64 10 384 576 1 > gpurun_out/r5_by_layer.txt 2>&1; head -3 gpurun_out/r5_by_layer.txt
+for l in 256 128 64 0; do DFF_B200_TMAP_L2=$l timeout 200 python tools/by_op.py 16 bf16 > gpurun_out/ops_l2_$l.txt 2>&1; head -1 gpurun_out/ops_l2_$l.txt; done
+python tools/by_op.py --diff gpurun_out/ops_l2_256.txt gpurun_out/ops_l2_128.txt | grep -E "<<<|>>>|TOTAL"
+echo ---- 64
+python tools/by_op.py --diff gpurun_out/ops_l2_256.txt gpurun_out/ops_l2_64.txt | grep -E "<<<|>>>|TOTAL"
+echo ---- 0
+python tools/by_op.py --diff gpurun_out/ops_l2_256.txt gpurun_out/ops_l2_0.txt | grep -E "<<<|>>>|TOTAL"
