@@ -441,6 +441,8 @@ struct Wg2Args {
   int isx, isy, dzmin, dymin, dxmin, RX, RY, REGP;
   int TX, TY, NP;
   int CK, s8, nsub, ncta;
+  int ksplit;                   // warps sharing one accumulator block, each taking every ksplit-th k-row group of a tile (few-tap layers
+                                 // have fewer blocks than warps: one warp walking all 64 k-steps of a tile alone was instruction-latency-bound)
   int nst, cs;                  // pipeline stages (2..4); CTAs per cluster (1, 2, 4, 8: the accumulators of a cluster are summed
                                  // through distributed shared memory before they go to the gradient)
   int MT, NT, NB, MB, mper, nslots;
@@ -493,8 +495,10 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_tma_kernel(const __g
     }
 
   // ---- this warp's block of accumulators: m16-tiles [mt0, mt0 + mcount) x n8-tiles [nt0, nt0 + NW) ----
-  const int item = sub * (kWgThreads / 32) + warp;
-  const bool active = item < g.MB * g.NB;
+  const int nblk = g.MB * g.NB, ks = g.ksplit;
+  const int item = ks > 1 ? warp % nblk : sub * (kWgThreads / 32) + warp;
+  const int kpart = ks > 1 ? warp / nblk : 0;
+  const bool active = ks > 1 ? kpart < ks : item < nblk;
   const int mb = active ? item / g.NB : 0, nb = active ? item - mb * g.NB : 0;
   const int mt0 = mb * g.mper;
   const int mcount = active ? max(0, min(g.mper, g.MT - mt0)) : 0;
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_tma_kernel(const __g
     const uint32_t sb = s0 + (uint32_t)stage * stage_bytes;
     if (mcount > 0) {
 #pragma unroll 1
-      for (int rr = 0; rr < nrow; ++rr) {
+      for (int rr = kpart; rr < nrow; rr += ks) {
 #pragma unroll 1
         for (int h = 0; h < nh; ++h) {
           const uint32_t ka = sb + (uint32_t)rr * rowstep + (uint32_t)h * halfstep;
@@ -589,8 +593,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) conv_wgrad_tma_kernel(const __g
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     for (int ws = (int)rank; ws < kWgThreads / 32; ws += g.cs) {
-      const int it2 = sub * (kWgThreads / 32) + ws;
-      if (it2 >= g.MB * g.NB) continue;
+      const int it2 = ks > 1 ? ws % nblk : sub * (kWgThreads / 32) + ws;   // (k-split: every warp slot of a block is one more addend)
+      if (ks > 1 ? ws >= nblk * ks : it2 >= nblk) continue;
       const int mb2 = it2 / g.NB, nb2 = it2 - mb2 * g.NB;
       const int mt02 = mb2 * g.mper, mc2 = max(0, min(g.mper, g.MT - mt02)), nt02 = nb2 * NW;
       for (int pi = warp; pi < mc2 * NW; pi += kWgThreads / 32) {
@@ -728,6 +732,8 @@ int launch_conv_wgrad_tma(const ConvArgs& a, const TapTable* pt, int nph, const 
   ga.isx = a.isx; ga.isy = a.isy; ga.RX = RX; ga.RY = RY; ga.REGP = REGP;
   ga.TX = TX; ga.TY = TY; ga.NP = TX * TY;
   ga.CK = CK; ga.s8 = s8; ga.nsub = nsub;
+  static const bool no_ksplit = getenv("DFF_B200_WGRAD_NO_KSPLIT") != nullptr;   // (A/B knob)
+  ga.ksplit = (!no_ksplit && nsub == 1 && MB * NB <= (kWgThreads / 32) / 2) ? (kWgThreads / 32) / (MB * NB) : 1;
   ga.MT = MT; ga.NT = NT; ga.NB = NB; ga.MB = MB; ga.mper = mper; ga.nslots = nslots;
   ga.Cout = Cout; ga.Cin = Cin; ga.ci_base = ci_base; ga.ntaps_total = ntaps_total; ga.wt_transposed = wt_transposed;
   ga.dw = dw;

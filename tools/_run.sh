@@ -1,6 +1,7 @@
-for l in 256 128 64 0; do DFF_B200_TMAP_L2=$l timeout 200 python tools/by_op.py 16 bf16 > gpurun_out/ops_l2_$l.txt 2>&1; head -1 gpurun_out/ops_l2_$l.txt; done
-python tools/by_op.py --diff gpurun_out/ops_l2_256.txt gpurun_out/ops_l2_128.txt | grep -E "<<<|>>>|TOTAL"
-echo ---- 64
-python tools/by_op.py --diff gpurun_out/ops_l2_256.txt gpurun_out/ops_l2_64.txt | grep -E "<<<|>>>|TOTAL"
-echo ---- 0
-python tools/by_op.py --diff gpurun_out/ops_l2_256.txt gpurun_out/ops_l2_0.txt | grep -E "<<<|>>>|TOTAL"
+timeout 900 python -m pytest tests/test_gpu_train.py -x -q 2>&1 | tail -3
+for i in 1 2; do
+echo "ksplit : $(timeout 300 python tools/train_profile.py bf16 1 32 2>&1 | tail -1)"
+echo "nosplit: $(DFF_B200_WGRAD_NO_KSPLIT=1 timeout 300 python tools/train_profile.py bf16 1 32 2>&1 | tail -1)"
+done
+echo "ksplit B=4 : $(timeout 300 python tools/train_profile.py bf16 1 4 2>&1 | tail -1)"
+echo "nosplit B=4: $(DFF_B200_WGRAD_NO_KSPLIT=1 timeout 300 python tools/train_profile.py bf16 1 4 2>&1 | tail -1)"
