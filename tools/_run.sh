@@ -1,7 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_train.py -x -q 2>&1 | tail -3
-for i in 1 2; do
-echo "ksplit : $(timeout 300 python tools/train_profile.py bf16 1 32 2>&1 | tail -1)"
-echo "nosplit: $(DFF_B200_WGRAD_NO_KSPLIT=1 timeout 300 python tools/train_profile.py bf16 1 32 2>&1 | tail -1)"
-done
-echo "ksplit B=4 : $(timeout 300 python tools/train_profile.py bf16 1 4 2>&1 | tail -1)"
-echo "nosplit B=4: $(DFF_B200_WGRAD_NO_KSPLIT=1 timeout 300 python tools/train_profile.py bf16 1 4 2>&1 | tail -1)"
+timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on --launch-skip 66 --launch-count 3 -o gpurun_out/r5_wr_dres4c3 -f python tools/one_forward.py 16 10 384 576 bf16 > /dev/null 2>&1
+DFF_B200_NO_WR=1 timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on --launch-skip 66 --launch-count 3 -o gpurun_out/r5_nowr_dres4c3 -f python tools/one_forward.py 16 10 384 576 bf16 > /dev/null 2>&1
+ls -la gpurun_out/r5_*dres4c3*
