@@ -161,3 +161,37 @@ def test_streamed_weights_and_per_tap_leftovers(rt):
         ref = F.relu(_ref_conv(x, w, stride, 1, False))
         out = rt.conv3d_forward_plan(x.cuda(), w.cuda(), stride, 1, False, relu=True)["out"].cpu().double()
         assert (out - ref).abs().max().item() <= TOL * ref.abs().max().item(), (cin, cout, stride)
+
+
+# (name, C0, C1, Cout, k, stride, S, H, W): sources of 16 / 32 / 64n channels run the wide-row plane layout (pixel-major planes,
+# 32B / 64B / 128B-swizzled TMA boxes and A descriptors): every swizzle width, concat sources, the four stride-2 views, 1x3x3 and
+# focal-merged 3x3x3 schedules, resident and streamed weights, sizes whose tiles are ragged in x and y (halo / out-of-bounds fill)
+WIDE_ROW = [
+    ("wr32B_16_16_1x3x3", 16, 0, 16, (1, 3, 3), 1, 3, 24, 40),
+    ("wr32B_16_32_s2", 16, 0, 32, (3, 3, 3), 2, 3, 32, 48),
+    ("wr32B_16+16_16_ragged", 16, 16, 16, (3, 3, 3), 1, 2, 20, 44),
+    ("wr64B_32_32_1x3x3", 32, 0, 32, (1, 3, 3), 1, 2, 16, 24),
+    ("wr64B_32+32_32", 32, 32, 32, (3, 3, 3), 1, 3, 16, 24),
+    ("wr64B_32_64_s2", 32, 0, 64, (3, 3, 3), 2, 2, 16, 32),
+    ("wr128B_64_64_1x3x3", 64, 0, 64, (1, 3, 3), 1, 2, 8, 24),
+    ("wr128B_64+64_64", 64, 64, 64, (3, 3, 3), 1, 2, 8, 16),
+    ("wr128B_128+64_128", 128, 64, 128, (3, 3, 3), 1, 2, 8, 8),
+    ("wr32B_16_8_1x1x1", 16, 0, 8, (1, 1, 1), 1, 2, 16, 32),
+]
+
+
+@pytest.mark.parametrize("case", WIDE_ROW, ids=[c[0] for c in WIDE_ROW])
+def test_wide_row_plane_layout(rt, case):
+    """bf16 convolution with BN scale/shift, residual before the ReLU, on 16/32/64n-channel sources (wide-row planes) against torch
+    fp64 on the same bf16-rounded operands."""
+    name, c0, c1, cout, k, stride, S, H, W = case
+    cin = c0 + c1
+    x = _rand(2, cin, S, H, W, seed=51)
+    w = _rand(cout, cin, *k, seed=52, scale=(2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5 * 1.7)
+    scale, shift = _ss(cout)
+    res = _rand(2, cout, S, H // stride, W // stride, seed=53)
+    ref = F.relu(_ref_conv(x, w, stride, 1, False) * _bc(scale) + _bc(shift) + res.double())
+    out = rt.conv3d_forward_plan(x[:, :c0].contiguous().cuda(), w.cuda(), stride, 1, False, scale=scale.cuda(), shift=shift.cuda(),
+                                 res_pre=res.cuda(), relu=True, x2=x[:, c0:].contiguous().cuda() if c1 else None)["out"].cpu().double()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= TOL * ref.abs().max().item(), name
