@@ -140,6 +140,17 @@ __global__ void pair_weight_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
+// The stride-2 (1,2,2) 3x3 layer on a source read as pixel pairs (.., W/2, 2C): dst (Cout, 2C, kd, 3, 2) with pair tap q = 0, 1 <-> pair
+// offset -1, 0 and channel g*C + ci of a pair = pixel g of it: fine offset dx = 2*(q-1) + g in {-1, 0, 1} (dx = -2: zero).
+__global__ void xpair_weight_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin, int kd) {
+  const int n = Cout * 2 * Cin * kd * 6;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int q = i % 2, kb = (i / 2) % 3, ka = (i / 6) % kd, cp = (i / (6 * kd)) % (2 * Cin), co = i / (6 * kd * 2 * Cin);
+    const int g = cp / Cin, ci = cp - g * Cin, dx = 2 * (q - 1) + g;
+    dst[i] = dx < -1 ? 0.f : w[((((size_t)co * Cin + ci) * kd + ka) * 3 + kb) * 3 + (dx + 1)];
+  }
+}
+
 static inline int grid_for(size_t n, int threads, int cap = 148 * 16) {
   size_t g = (n + threads - 1) / threads;
   return (int)(g < (size_t)cap ? (g ? g : 1) : cap);
@@ -182,6 +193,11 @@ int launch_u8_to_planar(const unsigned char* src, int B, int S, int H0, int W0, 
 int launch_pair_weight(const float* w, float* dst, int Cout, cudaStream_t st) {
   pair_weight_kernel<<<cdiv(Cout * 360, 256), 256, 0, st>>>(w, dst, Cout);
   DFF_LAUNCH_CHECK("pair_weight");
+  return 0;
+}
+int launch_xpair_weight(const float* w, float* dst, int Cout, int Cin, int kd, cudaStream_t st) {
+  xpair_weight_kernel<<<cdiv(Cout * 2 * Cin * kd * 6, 256), 256, 0, st>>>(w, dst, Cout, Cin, kd);
+  DFF_LAUNCH_CHECK("xpair_weight");
   return 0;
 }
 int launch_from_cl(const void* src, int B, int C, int S, int H, int W, int Cp, bool bf16, float* dst, cudaStream_t st) {

@@ -33,6 +33,7 @@ int launch_srd_attention_mma(const void* F, const float* w0, const float* w1, vo
                              cudaStream_t st);
 int launch_fov_warp_cl(const void* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
                        cudaStream_t st);
+int launch_xpair_weight(const float* w, float* dst, int Cout, int Cin, int kd, cudaStream_t st);
 int launch_pair_volume(const void* feat, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
                        cudaStream_t st, int Cs = 0);
 int launch_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, const float* alpha_in, float s0, float s1, float s2,
@@ -128,6 +129,11 @@ struct Layer {
   size_t pk_w, pk_scale, pk_shift, pk_wtc, pk_wslab, pk_proj, pk_pair, pk_wfold, pk_ssfold;                  // byte offsets in the packed buffer
   size_t pk_wfoldy = 0;  // y-folded form of the 8-output-channel x-folded layers (8-channel sources: merged TMA rows, no x-stride views)
   bool has_foldy = false;
+  // x-paired form of the stride-2 layers with 8 / 16-channel sources: the source (.., W, C) is read as (.., W/2, 2C) — a stride-1 walk in x
+  // over pixel PAIRS with two taps (pair -1: its second pixel = dx -1; pair 0: dx 0 and +1) — so the planes have two (row-parity) views
+  // of 2C-channel pixels instead of four views of C-channel ones: half the TMA rows, twice as long (wide-row layout for 2C >= 16)
+  size_t pk_xpw = 0, pk_wxp = 0;   // the equivalent (Cout, 2C, kd, 3, 2) convolution weight (fp32) and its slab pack
+  bool has_xpair = false;
   size_t pk_wz = 0;      // focal-merged streaming layout (3x3x3 layers with >= 64 stored input channels, whose weights are streamed)
   bool has_wz = false;
 };
@@ -189,6 +195,13 @@ static void layout_layer(Layer& l, size_t& packed_bytes) {
   if (!transposed && kd == 3 && kh == 3 && kw == 3 && dil == 1 && l.CinT % 16 == 0 && l.CinT * l.Ntc >= 32 * 64) {
     l.has_wz = true;
     packed_bytes += align_up((size_t)27 * l.CinT * l.Ntc * 2, 256);
+  }
+  if (!transposed && stride == 2 && dil == 1 && kh == 3 && kw == 3 && (cin == 8 || cin == 16) && l.CinT == cin) {
+    l.has_xpair = true;
+    l.pk_xpw = packed_bytes;
+    packed_bytes += align_up((size_t)cout * 2 * cin * kd * 6 * sizeof(float), 256);
+    l.pk_wxp = packed_bytes;
+    packed_bytes += align_up((size_t)kd * 6 * l.Ntc * 2 * cin * 2, 256);
   }
 }
 struct Param {
@@ -498,6 +511,27 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     a.OHt = out.H; a.OWt = out.W;
     *nlaunch = 1;
     if (count_only) return 0;
+    static const bool no_xpair = getenv("DFF_B200_NO_XPAIR") != nullptr;   // (A/B knob)
+    static const int xpair_maxc = getenv("DFF_B200_XPAIR_MAXC") ? atoi(getenv("DFF_B200_XPAIR_MAXC")) : 16;
+    if (wtc && use_fold && packed_base && l.has_xpair && !no_xpair && a.C1 == 0 && a.C0 == l.cin && l.cin <= xpair_maxc && a.IW % 2 == 0 &&
+        a.Cout == out.C) {
+      // x-paired form of a stride-2 layer (see Layer::has_xpair): source read as (.., W/2, 2C), stride 1 in x, taps on pairs -1 and 0
+      ConvArgs f = a;
+      f.C0 = 2 * a.C0;
+      f.IW = a.IW / 2;
+      f.taps.n = 0;
+      for (int ka = 0; ka < l.kd; ++ka)
+        for (int kb = 0; kb < 3; ++kb)
+          for (int q = 0; q < 2; ++q) {
+            f.taps.dz[f.taps.n] = (int8_t)(ka - (l.kd - 1) / 2);
+            f.taps.dy[f.taps.n] = (int8_t)(kb - 1);
+            f.taps.dx[f.taps.n] = (int8_t)(q - 1);
+            f.taps.widx[f.taps.n] = (uint8_t)((ka * 3 + kb) * 2 + q);
+            ++f.taps.n;
+          }
+      f.isy = 2; f.isx = 1;
+      if (conv_slab_supported(f, nullptr, 1, l.Ntc)) return launch_conv_slab(f, nullptr, 1, packed_base + l.pk_wxp, l.Ntc, nsm, st);
+    }
     static const bool no_yfold = getenv("DFF_B200_NO_YFOLD") != nullptr;   // (A/B knob)
     if (wtc && use_fold && packed_base && l.has_foldy && !no_yfold && !a.proj_w && !a.aux_add && !a.out_f32 && a.Cout == l.cout &&
         a.C0 == 8 && (a.C1 == 0 || a.C1 == 8) && out.H % l.gfold == 0) {
@@ -1036,6 +1070,10 @@ static int pack_layer_weights(const Layer& l, const float* w, char* pk, cudaStre
     if (l.has_foldy) DFF_TRY(launch_pack_weight_slab_fold(w, pk + l.pk_wfoldy, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st, 1));
   }
   if (l.has_wz) DFF_TRY(launch_pack_weight_slab_zmerge(w, pk + l.pk_wz, l.cout, l.cin, l.CinT, l.Ntc, st));
+  if (l.has_xpair) {
+    DFF_TRY(launch_xpair_weight(w, (float*)(pk + l.pk_xpw), l.cout, l.cin, l.kd, st));
+    DFF_TRY(launch_pack_weight_slab((const float*)(pk + l.pk_xpw), pk + l.pk_wxp, l.cout, 2 * l.cin, 2 * l.cin, l.kd * 6, l.Ntc, 0, st));
+  }
   return 0;
 }
 // scale/shift of the folded forms (replicated per pixel of the GEMM row) from the layer's scale/shift in `pk`
@@ -1462,6 +1500,11 @@ size_t dff_conv3d_scratch_bytes(int Cin, int Cout, int kd, int kh, int kw) {
   size_t n = 0, m = 0;
   adhoc_layer(Cin, Cout, kd, kh, kw, 1, kh == 9 ? 2 : 1, false, true, &n);
   adhoc_layer(Cin, Cout, 3, 3, 3, 2, 1, true, true, &m);
+  if (kh == 3 && kw == 3) {   // (a stride-2 layer: its x-paired pack)
+    size_t q = 0;
+    adhoc_layer(Cin, Cout, kd, kh, kw, 2, 1, false, true, &q);
+    n = n > q ? n : q;
+  }
   return (n > m ? n : m) + align_up((size_t)align_up(Cout, 16) * 4 * sizeof(float), 256) + 1024;
 }
 

@@ -177,6 +177,11 @@ WIDE_ROW = [
     ("wr128B_64+64_64", 64, 64, 64, (3, 3, 3), 1, 2, 8, 16),
     ("wr128B_128+64_128", 128, 64, 128, (3, 3, 3), 1, 2, 8, 8),
     ("wr32B_16_8_1x1x1", 16, 0, 8, (1, 1, 1), 1, 2, 16, 32),
+    # stride-2 layers with 8 / 16-channel sources run x-paired: the source read as (.., W/2, 2C), two row-parity views
+    ("xpair_8_16_s2", 8, 0, 16, (3, 3, 3), 2, 3, 32, 48),
+    ("xpair_8_16_s2_ragged", 8, 0, 16, (3, 3, 3), 2, 2, 20, 44),
+    ("xpair_16_16_s2", 16, 0, 16, (3, 3, 3), 2, 2, 24, 40),
+    ("xpair_8_8_1x3x3_s2", 8, 0, 8, (1, 3, 3), 2, 2, 16, 32),
 ]
 
 
