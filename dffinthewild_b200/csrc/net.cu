@@ -512,7 +512,7 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     *nlaunch = 1;
     if (count_only) return 0;
     static const bool no_xpair = getenv("DFF_B200_NO_XPAIR") != nullptr;   // (A/B knob)
-    static const int xpair_maxc = getenv("DFF_B200_XPAIR_MAXC") ? atoi(getenv("DFF_B200_XPAIR_MAXC")) : 16;
+    static const int xpair_maxc = getenv("DFF_B200_XPAIR_MAXC") ? atoi(getenv("DFF_B200_XPAIR_MAXC")) : 8;   // (16-channel sources: measured neutral — half the rows against +33 % MMAs)
     if (wtc && use_fold && packed_base && l.has_xpair && !no_xpair && a.C1 == 0 && a.C0 == l.cin && l.cin <= xpair_maxc && a.IW % 2 == 0 &&
         a.Cout == out.C) {
       // x-paired form of a stride-2 layer (see Layer::has_xpair): source read as (.., W/2, 2C), stride 1 in x, taps on pairs -1 and 0
