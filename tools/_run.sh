@@ -1,7 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_forms.py -x -q -k "wide_row" 2>&1 | tail -5
-timeout 200 python tools/by_op.py 16 bf16 > gpurun_out/ops_xp.txt 2> gpurun_out/ops_xp.err; tail -3 gpurun_out/ops_xp.err
-DFF_B200_XPAIR_MAXC=8 timeout 200 python tools/by_op.py 16 bf16 > gpurun_out/ops_xp8.txt 2>&1
-DFF_B200_NO_XPAIR=1 timeout 200 python tools/by_op.py 16 bf16 > gpurun_out/ops_noxp.txt 2>&1
-python tools/by_op.py --diff gpurun_out/ops_noxp.txt gpurun_out/ops_xp.txt | grep -E "<<<|>>>|TOTAL"
-echo ---- maxc 8
-python tools/by_op.py --diff gpurun_out/ops_noxp.txt gpurun_out/ops_xp8.txt | grep -E "<<<|>>>|TOTAL"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r6_pytest.log 2>&1; tail -3 gpurun_out/r6_pytest.log
+timeout 900 python bench.py > gpurun_out/r6_bench.json 2> gpurun_out/r6_bench.err; tail -2 gpurun_out/r6_bench.err; head -c 200 gpurun_out/r6_bench.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r6_launches_bf16.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train > /dev/null 2>&1
+timeout 120 python tools/launch_by_layer.py gpurun_out/r6_launches_bf16.csv 64 10 384 576 1 > gpurun_out/r6_by_layer.txt 2>&1; head -1 gpurun_out/r6_by_layer.txt
