@@ -1,4 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r6_pytest.log 2>&1; tail -3 gpurun_out/r6_pytest.log
-timeout 900 python bench.py > gpurun_out/r6_bench.json 2> gpurun_out/r6_bench.err; tail -2 gpurun_out/r6_bench.err; head -c 200 gpurun_out/r6_bench.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r6_launches_bf16.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train > /dev/null 2>&1
-timeout 120 python tools/launch_by_layer.py gpurun_out/r6_launches_bf16.csv 64 10 384 576 1 > gpurun_out/r6_by_layer.txt 2>&1; head -1 gpurun_out/r6_by_layer.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+for k in 2 3 4; do echo "ZM_NPMIN=$k $(DFF_ZM_NPMIN=$k timeout 200 python tools/quick_time.py 16 10 384 576 bf16 2>&1 | tail -1)"; done
+echo "base $(timeout 200 python tools/quick_time.py 16 10 384 576 bf16 2>&1 | tail -1)"
