@@ -416,15 +416,21 @@ def run_ours(args):
     hp2 = (ctypes.c_void_p * 4)(*[o.data_ptr() for o in houts2])
     slots = [(hp, dev_io, ws), (hp2, dev_io2, ws2)]
 
-    def e2e_begin(t):
+    def e2e_begin(t, final_only=False):
         o, io, w = slots[t]
+        if final_only:
+            o = hp_f[t]
         rt.check(lib.dff_forward_host_u8_async(packed.data_ptr(), hU8.data_ptr(), H0, W0, hfd.data_ptr(), strides, n_local, emb, S, H, W, o,
                                                io.data_ptr(), w.data_ptr(), w.numel(), mode, local, sp, t))
 
-    def e2e_pipelined(k):
-        e2e_begin(0)
+    # what the reference's own call site takes to the host: `_, _, _, test_pred3 = model(...)`; `test_pred3.data.cpu()`
+    # (Depth_Estimation_Test/test.py:118-121) — the final depth map only; the library skips the read of a map whose host pointer is NULL
+    hp_f = [(ctypes.c_void_p * 4)(None, None, None, o[3].data_ptr()) for o in (houts, houts2)]
+
+    def e2e_pipelined(k, final_only=False):
+        e2e_begin(0, final_only)
         for i in range(1, k):
-            e2e_begin(i & 1)
+            e2e_begin(i & 1, final_only)
             rt.check(lib.dff_forward_host_wait(local, (i - 1) & 1))
         rt.check(lib.dff_forward_host_wait(local, (k - 1) & 1))
 
@@ -442,27 +448,43 @@ def run_ours(args):
     e2e_pipelined(e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    same = all(torch.equal(h.to(dev), o) for h, o in zip(houts, outs)) and all(torch.equal(h.to(dev), o) for h, o in zip(houts2, outs))
+    for h in (houts[3], houts2[3]):
+        h.zero_()
+    e2e_pipelined(2, True)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_pipelined(e2e_steps, True)
+    barrier()
+    e2e_f_s = time.perf_counter() - t0
+    same_f = torch.equal(houts[3].to(dev), outs[3]) and torch.equal(houts2[3].to(dev), outs[3])
     if world > 1:
-        t = torch.tensor([e2e_s, e2e_sync_s], device=dev)
+        t = torch.tensor([e2e_s, e2e_sync_s, e2e_f_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, e2e_sync_s = float(t[0].item()), float(t[1].item())
+        e2e_s, e2e_sync_s, e2e_f_s = float(t[0].item()), float(t[1].item()), float(t[2].item())
     e2e_val = PER_GPU_BATCH * world * e2e_steps / e2e_s
     h2d = n_local * (3 * S * H0 * W0 + S * 4)
     d2h = n_local * 4 * H * W * 4
-    same = all(torch.equal(h.to(dev), o) for h, o in zip(houts, outs)) and all(torch.equal(h.to(dev), o) for h, o in zip(houts2, outs))
     line = {
         "metric": METRIC, "value": value, "unit": "stacks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": workload_config(world, mb, args.precision),
         "clocks": clk.summary(),
-        "e2e": {"value": e2e_val, "unit": "stacks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "dff_forward_host_u8_async + dff_forward_host_wait (C-ABI, pinned host buffers: uint8 stacks + "
-                                           "S focus distances in, four fp32 maps out; double-buffered: step i+1 is queued before step i is "
-                                           "waited for; inside a call copies are pipelined with kernels over micro-batches of <= %d)" % emb,
-                "synchronous": {"value": PER_GPU_BATCH * world * e2e_steps / e2e_sync_s, "unit": "stacks/s",
-                                "api": "dff_forward_host_u8: one blocking call per step (first upload and last read of every step exposed)"},
-                "matches_device_run": bool(same)},
+        # primary: what the reference's inference call site delivers (the final depth map of every stack in host memory); the four-map
+        # variant (all heads read back: 4x the device->host bytes) is reported next to it
+        "e2e": {"value": PER_GPU_BATCH * world * e2e_steps / e2e_f_s, "unit": "stacks/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": n_local * H * W * 4, "steps": e2e_steps,
+                "api": "dff_forward_host_u8_async + dff_forward_host_wait (C-ABI, pinned host buffers: uint8 stacks + S focus distances in, "
+                       "the final fp32 depth map of every stack out — what the reference's call site takes to the host, test.py:118-121: "
+                       "`_, _, _, test_pred3 = model(...)`; `test_pred3.data.cpu()`; all four heads are computed, a map whose host "
+                       "pointer is NULL is not read back; double-buffered: step i+1 is queued before step i is waited for; inside a "
+                       "call copies are pipelined with kernels over micro-batches of <= %d)" % emb,
+                "all_four_maps": {"value": e2e_val, "unit": "stacks/s", "d2h_bytes_per_step": d2h, "matches_device_run": bool(same),
+                                  "api": "the same calls with all four depth maps (mid_out, pred1, pred2, pred3) read back"},
+                "synchronous": {"value": PER_GPU_BATCH * world * e2e_steps / e2e_sync_s, "unit": "stacks/s", "d2h_bytes_per_step": d2h,
+                                "api": "dff_forward_host_u8: one blocking call per step, four maps (first upload and last read of every step exposed)"},
+                "matches_device_run": bool(same_f and same)},
         "gpu_launches": launches_per_chunk * (n_local // mb) * args.steps,
         "roofline": roof,
     }
