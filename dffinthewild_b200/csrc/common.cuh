@@ -120,6 +120,8 @@ struct ConvArgs {
   int grp_rows;
   int proj_c;              // channels per pixel of the projection when a GEMM row holds several pixels (x-folded layers), 0 = all
   const void* wz;          // slab kernel, optional: the layer's weights in the focal-merged streaming layout (pack_weight_slab_zmerge)
+  int use_kmask;           // slab kernel, single-phase launches: tap_kmask[t] != 0 lists the 16-channel K steps of tap t whose weights are
+  uint8_t tap_kmask[kMaxTaps];   // not all zero (bit j = channels [16 j, 16 j + 16)); the others are not issued (banded weights of the x-grouped forms)
   TapTable taps;
 };
 

@@ -755,7 +755,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
   p.nviews = p.sty * p.stx;
   for (int v = 0; v < 4; ++v) { p.vpy[v] = v / p.stx; p.vpx[v] = v % p.stx; }
   // ---- taps in view coordinates -------------------------------------------------------------------------------------
-  struct VT { int dz, view, vy, vx, widx, ph; };
+  struct VT { int dz, view, vy, vx, widx, ph, kmask; };
   std::vector<VT> vt;
   int vymin = 1000, vymax = -1000, vxmin = 1000, vxmax = -1000, dzmin = 1000, dzmax = -1000;
   if (nph != 1 && nph != 2 && nph != 4) return_false;
@@ -770,6 +770,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     VT x;
     x.ph = ph;
     x.dz = tt.dz[t]; x.widx = tt.widx[t];
+    x.kmask = (a.use_kmask && nph == 1 && ptaps == &a.taps) ? a.tap_kmask[t] : 0;
     int dy = tt.dy[t], dx = tt.dx[t];
     {  // input coordinate sty*o + d  ->  view (d mod sty, d mod stx), view coordinate o + floor(d / st)
       const int py = ((dy % p.sty) + p.sty) % p.sty, px = ((dx % p.stx) + p.stx) % p.stx;
@@ -831,6 +832,7 @@ static bool slab_plan(const ConvArgs& a, const TapTable* ptaps, int nph, int Ntc
     if (nchunk > 1) {
       for (auto& x : grp)
         for (int j = 0; j < nchunk; j += 2) {
+          if (x.kmask && !((x.kmask >> (j >> 1)) & 1)) continue;   // (a K step of all-zero weights: banded x-grouped forms)
           if (nops >= kSlabMaxOps) return_false;
           if (p.wr) {   // 16 channels = one 32-byte K step of the pixel's row in block (8 j) / cb
             const int cb = p.rb >> 1, c = 8 * j, blk = c / cb;

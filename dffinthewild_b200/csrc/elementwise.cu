@@ -195,6 +195,30 @@ int launch_pair_weight(const float* w, float* dst, int Cout, cudaStream_t st) {
   DFF_LAUNCH_CHECK("pair_weight");
   return 0;
 }
+// x-grouped forms: the source (.., W, C) is read as groups of P pixels (.., W/P, P*C) and G = P / s adjacent outputs of a stride-s layer
+// are the G*Cout channels of one GEMM row.  dst (G*Cout, P*C, kd, 3, nq) = the equivalent stride-1 convolution over groups with nq
+// group taps (group offset q - 1): output g of a group reads the fine offsets s*g + dx, dx in {-1, 0, 1}, i.e. pixel p of the group
+// q - 1 with P*(q - 1) + p = s*g + dx — a banded weight, zero elsewhere.
+__global__ void xgroup_weight_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin, int kd, int s, int G, int P,
+                                     int nq) {
+  const int n = G * Cout * P * Cin * kd * 3 * nq;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int r = i;
+    const int q = r % nq; r /= nq;
+    const int kb = r % 3; r /= 3;
+    const int ka = r % kd; r /= kd;
+    const int cp = r % (P * Cin); r /= P * Cin;
+    const int p = cp / Cin, ci = cp - p * Cin;
+    const int g = r / Cout, co = r - g * Cout;
+    const int dx = P * (q - 1) + p - s * g;
+    dst[i] = (dx < -1 || dx > 1) ? 0.f : w[((((size_t)co * Cin + ci) * kd + ka) * 3 + kb) * 3 + (dx + 1)];
+  }
+}
+int launch_xgroup_weight(const float* w, float* dst, int Cout, int Cin, int kd, int s, int G, int P, int nq, cudaStream_t st) {
+  xgroup_weight_kernel<<<cdiv(G * Cout * P * Cin * kd * 3 * nq, 256), 256, 0, st>>>(w, dst, Cout, Cin, kd, s, G, P, nq);
+  DFF_LAUNCH_CHECK("xgroup_weight");
+  return 0;
+}
 int launch_xpair_weight(const float* w, float* dst, int Cout, int Cin, int kd, cudaStream_t st) {
   xpair_weight_kernel<<<cdiv(Cout * 2 * Cin * kd * 6, 256), 256, 0, st>>>(w, dst, Cout, Cin, kd);
   DFF_LAUNCH_CHECK("xpair_weight");

@@ -34,6 +34,7 @@ int launch_srd_attention_mma(const void* F, const float* w0, const float* w1, vo
 int launch_fov_warp_cl(const void* x, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
                        cudaStream_t st);
 int launch_xpair_weight(const float* w, float* dst, int Cout, int Cin, int kd, cudaStream_t st);
+int launch_xgroup_weight(const float* w, float* dst, int Cout, int Cin, int kd, int s, int G, int P, int nq, cudaStream_t st);
 int launch_pair_volume(const void* feat, const float* alpha, const float* fov, int B, int C, int S, int H, int W, void* out, bool bf16,
                        cudaStream_t st, int Cs = 0);
 int launch_spatial_mean_accum(const float* x, int Cs, int B, int S, int H, int W, const float* alpha_in, float s0, float s1, float s2,
@@ -134,6 +135,12 @@ struct Layer {
   // of 2C-channel pixels instead of four views of C-channel ones: half the TMA rows, twice as long (wide-row layout for 2C >= 16)
   size_t pk_xpw = 0, pk_wxp = 0;   // the equivalent (Cout, 2C, kd, 3, 2) convolution weight (fp32) and its slab pack
   bool has_xpair = false;
+  // x-grouped forms of the layers with 8-channel sources whose planes were strided views of 16-byte TMA rows: the source read as groups of
+  // P = 4 pixels (64-byte rows, wide-row layout), G = P / stride adjacent outputs per GEMM row, banded group-tap weights, all-zero K steps
+  // not issued (ConvArgs::tap_kmask).  Stride 2 (8 -> <= 16): G = 2, group taps -1, 0.  Stride-1 1x3x3 8 -> 8: G = 4, group taps -1, 0, +1.
+  bool has_xgroup = false;
+  int xg_G = 0, xg_P = 0, xg_nq = 0;
+  size_t pk_xgw = 0, pk_wxg = 0, pk_ssxg = 0;
   size_t pk_wz = 0;      // focal-merged streaming layout (3x3x3 layers with >= 64 stored input channels, whose weights are streamed)
   bool has_wz = false;
 };
@@ -195,6 +202,18 @@ static void layout_layer(Layer& l, size_t& packed_bytes) {
   if (!transposed && kd == 3 && kh == 3 && kw == 3 && dil == 1 && l.CinT % 16 == 0 && l.CinT * l.Ntc >= 32 * 64) {
     l.has_wz = true;
     packed_bytes += align_up((size_t)27 * l.CinT * l.Ntc * 2, 256);
+  }
+  if (!transposed && dil == 1 && kh == 3 && kw == 3 && cin == 8 && l.CinT == 8 && cout % 8 == 0 &&
+      ((stride == 2 && cout <= 16) || (stride == 1 && kd == 1 && cout == 8))) {
+    l.has_xgroup = true;
+    l.xg_P = 4; l.xg_G = 4 / stride; l.xg_nq = stride == 2 ? 2 : 3;
+    const int Ng = (int)align_up(l.xg_G * cout, 16);
+    l.pk_xgw = packed_bytes;
+    packed_bytes += align_up((size_t)l.xg_G * cout * l.xg_P * cin * kd * 3 * l.xg_nq * sizeof(float), 256);
+    l.pk_wxg = packed_bytes;
+    packed_bytes += align_up((size_t)kd * 3 * l.xg_nq * Ng * l.xg_P * cin * 2, 256);
+    l.pk_ssxg = packed_bytes;
+    packed_bytes += align_up((size_t)2 * Ng * sizeof(float), 256);
   }
   if (!transposed && stride == 2 && dil == 1 && kh == 3 && kw == 3 && (cin == 8 || cin == 16) && l.CinT == cin) {
     l.has_xpair = true;
@@ -511,6 +530,36 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     a.OHt = out.H; a.OWt = out.W;
     *nlaunch = 1;
     if (count_only) return 0;
+    static const bool no_xgroup = getenv("DFF_B200_NO_XGROUP") != nullptr;   // (A/B knob)
+    static const int xgroup_sel = getenv("DFF_B200_XGROUP") ? atoi(getenv("DFF_B200_XGROUP")) : 3;   // (bit 0: stride-2 layers, bit 1: 1x3x3)
+    if (wtc && use_fold && packed_base && l.has_xgroup && !no_xgroup && ((xgroup_sel >> (l.stride == 2 ? 0 : 1)) & 1) && a.C1 == 0 &&
+        a.C0 == 8 && a.IW % l.xg_P == 0 && a.OW % (8 * l.xg_G) == 0 && !a.proj_w && !a.aux_add && !a.out_f32 && a.Cout == l.cout) {
+      // x-grouped form (see Layer::has_xgroup)
+      const int G = l.xg_G, P = l.xg_P, nq = l.xg_nq, Ng = (int)align_up(G * l.cout, 16);
+      ConvArgs f = a;
+      f.C0 = P * a.C0;
+      f.IW = a.IW / P;
+      f.taps.n = 0;
+      f.use_kmask = 1;
+      for (int ka = 0; ka < l.kd; ++ka)
+        for (int kb = 0; kb < 3; ++kb)
+          for (int q = 0; q < nq; ++q) {
+            const int t = f.taps.n;
+            f.taps.dz[t] = (int8_t)(ka - (l.kd - 1) / 2);
+            f.taps.dy[t] = (int8_t)(kb - 1);
+            f.taps.dx[t] = (int8_t)(q - 1);
+            f.taps.widx[t] = (uint8_t)((ka * 3 + kb) * nq + q);
+            // group -1 contributes its last pixel only (channels [24, 32): K step 1), group +1 its first (K step 0)
+            f.tap_kmask[t] = (uint8_t)(q == 0 ? 2 : (q == 2 ? 1 : 0));
+            ++f.taps.n;
+          }
+      f.isy = l.stride; f.isx = 1;
+      f.OW = a.OW / G; f.OWt = f.OW;
+      f.Cout = G * l.cout;
+      f.scale = (const float*)(packed_base + l.pk_ssxg);
+      f.shift = f.scale + G * l.cout;
+      if (conv_slab_supported(f, nullptr, 1, Ng)) return launch_conv_slab(f, nullptr, 1, packed_base + l.pk_wxg, Ng, nsm, st);
+    }
     static const bool no_xpair = getenv("DFF_B200_NO_XPAIR") != nullptr;   // (A/B knob)
     static const int xpair_maxc = getenv("DFF_B200_XPAIR_MAXC") ? atoi(getenv("DFF_B200_XPAIR_MAXC")) : 8;   // (16-channel sources: measured neutral — half the rows against +33 % MMAs)
     if (wtc && use_fold && packed_base && l.has_xpair && !no_xpair && a.C1 == 0 && a.C0 == l.cin && l.cin <= xpair_maxc && a.IW % 2 == 0 &&
@@ -1070,6 +1119,12 @@ static int pack_layer_weights(const Layer& l, const float* w, char* pk, cudaStre
     if (l.has_foldy) DFF_TRY(launch_pack_weight_slab_fold(w, pk + l.pk_wfoldy, l.cout, l.cin, l.CinT, l.kd, l.kh, l.kw, l.gfold, st, 1));
   }
   if (l.has_wz) DFF_TRY(launch_pack_weight_slab_zmerge(w, pk + l.pk_wz, l.cout, l.cin, l.CinT, l.Ntc, st));
+  if (l.has_xgroup) {
+    const int Ng = (int)align_up(l.xg_G * l.cout, 16);
+    DFF_TRY(launch_xgroup_weight(w, (float*)(pk + l.pk_xgw), l.cout, l.cin, l.kd, l.stride, l.xg_G, l.xg_P, l.xg_nq, st));
+    DFF_TRY(launch_pack_weight_slab((const float*)(pk + l.pk_xgw), pk + l.pk_wxg, l.xg_G * l.cout, l.xg_P * l.cin, l.xg_P * l.cin,
+                                    l.kd * 3 * l.xg_nq, Ng, 0, st));
+  }
   if (l.has_xpair) {
     DFF_TRY(launch_xpair_weight(w, (float*)(pk + l.pk_xpw), l.cout, l.cin, l.kd, st));
     DFF_TRY(launch_pack_weight_slab((const float*)(pk + l.pk_xpw), pk + l.pk_wxp, l.cout, 2 * l.cin, 2 * l.cin, l.kd * 6, l.Ntc, 0, st));
@@ -1081,6 +1136,8 @@ static int pack_layer_folded_ss(const Layer& l, char* pk, cudaStream_t st) {
   const int G = (l.pair_x && l.pk_wfold != l.pk_ssfold) ? 4 : l.gfold;
   if (G > 1)
     DFF_TRY(launch_replicate_ss((const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), (float*)(pk + l.pk_ssfold), l.cout, G, st));
+  if (l.has_xgroup)
+    DFF_TRY(launch_replicate_ss((const float*)(pk + l.pk_scale), (const float*)(pk + l.pk_shift), (float*)(pk + l.pk_ssxg), l.cout, l.xg_G, st));
   return 0;
 }
 

@@ -182,6 +182,13 @@ WIDE_ROW = [
     ("xpair_8_16_s2_ragged", 8, 0, 16, (3, 3, 3), 2, 2, 20, 44),
     ("xpair_16_16_s2", 16, 0, 16, (3, 3, 3), 2, 2, 24, 40),
     ("xpair_8_8_1x3x3_s2", 8, 0, 8, (1, 3, 3), 2, 2, 16, 32),
+    # x-grouped forms (widths that are multiples of 8 G output pixels): the source read as groups of four pixels, banded group-tap weights,
+    # all-zero K steps not issued
+    ("xgroup_8_16_s2", 8, 0, 16, (3, 3, 3), 2, 3, 32, 64),
+    ("xgroup_8_8_s2", 8, 0, 8, (3, 3, 3), 2, 2, 16, 32),
+    ("xgroup_8_16_s2_1x3x3", 8, 0, 16, (1, 3, 3), 2, 2, 20, 96),
+    ("xgroup_8_8_1x3x3_G4", 8, 0, 8, (1, 3, 3), 1, 3, 24, 64),
+    ("xgroup_8_8_1x3x3_G4_wide", 8, 0, 8, (1, 3, 3), 1, 2, 12, 160),
 ]
 
 

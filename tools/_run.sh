@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_forms.py tests/test_e2e.py -x -q 2>&1 | tail -2
-timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on --launch-skip 65 --launch-count 1 -o gpurun_out/r8_xp_dres4c1 -f python tools/one_forward.py 16 10 384 576 bf16 > /dev/null 2>&1
-DFF_B200_NO_XPAIR=1 timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on --launch-skip 65 --launch-count 1 -o gpurun_out/r8_noxp_dres4c1 -f python tools/one_forward.py 16 10 384 576 bf16 > /dev/null 2>&1
-ls gpurun_out/r8_*dres4c1*
+timeout 600 python -m pytest tests/test_gpu_forms.py tests/test_gpu_forward.py tests/test_e2e.py -x -q 2>&1 | tail -4
+timeout 200 python tools/by_op.py 16 bf16 > gpurun_out/ops_xg.txt 2> gpurun_out/ops_xg.err; tail -2 gpurun_out/ops_xg.err
+DFF_B200_NO_XGROUP=1 timeout 200 python tools/by_op.py 16 bf16 > gpurun_out/ops_noxg.txt 2>&1
+python tools/by_op.py --diff gpurun_out/ops_noxg.txt gpurun_out/ops_xg.txt | grep -E "<<<|>>>|TOTAL"
