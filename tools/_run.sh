@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_forms.py tests/test_gpu_forward.py tests/test_e2e.py -x -q 2>&1 | tail -4
-timeout 200 python tools/by_op.py 16 bf16 > gpurun_out/ops_xg.txt 2> gpurun_out/ops_xg.err; tail -2 gpurun_out/ops_xg.err
-DFF_B200_NO_XGROUP=1 timeout 200 python tools/by_op.py 16 bf16 > gpurun_out/ops_noxg.txt 2>&1
-python tools/by_op.py --diff gpurun_out/ops_noxg.txt gpurun_out/ops_xg.txt | grep -E "<<<|>>>|TOTAL"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r9_pytest.log 2>&1; tail -3 gpurun_out/r9_pytest.log
+timeout 900 python bench.py > gpurun_out/r9_bench.json 2> gpurun_out/r9_bench.err; tail -2 gpurun_out/r9_bench.err | cut -c1-200; head -c 150 gpurun_out/r9_bench.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r9_launches_bf16.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-train > /dev/null 2>&1
+timeout 120 python tools/launch_by_layer.py gpurun_out/r9_launches_bf16.csv 64 10 384 576 1 > gpurun_out/r9_by_layer.txt 2>&1; head -1 gpurun_out/r9_by_layer.txt
