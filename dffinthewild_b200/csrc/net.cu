@@ -135,8 +135,8 @@ struct Layer {
   // of 2C-channel pixels instead of four views of C-channel ones: half the TMA rows, twice as long (wide-row layout for 2C >= 16)
   size_t pk_xpw = 0, pk_wxp = 0;   // the equivalent (Cout, 2C, kd, 3, 2) convolution weight (fp32) and its slab pack
   bool has_xpair = false;
-  // x-grouped forms of the layers with 8-channel sources whose planes were strided views of 16-byte TMA rows: the source read as groups of
-  // P = 4 pixels (64-byte rows, wide-row layout), G = P / stride adjacent outputs per GEMM row, banded group-tap weights, all-zero K steps
+  // x-grouped forms of the layers with 8-channel sources whose planes were strided views of 16-byte TMA rows (and of the 1x3x3 16 -> 16
+  // layers, P = 2): the source read as groups of P = 4 pixels (64-byte rows, wide-row layout), G = P / stride adjacent outputs per GEMM row, banded group-tap weights, all-zero K steps
   // not issued (ConvArgs::tap_kmask).  Stride 2 (8 -> <= 16): G = 2, group taps -1, 0.  Stride-1 1x3x3 8 -> 8: G = 4, group taps -1, 0, +1.
   bool has_xgroup = false;
   int xg_G = 0, xg_P = 0, xg_nq = 0;
@@ -203,10 +203,11 @@ static void layout_layer(Layer& l, size_t& packed_bytes) {
     l.has_wz = true;
     packed_bytes += align_up((size_t)27 * l.CinT * l.Ntc * 2, 256);
   }
-  if (!transposed && dil == 1 && kh == 3 && kw == 3 && cin == 8 && l.CinT == 8 && cout % 8 == 0 &&
-      ((stride == 2 && cout <= 16) || (stride == 1 && kd == 1 && cout == 8))) {
+  const bool xg8 = cin == 8 && l.CinT == 8 && cout % 8 == 0 && ((stride == 2 && cout <= 16) || (stride == 1 && kd == 1 && cout == 8));
+  const bool xg16 = cin == 16 && l.CinT == 16 && cout == 16 && stride == 1 && kd == 1;   // 1x3x3 16 -> 16: pixel pairs, G = 2
+  if (!transposed && dil == 1 && kh == 3 && kw == 3 && (xg8 || xg16)) {
     l.has_xgroup = true;
-    l.xg_P = 4; l.xg_G = 4 / stride; l.xg_nq = stride == 2 ? 2 : 3;
+    l.xg_P = xg16 ? 2 : 4; l.xg_G = l.xg_P / stride; l.xg_nq = stride == 2 ? 2 : 3;
     const int Ng = (int)align_up(l.xg_G * cout, 16);
     l.pk_xgw = packed_bytes;
     packed_bytes += align_up((size_t)l.xg_G * cout * l.xg_P * cin * kd * 3 * l.xg_nq * sizeof(float), 256);
@@ -531,9 +532,9 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
     *nlaunch = 1;
     if (count_only) return 0;
     static const bool no_xgroup = getenv("DFF_B200_NO_XGROUP") != nullptr;   // (A/B knob)
-    static const int xgroup_sel = getenv("DFF_B200_XGROUP") ? atoi(getenv("DFF_B200_XGROUP")) : 3;   // (bit 0: stride-2 layers, bit 1: 1x3x3)
-    if (wtc && use_fold && packed_base && l.has_xgroup && !no_xgroup && ((xgroup_sel >> (l.stride == 2 ? 0 : 1)) & 1) && a.C1 == 0 &&
-        a.C0 == 8 && a.IW % l.xg_P == 0 && a.OW % (8 * l.xg_G) == 0 && !a.proj_w && !a.aux_add && !a.out_f32 && a.Cout == l.cout) {
+    static const int xgroup_sel = getenv("DFF_B200_XGROUP") ? atoi(getenv("DFF_B200_XGROUP")) : 7;   // (bit 0: stride-2 layers, bit 1: 1x3x3 8 -> 8, bit 2: 1x3x3 16 -> 16)
+    if (wtc && use_fold && packed_base && l.has_xgroup && !no_xgroup && ((xgroup_sel >> (l.stride == 2 ? 0 : (l.cin == 8 ? 1 : 2))) & 1) && a.C1 == 0 &&
+        a.C0 == l.cin && a.IW % l.xg_P == 0 && a.OW % (8 * l.xg_G) == 0 && !a.proj_w && !a.aux_add && !a.out_f32 && a.Cout == l.cout) {
       // x-grouped form (see Layer::has_xgroup)
       const int G = l.xg_G, P = l.xg_P, nq = l.xg_nq, Ng = (int)align_up(G * l.cout, 16);
       ConvArgs f = a;
@@ -549,7 +550,7 @@ static int run_conv(const Layer& l, const float* w, const float* scale, const fl
             f.taps.dy[t] = (int8_t)(kb - 1);
             f.taps.dx[t] = (int8_t)(q - 1);
             f.taps.widx[t] = (uint8_t)((ka * 3 + kb) * nq + q);
-            // group -1 contributes its last pixel only (channels [24, 32): K step 1), group +1 its first (K step 0)
+            // group -1 contributes its last pixel only (a group is 32 channels: K step 1), group +1 its first (K step 0)
             f.tap_kmask[t] = (uint8_t)(q == 0 ? 2 : (q == 2 ? 1 : 0));
             ++f.taps.n;
           }

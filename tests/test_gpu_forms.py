@@ -189,6 +189,8 @@ WIDE_ROW = [
     ("xgroup_8_16_s2_1x3x3", 8, 0, 16, (1, 3, 3), 2, 2, 20, 96),
     ("xgroup_8_8_1x3x3_G4", 8, 0, 8, (1, 3, 3), 1, 3, 24, 64),
     ("xgroup_8_8_1x3x3_G4_wide", 8, 0, 8, (1, 3, 3), 1, 2, 12, 160),
+    ("xgroup_16_16_1x3x3_G2", 16, 0, 16, (1, 3, 3), 1, 3, 24, 64),
+    ("xgroup_16_16_1x3x3_G2_wide", 16, 0, 16, (1, 3, 3), 1, 2, 20, 112),
 ]
 
 
